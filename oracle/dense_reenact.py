@@ -1,0 +1,414 @@
+"""TEST INFRASTRUCTURE ONLY -- tier-2 oracle: dense, literal numpy re-enactment of the reference loops.
+
+Nothing under oracle/ is part of the product.  Only tests/, __graft_entry__.smoke() and the
+cpu_baseline / --impl reference legs of bench.py may import this package.
+
+This module re-enacts, line by line and at toy sizes only, the reference's *dense* formulation:
+it builds the full 2M x P Jacobian, forms J^T J / J^T E densely and solves the full P x P system,
+calling cv2 exactly where the reference calls OpenCV.  It exists to pin that the block-sparse /
+Schur C oracle (oracle/mccba_oracle.c) and the CUDA path compute the same iterates.
+
+PARITY STATUS: parity unpinned by the reference's own tests (it has none) and the
+reference cannot be compiled here (no OpenCV C++ headers, no Eigen).  Pins used instead:
+  tier 0  cv2.projectPoints / cv2.Rodrigues / cv2.composeRT / cv2.matMulDeriv (third-party truth)
+  tier 1  the transcription of src/omnidir.cpp:126-243 below, finite-difference checked in tests
+  tier 2  this dense re-enactment
+
+Reference citations (relative to /root/reference):
+  optimize_extrinsics            src/multicalib.cpp:462-514
+  compute_jacobian_extrinsic     src/multicalib.cpp:593-703
+  compute_photo_camera_jacobian  src/multicalib.cpp:717-824
+  compose_motion                 src/multicalib.cpp:1008-1056
+  compute_project_error          src/multicalib.cpp:895-1006
+  omnidir_project_points         src/omnidir.cpp:84-245
+  omni_compute_jacobian          src/omnidir.cpp:851-935
+  omni_calibrate_loop            src/omnidir.cpp:1119-1147
+  flags2idx                      src/omnidir.cpp:2031-2076
+  omni_rms                       src/omnidir.cpp:1794-1802
+"""
+from __future__ import annotations
+
+import numpy as np
+
+try:  # cv2 is third-party truth for tier 0; present in this image (4.13.0)
+    import cv2
+except Exception:  # pragma: no cover
+    cv2 = None
+
+PINHOLE = 0
+OMNIDIRECTIONAL = 1
+
+CALIB_USE_GUESS = 1
+CALIB_FIX_SKEW = 2
+CALIB_FIX_K1 = 4
+CALIB_FIX_K2 = 8
+CALIB_FIX_P1 = 16
+CALIB_FIX_P2 = 32
+CALIB_FIX_XI = 64
+CALIB_FIX_GAMMA = 128
+CALIB_FIX_CENTER = 256
+
+
+# --------------------------------------------------------------------------------------------
+# Mei projection + 2x16 Jacobian: transcription of src/omnidir.cpp:126-243
+# --------------------------------------------------------------------------------------------
+def omnidir_project_points(obj, rvec, tvec, K, xi, D, want_jac=True):
+    """obj (N,3) float64; returns proj (N,2) float64 and jac (2N,16) float64.
+    Column layout (src/omnidir.cpp:65-73): dom(3) dT(3) df(2) ds(1) dc(2) dxi(1) dkp(4)."""
+    obj = np.asarray(obj, dtype=np.float64).reshape(-1, 3)
+    om = np.asarray(rvec, dtype=np.float64).reshape(3)
+    T = np.asarray(tvec, dtype=np.float64).reshape(3)
+    K = np.asarray(K, dtype=np.float64)
+    f = np.array([K[0, 0], K[1, 1]])
+    c = np.array([K[0, 2], K[1, 2]])
+    s = K[0, 1]
+    k1, k2, p1, p2 = [float(v) for v in np.asarray(D, dtype=np.float64).reshape(-1)[:4]]
+    R, dRdom = cv2.Rodrigues(om)  # dRdom is 3x9 (rows = d/dom_k)
+    n = obj.shape[0]
+    proj = np.zeros((n, 2))
+    jac = np.zeros((2 * n, 16)) if want_jac else None
+    for i in range(n):
+        Xw = obj[i]
+        Xc = R @ Xw + T
+        nrm = np.linalg.norm(Xc)
+        Xs = Xc / nrm
+        xu = np.array([Xs[0] / (Xs[2] + xi), Xs[1] / (Xs[2] + xi)])
+        r2 = xu[0] * xu[0] + xu[1] * xu[1]
+        r4 = r2 * r2
+        xd = np.array([
+            xu[0] * (1 + k1 * r2 + k2 * r4) + 2 * p1 * xu[0] * xu[1] + p2 * (r2 + 2 * xu[0] * xu[0]),
+            xu[1] * (1 + k1 * r2 + k2 * r4) + p1 * (r2 + 2 * xu[1] * xu[1]) + 2 * p2 * xu[0] * xu[1]])
+        proj[i, 0] = f[0] * xd[0] + s * xd[1] + c[0]
+        proj[i, 1] = f[1] * xd[1] + c[1]
+        if not want_jac:
+            continue
+        dXcdR = np.zeros((3, 9))
+        dXcdR[0, 0:3] = Xw
+        dXcdR[1, 3:6] = Xw
+        dXcdR[2, 6:9] = Xw
+        dXcdom = dXcdR @ dRdom.T
+        r_1 = 1.0 / nrm
+        r_3 = r_1 ** 3
+        dXsdXc = np.array([
+            [r_1 - Xc[0] * Xc[0] * r_3, -(Xc[0] * Xc[1]) * r_3, -(Xc[0] * Xc[2]) * r_3],
+            [-(Xc[0] * Xc[1]) * r_3, r_1 - Xc[1] * Xc[1] * r_3, -(Xc[1] * Xc[2]) * r_3],
+            [-(Xc[0] * Xc[2]) * r_3, -(Xc[1] * Xc[2]) * r_3, r_1 - Xc[2] * Xc[2] * r_3]])
+        den = Xs[2] + xi
+        dxudXs = np.array([[1 / den, 0, -Xs[0] / den / den],
+                           [0, 1 / den, -Xs[1] / den / den]])
+        temp1 = 2 * k1 * xu[0] + 4 * k2 * xu[0] * r2
+        temp2 = 2 * k1 * xu[1] + 4 * k2 * xu[1] * r2
+        dxddxu = np.array([
+            [k2 * r4 + 6 * p2 * xu[0] + 2 * p1 * xu[1] + xu[0] * temp1 + k1 * r2 + 1,
+             2 * p1 * xu[0] + 2 * p2 * xu[1] + xu[0] * temp2],
+            [2 * p1 * xu[0] + 2 * p2 * xu[1] + xu[1] * temp1,
+             k2 * r4 + 2 * p2 * xu[0] + 6 * p1 * xu[1] + xu[1] * temp2 + k1 * r2 + 1]])
+        dxpddxd = np.array([[f[0], s], [0, f[1]]])
+        dxpddXc = dxpddxd @ dxddxu @ dxudXs @ dXsdXc
+        dxpddom = dxpddXc @ dXcdom
+        dxpddT = dxpddXc
+        dxudxi = np.array([[-Xs[0] / den / den], [-Xs[1] / den / den]])
+        dxpddxi = dxpddxd @ dxddxu @ dxudxi
+        dxddkp = np.array([
+            [xu[0] * r2, xu[0] * r4, 2 * xu[0] * xu[1], r2 + 2 * xu[0] * xu[0]],
+            [xu[1] * r2, xu[1] * r4, r2 + 2 * xu[1] * xu[1], 2 * xu[0] * xu[1]]])
+        dxpddkp = dxpddxd @ dxddkp
+        row = jac[2 * i:2 * i + 2]
+        row[:, 0:3] = dxpddom
+        row[:, 3:6] = dxpddT
+        row[0, 6] = xd[0]; row[1, 7] = xd[1]          # df
+        row[0, 8] = xd[1]; row[1, 8] = 0.0            # ds
+        row[0, 9] = 1.0; row[1, 10] = 1.0             # dc
+        row[:, 11] = dxpddxi[:, 0]
+        row[:, 12:16] = dxpddkp
+    return proj, jac
+
+
+# --------------------------------------------------------------------------------------------
+# compose_motion: src/multicalib.cpp:1008-1056 (inputs widened to double at :1013-1016)
+# --------------------------------------------------------------------------------------------
+def compose_motion(om1, T1, om2, T2):
+    om1 = np.asarray(om1, dtype=np.float64).reshape(3, 1)
+    om2 = np.asarray(om2, dtype=np.float64).reshape(3, 1)
+    T1 = np.asarray(T1, dtype=np.float64).reshape(3, 1)
+    T2 = np.asarray(T2, dtype=np.float64).reshape(3, 1)
+    R1, dR1dom1 = cv2.Rodrigues(om1)
+    R2, dR2dom2 = cv2.Rodrigues(om2)
+    dR1dom1 = dR1dom1.T  # 9x3
+    dR2dom2 = dR2dom2.T
+    R3 = R2 @ R1
+    dR3dR2, dR3dR1 = cv2.matMulDeriv(R2, R1)
+    om3, dom3dR3 = cv2.Rodrigues(R3)
+    dom3dR3 = dom3dR3.T  # 3x9
+    dom3dom1 = dom3dR3 @ dR3dR1 @ dR1dom1
+    dom3dom2 = dom3dR3 @ dR3dR2 @ dR2dom2
+    dom3dT1 = np.zeros((3, 3)); dom3dT2 = np.zeros((3, 3))
+    T3t = R2 @ T1
+    dT3tdR2, dT3tdT1 = cv2.matMulDeriv(R2, T1)
+    dT3tdom2 = dT3tdR2 @ dR2dom2
+    T3 = T3t + T2
+    return (om3.reshape(3), T3.reshape(3), dom3dom1, dom3dT1, dom3dom2, dom3dT2,
+            np.zeros((3, 3)), dT3tdT1, dT3tdom2, np.eye(3))
+
+
+# --------------------------------------------------------------------------------------------
+# Problem container (follows the reference's members, include/opencv2/ccalib/multicalib.hpp:193-214)
+# --------------------------------------------------------------------------------------------
+class RigProblem:
+    """cam_type: PINHOLE or OMNIDIRECTIONAL per camera (the reference has one global type, fact 7).
+    K: (nC,3,3), dist: list of 1-D arrays (pinhole: >=4, omnidir: exactly 4), xi: (nC,).
+    edges: list of (cameraVertex, photoVertex, obj (N,3) f32, img (N,2) f32) in the reference's edge order.
+    n_vertex = nC + number of photo vertices.  params: 6*(n_vertex-1) = [rvec|tvec] per vertex 1..nV-1."""
+
+    def __init__(self, cam_type, K, dist, xi, edges, n_vertex):
+        self.cam_type = list(cam_type)
+        self.K = np.asarray(K, dtype=np.float64)
+        self.dist = [np.asarray(d, dtype=np.float64).reshape(-1) for d in dist]
+        self.xi = np.asarray(xi, dtype=np.float64).reshape(-1)
+        self.edges = edges
+        self.n_camera = len(self.cam_type)
+        self.n_vertex = int(n_vertex)
+
+    @property
+    def n_param(self):
+        return 6 * (self.n_vertex - 1)
+
+
+def _project_with_jac(prob, cam, obj, rvec, tvec):
+    if prob.cam_type[cam] == PINHOLE:
+        Kp = prob.K[cam].copy()
+        proj, jac = cv2.projectPoints(obj.reshape(-1, 1, 3), rvec.reshape(3, 1), tvec.reshape(3, 1), Kp,
+                                      prob.dist[cam].reshape(1, -1))
+        return proj.reshape(-1, 2), np.asarray(jac, dtype=np.float64)[:, 0:6]
+    proj, jac = omnidir_project_points(obj, rvec, tvec, prob.K[cam], float(prob.xi[cam]), prob.dist[cam])
+    return proj, jac[:, 0:6]
+
+
+def compute_photo_camera_jacobian(prob, e, rvecP, tvecP, rvecC, tvecC, policy):
+    """src/multicalib.cpp:717-824.  policy: 'fp64' or 'faithful_f32' (SURVEY.md appendix A)."""
+    cam, _, obj32, img32 = prob.edges[e]
+    (om3, T3, dom3dom1, dom3dT1, dom3dom2, dom3dT2,
+     dT3dom1, dT3dT1, dT3dom2, dT3dT2) = compose_motion(rvecP, tvecP, rvecC, tvecC)
+    if policy == 'faithful_f32':
+        om3 = om3.astype(np.float32)              # :742-749
+        T3 = T3.astype(np.float32)
+        obj = obj32.astype(np.float32)
+        proj, jac = _project_with_jac(prob, cam, obj, om3.astype(np.float64) if prob.cam_type[cam] else om3,
+                                      T3.astype(np.float64) if prob.cam_type[cam] else T3)
+        proj = proj.astype(np.float32)            # output depth follows objectPoints
+        E = (img32.astype(np.float32) - proj).astype(np.float64)   # :789-792 float32 subtraction
+    else:
+        obj = obj32.astype(np.float64)
+        proj, jac = _project_with_jac(prob, cam, obj, om3, T3)
+        E = img32.astype(np.float64) - proj
+    E = E.reshape(-1)                             # interleaved (x0,y0,x1,y1,...) :797
+    # camera pose is (om2,T2), photo pose is (om1,T1) at the call site :734
+    dx_drC = jac[:, 0:3] @ dom3dom2 + jac[:, 3:6] @ dT3dom2
+    dx_dtC = jac[:, 0:3] @ dom3dT2 + jac[:, 3:6] @ dT3dT2
+    dx_drP = jac[:, 0:3] @ dom3dom1 + jac[:, 3:6] @ dT3dom1
+    dx_dtP = jac[:, 0:3] @ dom3dT1 + jac[:, 3:6] @ dT3dT1
+    return np.hstack([dx_drP, dx_dtP]), np.hstack([dx_drC, dx_dtC]), E
+
+
+def compute_jacobian_extrinsic(prob, params, policy, dense_out=False):
+    """src/multicalib.cpp:593-703 -- dense J (2M x P), JTJ, JTE, and the full-system solve."""
+    nE = len(prob.edges)
+    loc = np.zeros(nE + 1, dtype=np.int64)
+    for e in range(nE):
+        loc[e + 1] = loc[e] + 2 * prob.edges[e][2].shape[0]          # :597-603
+    P = prob.n_param
+    J = np.zeros((loc[nE], P))
+    E = np.zeros(loc[nE])
+    for e in range(nE):
+        cam, pv = prob.edges[e][0], prob.edges[e][1]
+        rvecP = params[(pv - 1) * 6:(pv - 1) * 6 + 3]
+        tvecP = params[(pv - 1) * 6 + 3:(pv - 1) * 6 + 6]
+        if cam > 0:
+            rvecC = params[(cam - 1) * 6:(cam - 1) * 6 + 3]
+            tvecC = params[(cam - 1) * 6 + 3:(cam - 1) * 6 + 6]
+        else:
+            rvecC = np.zeros(3, dtype=params.dtype)
+            tvecC = np.zeros(3, dtype=params.dtype)
+        Jp, Jc, err = compute_photo_camera_jacobian(prob, e, rvecP, tvecP, rvecC, tvecC, policy)
+        if cam > 0:
+            J[loc[e]:loc[e + 1], (cam - 1) * 6:cam * 6] = Jc
+        J[loc[e]:loc[e + 1], (pv - 1) * 6:pv * 6] = Jp
+        E[loc[e]:loc[e + 1]] = err
+    JTJ = J.T @ J                                                       # :688
+    JTE = J.T @ E                                                       # :689
+    # Eigen CG on a SPD system converges to the exact solution; direct solve here.
+    x = np.linalg.solve(JTJ, JTE)
+    if dense_out:
+        return x, J, E, JTJ, JTE
+    return x, float(E @ E), loc
+
+
+def optimize_extrinsics(prob, params0, crit_type, max_count, eps, policy='fp64', record=None):
+    """src/multicalib.cpp:462-514.  Returns (params, n_iter, change)."""
+    if policy == 'faithful_f32':
+        params = np.asarray(params0, dtype=np.float32).copy()
+    else:
+        params = np.asarray(params0, dtype=np.float64).copy()
+    change = 1.0
+    it = 0
+    while True:
+        if ((crit_type == 1 and it >= max_count) or (crit_type == 2 and change <= eps) or
+                (crit_type == 3 and (change <= eps or it >= max_count))):
+            break
+        alpha = 0.95 ** (it + 1.0)                                      # :482-483
+        x, cost, _ = compute_jacobian_extrinsic(prob, params, policy)
+        G = alpha * x
+        if policy == 'faithful_f32':
+            G = G.astype(np.float32)                                    # :493-497
+            params = params + G                                         # float32 add :501
+        else:
+            params = params + G
+        change = float(np.linalg.norm(G.astype(np.float64)) / np.linalg.norm(params.astype(np.float64)))
+        if record is not None:
+            record.append(dict(iter=it, cost_before=cost, change=change, params=params.astype(np.float64).copy()))
+        it += 1
+    return params.astype(np.float64), it, change
+
+
+def compute_project_error(prob, params, policy='fp64'):
+    """src/multicalib.cpp:895-1006.  Returns dict with the reference's (quirky) mean error, the per-edge
+    means, and the fp64 RMS of src/omnidir.cpp:1794-1802 (the north star's 'fp64 final RMS')."""
+    f32 = policy == 'faithful_f32'
+    p = np.asarray(params, dtype=np.float32 if f32 else np.float64)
+    tot_err = np.float32(0) if f32 else 0.0
+    tot_n = 0
+    sq = 0.0
+    npts = 0
+    per_edge = []
+    for e, (cam, pv, obj32, img32) in enumerate(prob.edges):
+        dt = np.float32 if f32 else np.float64
+        RP = cv2.Rodrigues(p[(pv - 1) * 6:(pv - 1) * 6 + 3].reshape(3, 1))[0].astype(dt)
+        TP = p[(pv - 1) * 6 + 3:(pv - 1) * 6 + 6].reshape(3, 1).astype(dt)
+        if cam == 0:
+            R, T = RP, TP
+        else:
+            RC = cv2.Rodrigues(p[(cam - 1) * 6:(cam - 1) * 6 + 3].reshape(3, 1))[0].astype(dt)
+            TC = p[(cam - 1) * 6 + 3:(cam - 1) * 6 + 6].reshape(3, 1).astype(dt)
+            R = (RC @ RP).astype(dt)
+            T = (RC @ TP + TC).astype(dt)
+        rvec = cv2.Rodrigues(R)[0].astype(dt)
+        obj = obj32.astype(dt)
+        if prob.cam_type[cam] == PINHOLE:
+            proj = cv2.projectPoints(obj.reshape(-1, 1, 3), rvec, T, prob.K[cam], prob.dist[cam].reshape(1, -1))[0]
+            proj = proj.reshape(-1, 2)
+        else:
+            proj, _ = omnidir_project_points(obj, rvec.astype(np.float64), T.astype(np.float64), prob.K[cam],
+                                             float(prob.xi[cam]), prob.dist[cam], want_jac=False)
+            proj = proj.astype(dt)
+        err = img32.astype(dt) - proj.astype(dt)
+        nrm = np.sqrt(err[:, 0] * err[:, 0] + err[:, 1] * err[:, 1]).astype(dt)
+        epi = dt(0)
+        for v in nrm:
+            epi = dt(epi + v)
+        per_edge.append(float(epi / dt(err.shape[0])))
+        tot_err = dt(tot_err + epi)
+        # :983 error.total(): PINHOLE error is N x 2 single channel (2N), OMNIDIRECTIONAL N x 1 x 2ch (N)
+        tot_n += err.shape[0] * (2 if prob.cam_type[cam] == PINHOLE else 1)
+        e64 = img32.astype(np.float64) - proj.astype(np.float64)
+        sq += float((e64 * e64).sum())
+        npts += err.shape[0]
+    return dict(mean_reproj_error=float(tot_err) / tot_n, per_edge=np.array(per_edge),
+                rms=float(np.sqrt(sq / npts)), n_points=npts)
+
+
+# --------------------------------------------------------------------------------------------
+# omnidir::calibrate loop (row J)
+# --------------------------------------------------------------------------------------------
+def flags2idx(flags, n):
+    """src/omnidir.cpp:2031-2076 (>= / subtract cascade, reproduced literally)."""
+    idx = np.ones(6 * n + 10, dtype=np.int64)
+    f = int(flags)
+    if f >= CALIB_FIX_CENTER:
+        idx[6 * n + 3] = 0; idx[6 * n + 4] = 0; f -= CALIB_FIX_CENTER
+    if f >= CALIB_FIX_GAMMA:
+        idx[6 * n] = 0; idx[6 * n + 1] = 0; f -= CALIB_FIX_GAMMA
+    if f >= CALIB_FIX_XI:
+        idx[6 * n + 5] = 0; f -= CALIB_FIX_XI
+    if f >= CALIB_FIX_P2:
+        idx[6 * n + 9] = 0; f -= CALIB_FIX_P2
+    if f >= CALIB_FIX_P1:
+        idx[6 * n + 8] = 0; f -= CALIB_FIX_P1
+    if f >= CALIB_FIX_K2:
+        idx[6 * n + 7] = 0; f -= CALIB_FIX_K2
+    if f >= CALIB_FIX_K1:
+        idx[6 * n + 6] = 0; f -= CALIB_FIX_K1
+    if f >= CALIB_FIX_SKEW:
+        idx[6 * n + 2] = 0
+    return idx
+
+
+def omni_compute_jacobian(obj_list, img_list, param, flags, epsilon):
+    """src/omnidir.cpp:851-935.  param layout: [om_i,T_i]*n, fx, fy, s, cx, cy, xi, k1, k2, p1, p2."""
+    n = len(obj_list)
+    P = 6 * n + 10
+    JTJ = np.zeros((P, P))
+    JTE = np.zeros(P)
+    K = np.array([[param[6 * n], param[6 * n + 2], param[6 * n + 3]],
+                  [0, param[6 * n + 1], param[6 * n + 4]], [0, 0, 1.0]])
+    D = param[6 * n + 6:6 * n + 10]
+    xi = param[6 * n + 5]
+    cost = 0.0
+    for i in range(n):
+        proj, jac = omnidir_project_points(obj_list[i], param[6 * i:6 * i + 3], param[6 * i + 3:6 * i + 6], K, xi, D)
+        err = (np.asarray(img_list[i], dtype=np.float64).reshape(-1, 2) - proj).reshape(-1)
+        JIn = jac[:, 6:16]
+        JEx = jac[:, 0:6]
+        JTJ[6 * n:, 6 * n:] += JIn.T @ JIn
+        JTJ[6 * i:6 * i + 6, 6 * i:6 * i + 6] = JEx.T @ JEx
+        JTJ[6 * i:6 * i + 6, 6 * n:] = JEx.T @ JIn
+        JTJ[6 * n:, 6 * i:6 * i + 6] = JIn.T @ JEx
+        JTE[6 * n:] += JIn.T @ err
+        JTE[6 * i:6 * i + 6] = JEx.T @ err
+        cost += float(err @ err)
+    idx = flags2idx(flags, n).astype(bool)
+    JTJs = JTJ[np.ix_(idx, idx)]
+    JTEs = JTE[idx]
+    JTJ_inv = np.linalg.inv(JTJs + epsilon)          # :934 -- scalar added to EVERY element
+    return JTJ_inv, JTEs, idx, cost
+
+
+def omni_calibrate_loop(obj_list, img_list, param0, flags, crit_type, max_count, eps, record=None):
+    """src/omnidir.cpp:1119-1147."""
+    cur = np.asarray(param0, dtype=np.float64).copy()
+    change = 1.0
+    it = 0
+    while True:
+        if ((crit_type == 1 and it >= max_count) or (crit_type == 2 and change <= eps) or
+                (crit_type == 3 and (change <= eps or it >= max_count))):
+            break
+        alpha = 1 - (1 - 0.01) ** (it + 1.0)
+        epsilon = 0.01 * 0.9 ** (it / 10.0)
+        JTJ_inv, JTE, idx, cost = omni_compute_jacobian(obj_list, img_list, cur, flags, epsilon)
+        Gs = alpha * (JTJ_inv @ JTE)
+        G = np.zeros_like(cur)
+        G[idx] = Gs                                   # fillFixed :2138-2153
+        new = cur + G
+        change = float(np.linalg.norm(G) / np.linalg.norm(cur))     # :1141 norm of the OLD parameters
+        cur = new
+        if record is not None:
+            record.append(dict(iter=it, cost_before=cost, change=change, params=cur.copy()))
+        it += 1
+    return cur, it, change
+
+
+def omni_rms(obj_list, img_list, param):
+    """src/omnidir.cpp:1794-1802."""
+    n = len(obj_list)
+    K = np.array([[param[6 * n], param[6 * n + 2], param[6 * n + 3]],
+                  [0, param[6 * n + 1], param[6 * n + 4]], [0, 0, 1.0]])
+    D = param[6 * n + 6:6 * n + 10]
+    xi = param[6 * n + 5]
+    sq = 0.0
+    cnt = 0
+    for i in range(n):
+        proj, _ = omnidir_project_points(obj_list[i], param[6 * i:6 * i + 3], param[6 * i + 3:6 * i + 6], K, xi, D,
+                                         want_jac=False)
+        e = np.asarray(img_list[i], dtype=np.float64).reshape(-1, 2) - proj
+        sq += float((e * e).sum())
+        cnt += e.shape[0]
+    return float(np.sqrt(sq / cnt))
