@@ -1,0 +1,166 @@
+/*
+ * mccba.h -- C ABI of the B200-native calibration bundle-adjustment core ("multi-camera calibration BA").
+ *
+ * This is the drop-in boundary for the hot path of yulong314/multi_camera_calibration: the iteration loop of
+ * cv::multicalib::MultiCameraCalibration::optimizeExtrinsics and everything it calls.  The reference has no
+ * FFI; its seam is C++ virtual dispatch on MultiCameraCalibration (include/opencv2/ccalib/multicalib.hpp:
+ * 138-191).  Each entry point below names the reference member(s) it replaces; the host-side C++17 class in
+ * include/mccba_host.hpp mirrors the reference class on top of this ABI, and INTEGRATION.md shows the binding a
+ * maintainer of the reference would add.
+ *
+ * Conventions
+ *  - extern "C", plain pointers and sizes, no C++ / torch / OpenCV types.
+ *  - every function returns an int status (MCCBA_OK == 0) and never throws; mccba_last_error(handle) returns a
+ *    message owned by the handle (valid until the next call on that handle).
+ *  - host buffers are caller-owned and COPIED by the set_* calls; device memory is owned by the handle.
+ *  - one handle = one CUDA device + one stream.  A handle is not thread-safe; distinct handles are independent.
+ *  - there is no CPU fallback: without a CUDA device mccba_create fails with MCCBA_ERR_CUDA.
+ *
+ * Indexing contract (bit-exact with the reference):
+ *  - vertices 0..nC-1 are cameras, vertices nC..nC+F-1 are pattern poses ("photo vertices") in first-seen order;
+ *  - edge e connects cameraVertex edge_cam[e] and photoVertex edge_pv[e] (multicalib.hpp:86-103);
+ *  - the parameter vector has 6*(nC+F-1) doubles: [rvec | tvec] of vertex v at 6*(v-1); vertex 0 (camera 0) is
+ *    the gauge (src/multicalib.cpp:422-440, 636-640);
+ *  - X_cam = R_cam (R_photo X + t_photo) + t_cam (call order at src/multicalib.cpp:734);
+ *  - corner i of edge e is row pair (2i, 2i+1) of the reference's Jacobian block starting at 2*edge_off[e]
+ *    (pointsLocation, src/multicalib.cpp:597-603).
+ *
+ * Multi-GPU: frames shard across ranks.  Each rank creates its own handle (rank, nranks, shared ncclUniqueId),
+ * passes ALL cameras and only ITS frames/edges (photo vertices renumbered nC..nC+F_local-1), and calls
+ * mccba_solve collectively.  One ncclAllReduce per iteration sums the reduced camera system; every rank solves it
+ * redundantly.  Camera parameters are replicated, frame parameters stay on their rank.
+ */
+#ifndef MCCBA_H_
+#define MCCBA_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MCCBA_VERSION 1
+
+/* status codes */
+#define MCCBA_OK 0
+#define MCCBA_ERR_ARG 1        /* bad argument / inconsistent sizes / unsupported model (CV_Assert in the reference) */
+#define MCCBA_ERR_CUDA 2       /* CUDA runtime error or no device */
+#define MCCBA_ERR_STATE 3      /* call order violated (e.g. solve before set_observations) */
+#define MCCBA_ERR_NUMERIC 4    /* non-finite cost or reduced system not positive definite */
+#define MCCBA_ERR_NCCL 5       /* NCCL unavailable or collective failed */
+
+/* camera models: values of MultiCameraCalibration::PINHOLE / OMNIDIRECTIONAL (multicalib.hpp:76-80) */
+#define MCCBA_PINHOLE 0
+#define MCCBA_OMNIDIRECTIONAL 1
+
+/* cv::TermCriteria type bits as decoded at src/multicalib.cpp:475-477 */
+#define MCCBA_CRIT_COUNT 1
+#define MCCBA_CRIT_EPS 2
+
+/* solver modes */
+#define MCCBA_MODE_REFERENCE_GN 0 /* step-scaled Gauss-Newton, G = 0.95^(iter+1) x (src/multicalib.cpp:482-504) */
+#define MCCBA_MODE_LM 1           /* Levenberg-Marquardt: damping, accept/reject on device (north star) */
+
+typedef struct mccba_handle_s *mccba_handle;
+
+typedef struct {
+    int device;                 /* CUDA device ordinal */
+    int rank, nranks;           /* frame-sharding rank / world size (1 = single GPU) */
+    unsigned char nccl_id[128]; /* ncclUniqueId bytes, identical on all ranks; ignored when nranks == 1 */
+    int use_graph;              /* 1: capture one LM iteration in a CUDA graph (default); 0: plain stream launches */
+    int verbose;
+} mccba_options;
+
+typedef struct {
+    int mode;           /* MCCBA_MODE_* */
+    int crit_type;      /* MCCBA_CRIT_COUNT | MCCBA_CRIT_EPS, same decoding as the reference */
+    int max_count;      /* criteria.maxCount */
+    double epsilon;     /* criteria.epsilon, compared with change = |step| / |params| */
+    double lambda0;     /* LM: initial damping (H + lambda diag H), tangent-space diag; default 1e-3 */
+    double lambda_up;   /* LM: factor on reject (default 10) */
+    double lambda_down; /* LM: factor on accept (default 1/3) */
+} mccba_solve_opts;
+
+typedef struct {
+    int iterations;     /* trial evaluations performed (== the reference's iter counter at loop exit) */
+    int accepted, rejected;
+    int status;         /* MCCBA_OK or MCCBA_ERR_NUMERIC */
+    int graph_launches; /* iteration graphs (or stream sequences) enqueued */
+    int kernel_launches;/* CUDA kernels of this library launched by the call */
+    double change;      /* last |step| / |params| */
+    double cost;        /* sum of squared residuals at the returned parameters (all ranks) */
+    double lambda;      /* final damping */
+    double device_ms;   /* CUDA-event time of the whole call on the handle's stream */
+} mccba_report;
+
+typedef struct {
+    double mean_reproj_error; /* the reference's meanReprojectError: sum ||e|| / totalNPoints, where PINHOLE edges
+                                 count 2N points and OMNIDIRECTIONAL edges N (src/multicalib.cpp:983, 989) */
+    double rms;               /* fp64 RMS sqrt(sum(ex^2+ey^2)/Npoints) (src/omnidir.cpp:1794-1802) */
+    double sum_norm, sum_sq;  /* local (this rank's edges) sums; the two ratios above are global when nranks>1 */
+    int64_t n_points;
+} mccba_error_stats;
+
+/* ---- lifecycle ------------------------------------------------------------------------------------------- */
+/* fills defaults (device 0, single rank, graph on) */
+int mccba_default_options(mccba_options *opts);
+int mccba_default_solve_opts(mccba_solve_opts *opts);
+/* rank 0 obtains an ncclUniqueId to broadcast to the other ranks (any transport); MCCBA_ERR_NCCL if libnccl absent */
+int mccba_nccl_unique_id(unsigned char out[128]);
+/* replaces the MultiCameraCalibration constructor's numerical state (src/multicalib.cpp:75-104) */
+int mccba_create(const mccba_options *opts, mccba_handle *out);
+int mccba_destroy(mccba_handle h);
+const char *mccba_last_error(mccba_handle h);
+
+/* ---- problem ----------------------------------------------------------------------------------------------- */
+/* Replaces _cameraMatrix / _distortCoeffs / _xi (multicalib.hpp:211-213).  K5 = fx fy cx cy skew per camera
+ * (skew is used by the Mei model only: cv::projectPoints ignores K(0,1)); dist8 = k1 k2 p1 p2 k3 k4 k5 k6 per
+ * camera, ndist in {0,4,5,8} for PINHOLE and exactly 4 for OMNIDIRECTIONAL (src/omnidir.cpp:92). */
+int mccba_set_cameras(mccba_handle h, int n_cam, const int *model, const double *K5, const double *dist8,
+                      const int *ndist, const double *xi);
+/* Replaces _edgeList + _objectPointsForEachCamera / _imagePointsForEachCamera (multicalib.hpp:207-210).
+ * obj_xyz / img_uv are the reference's CV_32F points concatenated edge by edge (AoS, 3 / 2 floats per corner);
+ * the library re-lays them out as SoA planes in HBM.  edge_off has n_edge+1 entries (in corners). */
+int mccba_set_observations(mccba_handle h, int n_frame, int n_edge, const int *edge_cam, const int *edge_pv,
+                           const int64_t *edge_off, const float *obj_xyz, const float *img_uv);
+/* Replaces buildParas / paras2vertex (src/multicalib.cpp:422-459): n = 6*(nC+F-1) doubles. */
+int mccba_set_parameters(mccba_handle h, int64_t n, const double *params);
+int mccba_get_parameters(mccba_handle h, int64_t n, double *params);
+
+/* ---- hot path ---------------------------------------------------------------------------------------------- */
+/* One residual+Jacobian evaluation at the current parameters: the per-edge work of computeJacobianExtrinsic +
+ * computePhotoCameraJacobian (src/multicalib.cpp:611-678, 717-824) with the per-edge normal-equation blocks
+ * accumulated instead of a dense J.  Outputs (each optional, host buffers, reference edge order):
+ *   cost      sum of squared residuals over this rank's edges
+ *   edge_H6   n_edge x 21: upper triangle (row-major) of sum_i J_i^T J_i, J_i = d(u,v)/d(phi3, tau3) the 2x6
+ *             Jacobian wrt a LEFT perturbation of the composed pose (R3 <- exp(phi3) R3, T3 <- T3 + tau3)
+ *   edge_g6   n_edge x 6: sum_i J_i^T e_i,  e = observed - projected
+ *   edge_cost n_edge: sum_i |e_i|^2
+ * This is the "residual+Jacobian evals/sec" unit of the benchmark. */
+int mccba_eval(mccba_handle h, double *cost, double *edge_H6, double *edge_g6, double *edge_cost);
+/* Reduced camera system at the current parameters for damping lambda (Schur complement of the frame blocks, in
+ * tangent coordinates): S is n_s x n_s row-major, gs n_s, n_s = 6*(nC-1).  Summed over ranks. Test/diagnostic. */
+int mccba_reduced_system(mccba_handle h, double lambda, double *S, double *gs);
+/* The whole optimisation loop of optimizeExtrinsics (src/multicalib.cpp:473-507) on the device: no host round
+ * trip per iteration.  Parameters are updated in place (read back with mccba_get_parameters). */
+int mccba_solve(mccba_handle h, const mccba_solve_opts *opts, mccba_report *report);
+/* computeProjectError (src/multicalib.cpp:895-1006) at the current parameters, in fp64.
+ * per_edge_mean (optional, n_edge) = edge.reprojecterror. */
+int mccba_reproj_error(mccba_handle h, mccba_error_stats *stats, double *per_edge_mean);
+
+/* ---- utilities --------------------------------------------------------------------------------------------- */
+/* sum a small host array of doubles over all ranks (NCCL); identity when nranks == 1 */
+int mccba_allreduce_sum(mccba_handle h, double *buf, int n);
+/* With the environment variable MCCBA_PROFILE=1 mccba_solve launches every kernel separately (no graph) with a
+ * CUDA event between each; this returns the average ms per iteration of
+ * out[0] frame_schur, out[1] reduce_records, out[2] allreduce, out[3] decide_solve, out[4] frame_update,
+ * out[5] resid_jac_accum (diagnostic only -- the events serialise the stream). */
+int mccba_last_kernel_ms(mccba_handle h, double out[6]);
+/* time `reps` back-to-back launches of the residual+Jacobian kernel at the current parameters with CUDA events on
+ * the handle's stream; returns average ms per launch (benchmark helper, no other side effects) */
+int mccba_time_eval(mccba_handle h, int reps, double *avg_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MCCBA_H_ */

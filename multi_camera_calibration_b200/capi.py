@@ -1,0 +1,206 @@
+"""ctypes binding of include/mccba.h (the C ABI of the CUDA core).  Plumbing only: every numerical operation happens
+inside libmccba.so on the GPU.  There is no CPU fallback -- if the library or a CUDA device is missing this raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmccba.so")
+
+OK, ERR_ARG, ERR_CUDA, ERR_STATE, ERR_NUMERIC, ERR_NCCL = 0, 1, 2, 3, 4, 5
+PINHOLE, OMNIDIRECTIONAL = 0, 1
+CRIT_COUNT, CRIT_EPS = 1, 2
+MODE_REFERENCE_GN, MODE_LM = 0, 1
+
+
+class Options(C.Structure):
+    _fields_ = [("device", C.c_int), ("rank", C.c_int), ("nranks", C.c_int), ("nccl_id", C.c_ubyte * 128),
+                ("use_graph", C.c_int), ("verbose", C.c_int)]
+
+
+class SolveOpts(C.Structure):
+    _fields_ = [("mode", C.c_int), ("crit_type", C.c_int), ("max_count", C.c_int), ("epsilon", C.c_double),
+                ("lambda0", C.c_double), ("lambda_up", C.c_double), ("lambda_down", C.c_double)]
+
+
+class Report(C.Structure):
+    _fields_ = [("iterations", C.c_int), ("accepted", C.c_int), ("rejected", C.c_int), ("status", C.c_int),
+                ("graph_launches", C.c_int), ("kernel_launches", C.c_int), ("change", C.c_double), ("cost", C.c_double),
+                ("lambda_", C.c_double), ("device_ms", C.c_double)]
+
+
+class ErrorStats(C.Structure):
+    _fields_ = [("mean_reproj_error", C.c_double), ("rms", C.c_double), ("sum_norm", C.c_double), ("sum_sq", C.c_double),
+                ("n_points", C.c_int64)]
+
+
+EXPORTS = ["mccba_default_options", "mccba_default_solve_opts", "mccba_nccl_unique_id", "mccba_create", "mccba_destroy",
+           "mccba_last_error", "mccba_set_cameras", "mccba_set_observations", "mccba_set_parameters",
+           "mccba_get_parameters", "mccba_eval", "mccba_reduced_system", "mccba_solve", "mccba_reproj_error",
+           "mccba_allreduce_sum", "mccba_last_kernel_ms", "mccba_time_eval"]
+
+_lib = None
+
+
+class MccbaError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("mccba status %d: %s" % (code, msg))
+        self.code = code
+
+
+def lib():
+    """Load libmccba.so.  Fails loudly when the CUDA extension has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError("%s is missing: build it with `python -m multi_camera_calibration_b200.build` "
+                              "(nvcc, sm_100a); there is no CPU fallback" % LIB_PATH)
+        _lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+        _lib.mccba_last_error.restype = C.c_char_p
+        _lib.mccba_last_error.argtypes = [C.c_void_p]
+    return _lib
+
+
+def _ptr(a, t):
+    return a.ctypes.data_as(C.POINTER(t)) if a is not None else None
+
+
+def nccl_unique_id():
+    buf = (C.c_ubyte * 128)()
+    rc = lib().mccba_nccl_unique_id(buf)
+    if rc:
+        raise MccbaError(rc, "libnccl.so.2 not available")
+    return bytes(buf)
+
+
+class Solver:
+    """One handle = one GPU + one stream (include/mccba.h)."""
+
+    def __init__(self, device=0, rank=0, nranks=1, nccl_id=None, use_graph=True):
+        L = lib()
+        o = Options()
+        L.mccba_default_options(C.byref(o))
+        o.device, o.rank, o.nranks, o.use_graph = int(device), int(rank), int(nranks), int(bool(use_graph))
+        if nranks > 1:
+            assert nccl_id is not None and len(nccl_id) == 128
+            C.memmove(o.nccl_id, nccl_id, 128)
+        self._h = C.c_void_p()
+        rc = L.mccba_create(C.byref(o), C.byref(self._h))
+        if rc:
+            msg = L.mccba_last_error(self._h).decode() if self._h else "mccba_create failed (no CUDA device?)"
+            if self._h:
+                L.mccba_destroy(self._h)
+                self._h = C.c_void_p()
+            raise MccbaError(rc, msg)
+        self.n_cam = self.n_frame = self.n_edge = 0
+        self.nranks = nranks
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().mccba_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc:
+            raise MccbaError(rc, lib().mccba_last_error(self._h).decode())
+
+    @property
+    def n_param(self):
+        return 6 * (self.n_cam + self.n_frame - 1)
+
+    def set_cameras(self, model, K5, dist8, ndist, xi):
+        model = np.ascontiguousarray(model, dtype=np.int32)
+        n = model.size
+        K5 = np.ascontiguousarray(K5, dtype=np.float64).reshape(n, 5)
+        dist8 = np.ascontiguousarray(dist8, dtype=np.float64).reshape(n, 8)
+        ndist = np.ascontiguousarray(ndist, dtype=np.int32).reshape(n)
+        xi = np.ascontiguousarray(xi, dtype=np.float64).reshape(n)
+        self._check(lib().mccba_set_cameras(self._h, n, _ptr(model, C.c_int), _ptr(K5, C.c_double),
+                                            _ptr(dist8, C.c_double), _ptr(ndist, C.c_int), _ptr(xi, C.c_double)))
+        self.n_cam = n
+
+    def set_observations(self, n_frame, edge_cam, edge_pv, edge_off, obj_xyz, img_uv):
+        edge_cam = np.ascontiguousarray(edge_cam, dtype=np.int32)
+        edge_pv = np.ascontiguousarray(edge_pv, dtype=np.int32)
+        edge_off = np.ascontiguousarray(edge_off, dtype=np.int64)
+        obj = np.ascontiguousarray(obj_xyz, dtype=np.float32)
+        img = np.ascontiguousarray(img_uv, dtype=np.float32)
+        ne = edge_cam.size
+        if edge_pv.size != ne or edge_off.size != ne + 1 or obj.size != 3 * int(edge_off[-1]) or img.size != 2 * int(edge_off[-1]):
+            raise MccbaError(ERR_ARG, "set_observations: inconsistent array sizes")
+        self._check(lib().mccba_set_observations(self._h, int(n_frame), ne, _ptr(edge_cam, C.c_int),
+                                                 _ptr(edge_pv, C.c_int), _ptr(edge_off, C.c_int64),
+                                                 _ptr(obj, C.c_float), _ptr(img, C.c_float)))
+        self.n_frame, self.n_edge = int(n_frame), ne
+
+    def set_rig(self, rig):
+        """rig: dict in the C-ABI layout (tests/rigs.py, synth.make_rig)."""
+        self.set_cameras(rig["cam_model"], rig["cam_K5"], rig["cam_dist8"], rig["cam_ndist"], rig["cam_xi"])
+        self.set_observations(rig["n_frame"], rig["edge_cam"], rig["edge_pv"], rig["edge_off"], rig["obj"], rig["img"])
+
+    def set_parameters(self, params):
+        p = np.ascontiguousarray(params, dtype=np.float64)
+        self._check(lib().mccba_set_parameters(self._h, C.c_int64(p.size), _ptr(p, C.c_double)))
+
+    def get_parameters(self):
+        p = np.zeros(self.n_param)
+        self._check(lib().mccba_get_parameters(self._h, C.c_int64(p.size), _ptr(p, C.c_double)))
+        return p
+
+    def eval(self, want_blocks=True):
+        cost = C.c_double()
+        H6 = np.zeros((self.n_edge, 21)) if want_blocks else None
+        g6 = np.zeros((self.n_edge, 6)) if want_blocks else None
+        ec = np.zeros(self.n_edge) if want_blocks else None
+        self._check(lib().mccba_eval(self._h, C.byref(cost), _ptr(H6, C.c_double), _ptr(g6, C.c_double),
+                                     _ptr(ec, C.c_double)))
+        return dict(cost=cost.value, H6=H6, g6=g6, edge_cost=ec)
+
+    def reduced_system(self, lam=0.0):
+        ns = 6 * (self.n_cam - 1)
+        S = np.zeros((ns, ns)); gs = np.zeros(ns)
+        self._check(lib().mccba_reduced_system(self._h, C.c_double(lam), _ptr(S, C.c_double), _ptr(gs, C.c_double)))
+        return S, gs
+
+    def solve(self, mode=MODE_REFERENCE_GN, crit_type=CRIT_COUNT, max_count=20, eps=1e-7, lambda0=1e-3, lambda_up=10.0,
+              lambda_down=1.0 / 3.0, check=True):
+        o = SolveOpts(int(mode), int(crit_type), int(max_count), float(eps), float(lambda0), float(lambda_up),
+                      float(lambda_down))
+        r = Report()
+        rc = lib().mccba_solve(self._h, C.byref(o), C.byref(r))
+        if rc and check:
+            self._check(rc)
+        return dict(rc=rc, iterations=r.iterations, accepted=r.accepted, rejected=r.rejected, status=r.status,
+                    graph_launches=r.graph_launches, kernel_launches=r.kernel_launches, change=r.change, cost=r.cost,
+                    lam=r.lambda_, device_ms=r.device_ms)
+
+    def reproj_error(self):
+        st = ErrorStats()
+        pe = np.zeros(self.n_edge)
+        self._check(lib().mccba_reproj_error(self._h, C.byref(st), _ptr(pe, C.c_double)))
+        return dict(mean_reproj_error=st.mean_reproj_error, rms=st.rms, sum_norm=st.sum_norm, sum_sq=st.sum_sq,
+                    n_points=int(st.n_points), per_edge=pe)
+
+    def allreduce_sum(self, arr):
+        a = np.ascontiguousarray(arr, dtype=np.float64).copy()
+        self._check(lib().mccba_allreduce_sum(self._h, _ptr(a, C.c_double), int(a.size)))
+        return a
+
+    def last_kernel_ms(self):
+        out = np.zeros(6)
+        self._check(lib().mccba_last_kernel_ms(self._h, _ptr(out, C.c_double)))
+        return out
+
+    def time_eval(self, reps=10):
+        ms = C.c_double()
+        self._check(lib().mccba_time_eval(self._h, int(reps), C.byref(ms)))
+        return ms.value

@@ -1,0 +1,763 @@
+// mccba_capi.cu -- the thin C-ABI shim declared in include/mccba.h: handle, host-side problem layout, stream /
+// CUDA-graph orchestration and the NCCL hook.  All arithmetic lives in mccba_kernels.cuh / mccba_math.cuh.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/mccba.h"
+#include "mccba_kernels.cuh"
+
+using namespace mccba;
+
+// ---------------------------------------------------------------------------------------------------------
+// NCCL, resolved at run time (no link-time dependency; a single-GPU run never touches it)
+// ---------------------------------------------------------------------------------------------------------
+namespace {
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+typedef int ncclResult_t;
+struct NcclApi {
+    void* lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    bool ok = false;
+};
+NcclApi& nccl()
+{
+    static NcclApi api;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        const char* names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char* n : names) {
+            api.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+            if (api.lib) break;
+        }
+        if (api.lib) {
+            api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(api.lib, "ncclGetUniqueId");
+            api.CommInitRank = (decltype(api.CommInitRank))dlsym(api.lib, "ncclCommInitRank");
+            api.CommDestroy = (decltype(api.CommDestroy))dlsym(api.lib, "ncclCommDestroy");
+            api.AllReduce = (decltype(api.AllReduce))dlsym(api.lib, "ncclAllReduce");
+            api.GetErrorString = (decltype(api.GetErrorString))dlsym(api.lib, "ncclGetErrorString");
+            api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllReduce;
+        }
+    }
+    return api;
+}
+constexpr int kNcclFloat64 = 8;  // ncclDouble
+constexpr int kNcclSum = 0;
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------------
+// handle
+// ---------------------------------------------------------------------------------------------------------
+struct mccba_handle_s {
+    mccba_options opts;
+    std::string err;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    ncclComm_t comm = nullptr;
+    int num_sms = 148;
+    // cameras
+    int n_cam = 0;
+    std::vector<CamParams> cams;
+    bool have_cams = false, have_obs = false, have_params = false;
+    // problem (host copies of what is needed after set_observations)
+    int n_frame = 0, n_edge = 0;
+    int64_t n_pts = 0;
+    std::vector<int> int_of_edge;     // reference edge index -> internal edge
+    std::vector<int> edge_cam_h;      // reference order
+    std::vector<int64_t> edge_n_h;    // corners per reference edge
+    Problem P;
+    std::vector<void*> allocs;        // device allocations owned by the problem
+    CamParams* d_cams = nullptr;
+    int cur = 0;                      // host mirror of DevState::cur between calls
+    int ar_len = 0;
+    int k1_grid = 0, k1_smem = 0, k5_smem = 0;
+    cudaGraphExec_t graph = nullptr;
+    int* h_done = nullptr;            // pinned
+    DevState* h_state = nullptr;      // pinned
+    double* h_small = nullptr;        // pinned scratch (64 doubles)
+    double* d_small = nullptr;
+    double prof_ms[6] = {0, 0, 0, 0, 0, 0};
+    int profile = 0;
+};
+
+namespace {
+
+int fail(mccba_handle h, int code, const char* fmt, ...)
+{
+    if (h) {
+        char buf[512];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(buf, sizeof(buf), fmt, ap);
+        va_end(ap);
+        h->err = buf;
+    }
+    return code;
+}
+
+#define CUDA_TRY(h, expr)                                                                                  \
+    do {                                                                                                   \
+        cudaError_t e__ = (expr);                                                                          \
+        if (e__ != cudaSuccess)                                                                            \
+            return fail(h, MCCBA_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+template <typename T>
+int dev_alloc(mccba_handle h, T** p, size_t count, bool zero = false)
+{
+    void* q = nullptr;
+    const size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+    CUDA_TRY(h, cudaMalloc(&q, bytes));
+    if (zero) CUDA_TRY(h, cudaMemsetAsync(q, 0, bytes, h->stream));
+    h->allocs.push_back(q);
+    *p = (T*)q;
+    return MCCBA_OK;
+}
+template <typename T>
+int dev_upload(mccba_handle h, const T** p, const std::vector<T>& v)
+{
+    T* q = nullptr;
+    int rc = dev_alloc(h, &q, v.size());
+    if (rc) return rc;
+    if (!v.empty()) CUDA_TRY(h, cudaMemcpyAsync(q, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+    *p = q;
+    return MCCBA_OK;
+}
+
+void free_problem(mccba_handle h)
+{
+    if (h->graph) { cudaGraphExecDestroy(h->graph); h->graph = nullptr; }
+    for (void* p : h->allocs) cudaFree(p);
+    h->allocs.clear();
+    h->have_obs = false;
+    h->have_params = false;
+}
+
+int64_t n_param(mccba_handle h) { return 6 * (int64_t)(h->n_cam + h->n_frame - 1); }
+
+// enqueue one iteration: [memset S] K2 K3a [allreduce] K5 K4 K1
+int enqueue_iteration(mccba_handle h, bool timed)
+{
+    Problem& P = h->P;
+    cudaStream_t s = h->stream;
+    cudaEvent_t ev[7];
+    if (timed)
+        for (auto& e : ev) cudaEventCreate(&e);
+    if (timed) cudaEventRecord(ev[0], s);
+    CUDA_TRY(h, cudaMemsetAsync(P.ar, 0, sizeof(double) * (size_t)P.ns * P.ns, s));
+    frame_schur_kernel<<<(P.n_warps * 32 + kK2Threads - 1) / kK2Threads, kK2Threads, 0, s>>>(P, -1, 0.0);
+    if (timed) cudaEventRecord(ev[1], s);
+    reduce_records_kernel<<<(P.n_dest * 32 + 127) / 128, 128, 0, s>>>(P, 0);
+    if (timed) cudaEventRecord(ev[2], s);
+    if (h->opts.nranks > 1) {
+        ncclResult_t r = nccl().AllReduce(P.ar, P.ar, (size_t)h->ar_len, kNcclFloat64, kNcclSum, h->comm, s);
+        if (r != 0) return fail(h, MCCBA_ERR_NCCL, "ncclAllReduce failed: %s", nccl().GetErrorString ? nccl().GetErrorString(r) : "?");
+    }
+    if (timed) cudaEventRecord(ev[3], s);
+    decide_solve_kernel<<<1, kK5Threads, h->k5_smem, s>>>(P, h->opts.nranks);
+    if (timed) cudaEventRecord(ev[4], s);
+    frame_update_kernel<<<P.n_k4_blocks, kK4Threads, 0, s>>>(P);
+    if (timed) cudaEventRecord(ev[5], s);
+    resid_jac_accum_kernel<<<h->k1_grid, kK1Threads, h->k1_smem, s>>>(P, 0);
+    if (timed) {
+        cudaEventRecord(ev[6], s);
+        cudaEventSynchronize(ev[6]);
+        for (int i = 0; i < 6; ++i) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
+            h->prof_ms[i] += ms;
+        }
+        for (auto& e : ev) cudaEventDestroy(e);
+    }
+    CUDA_TRY(h, cudaGetLastError());
+    return MCCBA_OK;
+}
+
+int launch_forced_eval(mccba_handle h)
+{
+    Problem& P = h->P;
+    vertex_prep_kernel<<<(P.n_vertex + 127) / 128, 128, 0, h->stream>>>(P, -1);
+    resid_jac_accum_kernel<<<h->k1_grid, kK1Threads, h->k1_smem, h->stream>>>(P, 1);
+    CUDA_TRY(h, cudaGetLastError());
+    return MCCBA_OK;
+}
+
+// make DevState::cur on the device agree with the host mirror (parameters live in x[cur])
+int sync_state_cur(mccba_handle h)
+{
+    init_state_kernel<<<1, 1, 0, h->stream>>>(h->P.st, 0, 1, 0, 0.0, 0.0, 1.0, 1.0, h->cur);
+    CUDA_TRY(h, cudaGetLastError());
+    return MCCBA_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mccba_default_options(mccba_options* o)
+{
+    if (!o) return MCCBA_ERR_ARG;
+    memset(o, 0, sizeof(*o));
+    o->device = 0; o->rank = 0; o->nranks = 1; o->use_graph = 1; o->verbose = 0;
+    return MCCBA_OK;
+}
+
+int mccba_default_solve_opts(mccba_solve_opts* o)
+{
+    if (!o) return MCCBA_ERR_ARG;
+    o->mode = MCCBA_MODE_REFERENCE_GN;
+    o->crit_type = MCCBA_CRIT_COUNT;  // TermCriteria(COUNT, 20, 1e-7), multicalib.hpp:140
+    o->max_count = 20;
+    o->epsilon = 1e-7;
+    o->lambda0 = 1e-3; o->lambda_up = 10.0; o->lambda_down = 1.0 / 3.0;
+    return MCCBA_OK;
+}
+
+int mccba_nccl_unique_id(unsigned char out[128])
+{
+    if (!nccl().ok) return MCCBA_ERR_NCCL;
+    ncclUniqueId id;
+    if (nccl().GetUniqueId(&id) != 0) return MCCBA_ERR_NCCL;
+    memcpy(out, id.internal, 128);
+    return MCCBA_OK;
+}
+
+int mccba_create(const mccba_options* opts, mccba_handle* out)
+{
+    if (!opts || !out) return MCCBA_ERR_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return MCCBA_ERR_CUDA;  // no CPU fallback
+    if (opts->device < 0 || opts->device >= ndev || opts->nranks < 1 || opts->rank < 0 || opts->rank >= opts->nranks)
+        return MCCBA_ERR_ARG;
+    mccba_handle h = new mccba_handle_s();
+    h->opts = *opts;
+    memset(&h->P, 0, sizeof(h->P));
+    if (cudaSetDevice(opts->device) != cudaSuccess) { delete h; return MCCBA_ERR_CUDA; }
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, opts->device);
+    h->num_sms = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return MCCBA_ERR_CUDA; }
+    cudaEventCreate(&h->ev0);
+    cudaEventCreate(&h->ev1);
+    cudaMallocHost((void**)&h->h_done, 64 * sizeof(int));
+    cudaMallocHost((void**)&h->h_state, sizeof(DevState));
+    cudaMallocHost((void**)&h->h_small, 64 * sizeof(double));
+    cudaMalloc((void**)&h->d_small, 64 * sizeof(double));
+    const char* prof = getenv("MCCBA_PROFILE");
+    h->profile = prof && prof[0] == '1';
+    if (opts->nranks > 1) {
+        if (!nccl().ok) { *out = h; return fail(h, MCCBA_ERR_NCCL, "libnccl.so.2 could not be loaded"); }
+        ncclUniqueId id;
+        memcpy(id.internal, opts->nccl_id, 128);
+        ncclResult_t r = nccl().CommInitRank(&h->comm, opts->nranks, id, opts->rank);
+        if (r != 0) { *out = h; return fail(h, MCCBA_ERR_NCCL, "ncclCommInitRank failed: %d", r); }
+    }
+    *out = h;
+    return MCCBA_OK;
+}
+
+int mccba_destroy(mccba_handle h)
+{
+    if (!h) return MCCBA_OK;
+    cudaSetDevice(h->opts.device);
+    cudaStreamSynchronize(h->stream);
+    free_problem(h);
+    if (h->d_cams) cudaFree(h->d_cams);
+    if (h->comm) nccl().CommDestroy(h->comm);
+    cudaFreeHost(h->h_done);
+    cudaFreeHost(h->h_state);
+    cudaFreeHost(h->h_small);
+    cudaFree(h->d_small);
+    cudaEventDestroy(h->ev0);
+    cudaEventDestroy(h->ev1);
+    cudaStreamDestroy(h->stream);
+    delete h;
+    return MCCBA_OK;
+}
+
+const char* mccba_last_error(mccba_handle h) { return h ? h->err.c_str() : "null handle"; }
+
+int mccba_set_cameras(mccba_handle h, int n_cam, const int* model, const double* K5, const double* dist8,
+                      const int* ndist, const double* xi)
+{
+    if (!h) return MCCBA_ERR_ARG;
+    if (n_cam < 1 || !model || !K5 || !dist8 || !ndist || !xi) return fail(h, MCCBA_ERR_ARG, "set_cameras: null or empty input");
+    CUDA_TRY(h, cudaSetDevice(h->opts.device));
+    std::vector<CamParams> cams((size_t)n_cam);
+    for (int c = 0; c < n_cam; ++c) {
+        CamParams& p = cams[c];
+        memset(&p, 0, sizeof(p));
+        if (model[c] != MCCBA_PINHOLE && model[c] != MCCBA_OMNIDIRECTIONAL)
+            return fail(h, MCCBA_ERR_ARG, "camera %d: unknown model %d", c, model[c]);
+        const int nd = ndist[c];
+        if (model[c] == MCCBA_OMNIDIRECTIONAL && nd != 4)
+            return fail(h, MCCBA_ERR_ARG, "camera %d: the Mei model needs exactly 4 distortion coefficients (src/omnidir.cpp:92)", c);
+        if (model[c] == MCCBA_PINHOLE && nd != 0 && nd != 4 && nd != 5 && nd != 8)
+            return fail(h, MCCBA_ERR_ARG, "camera %d: %d distortion coefficients unsupported (0, 4, 5 or 8)", c, nd);
+        p.model = model[c];
+        p.fx = K5[5 * c]; p.fy = K5[5 * c + 1]; p.cx = K5[5 * c + 2]; p.cy = K5[5 * c + 3]; p.skew = K5[5 * c + 4];
+        p.xi = xi[c];
+        double k[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (int i = 0; i < nd; ++i) k[i] = dist8[8 * c + i];
+        p.k1 = k[0]; p.k2 = k[1]; p.p1 = k[2]; p.p2 = k[3]; p.k3 = k[4]; p.k4 = k[5]; p.k5 = k[6]; p.k6 = k[7];
+        p.rational = (p.model == MCCBA_PINHOLE) && (k[5] != 0 || k[6] != 0 || k[7] != 0);
+    }
+    if (h->have_obs && n_cam != h->n_cam) free_problem(h);
+    if (h->d_cams) { cudaFree(h->d_cams); h->d_cams = nullptr; }
+    CUDA_TRY(h, cudaMalloc((void**)&h->d_cams, sizeof(CamParams) * (size_t)n_cam));
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_cams, cams.data(), sizeof(CamParams) * (size_t)n_cam, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    h->cams.swap(cams);
+    h->n_cam = n_cam;
+    h->have_cams = true;
+    if (h->have_obs) h->P.cams = h->d_cams;
+    return MCCBA_OK;
+}
+
+int mccba_set_observations(mccba_handle h, int n_frame, int n_edge, const int* edge_cam, const int* edge_pv,
+                           const int64_t* edge_off, const float* obj_xyz, const float* img_uv)
+{
+    if (!h) return MCCBA_ERR_ARG;
+    if (!h->have_cams) return fail(h, MCCBA_ERR_STATE, "set_observations before set_cameras");
+    if (n_frame < 1 || n_edge < 1 || !edge_cam || !edge_pv || !edge_off || !obj_xyz || !img_uv)
+        return fail(h, MCCBA_ERR_ARG, "set_observations: null or empty input");
+    CUDA_TRY(h, cudaSetDevice(h->opts.device));
+    const int nC = h->n_cam;
+    if (edge_off[0] != 0) return fail(h, MCCBA_ERR_ARG, "edge_off[0] must be 0");
+    const int64_t M = edge_off[n_edge];
+    if (M <= 0 || M >= (int64_t)2000000000) return fail(h, MCCBA_ERR_ARG, "corner count %lld out of range", (long long)M);
+    // per-frame view lists sorted by camera
+    std::vector<std::vector<std::pair<int, int>>> views((size_t)n_frame);
+    for (int e = 0; e < n_edge; ++e) {
+        const int c = edge_cam[e], f = edge_pv[e] - nC;
+        if (c < 0 || c >= nC) return fail(h, MCCBA_ERR_ARG, "edge %d: cameraVertex %d out of range", e, c);
+        if (f < 0 || f >= n_frame) return fail(h, MCCBA_ERR_ARG, "edge %d: photoVertex %d out of range [%d,%d)", e, edge_pv[e], nC, nC + n_frame);
+        if (edge_off[e + 1] < edge_off[e]) return fail(h, MCCBA_ERR_ARG, "edge_off not monotone at edge %d", e);
+        views[f].push_back({c, e});
+    }
+    std::map<std::vector<int>, std::vector<int>> groups;  // camera set -> frames (ascending)
+    for (int f = 0; f < n_frame; ++f) {
+        auto& v = views[f];
+        if (v.empty()) return fail(h, MCCBA_ERR_ARG, "photo vertex %d has no observation", nC + f);
+        std::sort(v.begin(), v.end());
+        std::vector<int> key;
+        for (size_t i = 0; i < v.size(); ++i) {
+            if (i && v[i].first == v[i - 1].first)
+                return fail(h, MCCBA_ERR_ARG, "photo vertex %d is observed twice by camera %d", nC + f, v[i].first);
+            key.push_back(v[i].first);
+        }
+        groups[key].push_back(f);
+    }
+    free_problem(h);
+    Problem& P = h->P;
+    memset(&P, 0, sizeof(P));
+    P.n_cam = nC; P.n_frame = n_frame; P.n_vertex = nC + n_frame; P.ns = 6 * (nC - 1);
+    P.n_param = 6 * (int64_t)(nC + n_frame - 1);
+    P.cams = h->d_cams;
+
+    std::vector<int> slot_frame, warp_group, group_V, group_cam0, group_cams, group_ebase, group_stride, group_slot0, warp_rec;
+    std::vector<int> e_cam, e_frame, e_off;
+    std::vector<int64_t> e_src;
+    h->int_of_edge.assign((size_t)n_edge, -1);
+    std::map<std::pair<int, int>, std::vector<int>> dest_blocks;  // (A,B) -> record offsets
+    std::map<int, std::vector<int>> dest_g;
+    int64_t rec_total = 0;
+    e_off.push_back(0);
+    int gi = 0;
+    for (auto& kv : groups) {
+        const std::vector<int>& cams = kv.first;
+        const std::vector<int>& frames = kv.second;
+        const int V = (int)cams.size();
+        const int nw = ((int)frames.size() + 31) / 32, stride = nw * 32;
+        group_V.push_back(V);
+        group_cam0.push_back((int)group_cams.size());
+        for (int c : cams) group_cams.push_back(c);
+        group_ebase.push_back((int)e_cam.size());
+        group_stride.push_back(stride);
+        group_slot0.push_back((int)slot_frame.size());
+        for (int ls = 0; ls < stride; ++ls) slot_frame.push_back(ls < (int)frames.size() ? frames[ls] : -1);
+        for (int v = 0; v < V; ++v)
+            for (int ls = 0; ls < stride; ++ls) {
+                int frame = -1;
+                int64_t src = 0, cnt = 0;
+                if (ls < (int)frames.size()) {
+                    frame = frames[ls];
+                    const int oe = views[frame][v].second;
+                    src = edge_off[oe];
+                    cnt = edge_off[oe + 1] - edge_off[oe];
+                    h->int_of_edge[oe] = (int)e_cam.size();
+                }
+                e_cam.push_back(cams[v]);
+                e_frame.push_back(frame);
+                e_src.push_back(src);
+                e_off.push_back(e_off.back() + (int)cnt);
+            }
+        std::vector<int> act;
+        for (int c : cams)
+            if (c != 0) act.push_back(c);
+        const int Va = (int)act.size();
+        const int rec_len = 2 + 42 * Va + 36 * (Va * (Va - 1) / 2);
+        for (int w = 0; w < nw; ++w) {
+            warp_group.push_back(gi);
+            if (rec_total + rec_len >= (int64_t)2000000000) return fail(h, MCCBA_ERR_ARG, "record buffer too large");
+            const int ro = (int)rec_total;
+            warp_rec.push_back(ro);
+            for (int i = 0; i < Va; ++i) {
+                dest_blocks[{act[i] - 1, act[i] - 1}].push_back(ro + 2 + 36 * i);
+                dest_g[act[i] - 1].push_back(ro + 2 + 36 * Va + 6 * i);
+            }
+            int pi = 0;
+            for (int i = 0; i < Va; ++i)
+                for (int j = i + 1; j < Va; ++j) dest_blocks[{act[i] - 1, act[j] - 1}].push_back(ro + 2 + 42 * Va + 36 * pi++);
+            rec_total += rec_len;
+        }
+        ++gi;
+    }
+    std::vector<int> dest_info, dest_src0, dest_src;
+    dest_src0.push_back(0);
+    for (auto& kv : dest_blocks) {
+        dest_info.insert(dest_info.end(), {0, kv.first.first, kv.first.second, 0});
+        dest_src.insert(dest_src.end(), kv.second.begin(), kv.second.end());
+        dest_src0.push_back((int)dest_src.size());
+    }
+    for (auto& kv : dest_g) {
+        dest_info.insert(dest_info.end(), {1, kv.first, 0, 0});
+        dest_src.insert(dest_src.end(), kv.second.begin(), kv.second.end());
+        dest_src0.push_back((int)dest_src.size());
+    }
+    dest_info.insert(dest_info.end(), {2, 0, 0, 0});
+    dest_src0.push_back((int)dest_src.size());
+
+    P.n_edge_int = (int)e_cam.size();
+    P.n_slots = (int)slot_frame.size();
+    P.n_warps = P.n_slots / 32;
+    P.n_dest = (int)dest_info.size() / 4;
+    P.n_k4_blocks = (P.n_slots + kK4Threads - 1) / kK4Threads;
+    h->n_frame = n_frame; h->n_edge = n_edge; h->n_pts = M;
+    h->edge_cam_h.assign(edge_cam, edge_cam + n_edge);
+    h->edge_n_h.resize((size_t)n_edge);
+    for (int e = 0; e < n_edge; ++e) h->edge_n_h[e] = edge_off[e + 1] - edge_off[e];
+    h->ar_len = P.ns * P.ns + P.ns + 4;
+
+    int rc;
+#define UP(field, vec) if ((rc = dev_upload(h, &P.field, vec))) return rc
+    UP(e_off, e_off); UP(e_cam, e_cam); UP(e_frame, e_frame);
+    UP(slot_frame, slot_frame); UP(warp_group, warp_group); UP(group_V, group_V); UP(group_cam0, group_cam0);
+    UP(group_cams, group_cams); UP(group_ebase, group_ebase); UP(group_stride, group_stride); UP(group_slot0, group_slot0);
+    UP(warp_rec, warp_rec); UP(dest_info, dest_info); UP(dest_src0, dest_src0); UP(dest_src, dest_src);
+#undef UP
+    const int64_t* d_esrc = nullptr;
+    if ((rc = dev_upload(h, &d_esrc, e_src))) return rc;
+    // observation planes: one allocation, each plane 256-byte aligned
+    const size_t plane = ((size_t)M + 63) / 64 * 64;
+    float* planes = nullptr;
+    if ((rc = dev_alloc(h, &planes, plane * 5))) return rc;
+    P.ox = planes; P.oy = planes + plane; P.oz = planes + 2 * plane; P.iu = planes + 3 * plane; P.iv = planes + 4 * plane;
+    float *d_obj = nullptr, *d_img = nullptr;
+    CUDA_TRY(h, cudaMalloc((void**)&d_obj, sizeof(float) * 3 * (size_t)M));
+    CUDA_TRY(h, cudaMalloc((void**)&d_img, sizeof(float) * 2 * (size_t)M));
+    CUDA_TRY(h, cudaMemcpyAsync(d_obj, obj_xyz, sizeof(float) * 3 * (size_t)M, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(d_img, img_uv, sizeof(float) * 2 * (size_t)M, cudaMemcpyHostToDevice, h->stream));
+    gather_obs_kernel<<<h->num_sms * 8, 256, 0, h->stream>>>(P.n_edge_int, P.e_off, d_esrc, d_obj, d_img, planes,
+                                                            planes + plane, planes + 2 * plane, planes + 3 * plane,
+                                                            planes + 4 * plane);
+    CUDA_TRY(h, cudaGetLastError());
+    // work buffers
+    if ((rc = dev_alloc(h, &P.st, 1, true))) return rc;
+    for (int b = 0; b < 2; ++b) {
+        if ((rc = dev_alloc(h, &P.x[b], (size_t)P.n_param, true))) return rc;
+        if ((rc = dev_alloc(h, &P.vR[b], 9 * (size_t)P.n_vertex, true))) return rc;
+        if ((rc = dev_alloc(h, &P.blocks[b], (size_t)kBlk * P.n_edge_int, true))) return rc;
+    }
+    {   // vertex 0 is the gauge: identity rotation in both rotation buffers (never rewritten by the update kernels)
+        const double I9[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+        for (int b = 0; b < 2; ++b)
+            CUDA_TRY(h, cudaMemcpyAsync(P.vR[b], I9, sizeof(I9), cudaMemcpyHostToDevice, h->stream));
+        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    }
+    if ((rc = dev_alloc(h, &P.frameL, 27 * (size_t)P.n_slots, true))) return rc;
+    if ((rc = dev_alloc(h, &P.edgeY, 36 * (size_t)P.n_edge_int, true))) return rc;
+    if ((rc = dev_alloc(h, &P.records, (size_t)rec_total, true))) return rc;
+    if ((rc = dev_alloc(h, &P.ar, (size_t)h->ar_len, true))) return rc;
+    if ((rc = dev_alloc(h, &P.dc, (size_t)std::max(P.ns, 1), true))) return rc;
+    if ((rc = dev_alloc(h, &P.norm_part, 2 * (size_t)P.n_k4_blocks, true))) return rc;
+    if ((rc = dev_alloc(h, &P.err_sq, (size_t)P.n_edge_int, true))) return rc;
+    if ((rc = dev_alloc(h, &P.err_nrm, (size_t)P.n_edge_int, true))) return rc;
+    // launch geometry
+    h->k1_smem = (int)(sizeof(K1Shared) + (size_t)nC * (sizeof(CamParams) + 12 * sizeof(double)));
+    h->k5_smem = (int)(sizeof(double) * (size_t)(P.ns + 2));
+    if (h->k1_smem > 48 * 1024)
+        CUDA_TRY(h, cudaFuncSetAttribute(resid_jac_accum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->k1_smem));
+    int per_sm = 1;
+    CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, resid_jac_accum_kernel, kK1Threads, h->k1_smem));
+    per_sm = std::max(per_sm, 1);
+    h->k1_grid = std::max(1, std::min(P.n_edge_int / kEdgesPerBlock, h->num_sms * per_sm));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    cudaFree(d_obj);
+    cudaFree(d_img);
+    h->cur = 0;
+    h->have_obs = true;
+    h->have_params = false;
+    return MCCBA_OK;
+}
+
+int mccba_set_parameters(mccba_handle h, int64_t n, const double* params)
+{
+    if (!h) return MCCBA_ERR_ARG;
+    if (!h->have_obs) return fail(h, MCCBA_ERR_STATE, "set_parameters before set_observations");
+    if (!params || n != n_param(h)) return fail(h, MCCBA_ERR_ARG, "set_parameters: expected %lld doubles, got %lld", (long long)n_param(h), (long long)n);
+    CUDA_TRY(h, cudaSetDevice(h->opts.device));
+    CUDA_TRY(h, cudaMemcpyAsync(h->P.x[h->cur], params, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    h->have_params = true;
+    return MCCBA_OK;
+}
+
+int mccba_get_parameters(mccba_handle h, int64_t n, double* params)
+{
+    if (!h) return MCCBA_ERR_ARG;
+    if (!h->have_params) return fail(h, MCCBA_ERR_STATE, "get_parameters before set_parameters");
+    if (!params || n != n_param(h)) return fail(h, MCCBA_ERR_ARG, "get_parameters: expected %lld doubles", (long long)n_param(h));
+    CUDA_TRY(h, cudaSetDevice(h->opts.device));
+    CUDA_TRY(h, cudaMemcpyAsync(params, h->P.x[h->cur], sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return MCCBA_OK;
+}
+
+int mccba_eval(mccba_handle h, double* cost, double* edge_H6, double* edge_g6, double* edge_cost)
+{
+    if (!h) return MCCBA_ERR_ARG;
+    if (!h->have_params) return fail(h, MCCBA_ERR_STATE, "eval before set_parameters");
+    CUDA_TRY(h, cudaSetDevice(h->opts.device));
+    int rc;
+    if ((rc = sync_state_cur(h))) return rc;
+    if ((rc = launch_forced_eval(h))) return rc;
+    const Problem& P = h->P;
+    const size_t E = (size_t)P.n_edge_int;
+    const bool full = edge_H6 || edge_g6;
+    std::vector<double> buf(full ? kBlk * E : E);
+    const double* src = P.blocks[h->cur] + (full ? 0 : 27 * E);
+    CUDA_TRY(h, cudaMemcpyAsync(buf.data(), src, sizeof(double) * buf.size(), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    double total = 0;
+    for (int e = 0; e < h->n_edge; ++e) {
+        const size_t ie = (size_t)h->int_of_edge[e];
+        const double c = full ? buf[27 * E + ie] : buf[ie];
+        total += c;
+        if (edge_cost) edge_cost[e] = c;
+        if (edge_H6)
+            for (int k = 0; k < 21; ++k) edge_H6[21 * (size_t)e + k] = buf[k * E + ie];
+        if (edge_g6)
+            for (int k = 0; k < 6; ++k) edge_g6[6 * (size_t)e + k] = buf[(21 + k) * E + ie];
+    }
+    if (cost) *cost = total;
+    return MCCBA_OK;
+}
+
+int mccba_reduced_system(mccba_handle h, double lambda, double* S, double* gs)
+{
+    if (!h) return MCCBA_ERR_ARG;
+    if (!h->have_params) return fail(h, MCCBA_ERR_STATE, "reduced_system before set_parameters");
+    CUDA_TRY(h, cudaSetDevice(h->opts.device));
+    int rc;
+    if ((rc = sync_state_cur(h))) return rc;
+    if ((rc = launch_forced_eval(h))) return rc;
+    Problem& P = h->P;
+    CUDA_TRY(h, cudaMemsetAsync(P.ar, 0, sizeof(double) * (size_t)h->ar_len, h->stream));
+    frame_schur_kernel<<<(P.n_warps * 32 + kK2Threads - 1) / kK2Threads, kK2Threads, 0, h->stream>>>(P, h->cur, lambda);
+    reduce_records_kernel<<<(P.n_dest * 32 + 127) / 128, 128, 0, h->stream>>>(P, 1);
+    CUDA_TRY(h, cudaGetLastError());
+    if (h->opts.nranks > 1) {
+        ncclResult_t r = nccl().AllReduce(P.ar, P.ar, (size_t)h->ar_len, kNcclFloat64, kNcclSum, h->comm, h->stream);
+        if (r != 0) return fail(h, MCCBA_ERR_NCCL, "ncclAllReduce failed: %d", r);
+    }
+    const size_t ns = (size_t)P.ns;
+    if (S && ns) CUDA_TRY(h, cudaMemcpyAsync(S, P.ar, sizeof(double) * ns * ns, cudaMemcpyDeviceToHost, h->stream));
+    if (gs && ns) CUDA_TRY(h, cudaMemcpyAsync(gs, P.ar + ns * ns, sizeof(double) * ns, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return MCCBA_OK;
+}
+
+int mccba_solve(mccba_handle h, const mccba_solve_opts* o, mccba_report* rep)
+{
+    if (!h) return MCCBA_ERR_ARG;
+    if (!o) return fail(h, MCCBA_ERR_ARG, "solve: null options");
+    if (!h->have_params) return fail(h, MCCBA_ERR_STATE, "solve before set_parameters");
+    if (o->mode != MCCBA_MODE_REFERENCE_GN && o->mode != MCCBA_MODE_LM) return fail(h, MCCBA_ERR_ARG, "solve: unknown mode %d", o->mode);
+    if (o->crit_type < 1 || o->crit_type > 3) return fail(h, MCCBA_ERR_ARG, "solve: criteria type %d (1=COUNT, 2=EPS, 3=both)", o->crit_type);
+    if (o->max_count < 0) return fail(h, MCCBA_ERR_ARG, "solve: negative max_count");
+    CUDA_TRY(h, cudaSetDevice(h->opts.device));
+    Problem& P = h->P;
+    cudaStream_t s = h->stream;
+    int rc;
+    int kernels = 0;
+    CUDA_TRY(h, cudaEventRecord(h->ev0, s));
+    init_state_kernel<<<1, 1, 0, s>>>(P.st, o->mode, o->crit_type, o->max_count, o->epsilon, o->lambda0, o->lambda_up,
+                                      o->lambda_down, h->cur);
+    CUDA_TRY(h, cudaMemsetAsync(P.norm_part, 0, sizeof(double) * 2 * (size_t)P.n_k4_blocks, s));
+    if ((rc = launch_forced_eval(h))) return rc;
+    kernels += 3;
+    // one iteration as a CUDA graph (captured once per problem)
+    const bool use_graph = h->opts.use_graph && !h->profile;
+    if (use_graph && !h->graph) {
+        cudaGraph_t g = nullptr;
+        CUDA_TRY(h, cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed));
+        rc = enqueue_iteration(h, false);
+        cudaError_t ce = cudaStreamEndCapture(s, &g);
+        if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+        if (ce != cudaSuccess) return fail(h, MCCBA_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(ce));
+        ce = cudaGraphInstantiate(&h->graph, g, 0);
+        cudaGraphDestroy(g);
+        if (ce != cudaSuccess) return fail(h, MCCBA_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(ce));
+    }
+    for (double& v : h->prof_ms) v = 0;
+    const bool has_count = (o->crit_type & MCCBA_CRIT_COUNT) != 0;
+    int64_t max_launches = has_count ? (o->mode == MCCBA_MODE_REFERENCE_GN ? (int64_t)o->max_count + 1 : 2 * (int64_t)o->max_count + 4)
+                                     : 200000;
+    const bool exact = has_count && o->mode == MCCBA_MODE_REFERENCE_GN && !(o->crit_type & MCCBA_CRIT_EPS);
+    const int chunk = 8;
+    int64_t launched = 0;
+    int slot = 0;
+    cudaEvent_t evs[2];
+    cudaEventCreateWithFlags(&evs[0], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&evs[1], cudaEventDisableTiming);
+    bool pending[2] = {false, false};
+    bool stop = false;
+    while (launched < max_launches && !stop) {
+        const int n = (int)std::min<int64_t>(exact ? max_launches : chunk, max_launches - launched);
+        for (int i = 0; i < n; ++i) {
+            if (use_graph) CUDA_TRY(h, cudaGraphLaunch(h->graph, s));
+            else if ((rc = enqueue_iteration(h, h->profile != 0))) return rc;
+        }
+        launched += n;
+        if (exact) break;
+        CUDA_TRY(h, cudaMemcpyAsync(h->h_done + slot, &P.st->done, sizeof(int), cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(h, cudaEventRecord(evs[slot], s));
+        pending[slot] = true;
+        const int prev = slot ^ 1;
+        if (pending[prev]) {  // look one chunk behind so the device never waits for the host
+            CUDA_TRY(h, cudaEventSynchronize(evs[prev]));
+            if (h->h_done[prev]) stop = true;
+            pending[prev] = false;
+        }
+        slot ^= 1;
+    }
+    cudaEventDestroy(evs[0]);
+    cudaEventDestroy(evs[1]);
+    kernels += (int)launched * 5;
+    CUDA_TRY(h, cudaMemcpyAsync(h->h_state, P.st, sizeof(DevState), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(h, cudaEventRecord(h->ev1, s));
+    CUDA_TRY(h, cudaStreamSynchronize(s));
+    CUDA_TRY(h, cudaGetLastError());
+    const DevState& st = *h->h_state;
+    h->cur = st.cur;
+    float ms = 0;
+    cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+    if (h->profile && st.launches > 0)
+        for (double& v : h->prof_ms) v /= (double)launched;
+    if (rep) {
+        rep->iterations = st.iter; rep->accepted = st.n_accept; rep->rejected = st.n_reject;
+        rep->status = st.status; rep->graph_launches = (int)launched; rep->kernel_launches = kernels;
+        rep->change = st.change; rep->cost = st.cost_cur; rep->lambda = st.lambda; rep->device_ms = ms;
+    }
+    if (st.status != 0)
+        return fail(h, MCCBA_ERR_NUMERIC, "solve: numeric failure at iteration %d (non-finite cost or a block that is not positive definite)", st.iter);
+    if (!st.done)
+        return fail(h, MCCBA_ERR_NUMERIC, "solve: launch budget exhausted before the termination test fired (iter %d)", st.iter);
+    return MCCBA_OK;
+}
+
+int mccba_allreduce_sum(mccba_handle h, double* buf, int n)
+{
+    if (!h || !buf || n < 0 || n > 64) return MCCBA_ERR_ARG;
+    if (h->opts.nranks == 1 || n == 0) return MCCBA_OK;
+    CUDA_TRY(h, cudaSetDevice(h->opts.device));
+    memcpy(h->h_small, buf, sizeof(double) * (size_t)n);
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_small, h->h_small, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, h->stream));
+    ncclResult_t r = nccl().AllReduce(h->d_small, h->d_small, (size_t)n, kNcclFloat64, kNcclSum, h->comm, h->stream);
+    if (r != 0) return fail(h, MCCBA_ERR_NCCL, "ncclAllReduce failed: %d", r);
+    CUDA_TRY(h, cudaMemcpyAsync(h->h_small, h->d_small, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    memcpy(buf, h->h_small, sizeof(double) * (size_t)n);
+    return MCCBA_OK;
+}
+
+int mccba_reproj_error(mccba_handle h, mccba_error_stats* stats, double* per_edge_mean)
+{
+    if (!h) return MCCBA_ERR_ARG;
+    if (!h->have_params) return fail(h, MCCBA_ERR_STATE, "reproj_error before set_parameters");
+    CUDA_TRY(h, cudaSetDevice(h->opts.device));
+    int rc;
+    if ((rc = sync_state_cur(h))) return rc;
+    Problem& P = h->P;
+    vertex_prep_kernel<<<(P.n_vertex + 127) / 128, 128, 0, h->stream>>>(P, -1);
+    reproj_error_kernel<<<h->num_sms * 4, kK1Threads, 0, h->stream>>>(P);
+    CUDA_TRY(h, cudaGetLastError());
+    const size_t E = (size_t)P.n_edge_int;
+    std::vector<double> sq(E), nr(E);
+    CUDA_TRY(h, cudaMemcpyAsync(sq.data(), P.err_sq, sizeof(double) * E, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(nr.data(), P.err_nrm, sizeof(double) * E, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    double acc[4] = {0, 0, 0, 0};  // sum_norm, sum_sq, reference point count, points
+    for (int e = 0; e < h->n_edge; ++e) {
+        const size_t ie = (size_t)h->int_of_edge[e];
+        const int64_t n = h->edge_n_h[e];
+        if (per_edge_mean) per_edge_mean[e] = n ? nr[ie] / (double)n : 0.0;
+        acc[0] += nr[ie];
+        acc[1] += sq[ie];
+        // src/multicalib.cpp:983: error.total() is 2N for PINHOLE (N x 2 single channel) and N for OMNIDIRECTIONAL
+        acc[2] += (double)(h->cams[h->edge_cam_h[e]].model == MCCBA_PINHOLE ? 2 * n : n);
+        acc[3] += (double)n;
+    }
+    const double local_norm = acc[0], local_sq = acc[1], local_n = acc[3];
+    if ((rc = mccba_allreduce_sum(h, acc, 4))) return rc;
+    if (stats) {
+        stats->mean_reproj_error = acc[2] > 0 ? acc[0] / acc[2] : 0.0;
+        stats->rms = acc[3] > 0 ? sqrt(acc[1] / acc[3]) : 0.0;
+        stats->sum_norm = local_norm; stats->sum_sq = local_sq; stats->n_points = (int64_t)local_n;
+    }
+    return MCCBA_OK;
+}
+
+int mccba_last_kernel_ms(mccba_handle h, double out[6])
+{
+    if (!h || !out) return MCCBA_ERR_ARG;
+    for (int i = 0; i < 6; ++i) out[i] = h->prof_ms[i];
+    return MCCBA_OK;
+}
+
+int mccba_time_eval(mccba_handle h, int reps, double* avg_ms)
+{
+    if (!h || reps < 1 || !avg_ms) return MCCBA_ERR_ARG;
+    if (!h->have_params) return fail(h, MCCBA_ERR_STATE, "time_eval before set_parameters");
+    CUDA_TRY(h, cudaSetDevice(h->opts.device));
+    int rc;
+    if ((rc = sync_state_cur(h))) return rc;
+    if ((rc = launch_forced_eval(h))) return rc;  // warm-up, also computes the rotations
+    CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));
+    for (int i = 0; i < reps; ++i)
+        resid_jac_accum_kernel<<<h->k1_grid, kK1Threads, h->k1_smem, h->stream>>>(h->P, 1);
+    CUDA_TRY(h, cudaEventRecord(h->ev1, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    CUDA_TRY(h, cudaGetLastError());
+    float ms = 0;
+    cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+    *avg_ms = (double)ms / reps;
+    return MCCBA_OK;
+}
+
+}  // extern "C"

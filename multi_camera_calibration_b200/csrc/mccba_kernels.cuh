@@ -1,0 +1,772 @@
+// mccba_kernels.cuh -- sm_100a kernels of the calibration bundle adjustment (included once by mccba_capi.cu).
+//
+// Kernel map (reference code each one replaces; all paths relative to /root/reference):
+//   gather_obs_kernel        layout change only: AoS CV_32F points -> SoA planes in processing order
+//   vertex_prep_kernel       cv::Rodrigues per vertex (src/multicalib.cpp:1023-1024 inside compose_motion)
+//   resid_jac_accum_kernel   computePhotoCameraJacobian + scatter + J^T J / J^T E, per edge
+//                            (src/multicalib.cpp:611-678, 688-689, 717-824; src/omnidir.cpp:141-244)
+//   reproj_error_kernel      computeProjectError (src/multicalib.cpp:912-984)
+//   frame_schur_kernel       (new math) eliminates the per-frame pattern-pose blocks; replaces the P x P solve
+//   reduce_records_kernel    deterministic, atomic-free sum of the warp records into the reduced camera system
+//   decide_solve_kernel      optimizeExtrinsics' loop control (src/multicalib.cpp:473-507) + Cholesky of the
+//                            reduced system (replaces Eigen CG, :565-592) + accept/reject (LM)
+//   frame_update_kernel      back-substitution + parameter update (:491-504)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "mccba_math.cuh"
+
+namespace mccba {
+
+constexpr int kLanesPerEdge = 8;
+constexpr int kK1Threads = 256;
+constexpr int kEdgesPerBlock = kK1Threads / kLanesPerEdge;  // 32
+constexpr int kK2Threads = 128;
+constexpr int kK4Threads = 128;
+constexpr int kK5Threads = 1024;
+constexpr int kMaxViews = 64;
+constexpr unsigned kFull = 0xffffffffu;
+
+enum Phase { kPhaseFirst = 0, kPhaseDecide = 1, kPhaseRebuild = 2 };
+
+// Loop state, resident in global memory; only decide_solve_kernel writes it (single CTA).
+struct DevState {
+    int mode, crit_type, max_count;
+    int iter, done, phase, cur, status;
+    int n_accept, n_reject, launches, solved;  // solved: the last decide_solve produced a step (update/eval may run)
+    double eps, lambda, lambda_up, lambda_down, lambda_spec;
+    double cost_cur, cost_trial, change, alpha;
+    double cam_step2, cam_param2;  // camera part of |step|^2 and |params|^2 of the current trial
+};
+
+struct Problem {
+    int n_cam, n_frame, n_vertex, ns;
+    int n_edge_int;   // internal edges (padded per group to 32-frame warps), multiple of 32
+    int n_slots;      // frame slots = 32 * n_warps
+    int n_warps;      // frame_schur warps
+    int n_dest;       // reduce_records destinations
+    int n_k4_blocks;
+    int64_t n_param;  // 6 * (n_vertex - 1)
+    // observations, SoA planes in internal edge order
+    const float *ox, *oy, *oz, *iu, *iv;
+    const int* e_off;    // n_edge_int + 1 corner offsets
+    const int* e_cam;    // camera of internal edge
+    const int* e_frame;  // frame (0-based) of internal edge, -1 for padding
+    const CamParams* cams;
+    // frame slots / groups
+    const int* slot_frame;   // n_slots, -1 = padding
+    const int* warp_group;   // n_warps
+    const int* group_V;      // per group: number of views
+    const int* group_cam0;   // per group: offset into group_cams
+    const int* group_cams;   // concatenated sorted camera lists
+    const int* group_ebase;  // per group: first internal edge
+    const int* group_stride; // per group: slots (multiple of 32); edge(v, ls) = ebase + v*stride + ls
+    const int* group_slot0;  // per group: first slot
+    const int* warp_rec;     // per warp: offset of its record (in doubles)
+    // reduce destinations
+    const int* dest_info;    // n_dest x 4: kind (0 block, 1 g, 2 scalars), A (cam-1), B (cam-1), unused
+    const int* dest_src0;    // n_dest + 1
+    const int* dest_src;     // record offsets (doubles)
+    // state and work buffers
+    DevState* st;
+    double* x[2];        // parameter vectors (reference layout)
+    double* vR[2];       // n_vertex x 9 rotation matrices
+    double* blocks[2];   // kBlk x n_edge_int (SoA)
+    double* frameL;      // 27 x n_slots (21 packed factor + 6 z)
+    double* edgeY;       // 36 x n_edge_int
+    double* records;     // warp records
+    double* ar;          // allreduce buffer: S (ns x ns) | g (ns) | cost, step2, param2, bad
+    double* dc;          // ns: camera step in tangent coordinates
+    double* norm_part;   // 2 x n_k4_blocks: per-block |step|^2, |trial|^2 of the frames
+    double* err_sq;      // n_edge_int
+    double* err_nrm;     // n_edge_int
+};
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+    return v;
+}
+
+// --------------------------------------------------------------------------------------------------------
+// observations: AoS host layout -> SoA planes in internal edge order.  One warp per internal edge.
+// --------------------------------------------------------------------------------------------------------
+__global__ void gather_obs_kernel(int n_edge_int, const int* __restrict__ e_off, const int64_t* __restrict__ e_src,
+                                  const float* __restrict__ obj, const float* __restrict__ img, float* ox, float* oy,
+                                  float* oz, float* iu, float* iv)
+{
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const int nw = (gridDim.x * blockDim.x) >> 5;
+    for (int e = warp; e < n_edge_int; e += nw) {
+        const int b = e_off[e], n = e_off[e + 1] - b;
+        const int64_t s = e_src[e];
+        for (int i = lane; i < n; i += 32) {
+            ox[b + i] = obj[3 * (s + i)];
+            oy[b + i] = obj[3 * (s + i) + 1];
+            oz[b + i] = obj[3 * (s + i) + 2];
+            iu[b + i] = img[2 * (s + i)];
+            iv[b + i] = img[2 * (s + i) + 1];
+        }
+    }
+}
+
+// --------------------------------------------------------------------------------------------------------
+// vertex prep: R_v = exp([om_v]x) for every vertex of parameter buffer `which` (-1: the state's current buffer)
+// --------------------------------------------------------------------------------------------------------
+__global__ void vertex_prep_kernel(Problem P, int which)
+{
+    if (which < 0) which = P.st->cur;
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= P.n_vertex) return;
+    double R[9];
+    if (v == 0) {
+        R[0] = R[4] = R[8] = 1; R[1] = R[2] = R[3] = R[5] = R[6] = R[7] = 0;
+    } else {
+        const double* p = P.x[which] + 6 * (int64_t)(v - 1);
+        const double om[3] = {p[0], p[1], p[2]};
+        rodrigues(om, R);
+    }
+#pragma unroll
+    for (int i = 0; i < 9; ++i) P.vR[which][9 * (int64_t)v + i] = R[i];
+}
+
+// --------------------------------------------------------------------------------------------------------
+// K1: residual + Jacobian + per-edge normal-equation block.  8 lanes per edge, 32 edges per CTA iteration,
+// persistent grid-stride over edge chunks.  Intrinsics and camera poses staged in shared memory once per CTA.
+// Output: blocks[which][k * n_edge_int + e], k < 28, written coalesced through a shared-memory transpose.
+// --------------------------------------------------------------------------------------------------------
+struct K1Shared {
+    double stage[kBlk][kEdgesPerBlock + 1];
+};
+
+template <int kModel, bool kRational>
+__device__ __forceinline__ void edge_corner_loop(const Problem& P, const CamParams& cam, const double* R3,
+                                                 const double* T3, int begin, int end, int sub, double* acc)
+{
+    for (int i = begin + sub; i < end; i += kLanesPerEdge) {
+        const float ox = __ldg(P.ox + i), oy = __ldg(P.oy + i), oz = __ldg(P.oz + i);
+        const float iu = __ldg(P.iu + i), iv = __ldg(P.iv + i);
+        corner_accumulate<kModel, kRational>(cam, R3, T3, ox, oy, oz, iu, iv, acc);
+    }
+}
+
+// mode: 0 = loop launch (evaluate the trial buffer iff the state says a step was produced), 1 = forced on `cur`
+__global__ void __launch_bounds__(kK1Threads, 2) resid_jac_accum_kernel(Problem P, int forced)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    K1Shared* sh = reinterpret_cast<K1Shared*>(smem_raw);
+    CamParams* s_cam = reinterpret_cast<CamParams*>(smem_raw + sizeof(K1Shared));
+    double* s_camR = reinterpret_cast<double*>(s_cam + P.n_cam);  // n_cam x 12: R (9) | t (3)
+
+    const DevState* st = P.st;
+    int which;
+    if (forced) which = st->cur;
+    else {
+        if (st->done || !st->solved) return;
+        which = 1 - st->cur;
+    }
+    const double* __restrict__ x = P.x[which];
+    const double* __restrict__ vR = P.vR[which];
+    double* __restrict__ out = P.blocks[which];
+
+    for (int c = threadIdx.x; c < P.n_cam; c += blockDim.x) {
+        s_cam[c] = P.cams[c];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) s_camR[12 * c + i] = vR[9 * c + i];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) s_camR[12 * c + 9 + i] = c == 0 ? 0.0 : x[6 * (c - 1) + 3 + i];
+    }
+    __syncthreads();
+
+    const int sub = threadIdx.x & (kLanesPerEdge - 1);
+    const int eb = threadIdx.x / kLanesPerEdge;
+    const int n_chunks = P.n_edge_int / kEdgesPerBlock;
+    for (int chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+        const int e = chunk * kEdgesPerBlock + eb;
+        double acc[kBlk];
+#pragma unroll
+        for (int k = 0; k < kBlk; ++k) acc[k] = 0.0;
+        const int frame = P.e_frame[e];
+        if (frame >= 0) {
+            const int c = P.e_cam[e];
+            const int64_t pv = P.n_cam + frame;
+            double Rp[9], tp[3], R3[9], T3[3];
+#pragma unroll
+            for (int i = 0; i < 9; ++i) Rp[i] = __ldg(vR + 9 * pv + i);
+#pragma unroll
+            for (int i = 0; i < 3; ++i) tp[i] = __ldg(x + 6 * (pv - 1) + 3 + i);
+            compose_pose(s_camR + 12 * c, s_camR + 12 * c + 9, Rp, tp, R3, T3);
+            const CamParams& cam = s_cam[c];
+            const int b = P.e_off[e], n = P.e_off[e + 1];
+            if (cam.model == kPinhole) {
+                if (cam.rational) edge_corner_loop<kPinhole, true>(P, cam, R3, T3, b, n, sub, acc);
+                else edge_corner_loop<kPinhole, false>(P, cam, R3, T3, b, n, sub, acc);
+            } else {
+                edge_corner_loop<kOmnidir, false>(P, cam, R3, T3, b, n, sub, acc);
+            }
+        }
+        // transposed reduction over the 8 lanes of the edge: 28 -> 14 -> 7 -> 3(+1) values per lane, 25 adds
+        int base = 0;
+        {
+            const bool up = (sub & 4) != 0;
+#pragma unroll
+            for (int i = 0; i < 14; ++i) {
+                const double a = acc[i], b2 = acc[i + 14];
+                const double send = up ? a : b2, keep = up ? b2 : a;
+                acc[i] = keep + __shfl_xor_sync(kFull, send, 4);
+            }
+            base += up ? 14 : 0;
+        }
+        {
+            const bool up = (sub & 2) != 0;
+#pragma unroll
+            for (int i = 0; i < 7; ++i) {
+                const double a = acc[i], b2 = acc[i + 7];
+                const double send = up ? a : b2, keep = up ? b2 : a;
+                acc[i] = keep + __shfl_xor_sync(kFull, send, 2);
+            }
+            base += up ? 7 : 0;
+        }
+        {
+            const bool up = (sub & 1) != 0;
+            const double last = acc[6] + __shfl_xor_sync(kFull, acc[6], 1);
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                const double a = acc[i], b2 = acc[i + 3];
+                const double send = up ? a : b2, keep = up ? b2 : a;
+                acc[i] = keep + __shfl_xor_sync(kFull, send, 1);
+            }
+            if (!up) sh->stage[base + 6][eb] = last;
+            base += up ? 3 : 0;
+        }
+#pragma unroll
+        for (int i = 0; i < 3; ++i) sh->stage[base + i][eb] = acc[i];
+        __syncthreads();
+        for (int t = threadIdx.x; t < kBlk * kEdgesPerBlock; t += kK1Threads) {
+            const int k = t / kEdgesPerBlock, col = t % kEdgesPerBlock;
+            out[(int64_t)k * P.n_edge_int + chunk * kEdgesPerBlock + col] = sh->stage[k][col];
+        }
+        __syncthreads();
+    }
+}
+
+// Residual-only variant for computeProjectError: per edge sum |e|^2 and sum |e| at the current parameters.
+template <int kModel, bool kRational>
+__device__ __forceinline__ void edge_error_loop(const Problem& P, const CamParams& cam, const double* R3,
+                                                const double* T3, int begin, int end, int sub, double* sq, double* nrm)
+{
+    for (int i = begin + sub; i < end; i += kLanesPerEdge)
+        corner_error<kModel, kRational>(cam, R3, T3, __ldg(P.ox + i), __ldg(P.oy + i), __ldg(P.oz + i), __ldg(P.iu + i),
+                                        __ldg(P.iv + i), sq, nrm);
+}
+
+__global__ void __launch_bounds__(kK1Threads, 2) reproj_error_kernel(Problem P)
+{
+    const int which = P.st->cur;
+    const double* __restrict__ x = P.x[which];
+    const double* __restrict__ vR = P.vR[which];
+    const int sub = threadIdx.x & (kLanesPerEdge - 1);
+    const int n_groups = (gridDim.x * blockDim.x) / kLanesPerEdge;
+    for (int e = (blockIdx.x * blockDim.x + threadIdx.x) / kLanesPerEdge; e < P.n_edge_int; e += n_groups) {
+        double sq = 0, nrm = 0;
+        const int frame = P.e_frame[e];
+        if (frame >= 0) {
+            const int c = P.e_cam[e];
+            const int64_t pv = P.n_cam + frame;
+            double Rc[9], tc[3], Rp[9], tp[3], R3[9], T3[3];
+#pragma unroll
+            for (int i = 0; i < 9; ++i) { Rc[i] = vR[9 * c + i]; Rp[i] = vR[9 * pv + i]; }
+#pragma unroll
+            for (int i = 0; i < 3; ++i) { tc[i] = c == 0 ? 0.0 : x[6 * (c - 1) + 3 + i]; tp[i] = x[6 * (pv - 1) + 3 + i]; }
+            compose_pose(Rc, tc, Rp, tp, R3, T3);
+            const CamParams cam = P.cams[c];
+            const int b = P.e_off[e], n = P.e_off[e + 1];
+            if (cam.model == kPinhole) {
+                if (cam.rational) edge_error_loop<kPinhole, true>(P, cam, R3, T3, b, n, sub, &sq, &nrm);
+                else edge_error_loop<kPinhole, false>(P, cam, R3, T3, b, n, sub, &sq, &nrm);
+            } else {
+                edge_error_loop<kOmnidir, false>(P, cam, R3, T3, b, n, sub, &sq, &nrm);
+            }
+        }
+#pragma unroll
+        for (int o = kLanesPerEdge / 2; o > 0; o >>= 1) {
+            sq += __shfl_xor_sync(kFull, sq, o);
+            nrm += __shfl_xor_sync(kFull, nrm, o);
+        }
+        if (sub == 0) { P.err_sq[e] = sq; P.err_nrm[e] = nrm; }
+    }
+}
+
+// --------------------------------------------------------------------------------------------------------
+// K2: per-frame Schur elimination.  One thread per frame slot; the 32 slots of a warp belong to one group
+// (frames seen by the same camera set), so their contributions to the reduced camera system land in the same
+// 6x6 blocks and are summed with warp shuffles into ONE record per warp -- no atomics.
+// Record layout: [cost, bad] | Va x 36 diagonal blocks | Va x 6 gradient | Va(Va-1)/2 x 36 off-diagonal blocks,
+// Va = number of non-gauge views of the group.
+// --------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void reduce_store36(const double* v, double* dst, int lane)
+{
+    double o0 = 0, o1 = 0;
+#pragma unroll
+    for (int k = 0; k < 36; ++k) {
+        const double t = warp_sum(v[k]);
+        if (k < 32) { if (lane == k) o0 = t; }
+        else { if (lane == k - 32) o1 = t; }
+    }
+    dst[lane] = o0;
+    if (lane < 4) dst[32 + lane] = o1;
+}
+
+// sel: -1 = decide from the state (loop), 0/1 = explicit buffer with explicit lambda (diagnostics)
+__global__ void __launch_bounds__(kK2Threads) frame_schur_kernel(Problem P, int sel_arg, double lambda_arg)
+{
+    const DevState* st = P.st;
+    int sel;
+    double lambda;
+    if (sel_arg >= 0) { sel = sel_arg; lambda = lambda_arg; }
+    else {
+        if (st->done) return;
+        if (st->phase == kPhaseDecide) { sel = 1 - st->cur; lambda = st->lambda_spec; }
+        else { sel = st->cur; lambda = st->lambda; }
+    }
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= P.n_warps) return;
+    const int g = P.warp_group[warp];
+    const int V = P.group_V[g];
+    const int* gc = P.group_cams + P.group_cam0[g];
+    const int slot = warp * 32 + lane;
+    const int ls = slot - P.group_slot0[g];
+    const int ebase = P.group_ebase[g], stride = P.group_stride[g];
+    const int frame = P.slot_frame[slot];
+    const bool active = frame >= 0;
+    const double* __restrict__ x = P.x[sel];
+    const double* __restrict__ vR = P.vR[sel];
+    const double* __restrict__ blk = P.blocks[sel];
+    const int64_t E = P.n_edge_int;
+    double* rec = P.records + P.warp_rec[warp];
+
+    double tp[3] = {0, 0, 0};
+    if (active) {
+        const int64_t pv = P.n_cam + frame;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) tp[i] = x[6 * (pv - 1) + 3 + i];
+    }
+    double U[21], z[6], cost = 0;
+#pragma unroll
+    for (int i = 0; i < 21; ++i) U[i] = 0;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) z[i] = 0;
+    int Va = 0;
+    // pass 1: pattern-pose block
+    for (int v = 0; v < V; ++v) {
+        const int c = gc[v];
+        if (c != 0) ++Va;
+        if (!active) continue;
+        const int64_t e = ebase + (int64_t)v * stride + ls;
+        double t[kBlk], H[36], Rc[9];
+#pragma unroll
+        for (int k = 0; k < kBlk; ++k) t[k] = blk[k * E + e];
+        cost += t[27];
+        unpack_sym6(t, H);
+        if (c != 0) {
+#pragma unroll
+            for (int i = 0; i < 9; ++i) Rc[i] = vR[9 * c + i];
+        }
+        lift_frame(H, t + 21, Rc, c == 0, U, z);
+    }
+    int bad = 0;
+    if (active) {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) U[tri6(i, i)] *= (1.0 + lambda);
+        if (!chol6_packed(U)) bad = 1;
+        chol6_forward(U, z, 1);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) U[tri6(i, i)] = 1.0;
+    }
+#pragma unroll
+    for (int k = 0; k < 21; ++k) P.frameL[(int64_t)k * P.n_slots + slot] = U[k];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) P.frameL[(int64_t)(21 + k) * P.n_slots + slot] = z[k];
+    {
+        const double c2 = warp_sum(cost), b2 = warp_sum((double)bad);
+        if (lane == 0) { rec[0] = c2; rec[1] = b2; }
+    }
+    // pass 2: camera blocks of each non-gauge view
+    int ai = 0;
+    for (int v = 0; v < V; ++v) {
+        const int c = gc[v];
+        if (c == 0) continue;
+        const int64_t e = ebase + (int64_t)v * stride + ls;
+        double D[36], gd[6];
+#pragma unroll
+        for (int i = 0; i < 36; ++i) D[i] = 0;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) gd[i] = 0;
+        if (active) {
+            double t[kBlk], H[36], Rc[9], s[3], Y[36], gcv[6];
+#pragma unroll
+            for (int k = 0; k < kBlk; ++k) t[k] = blk[k * E + e];
+            unpack_sym6(t, H);
+#pragma unroll
+            for (int i = 0; i < 9; ++i) Rc[i] = vR[9 * c + i];
+            mat3_vec(Rc, tp, s);
+            lift_camera(H, t + 21, Rc, s, D, gcv, Y);
+#pragma unroll
+            for (int j = 0; j < 6; ++j) chol6_forward(U, Y + j, 6);  // Y = L^-1 W, column by column
+#pragma unroll
+            for (int k = 0; k < 36; ++k) P.edgeY[k * E + e] = Y[k];
+#pragma unroll
+            for (int i = 0; i < 6; ++i) D[i * 6 + i] *= (1.0 + lambda);
+#pragma unroll
+            for (int i = 0; i < 6; ++i) {
+#pragma unroll
+                for (int j = 0; j < 6; ++j) {
+                    double acc = 0;
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) acc += Y[k * 6 + i] * Y[k * 6 + j];
+                    D[i * 6 + j] -= acc;
+                }
+                double acc = 0;
+#pragma unroll
+                for (int k = 0; k < 6; ++k) acc += Y[k * 6 + i] * z[k];
+                gd[i] = gcv[i] - acc;
+            }
+        }
+        reduce_store36(D, rec + 2 + 36 * ai, lane);
+        {
+            double o = 0;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) {
+                const double t2 = warp_sum(gd[k]);
+                if (lane == k) o = t2;
+            }
+            if (lane < 6) rec[2 + 36 * Va + 6 * ai + lane] = o;
+        }
+        ++ai;
+    }
+    // pass 3: off-diagonal blocks  -Y_a^T Y_b  for non-gauge views a < b
+    int pi = 0;
+    for (int va = 0; va < V; ++va) {
+        if (gc[va] == 0) continue;
+        for (int vb = va + 1; vb < V; ++vb) {
+            if (gc[vb] == 0) continue;
+            double D[36];
+#pragma unroll
+            for (int i = 0; i < 36; ++i) D[i] = 0;
+            if (active) {
+                const int64_t ea = ebase + (int64_t)va * stride + ls, ebx = ebase + (int64_t)vb * stride + ls;
+                double Ya[36], Yb[36];
+#pragma unroll
+                for (int k = 0; k < 36; ++k) { Ya[k] = P.edgeY[k * E + ea]; Yb[k] = P.edgeY[k * E + ebx]; }
+#pragma unroll
+                for (int i = 0; i < 6; ++i)
+#pragma unroll
+                    for (int j = 0; j < 6; ++j) {
+                        double acc = 0;
+#pragma unroll
+                        for (int k = 0; k < 6; ++k) acc += Ya[k * 6 + i] * Yb[k * 6 + j];
+                        D[i * 6 + j] = -acc;
+                    }
+            }
+            reduce_store36(D, rec + 2 + 42 * Va + 36 * pi, lane);
+            ++pi;
+        }
+    }
+}
+
+// --------------------------------------------------------------------------------------------------------
+// K3a: sum the warp records into the reduced system, one warp per destination, sources in fixed order.
+// ar must be zeroed beforehand (blocks without sources stay zero).
+// --------------------------------------------------------------------------------------------------------
+__global__ void reduce_records_kernel(Problem P, int forced)
+{
+    if (!forced && P.st->done) return;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= P.n_dest) return;
+    const int kind = P.dest_info[4 * warp], A = P.dest_info[4 * warp + 1], B = P.dest_info[4 * warp + 2];
+    const int s0 = P.dest_src0[warp], s1 = P.dest_src0[warp + 1];
+    const int ns = P.ns;
+    double* S = P.ar;
+    double* gs = P.ar + (int64_t)ns * ns;
+    double* sc = gs + ns;
+    if (kind == 0) {
+        double a0 = 0, a1 = 0;
+        for (int s = s0; s < s1; ++s) {
+            const double* src = P.records + P.dest_src[s];
+            a0 += src[lane];
+            if (lane < 4) a1 += src[32 + lane];
+        }
+        {
+            const int i = lane / 6, j = lane % 6;
+            S[(int64_t)(6 * A + i) * ns + 6 * B + j] = a0;
+            if (A != B) S[(int64_t)(6 * B + j) * ns + 6 * A + i] = a0;
+        }
+        if (lane < 4) {
+            const int k = 32 + lane, i = k / 6, j = k % 6;
+            S[(int64_t)(6 * A + i) * ns + 6 * B + j] = a1;
+            if (A != B) S[(int64_t)(6 * B + j) * ns + 6 * A + i] = a1;
+        }
+    } else if (kind == 1) {
+        double a0 = 0;
+        if (lane < 6)
+            for (int s = s0; s < s1; ++s) a0 += P.records[P.dest_src[s] + lane];
+        if (lane < 6) gs[6 * A + lane] = a0;
+    } else {
+        // scalars: cost and bad from every warp record; frame step / param norms from frame_update's partials
+        double c = 0, b = 0, n0 = 0, n1 = 0;
+        for (int w = lane; w < P.n_warps; w += 32) {
+            c += P.records[P.warp_rec[w]];
+            b += P.records[P.warp_rec[w] + 1];
+        }
+        for (int k = lane; k < P.n_k4_blocks; k += 32) {
+            n0 += P.norm_part[k];
+            n1 += P.norm_part[P.n_k4_blocks + k];
+        }
+        c = warp_sum(c); b = warp_sum(b); n0 = warp_sum(n0); n1 = warp_sum(n1);
+        if (lane == 0) { sc[0] = c; sc[1] = n0; sc[2] = n1; sc[3] = b; }
+    }
+}
+
+// --------------------------------------------------------------------------------------------------------
+// K5: loop control + Cholesky solve of the reduced camera system.  Single CTA.
+// Augmented matrix A = [S; g^T] ((ns+1) x ns, exactly the allreduce buffer layout): the right-looking
+// factorisation also produces y = L^-1 g in the extra row; a backward sweep gives dc.
+// --------------------------------------------------------------------------------------------------------
+__device__ int chol_solve_cta(double* A, int n, double* xout, double* s_col, double* s_bcast)
+{
+    const int tid = threadIdx.x, nt = blockDim.x;
+    __shared__ int s_fail;
+    if (tid == 0) s_fail = 0;
+    __syncthreads();
+    for (int j = 0; j < n; ++j) {
+        if (tid == 0) {
+            const double d = A[(int64_t)j * n + j];
+            if (!(d > 0.0) || !isfinite(d)) s_fail = 1;
+            const double inv = 1.0 / sqrt(d > 0.0 ? d : 1.0);
+            s_bcast[0] = inv;
+            A[(int64_t)j * n + j] = d * inv;
+        }
+        __syncthreads();
+        const double inv = s_bcast[0];
+        for (int i = j + 1 + tid; i <= n; i += nt) {
+            const double v = A[(int64_t)i * n + j] * inv;
+            A[(int64_t)i * n + j] = v;
+            s_col[i] = v;
+        }
+        __syncthreads();
+        const int w = n - 1 - j;  // trailing columns j+1 .. n-1
+        if (w > 0) {
+            const int rows = n - j;  // rows j+1 .. n
+            for (int idx = tid; idx < rows * w; idx += nt) {
+                const int i = j + 1 + idx / w, k = j + 1 + idx % w;
+                if (k <= i) A[(int64_t)i * n + k] -= s_col[i] * s_col[k];
+            }
+        }
+        __syncthreads();
+    }
+    // backward: L^T x = y, y = row n of A
+    for (int i = tid; i < n; i += nt) s_col[i] = A[(int64_t)n * n + i];
+    __syncthreads();
+    for (int j = n - 1; j >= 0; --j) {
+        if (tid == 0) s_bcast[0] = s_col[j] / A[(int64_t)j * n + j];
+        __syncthreads();
+        const double xj = s_bcast[0];
+        for (int i = tid; i < j; i += nt) s_col[i] -= A[(int64_t)j * n + i] * xj;
+        if (tid == 0) xout[j] = xj;
+        __syncthreads();
+    }
+    return s_fail;
+}
+
+__global__ void __launch_bounds__(kK5Threads) decide_solve_kernel(Problem P, int nranks)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* s_col = reinterpret_cast<double*>(smem_raw);  // ns + 1
+    __shared__ double s_bcast[2];
+    __shared__ int s_go;
+    DevState* st = P.st;
+    const int ns = P.ns;
+    const double* sc = P.ar + (int64_t)ns * ns + ns;
+    (void)nranks;
+    if (threadIdx.x == 0) {
+        int go = 0;
+        if (!st->done) {
+            st->launches += 1;
+            st->solved = 0;
+            const double cost_sel = sc[0];
+            const bool numeric_ok = (sc[3] == 0.0) && isfinite(cost_sel);
+            if (!numeric_ok && !(st->phase == kPhaseDecide && st->mode == 1)) {
+                // a non-SPD pattern-pose block or a non-finite cost at an ACCEPTED point is fatal; at an LM
+                // trial point it is just a rejected step
+                st->status = 4;
+                st->done = 1;
+            }
+            if (!st->done) {
+                if (st->phase == kPhaseDecide) {
+                    st->iter += 1;
+                    st->cost_trial = cost_sel;
+                    const bool accept = (st->mode == 0) || (numeric_ok && cost_sel < st->cost_cur);
+                    if (accept) {
+                        st->cur = 1 - st->cur;
+                        st->cost_cur = cost_sel;
+                        st->change = sqrt(sc[1] + st->cam_step2) / sqrt(sc[2] + st->cam_param2);
+                        st->lambda = st->lambda_spec;
+                        st->n_accept += 1;
+                        go = 1;
+                    } else {
+                        st->lambda = fmin(st->lambda * st->lambda_up, 1e15);
+                        st->n_reject += 1;
+                        st->phase = kPhaseRebuild;
+                    }
+                } else {
+                    if (st->phase == kPhaseFirst) st->cost_cur = cost_sel;
+                    go = 1;
+                }
+                const int t = st->crit_type;
+                const bool stop = (t == 1 && st->iter >= st->max_count) || (t == 2 && st->change <= st->eps) ||
+                                  (t == 3 && (st->change <= st->eps || st->iter >= st->max_count));
+                if (stop) { st->done = 1; go = 0; }
+            }
+        }
+        s_go = go;
+    }
+    __syncthreads();
+    if (!s_go) return;
+    // solve S dc = g (every rank redundantly, identical inputs after the allreduce)
+    int fail = 0;
+    if (ns > 0) fail = chol_solve_cta(P.ar, ns, P.dc, s_col, s_bcast);
+    __syncthreads();
+    // camera update (replicated on every rank): tangent step -> additive Rodrigues step, scaled, trial parameters
+    const int cur = st->cur, tr = 1 - cur;
+    const double alpha = st->mode == 0 ? pow(0.95, (double)st->iter + 1.0) : 1.0;
+    double step2 = 0, par2 = 0;
+    for (int c = 1 + threadIdx.x; c < P.n_cam; c += blockDim.x) {
+        const double* p = P.x[cur] + 6 * (c - 1);
+        const double om[3] = {p[0], p[1], p[2]};
+        const double* d = P.dc + 6 * (c - 1);
+        double dom[3], R[9];
+        left_jacobian_inv_apply(om, d, dom);
+        double q[6];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const double s0 = alpha * dom[i], s1 = alpha * d[3 + i];
+            q[i] = p[i] + s0; q[3 + i] = p[3 + i] + s1;
+            step2 += s0 * s0 + s1 * s1;
+        }
+#pragma unroll
+        for (int i = 0; i < 6; ++i) { P.x[tr][6 * (c - 1) + i] = q[i]; par2 += q[i] * q[i]; }
+        rodrigues(q, R);
+#pragma unroll
+        for (int i = 0; i < 9; ++i) P.vR[tr][9 * c + i] = R[i];
+    }
+    // block reduction of the camera norms (fixed order: warp shuffle, then warp 0 over the warp sums)
+    __shared__ double s_red[2][32];
+    step2 = warp_sum(step2); par2 = warp_sum(par2);
+    if ((threadIdx.x & 31) == 0) { s_red[0][threadIdx.x >> 5] = step2; s_red[1][threadIdx.x >> 5] = par2; }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double a = threadIdx.x < (blockDim.x >> 5) ? s_red[0][threadIdx.x] : 0.0;
+        double b = threadIdx.x < (blockDim.x >> 5) ? s_red[1][threadIdx.x] : 0.0;
+        a = warp_sum(a); b = warp_sum(b);
+        if (threadIdx.x == 0) {
+            st->cam_step2 = a;
+            st->cam_param2 = b;
+            st->alpha = alpha;
+            if (fail) { st->status = 4; st->done = 1; }
+            else {
+                st->solved = 1;
+                st->phase = kPhaseDecide;
+                st->lambda_spec = st->mode == 1 ? fmax(st->lambda * st->lambda_down, 1e-15) : 0.0;
+            }
+        }
+    }
+}
+
+// --------------------------------------------------------------------------------------------------------
+// K4: back-substitution of the pattern-pose steps + trial parameters + rotations of the trial point.
+// One thread per frame slot.  d_p = L^-T (z - sum_v Y_v dc_v).
+// --------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kK4Threads) frame_update_kernel(Problem P)
+{
+    const DevState* st = P.st;
+    if (st->done || !st->solved) return;
+    const int cur = st->cur, tr = 1 - cur;
+    const double alpha = st->alpha;
+    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    double step2 = 0, par2 = 0;
+    if (slot < P.n_slots) {
+        const int frame = P.slot_frame[slot];
+        if (frame >= 0) {
+            const int warp = slot >> 5;
+            const int g = P.warp_group[warp];
+            const int V = P.group_V[g];
+            const int* gc = P.group_cams + P.group_cam0[g];
+            const int ls = slot - P.group_slot0[g];
+            const int64_t E = P.n_edge_int;
+            double U[21], r[6];
+#pragma unroll
+            for (int k = 0; k < 21; ++k) U[k] = P.frameL[(int64_t)k * P.n_slots + slot];
+#pragma unroll
+            for (int k = 0; k < 6; ++k) r[k] = P.frameL[(int64_t)(21 + k) * P.n_slots + slot];
+            for (int v = 0; v < V; ++v) {
+                const int c = gc[v];
+                if (c == 0) continue;
+                const int64_t e = P.group_ebase[g] + (int64_t)v * P.group_stride[g] + ls;
+                const double* d = P.dc + 6 * (c - 1);
+#pragma unroll
+                for (int i = 0; i < 6; ++i) {
+                    double acc = 0;
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) acc += P.edgeY[(int64_t)(i * 6 + k) * E + e] * d[k];
+                    r[i] -= acc;
+                }
+            }
+            chol6_backward(U, r);
+            const int64_t pv = P.n_cam + frame;
+            const double* p = P.x[cur] + 6 * (pv - 1);
+            const double om[3] = {p[0], p[1], p[2]};
+            double dom[3], q[6], R[9];
+            left_jacobian_inv_apply(om, r, dom);
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                const double s0 = alpha * dom[i], s1 = alpha * r[3 + i];
+                q[i] = p[i] + s0; q[3 + i] = p[3 + i] + s1;
+                step2 += s0 * s0 + s1 * s1;
+            }
+#pragma unroll
+            for (int i = 0; i < 6; ++i) { P.x[tr][6 * (pv - 1) + i] = q[i]; par2 += q[i] * q[i]; }
+            rodrigues(q, R);
+#pragma unroll
+            for (int i = 0; i < 9; ++i) P.vR[tr][9 * pv + i] = R[i];
+        }
+    }
+    __shared__ double s_red[2][kK4Threads / 32];
+    step2 = warp_sum(step2); par2 = warp_sum(par2);
+    if ((threadIdx.x & 31) == 0) { s_red[0][threadIdx.x >> 5] = step2; s_red[1][threadIdx.x >> 5] = par2; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0, b = 0;
+#pragma unroll
+        for (int w = 0; w < kK4Threads / 32; ++w) { a += s_red[0][w]; b += s_red[1][w]; }
+        P.norm_part[blockIdx.x] = a;
+        P.norm_part[P.n_k4_blocks + blockIdx.x] = b;
+    }
+}
+
+// initialise the loop state for a solve (single thread)
+__global__ void init_state_kernel(DevState* st, int mode, int crit_type, int max_count, double eps, double lambda0,
+                                  double up, double down, int cur)
+{
+    st->mode = mode; st->crit_type = crit_type; st->max_count = max_count;
+    st->iter = 0; st->done = 0; st->phase = kPhaseFirst; st->cur = cur; st->status = 0;
+    st->n_accept = 0; st->n_reject = 0; st->launches = 0; st->solved = 0;
+    st->eps = eps; st->lambda = mode == 1 ? lambda0 : 0.0; st->lambda_up = up; st->lambda_down = down;
+    st->lambda_spec = st->lambda;
+    st->cost_cur = 0; st->cost_trial = 0; st->change = 1.0; st->alpha = 1.0;
+    st->cam_step2 = 0; st->cam_param2 = 0;
+}
+
+}  // namespace mccba
