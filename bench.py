@@ -1,0 +1,310 @@
+#!/usr/bin/env python
+"""Benchmark of the calibration bundle-adjustment hot path (BASELINE.json metric: LM iterations/sec and
+residual+Jacobian evals/sec at 1/2/4/8 B200 vs host CPU).
+
+  python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+Workload (config.workload): BASELINE.json configs[4] -- synthetic 64-camera pinhole rig, 100k frames, 9x6 board,
+2 views per frame = 10.8 M corner observations PER GPU (frames shard across ranks; every rank holds the 64 cameras and
+its own 100k frames: weak scaling, one NCCL all-reduce of the 378x378 reduced camera system per iteration).
+A "step" = one optimizeExtrinsics call = `iters` (default 20, the reference's TermCriteria(COUNT, 20)) full LM
+iterations on that rig.  value = corner observations processed per second through full LM iterations, whole job.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "lm_corner_observations_per_sec"
+UNIT = "corner observations/s through full LM iterations (whole job)"
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def _k1_traffic():
+    p = os.path.join(ROOT, "profiles", "k1_traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p))
+        except Exception:
+            return None
+    return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                       "-i", str(gpu_index), "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[], samples=0)
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = []
+        for line in open(self.f.name):
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) >= 9:
+                rows.append(parts)
+        os.unlink(self.f.name)
+        if not rows:
+            return out
+        try:
+            sm = sorted(float(r[1]) for r in rows)
+            out["sm_mhz"] = sm[len(sm) // 2]
+            out["sm_max_mhz"] = float(rows[0][2])
+            out["power_w_max"] = max(float(r[3]) for r in rows)
+        except Exception:
+            pass
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = set()
+        for r in rows:
+            for i, n in enumerate(names):
+                if r[5 + i].lower().startswith("active"):
+                    reasons.add(n)
+        out["reasons"] = sorted(reasons)
+        out["samples"] = len(rows)
+        return out
+
+
+def _rig(args, rank):
+    from multi_camera_calibration_b200 import synth
+    cams = synth.make_cameras(args.cams, args.seed)
+    return synth.make_rig(n_cam=args.cams, n_frame=args.frames, seed=args.seed, cameras=cams, frame_stream=rank)
+
+
+def _oracle_rig(rig):
+    from oracle import oracle as orc                      # cpu_baseline / reference arm only
+    return orc, orc.Rig(rig["n_cam"], rig["n_frame"], rig["edge_cam"], rig["edge_pv"], rig["edge_off"], rig["obj"],
+                        rig["img"], rig["cam_model"], rig["cam_K5"], rig["cam_dist8"], rig["cam_ndist"], rig["cam_xi"])
+
+
+def config_dict(args, world):
+    return {"workload": "BASELINE configs[4]: synthetic %d-camera pinhole rig, %d frames per GPU, 9x6 board, 2 views "
+                        "per frame; one step = %d LM iterations (TermCriteria COUNT)" % (args.cams, args.frames, args.iters),
+            "n_cameras": args.cams, "frames_per_gpu": args.frames, "corners_per_gpu": args.frames * 2 * 54,
+            "reduced_system_n": 6 * (args.cams - 1), "lm_iterations_per_step": args.iters, "sharding": "frames x%d" % world,
+            "l2": "inputs larger than L2 (216 MB of observations + 90 MB of per-edge blocks per pass vs 126 MB L2)",
+            "seed": args.seed}
+
+
+def run_reference(args):
+    """CPU arm: the restated reference algorithm (oracle port -- the reference itself needs OpenCV C++ and Eigen and
+    cannot be built in this image) with all host threads, on a bounded sample of the same workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    rig = _rig(args, 0)
+    orc, O = _oracle_rig(rig)
+    cores = orc.num_threads()
+    iters = args.ref_iters
+    M = rig["n_points"]
+    kw = dict(mode=1, crit_type=1, max_count=iters, lambda0=1e-3, lambda_up=10.0, lambda_down=1.0 / 3.0)
+    for _ in range(args.warmup):
+        O.solve(rig["params_init"], **kw)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        O.solve(rig["params_init"], **kw)
+    dt = (time.perf_counter() - t0) / args.steps
+    value = M * iters / dt
+    sample = "full rig (%d corners), %d LM iterations per step instead of %d" % (M, iters, args.iters)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config_dict(args, 1), "lm_iters_per_sec": iters / dt,
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import multi_camera_calibration_b200 as m
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    nccl_id = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt = torch.tensor(list(m.capi.nccl_unique_id()), dtype=torch.uint8, device="cuda")
+        dist.broadcast(idt, 0)
+        nccl_id = bytes(idt.cpu().tolist())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    rig = _rig(args, rank)
+    M = rig["n_points"]
+    # pinned host copies for the end-to-end leg
+    pin = {}
+    for k in ("obj", "img", "params_init"):
+        t = torch.from_numpy(np.ascontiguousarray(rig[k])).pin_memory()
+        pin[k] = t.numpy()
+    s = m.Solver(device=local, rank=rank, nranks=world, nccl_id=nccl_id)
+    s.set_cameras(rig["cam_model"], rig["cam_K5"], rig["cam_dist8"], rig["cam_ndist"], rig["cam_xi"])
+    s.set_observations(rig["n_frame"], rig["edge_cam"], rig["edge_pv"], rig["edge_off"], pin["obj"], pin["img"])
+    s.set_parameters(pin["params_init"])
+    s.save_parameters()
+    kw = dict(mode=m.capi.MODE_LM, crit_type=m.capi.CRIT_COUNT, max_count=args.iters, lambda0=1e-3, lambda_up=10.0,
+              lambda_down=1.0 / 3.0)
+
+    # ---- device-resident leg: inputs already in HBM --------------------------------------------------------
+    for _ in range(args.warmup):
+        s.restore_parameters()
+        rep = s.solve(**kw)
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
+    launches = 0
+    dev_ms = 0.0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        s.restore_parameters()
+        rep = s.solve(**kw)                      # timed on the library's own stream with CUDA events (device_ms)
+        dev_ms += rep["device_ms"]
+        launches += rep["kernel_launches"]
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    clocks = sampler.stop() if sampler else None
+    t = torch.tensor([dev_ms / args.steps, wall_ms / args.steps], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step, wall_step = float(t[0]), float(t[1])
+    iters_done = rep["iterations"]
+    value = world * M * iters_done / (ms_step * 1e-3)
+
+    # ---- dominant kernel alone (roofline) --------------------------------------------------------------------
+    k1_ms = s.time_eval(reps=20)
+    peak, peak_src = _peaks()
+    k1_gbs = 20.0 * M / (k1_ms * 1e-3) / 1e9
+    iter_gbs = 20.0 * M / (ms_step * 1e-3 / max(iters_done, 1)) / 1e9
+    traffic = _k1_traffic()
+
+    # ---- end-to-end leg: host buffers in, parameters out, every step -----------------------------------------
+    h2d = pin["obj"].nbytes + pin["img"].nbytes + pin["params_init"].nbytes + rig["edge_cam"].nbytes + \
+        rig["edge_pv"].nbytes + rig["edge_off"].nbytes
+    d2h = pin["params_init"].nbytes
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+
+    def e2e_step():
+        s.set_observations(rig["n_frame"], rig["edge_cam"], rig["edge_pv"], rig["edge_off"], pin["obj"], pin["img"])
+        s.set_parameters(pin["params_init"])
+        r = s.solve(**kw)
+        p = s.get_parameters()
+        return r, p
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        r2, p_out = e2e_step()
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+    t = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t[0])
+    e2e_value = world * M * r2["iterations"] / (e2e_ms * 1e-3)
+    err = s.reproj_error()
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        orc, O = _oracle_rig(rig)
+        ci = args.ref_iters
+        t0 = time.perf_counter()
+        ref = O.solve(rig["params_init"], mode=1, crit_type=1, max_count=ci, lambda0=1e-3, lambda_up=10.0,
+                      lambda_down=1.0 / 3.0)
+        cdt = time.perf_counter() - t0
+        cpu = {"value": M * ci / cdt, "unit": UNIT, "cores": orc.num_threads(), "kind": "port",
+               "sample": "full rig (%d corners), %d LM iterations (%.1f s of CPU work)" % (M, ci, cdt),
+               "lm_iters_per_sec": ci / cdt}
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_dict(args, world),
+                "lm_iters_per_sec": iters_done / (ms_step * 1e-3), "us_per_lm_iteration": ms_step * 1e3 / max(iters_done, 1),
+                "resjac_evals_per_sec": world * M / (k1_ms * 1e-3), "wall_ms_per_step": wall_step,
+                "lm": {"iterations": iters_done, "accepted": rep["accepted"], "rejected": rep["rejected"],
+                       "final_cost": rep["cost"], "rms_px": err["rms"]},
+                "roofline": {"bound": "hbm", "achieved": k1_gbs, "peak": peak, "unit": "GB/s", "frac": k1_gbs / peak,
+                             "traffic": (traffic or {}).get("dram_bytes_per_launch"), "peak_source": peak_src,
+                             "kernel": "resid_jac_accum_kernel", "kernel_ms": k1_ms,
+                             "algorithmic_bytes_per_launch": 20.0 * M,
+                             "whole_iteration_gbs": iter_gbs, "whole_iteration_frac": iter_gbs / peak,
+                             "note": "fp64 arithmetic: the kernel is FP64-pipe-bound, see DESIGN.md"},
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                        "ms_per_step": e2e_ms, "steps": e2e_steps},
+                "gpu_launches": int(launches), "clocks": clocks}
+        if cpu:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    s.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cams", type=int, default=64)
+    ap.add_argument("--frames", type=int, default=100000)
+    ap.add_argument("--iters", type=int, default=20)
+    ap.add_argument("--ref-iters", type=int, default=4, help="LM iterations per step of the CPU arm (bounded sample)")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--seed", type=int, default=1005)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 0)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

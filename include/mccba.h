@@ -127,6 +127,11 @@ int mccba_set_observations(mccba_handle h, int n_frame, int n_edge, const int *e
 int mccba_set_parameters(mccba_handle h, int64_t n, const double *params);
 int mccba_get_parameters(mccba_handle h, int64_t n, double *params);
 
+/* Device-side snapshot / restore of the parameter vector (no host copy): lets a benchmark or an outlier loop rerun
+ * the optimisation from the same starting point with everything resident in HBM. */
+int mccba_save_parameters(mccba_handle h);
+int mccba_restore_parameters(mccba_handle h);
+
 /* ---- hot path ---------------------------------------------------------------------------------------------- */
 /* One residual+Jacobian evaluation at the current parameters: the per-edge work of computeJacobianExtrinsic +
  * computePhotoCameraJacobian (src/multicalib.cpp:611-678, 717-824) with the per-edge normal-equation blocks

@@ -39,7 +39,7 @@ class ErrorStats(C.Structure):
 
 EXPORTS = ["mccba_default_options", "mccba_default_solve_opts", "mccba_nccl_unique_id", "mccba_create", "mccba_destroy",
            "mccba_last_error", "mccba_set_cameras", "mccba_set_observations", "mccba_set_parameters",
-           "mccba_get_parameters", "mccba_eval", "mccba_reduced_system", "mccba_solve", "mccba_reproj_error",
+           "mccba_get_parameters", "mccba_save_parameters", "mccba_restore_parameters", "mccba_eval", "mccba_reduced_system", "mccba_solve", "mccba_reproj_error",
            "mccba_allreduce_sum", "mccba_last_kernel_ms", "mccba_time_eval"]
 
 _lib = None
@@ -155,6 +155,12 @@ class Solver:
         p = np.zeros(self.n_param)
         self._check(lib().mccba_get_parameters(self._h, C.c_int64(p.size), _ptr(p, C.c_double)))
         return p
+
+    def save_parameters(self):
+        self._check(lib().mccba_save_parameters(self._h))
+
+    def restore_parameters(self):
+        self._check(lib().mccba_restore_parameters(self._h))
 
     def eval(self, want_blocks=True):
         cost = C.c_double()

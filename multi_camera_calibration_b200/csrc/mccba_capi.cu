@@ -91,6 +91,8 @@ struct mccba_handle_s {
     double* d_small = nullptr;
     double prof_ms[6] = {0, 0, 0, 0, 0, 0};
     int profile = 0;
+    double* x_saved = nullptr;        // device snapshot of the parameters (owned by the problem)
+    bool have_saved = false;
 };
 
 namespace {
@@ -144,6 +146,8 @@ void free_problem(mccba_handle h)
     h->allocs.clear();
     h->have_obs = false;
     h->have_params = false;
+    h->have_saved = false;
+    h->x_saved = nullptr;
 }
 
 int64_t n_param(mccba_handle h) { return 6 * (int64_t)(h->n_cam + h->n_frame - 1); }
@@ -493,6 +497,7 @@ int mccba_set_observations(mccba_handle h, int n_frame, int n_edge, const int* e
     if ((rc = dev_alloc(h, &P.edgeY, 36 * (size_t)P.n_edge_int, true))) return rc;
     if ((rc = dev_alloc(h, &P.records, (size_t)rec_total, true))) return rc;
     if ((rc = dev_alloc(h, &P.ar, (size_t)h->ar_len, true))) return rc;
+    if ((rc = dev_alloc(h, &h->x_saved, (size_t)P.n_param, true))) return rc;
     if ((rc = dev_alloc(h, &P.dc, (size_t)std::max(P.ns, 1), true))) return rc;
     if ((rc = dev_alloc(h, &P.norm_part, 2 * (size_t)P.n_k4_blocks, true))) return rc;
     if ((rc = dev_alloc(h, &P.err_sq, (size_t)P.n_edge_int, true))) return rc;
@@ -535,6 +540,25 @@ int mccba_get_parameters(mccba_handle h, int64_t n, double* params)
     CUDA_TRY(h, cudaSetDevice(h->opts.device));
     CUDA_TRY(h, cudaMemcpyAsync(params, h->P.x[h->cur], sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return MCCBA_OK;
+}
+
+int mccba_save_parameters(mccba_handle h)
+{
+    if (!h) return MCCBA_ERR_ARG;
+    if (!h->have_params) return fail(h, MCCBA_ERR_STATE, "save_parameters before set_parameters");
+    CUDA_TRY(h, cudaSetDevice(h->opts.device));
+    CUDA_TRY(h, cudaMemcpyAsync(h->x_saved, h->P.x[h->cur], sizeof(double) * (size_t)n_param(h), cudaMemcpyDeviceToDevice, h->stream));
+    h->have_saved = true;
+    return MCCBA_OK;
+}
+
+int mccba_restore_parameters(mccba_handle h)
+{
+    if (!h) return MCCBA_ERR_ARG;
+    if (!h->have_saved) return fail(h, MCCBA_ERR_STATE, "restore_parameters before save_parameters");
+    CUDA_TRY(h, cudaSetDevice(h->opts.device));
+    CUDA_TRY(h, cudaMemcpyAsync(h->P.x[h->cur], h->x_saved, sizeof(double) * (size_t)n_param(h), cudaMemcpyDeviceToDevice, h->stream));
     return MCCBA_OK;
 }
 
