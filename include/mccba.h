@@ -161,6 +161,10 @@ int mccba_allreduce_sum(mccba_handle h, double *buf, int n);
  * out[0] frame_schur, out[1] reduce_records, out[2] allreduce, out[3] decide_solve, out[4] frame_update,
  * out[5] resid_jac_accum (diagnostic only -- the events serialise the stream). */
 int mccba_last_kernel_ms(mccba_handle h, double out[6]);
+/* Test hook: solve the dense SPD system S x = g (n x n row-major, lower triangle read) on the device with the loop's
+ * own Cholesky code (blocked != 0: the blocked shared-memory version used when it fits; 0: plain column version).
+ * The kernel time in ms is left in mccba_last_kernel_ms()[0]. */
+int mccba_debug_solve_dense(mccba_handle h, int n, const double *S, const double *g, double *x, int blocked);
 /* time `reps` back-to-back launches of the residual+Jacobian kernel at the current parameters with CUDA events on
  * the handle's stream; returns average ms per launch (benchmark helper, no other side effects) */
 int mccba_time_eval(mccba_handle h, int reps, double *avg_ms);

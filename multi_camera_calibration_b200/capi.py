@@ -40,7 +40,7 @@ class ErrorStats(C.Structure):
 EXPORTS = ["mccba_default_options", "mccba_default_solve_opts", "mccba_nccl_unique_id", "mccba_create", "mccba_destroy",
            "mccba_last_error", "mccba_set_cameras", "mccba_set_observations", "mccba_set_parameters",
            "mccba_get_parameters", "mccba_save_parameters", "mccba_restore_parameters", "mccba_eval", "mccba_reduced_system", "mccba_solve", "mccba_reproj_error",
-           "mccba_allreduce_sum", "mccba_last_kernel_ms", "mccba_time_eval"]
+           "mccba_allreduce_sum", "mccba_last_kernel_ms", "mccba_time_eval", "mccba_debug_solve_dense"]
 
 _lib = None
 
@@ -205,6 +205,14 @@ class Solver:
         out = np.zeros(6)
         self._check(lib().mccba_last_kernel_ms(self._h, _ptr(out, C.c_double)))
         return out
+
+    def debug_solve_dense(self, S, g, blocked=True):
+        S = np.ascontiguousarray(S, dtype=np.float64); g = np.ascontiguousarray(g, dtype=np.float64)
+        n = g.size
+        x = np.zeros(n)
+        self._check(lib().mccba_debug_solve_dense(self._h, n, _ptr(S, C.c_double), _ptr(g, C.c_double),
+                                                  _ptr(x, C.c_double), int(bool(blocked))))
+        return x, self.last_kernel_ms()[0]
 
     def time_eval(self, reps=10):
         ms = C.c_double()

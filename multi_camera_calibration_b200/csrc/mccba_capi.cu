@@ -83,7 +83,7 @@ struct mccba_handle_s {
     CamParams* d_cams = nullptr;
     int cur = 0;                      // host mirror of DevState::cur between calls
     int ar_len = 0;
-    int k1_grid = 0, k1_smem = 0, k5_smem = 0;
+    int k1_grid = 0, k1_smem = 0, k5_smem = 0, k5_blocked = 0, panel_smem = 0, iter_kernels = 5;
     cudaGraphExec_t graph = nullptr;
     int* h_done = nullptr;            // pinned
     DevState* h_state = nullptr;      // pinned
@@ -171,7 +171,15 @@ int enqueue_iteration(mccba_handle h, bool timed)
         if (r != 0) return fail(h, MCCBA_ERR_NCCL, "ncclAllReduce failed: %s", nccl().GetErrorString ? nccl().GetErrorString(r) : "?");
     }
     if (timed) cudaEventRecord(ev[3], s);
-    decide_solve_kernel<<<1, kK5Threads, h->k5_smem, s>>>(P, h->opts.nranks);
+    decide_kernel<<<1, 32, 0, s>>>(P);
+    if (h->k5_blocked && P.ns > 0) {
+        const int ntc = chol_col_tiles(P.ns), ntr = chol_row_tiles(P.ns);
+        for (int k = 0; k < ntc; ++k) {
+            chol_panel_kernel<<<1, kPanelThreads, h->panel_smem, s>>>(P.ar, P.ns, k, &P.st->go, &P.st->chol_fail, P.rinv);
+            if (k + 1 < ntc) chol_update_kernel<<<dim3(ntc - k - 1, ntr - k - 1), kUpdThreads, 0, s>>>(P.ar, P.ns, k, &P.st->go);
+        }
+    }
+    camera_update_kernel<<<1, kK5Threads, h->k5_smem, s>>>(P, h->k5_blocked);
     if (timed) cudaEventRecord(ev[4], s);
     frame_update_kernel<<<P.n_k4_blocks, kK4Threads, 0, s>>>(P);
     if (timed) cudaEventRecord(ev[5], s);
@@ -499,14 +507,25 @@ int mccba_set_observations(mccba_handle h, int n_frame, int n_edge, const int* e
     if ((rc = dev_alloc(h, &P.ar, (size_t)h->ar_len, true))) return rc;
     if ((rc = dev_alloc(h, &h->x_saved, (size_t)P.n_param, true))) return rc;
     if ((rc = dev_alloc(h, &P.dc, (size_t)std::max(P.ns, 1), true))) return rc;
+    if ((rc = dev_alloc(h, &P.rinv, (size_t)std::max(P.ns, 1), true))) return rc;
     if ((rc = dev_alloc(h, &P.norm_part, 2 * (size_t)P.n_k4_blocks, true))) return rc;
     if ((rc = dev_alloc(h, &P.err_sq, (size_t)P.n_edge_int, true))) return rc;
     if ((rc = dev_alloc(h, &P.err_nrm, (size_t)P.n_edge_int, true))) return rc;
     // launch geometry
     h->k1_smem = (int)(sizeof(K1Shared) + (size_t)nC * (sizeof(CamParams) + 12 * sizeof(double)));
-    h->k5_smem = (int)(sizeof(double) * (size_t)(P.ns + 2));
-    if (h->k1_smem > 48 * 1024)
-        CUDA_TRY(h, cudaFuncSetAttribute(resid_jac_accum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->k1_smem));
+    {   // tiled Cholesky when one block column fits in shared memory (n_s <= ~870), else the plain column version
+        const size_t need = chol_panel_smem_bytes(P.ns);
+        const char* force = getenv("MCCBA_SIMPLE_CHOL");
+        h->k5_blocked = need <= 227 * 1024 && !(force && force[0] == '1');
+        h->panel_smem = (int)need;
+        h->k5_smem = h->k5_blocked ? (int)(sizeof(double) * ((size_t)P.ns + 2 + (kK5Threads / 32) * kCLD)) : (int)(sizeof(double) * (size_t)(P.ns + 2));
+        if (h->k5_blocked && h->panel_smem > 48 * 1024)
+            CUDA_TRY(h, cudaFuncSetAttribute(chol_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->panel_smem));
+        if (h->k5_smem > 48 * 1024)
+            CUDA_TRY(h, cudaFuncSetAttribute(camera_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->k5_smem));
+        const int ntc = chol_col_tiles(P.ns);
+        h->iter_kernels = 6 + ((h->k5_blocked && P.ns > 0) ? 2 * ntc - 1 : 0);
+    }
     int per_sm = 1;
     CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, resid_jac_accum_kernel, kK1Threads, h->k1_smem));
     per_sm = std::max(per_sm, 1);
@@ -682,7 +701,7 @@ int mccba_solve(mccba_handle h, const mccba_solve_opts* o, mccba_report* rep)
     }
     cudaEventDestroy(evs[0]);
     cudaEventDestroy(evs[1]);
-    kernels += (int)launched * 5;
+    kernels += (int)launched * h->iter_kernels;
     CUDA_TRY(h, cudaMemcpyAsync(h->h_state, P.st, sizeof(DevState), cudaMemcpyDeviceToHost, s));
     CUDA_TRY(h, cudaEventRecord(h->ev1, s));
     CUDA_TRY(h, cudaStreamSynchronize(s));
@@ -755,6 +774,46 @@ int mccba_reproj_error(mccba_handle h, mccba_error_stats* stats, double* per_edg
         stats->sum_norm = local_norm; stats->sum_sq = local_sq; stats->n_points = (int64_t)local_n;
     }
     return MCCBA_OK;
+}
+
+int mccba_debug_solve_dense(mccba_handle h, int n, const double* S, const double* g, double* x, int blocked)
+{
+    if (!h || n < 1 || !S || !g || !x) return MCCBA_ERR_ARG;
+    CUDA_TRY(h, cudaSetDevice(h->opts.device));
+    double *dA = nullptr, *dx = nullptr, *drinv = nullptr;
+    int* dfail = nullptr;
+    CUDA_TRY(h, cudaMalloc((void**)&dA, sizeof(double) * (size_t)(n + 1) * n));
+    CUDA_TRY(h, cudaMalloc((void**)&dx, sizeof(double) * (size_t)n));
+    CUDA_TRY(h, cudaMalloc((void**)&drinv, sizeof(double) * (size_t)n));
+    CUDA_TRY(h, cudaMalloc((void**)&dfail, sizeof(int)));
+    CUDA_TRY(h, cudaMemsetAsync(dfail, 0, sizeof(int), h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(dA, S, sizeof(double) * (size_t)n * n, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(dA + (size_t)n * n, g, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, h->stream));
+    const size_t pneed = chol_panel_smem_bytes(n);
+    if (blocked && pneed > 227 * 1024) { cudaFree(dA); cudaFree(dx); cudaFree(drinv); cudaFree(dfail); return fail(h, MCCBA_ERR_ARG, "n too large for the tiled solver"); }
+    const size_t bneed = blocked ? sizeof(double) * ((size_t)n + 2 + (kK5Threads / 32) * kCLD) : sizeof(double) * (size_t)(n + 2);
+    CUDA_TRY(h, cudaFuncSetAttribute(chol_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(pneed, 1024)));
+    CUDA_TRY(h, cudaFuncSetAttribute(dense_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(bneed, 1024)));
+    CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));
+    if (blocked) {
+        const int ntc = chol_col_tiles(n), ntr = chol_row_tiles(n);
+        for (int k = 0; k < ntc; ++k) {
+            chol_panel_kernel<<<1, kPanelThreads, pneed, h->stream>>>(dA, n, k, nullptr, dfail, drinv);
+            if (k + 1 < ntc) chol_update_kernel<<<dim3(ntc - k - 1, ntr - k - 1), kUpdThreads, 0, h->stream>>>(dA, n, k, nullptr);
+        }
+    }
+    dense_backward_kernel<<<1, kK5Threads, bneed, h->stream>>>(dA, n, drinv, dx, dfail, blocked);
+    CUDA_TRY(h, cudaEventRecord(h->ev1, h->stream));
+    int f = 0;
+    CUDA_TRY(h, cudaMemcpyAsync(x, dx, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(&f, dfail, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    CUDA_TRY(h, cudaGetLastError());
+    float ms = 0;
+    cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+    h->prof_ms[0] = ms;
+    cudaFree(dA); cudaFree(dx); cudaFree(drinv); cudaFree(dfail);
+    return f ? fail(h, MCCBA_ERR_NUMERIC, "matrix is not positive definite") : MCCBA_OK;
 }
 
 int mccba_last_kernel_ms(mccba_handle h, double out[6])

@@ -8,14 +8,16 @@
 //   reproj_error_kernel      computeProjectError (src/multicalib.cpp:912-984)
 //   frame_schur_kernel       (new math) eliminates the per-frame pattern-pose blocks; replaces the P x P solve
 //   reduce_records_kernel    deterministic, atomic-free sum of the warp records into the reduced camera system
-//   decide_solve_kernel      optimizeExtrinsics' loop control (src/multicalib.cpp:473-507) + Cholesky of the
-//                            reduced system (replaces Eigen CG, :565-592) + accept/reject (LM)
+//   decide_kernel            optimizeExtrinsics' loop control (src/multicalib.cpp:473-507) + accept/reject (LM)
+//   chol_panel/update_kernel tiled Cholesky of the reduced system (replaces Eigen CG, :565-592)
+//   camera_update_kernel     backward substitution + camera part of the update (:491-504)
 //   frame_update_kernel      back-substitution + parameter update (:491-504)
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 #include "mccba_math.cuh"
+#include "mccba_dense.cuh"
 
 namespace mccba {
 
@@ -24,17 +26,18 @@ constexpr int kK1Threads = 256;
 constexpr int kEdgesPerBlock = kK1Threads / kLanesPerEdge;  // 32
 constexpr int kK2Threads = 128;
 constexpr int kK4Threads = 128;
-constexpr int kK5Threads = 1024;
+constexpr int kK5Threads = 512;
 constexpr int kMaxViews = 64;
 constexpr unsigned kFull = 0xffffffffu;
 
 enum Phase { kPhaseFirst = 0, kPhaseDecide = 1, kPhaseRebuild = 2 };
 
-// Loop state, resident in global memory; only decide_solve_kernel writes it (single CTA).
+// Loop state, resident in global memory; written by decide_kernel / camera_update_kernel only (single thread).
 struct DevState {
     int mode, crit_type, max_count;
     int iter, done, phase, cur, status;
-    int n_accept, n_reject, launches, solved;  // solved: the last decide_solve produced a step (update/eval may run)
+    int n_accept, n_reject, launches, solved;  // solved: the last iteration produced a step (update/eval may run)
+    int go, chol_fail;                         // go: decide_kernel asks for a solve in this iteration
     double eps, lambda, lambda_up, lambda_down, lambda_spec;
     double cost_cur, cost_trial, change, alpha;
     double cam_step2, cam_param2;  // camera part of |step|^2 and |params|^2 of the current trial
@@ -78,6 +81,7 @@ struct Problem {
     double* records;     // warp records
     double* ar;          // allreduce buffer: S (ns x ns) | g (ns) | cost, step2, param2, bad
     double* dc;          // ns: camera step in tangent coordinates
+    double* rinv;        // ns: reciprocal diagonal of the Cholesky factor
     double* norm_part;   // 2 x n_k4_blocks: per-block |step|^2, |trial|^2 of the frames
     double* err_sq;      // n_edge_int
     double* err_nrm;     // n_edge_int
@@ -581,65 +585,91 @@ __device__ int chol_solve_cta(double* A, int n, double* xout, double* s_col, dou
     return s_fail;
 }
 
-__global__ void __launch_bounds__(kK5Threads) decide_solve_kernel(Problem P, int nranks)
+// loop control (single warp): accept/reject of the trial point, damping, termination; sets st->go
+__global__ void decide_kernel(Problem P)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    double* s_col = reinterpret_cast<double*>(smem_raw);  // ns + 1
-    __shared__ double s_bcast[2];
-    __shared__ int s_go;
+    if (threadIdx.x != 0) return;
     DevState* st = P.st;
     const int ns = P.ns;
     const double* sc = P.ar + (int64_t)ns * ns + ns;
-    (void)nranks;
-    if (threadIdx.x == 0) {
-        int go = 0;
-        if (!st->done) {
-            st->launches += 1;
-            st->solved = 0;
-            const double cost_sel = sc[0];
-            const bool numeric_ok = (sc[3] == 0.0) && isfinite(cost_sel);
-            if (!numeric_ok && !(st->phase == kPhaseDecide && st->mode == 1)) {
-                // a non-SPD pattern-pose block or a non-finite cost at an ACCEPTED point is fatal; at an LM
-                // trial point it is just a rejected step
-                st->status = 4;
-                st->done = 1;
-            }
-            if (!st->done) {
-                if (st->phase == kPhaseDecide) {
-                    st->iter += 1;
-                    st->cost_trial = cost_sel;
-                    const bool accept = (st->mode == 0) || (numeric_ok && cost_sel < st->cost_cur);
-                    if (accept) {
-                        st->cur = 1 - st->cur;
-                        st->cost_cur = cost_sel;
-                        st->change = sqrt(sc[1] + st->cam_step2) / sqrt(sc[2] + st->cam_param2);
-                        st->lambda = st->lambda_spec;
-                        st->n_accept += 1;
-                        go = 1;
-                    } else {
-                        st->lambda = fmin(st->lambda * st->lambda_up, 1e15);
-                        st->n_reject += 1;
-                        st->phase = kPhaseRebuild;
-                    }
-                } else {
-                    if (st->phase == kPhaseFirst) st->cost_cur = cost_sel;
-                    go = 1;
-                }
-                const int t = st->crit_type;
-                const bool stop = (t == 1 && st->iter >= st->max_count) || (t == 2 && st->change <= st->eps) ||
-                                  (t == 3 && (st->change <= st->eps || st->iter >= st->max_count));
-                if (stop) { st->done = 1; go = 0; }
-            }
+    int go = 0;
+    if (!st->done) {
+        st->launches += 1;
+        st->solved = 0;
+        const double cost_sel = sc[0];
+        const bool numeric_ok = (sc[3] == 0.0) && isfinite(cost_sel);
+        if (!numeric_ok && !(st->phase == kPhaseDecide && st->mode == 1)) {
+            // a non-SPD pattern-pose block or a non-finite cost at an ACCEPTED point is fatal; at an LM
+            // trial point it is just a rejected step
+            st->status = 4;
+            st->done = 1;
         }
-        s_go = go;
+        if (!st->done) {
+            if (st->phase == kPhaseDecide) {
+                st->iter += 1;
+                st->cost_trial = cost_sel;
+                const bool accept = (st->mode == 0) || (numeric_ok && cost_sel < st->cost_cur);
+                if (accept) {
+                    st->cur = 1 - st->cur;
+                    st->cost_cur = cost_sel;
+                    st->change = sqrt(sc[1] + st->cam_step2) / sqrt(sc[2] + st->cam_param2);
+                    st->lambda = st->lambda_spec;
+                    st->n_accept += 1;
+                    go = 1;
+                } else {
+                    st->lambda = fmin(st->lambda * st->lambda_up, 1e15);
+                    st->n_reject += 1;
+                    st->phase = kPhaseRebuild;
+                }
+            } else {
+                if (st->phase == kPhaseFirst) st->cost_cur = cost_sel;
+                go = 1;
+            }
+            const int t = st->crit_type;
+            const bool stop = (t == 1 && st->iter >= st->max_count) || (t == 2 && st->change <= st->eps) ||
+                              (t == 3 && (st->change <= st->eps || st->iter >= st->max_count));
+            if (stop) { st->done = 1; go = 0; }
+        }
+    }
+    st->go = go;
+    st->chol_fail = 0;
+}
+
+// Cholesky of the reduced system, one block column per launch pair (mccba_dense.cuh).  go == nullptr: always run.
+__global__ void __launch_bounds__(kPanelThreads) chol_panel_kernel(double* A, int n, int k, const int* go, int* fail, double* rinv)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    if (go && !*go) return;
+    chol_panel(A, n, k, fail, rinv, reinterpret_cast<double*>(smem_raw));
+}
+__global__ void __launch_bounds__(kUpdThreads) chol_update_kernel(double* A, int n, int k, const int* go)
+{
+    if (go && !*go) return;
+    const int ti = k + 1 + blockIdx.y, tj = k + 1 + blockIdx.x;
+    if (tj > ti) return;
+    chol_update_tile(A, n, k, ti, tj);
+}
+
+// backward substitution + camera update (replicated on every rank) + end-of-iteration state.  Single CTA.
+__global__ void __launch_bounds__(kK5Threads) camera_update_kernel(Problem P, int tiled)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* s_dyn = reinterpret_cast<double*>(smem_raw);
+    __shared__ double s_bcast[2];
+    DevState* st = P.st;
+    if (!st->go) return;
+    const int ns = P.ns;
+    int fail = 0;
+    if (ns > 0) {
+        if (tiled) {
+            chol_backward(P.ar, ns, P.rinv, P.dc, s_dyn);
+            fail = st->chol_fail;
+        } else {
+            fail = chol_solve_cta(P.ar, ns, P.dc, s_dyn, s_bcast);
+        }
     }
     __syncthreads();
-    if (!s_go) return;
-    // solve S dc = g (every rank redundantly, identical inputs after the allreduce)
-    int fail = 0;
-    if (ns > 0) fail = chol_solve_cta(P.ar, ns, P.dc, s_col, s_bcast);
-    __syncthreads();
-    // camera update (replicated on every rank): tangent step -> additive Rodrigues step, scaled, trial parameters
+    // tangent step -> additive Rodrigues step, scaled, trial parameters
     const int cur = st->cur, tr = 1 - cur;
     const double alpha = st->mode == 0 ? pow(0.95, (double)st->iter + 1.0) : 1.0;
     double step2 = 0, par2 = 0;
@@ -756,13 +786,26 @@ __global__ void __launch_bounds__(kK4Threads) frame_update_kernel(Problem P)
     }
 }
 
+// test hook: backward substitution of the tiled solver / the plain single-CTA solver on a standalone matrix
+__global__ void __launch_bounds__(kK5Threads) dense_backward_kernel(double* A, int n, const double* rinv, double* x, int* fail, int tiled)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* s_dyn = reinterpret_cast<double*>(smem_raw);
+    __shared__ double s_bcast[2];
+    if (tiled) chol_backward(A, n, rinv, x, s_dyn);
+    else {
+        const int f = chol_solve_cta(A, n, x, s_dyn, s_bcast);
+        if (threadIdx.x == 0 && f) *fail = 1;
+    }
+}
+
 // initialise the loop state for a solve (single thread)
 __global__ void init_state_kernel(DevState* st, int mode, int crit_type, int max_count, double eps, double lambda0,
                                   double up, double down, int cur)
 {
     st->mode = mode; st->crit_type = crit_type; st->max_count = max_count;
     st->iter = 0; st->done = 0; st->phase = kPhaseFirst; st->cur = cur; st->status = 0;
-    st->n_accept = 0; st->n_reject = 0; st->launches = 0; st->solved = 0;
+    st->n_accept = 0; st->n_reject = 0; st->launches = 0; st->solved = 0; st->go = 0; st->chol_fail = 0;
     st->eps = eps; st->lambda = mode == 1 ? lambda0 : 0.0; st->lambda_up = up; st->lambda_down = down;
     st->lambda_spec = st->lambda;
     st->cost_cur = 0; st->cost_trial = 0; st->change = 1.0; st->alpha = 1.0;
