@@ -83,6 +83,7 @@ struct mccba_handle_s {
     CamParams* d_cams = nullptr;
     int cur = 0;                      // host mirror of DevState::cur between calls
     int ar_len = 0;
+    int obs_cap = 0;                  // floats per plane per TMA stage of the residual kernel (0: no staging)
     int k1_grid = 0, k1_smem = 0, k5_smem = 0, k5_blocked = 0, panel_smem = 0, iter_kernels = 5;
     cudaGraphExec_t graph = nullptr;
     int* h_done = nullptr;            // pinned
@@ -183,7 +184,7 @@ int enqueue_iteration(mccba_handle h, bool timed)
     if (timed) cudaEventRecord(ev[4], s);
     frame_update_kernel<<<P.n_k4_blocks, kK4Threads, 0, s>>>(P);
     if (timed) cudaEventRecord(ev[5], s);
-    resid_jac_accum_kernel<<<h->k1_grid, kK1Threads, h->k1_smem, s>>>(P, 0);
+    resid_jac_accum_kernel<<<h->k1_grid, kK1Threads, h->k1_smem, s>>>(P, 0, h->obs_cap);
     if (timed) {
         cudaEventRecord(ev[6], s);
         cudaEventSynchronize(ev[6]);
@@ -202,7 +203,7 @@ int launch_forced_eval(mccba_handle h)
 {
     Problem& P = h->P;
     vertex_prep_kernel<<<(P.n_vertex + 127) / 128, 128, 0, h->stream>>>(P, -1);
-    resid_jac_accum_kernel<<<h->k1_grid, kK1Threads, h->k1_smem, h->stream>>>(P, 1);
+    resid_jac_accum_kernel<<<h->k1_grid, kK1Threads, h->k1_smem, h->stream>>>(P, 1, h->obs_cap);
     CUDA_TRY(h, cudaGetLastError());
     return MCCBA_OK;
 }
@@ -512,7 +513,24 @@ int mccba_set_observations(mccba_handle h, int n_frame, int n_edge, const int* e
     if ((rc = dev_alloc(h, &P.err_sq, (size_t)P.n_edge_int, true))) return rc;
     if ((rc = dev_alloc(h, &P.err_nrm, (size_t)P.n_edge_int, true))) return rc;
     // launch geometry
-    h->k1_smem = (int)(sizeof(K1Shared) + (size_t)nC * (sizeof(CamParams) + 12 * sizeof(double)));
+    {   // shared memory of the residual kernel: fixed part + two TMA stages sized for the largest 32-edge chunk,
+        // provided two CTAs still fit on an SM (otherwise no staging: direct global loads)
+        int max_chunk = 0;
+        for (int ch = 0; ch < P.n_edge_int / kEdgesPerBlock; ++ch) {
+            const int f0 = e_off[(size_t)ch * kEdgesPerBlock] & ~3, f1 = e_off[(size_t)(ch + 1) * kEdgesPerBlock];
+            max_chunk = std::max(max_chunk, (f1 - f0 + 3) & ~3);
+        }
+        const size_t off_cam = (sizeof(K1Shared) + 15) & ~(size_t)15;
+        const size_t fixed = ((off_cam + (size_t)nC * (sizeof(CamParams) + 12 * sizeof(double)) + 127) & ~(size_t)127);
+        const size_t budget = 110 * 1024;   // per CTA, two CTAs per SM
+        int cap = (max_chunk + 31) & ~31;
+        const char* nostage = getenv("MCCBA_NO_TMA");
+        if (nostage && nostage[0] == '1') cap = 0;
+        while (cap > 0 && fixed + (size_t)cap * 40 > budget) cap -= 256;   // large edges: partial staging is not worth it
+        if (cap < max_chunk) cap = (fixed + (size_t)max_chunk * 40 <= budget) ? ((max_chunk + 31) & ~31) : 0;
+        h->obs_cap = cap;
+        h->k1_smem = (int)(fixed + (size_t)cap * 40);
+    }
     {   // tiled Cholesky when one block column fits in shared memory (n_s <= ~870), else the plain column version
         const size_t need = chol_panel_smem_bytes(P.ns);
         const char* force = getenv("MCCBA_SIMPLE_CHOL");
@@ -526,6 +544,8 @@ int mccba_set_observations(mccba_handle h, int n_frame, int n_edge, const int* e
         const int ntc = chol_col_tiles(P.ns);
         h->iter_kernels = 6 + ((h->k5_blocked && P.ns > 0) ? 2 * ntc - 1 : 0);
     }
+    if (h->k1_smem > 48 * 1024)
+        CUDA_TRY(h, cudaFuncSetAttribute(resid_jac_accum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->k1_smem));
     int per_sm = 1;
     CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, resid_jac_accum_kernel, kK1Threads, h->k1_smem));
     per_sm = std::max(per_sm, 1);
@@ -833,7 +853,7 @@ int mccba_time_eval(mccba_handle h, int reps, double* avg_ms)
     if ((rc = launch_forced_eval(h))) return rc;  // warm-up, also computes the rotations
     CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));
     for (int i = 0; i < reps; ++i)
-        resid_jac_accum_kernel<<<h->k1_grid, kK1Threads, h->k1_smem, h->stream>>>(h->P, 1);
+        resid_jac_accum_kernel<<<h->k1_grid, kK1Threads, h->k1_smem, h->stream>>>(h->P, 1, h->obs_cap);
     CUDA_TRY(h, cudaEventRecord(h->ev1, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     CUDA_TRY(h, cudaGetLastError());

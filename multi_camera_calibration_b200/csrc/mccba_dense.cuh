@@ -38,9 +38,26 @@ __device__ inline void chol_panel(double* __restrict__ A, int n, int k, int* fai
     const int c0 = k * kCT;
     const int w = min(kCT, n - c0);
     const int R = n + 1 - c0;  // panel rows c0 .. n (row n is g)
-    for (int idx = tid; idx < R * kCT; idx += nt) {
-        const int r = idx >> 5, c = idx & 31;
-        panel[r * kCLD + c] = c < w ? A[(int64_t)(c0 + r) * n + c0 + c] : 0.0;
+    {   // load: 4 independent global loads in flight per thread
+        const int total = R * kCT;
+        int idx = tid;
+        for (; idx + 3 * nt < total; idx += 4 * nt) {
+            double v[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int id = idx + q * nt, r = id >> 5, c = id & 31;
+                v[q] = c < w ? A[(int64_t)(c0 + r) * n + c0 + c] : 0.0;
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int id = idx + q * nt;
+                panel[(id >> 5) * kCLD + (id & 31)] = v[q];
+            }
+        }
+        for (; idx < total; idx += nt) {
+            const int r = idx >> 5, c = idx & 31;
+            panel[r * kCLD + c] = c < w ? A[(int64_t)(c0 + r) * n + c0 + c] : 0.0;
+        }
     }
     __syncthreads();
     // diagonal tile, 8 columns at a time

@@ -143,26 +143,62 @@ __global__ void vertex_prep_kernel(Problem P, int which)
 // --------------------------------------------------------------------------------------------------------
 struct K1Shared {
     double stage[kBlk][kEdgesPerBlock + 1];
+    unsigned long long bar[2];   // mbarriers of the two observation stages
+    int first[2];                // first float index (16-byte aligned) held by each stage, -1 = not staged
 };
 
-template <int kModel, bool kRational>
-__device__ __forceinline__ void edge_corner_loop(const Problem& P, const CamParams& cam, const double* R3,
-                                                 const double* T3, int begin, int end, int sub, double* acc)
+// ---- TMA (1-D bulk copy) + mbarrier primitives, sm_90+/sm_100a PTX ---------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count)
 {
-    for (int i = begin + sub; i < end; i += kLanesPerEdge) {
-        const float ox = __ldg(P.ox + i), oy = __ldg(P.oy + i), oz = __ldg(P.oz + i);
-        const float iu = __ldg(P.iu + i), iv = __ldg(P.iv + i);
-        corner_accumulate<kModel, kRational>(cam, R3, T3, ox, oy, oz, iu, iv, acc);
-    }
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// global -> shared bulk copy (TMA engine), completion counted in bytes on the mbarrier; 16-byte aligned, size % 16 == 0
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, unsigned bytes, unsigned long long* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-// mode: 0 = loop launch (evaluate the trial buffer iff the state says a step was produced), 1 = forced on `cur`
-__global__ void __launch_bounds__(kK1Threads, 2) resid_jac_accum_kernel(Problem P, int forced)
+template <int kModel, bool kRational>
+__device__ __forceinline__ void edge_corner_loop(const float* __restrict__ ox, const float* __restrict__ oy,
+                                                 const float* __restrict__ oz, const float* __restrict__ iu,
+                                                 const float* __restrict__ iv, const CamParams& cam, const double* R3,
+                                                 const double* T3, int begin, int end, int sub, double* acc)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    for (int i = begin + sub; i < end; i += kLanesPerEdge)
+        corner_accumulate<kModel, kRational>(cam, R3, T3, ox[i], oy[i], oz[i], iu[i], iv[i], acc);
+}
+
+// forced: 0 = loop launch (evaluate the trial buffer iff the state says a step was produced), 1 = forced on `cur`.
+// Shared memory: K1Shared | camera table | camera poses | 2 stages x 5 planes x obs_cap floats.
+// The observation planes of the NEXT chunk are fetched by the TMA engine (cp.async.bulk + mbarrier) while the
+// current chunk is being evaluated; chunks whose data does not fit a stage fall back to direct global loads.
+__global__ void __launch_bounds__(kK1Threads, 2) resid_jac_accum_kernel(Problem P, int forced, int obs_cap)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     K1Shared* sh = reinterpret_cast<K1Shared*>(smem_raw);
-    CamParams* s_cam = reinterpret_cast<CamParams*>(smem_raw + sizeof(K1Shared));
+    const size_t off_cam = (sizeof(K1Shared) + 15) & ~(size_t)15;
+    CamParams* s_cam = reinterpret_cast<CamParams*>(smem_raw + off_cam);
     double* s_camR = reinterpret_cast<double*>(s_cam + P.n_cam);  // n_cam x 12: R (9) | t (3)
+    const size_t off_obs = (off_cam + (size_t)P.n_cam * (sizeof(CamParams) + 12 * sizeof(double)) + 127) & ~(size_t)127;
+    float* s_obs = reinterpret_cast<float*>(smem_raw + off_obs);   // [2][5][obs_cap]
 
     const DevState* st = P.st;
     int which;
@@ -182,33 +218,74 @@ __global__ void __launch_bounds__(kK1Threads, 2) resid_jac_accum_kernel(Problem 
 #pragma unroll
         for (int i = 0; i < 3; ++i) s_camR[12 * c + 9 + i] = c == 0 ? 0.0 : x[6 * (c - 1) + 3 + i];
     }
+    if (threadIdx.x == 0) {
+        mbar_init(&sh->bar[0], 1);
+        mbar_init(&sh->bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     __syncthreads();
 
     const int sub = threadIdx.x & (kLanesPerEdge - 1);
     const int eb = threadIdx.x / kLanesPerEdge;
     const int n_chunks = P.n_edge_int / kEdgesPerBlock;
-    for (int chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+    const float* planes[5] = {P.ox, P.oy, P.oz, P.iu, P.iv};
+
+    // producer: one thread programs the TMA engine for chunk `chunk` into stage `stg`
+    auto issue = [&](int chunk, int stg) {
+        const int f0 = P.e_off[chunk * kEdgesPerBlock] & ~3;
+        const int f1 = P.e_off[(chunk + 1) * kEdgesPerBlock];
+        const int nfl = (f1 - f0 + 3) & ~3;
+        if (obs_cap > 0 && nfl <= obs_cap && nfl > 0) {
+            sh->first[stg] = f0;
+            mbar_expect_tx(&sh->bar[stg], 5u * (unsigned)nfl * 4u);
+#pragma unroll
+            for (int pl = 0; pl < 5; ++pl)
+                tma_load_1d(s_obs + ((size_t)stg * 5 + pl) * obs_cap, planes[pl] + f0, (unsigned)nfl * 4u, &sh->bar[stg]);
+        } else {
+            sh->first[stg] = -1;
+            mbar_expect_tx(&sh->bar[stg], 0u);   // completes the phase immediately: consumers read global memory
+        }
+    };
+
+    if (threadIdx.x == 0 && blockIdx.x < n_chunks) issue(blockIdx.x, 0);
+    int it = 0;
+    for (int chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x, ++it) {
+        const int stg = it & 1;
+        if (threadIdx.x == 0 && chunk + (int)gridDim.x < n_chunks) issue(chunk + gridDim.x, stg ^ 1);
         const int e = chunk * kEdgesPerBlock + eb;
         double acc[kBlk];
 #pragma unroll
         for (int k = 0; k < kBlk; ++k) acc[k] = 0.0;
         const int frame = P.e_frame[e];
+        double R3[9], T3[3];
+        int c = 0, b = 0, n = 0;
         if (frame >= 0) {
-            const int c = P.e_cam[e];
+            c = P.e_cam[e];
             const int64_t pv = P.n_cam + frame;
-            double Rp[9], tp[3], R3[9], T3[3];
+            double Rp[9], tp[3];
 #pragma unroll
             for (int i = 0; i < 9; ++i) Rp[i] = __ldg(vR + 9 * pv + i);
 #pragma unroll
             for (int i = 0; i < 3; ++i) tp[i] = __ldg(x + 6 * (pv - 1) + 3 + i);
             compose_pose(s_camR + 12 * c, s_camR + 12 * c + 9, Rp, tp, R3, T3);
-            const CamParams& cam = s_cam[c];
-            const int b = P.e_off[e], n = P.e_off[e + 1];
-            if (cam.model == kPinhole) {
-                if (cam.rational) edge_corner_loop<kPinhole, true>(P, cam, R3, T3, b, n, sub, acc);
-                else edge_corner_loop<kPinhole, false>(P, cam, R3, T3, b, n, sub, acc);
+            b = P.e_off[e]; n = P.e_off[e + 1];
+        }
+        mbar_wait(&sh->bar[stg], (unsigned)((it >> 1) & 1));
+        if (frame >= 0) {
+            const int first = sh->first[stg];
+            const float *ox, *oy, *oz, *iu, *iv;
+            if (first >= 0) {
+                const float* base = s_obs + (size_t)stg * 5 * obs_cap - first;
+                ox = base; oy = base + obs_cap; oz = base + 2 * obs_cap; iu = base + 3 * obs_cap; iv = base + 4 * obs_cap;
             } else {
-                edge_corner_loop<kOmnidir, false>(P, cam, R3, T3, b, n, sub, acc);
+                ox = P.ox; oy = P.oy; oz = P.oz; iu = P.iu; iv = P.iv;
+            }
+            const CamParams& cam = s_cam[c];
+            if (cam.model == kPinhole) {
+                if (cam.rational) edge_corner_loop<kPinhole, true>(ox, oy, oz, iu, iv, cam, R3, T3, b, n, sub, acc);
+                else edge_corner_loop<kPinhole, false>(ox, oy, oz, iu, iv, cam, R3, T3, b, n, sub, acc);
+            } else {
+                edge_corner_loop<kOmnidir, false>(ox, oy, oz, iu, iv, cam, R3, T3, b, n, sub, acc);
             }
         }
         // transposed reduction over the 8 lanes of the edge: 28 -> 14 -> 7 -> 3(+1) values per lane, 25 adds
@@ -247,7 +324,7 @@ __global__ void __launch_bounds__(kK1Threads, 2) resid_jac_accum_kernel(Problem 
         }
 #pragma unroll
         for (int i = 0; i < 3; ++i) sh->stage[base + i][eb] = acc[i];
-        __syncthreads();
+        __syncthreads();   // also: every thread is done reading observation stage `stg`
         for (int t = threadIdx.x; t < kBlk * kEdgesPerBlock; t += kK1Threads) {
             const int k = t / kEdgesPerBlock, col = t % kEdgesPerBlock;
             out[(int64_t)k * P.n_edge_int + chunk * kEdgesPerBlock + col] = sh->stage[k][col];
@@ -497,8 +574,21 @@ __global__ void reduce_records_kernel(Problem P, int forced)
     double* gs = P.ar + (int64_t)ns * ns;
     double* sc = gs + ns;
     if (kind == 0) {
+        // sources summed in a fixed order; 8 independent loads in flight (the list is a gather over warp records)
         double a0 = 0, a1 = 0;
-        for (int s = s0; s < s1; ++s) {
+        int s = s0;
+        for (; s + 8 <= s1; s += 8) {
+            double v[8], u[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const double* src = P.records + P.dest_src[s + q];
+                v[q] = src[lane];
+                u[q] = lane < 4 ? src[32 + lane] : 0.0;
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) { a0 += v[q]; a1 += u[q]; }
+        }
+        for (; s < s1; ++s) {
             const double* src = P.records + P.dest_src[s];
             a0 += src[lane];
             if (lane < 4) a1 += src[32 + lane];
@@ -515,9 +605,18 @@ __global__ void reduce_records_kernel(Problem P, int forced)
         }
     } else if (kind == 1) {
         double a0 = 0;
-        if (lane < 6)
-            for (int s = s0; s < s1; ++s) a0 += P.records[P.dest_src[s] + lane];
-        if (lane < 6) gs[6 * A + lane] = a0;
+        if (lane < 6) {
+            int s = s0;
+            for (; s + 8 <= s1; s += 8) {
+                double v[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) v[q] = P.records[P.dest_src[s + q] + lane];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) a0 += v[q];
+            }
+            for (; s < s1; ++s) a0 += P.records[P.dest_src[s] + lane];
+            gs[6 * A + lane] = a0;
+        }
     } else {
         // scalars: cost and bad from every warp record; frame step / param norms from frame_update's partials
         double c = 0, b = 0, n0 = 0, n1 = 0;
@@ -638,7 +737,7 @@ __global__ void decide_kernel(Problem P)
 // Cholesky of the reduced system, one block column per launch pair (mccba_dense.cuh).  go == nullptr: always run.
 __global__ void __launch_bounds__(kPanelThreads) chol_panel_kernel(double* A, int n, int k, const int* go, int* fail, double* rinv)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     if (go && !*go) return;
     chol_panel(A, n, k, fail, rinv, reinterpret_cast<double*>(smem_raw));
 }
@@ -653,7 +752,7 @@ __global__ void __launch_bounds__(kUpdThreads) chol_update_kernel(double* A, int
 // backward substitution + camera update (replicated on every rank) + end-of-iteration state.  Single CTA.
 __global__ void __launch_bounds__(kK5Threads) camera_update_kernel(Problem P, int tiled)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     double* s_dyn = reinterpret_cast<double*>(smem_raw);
     __shared__ double s_bcast[2];
     DevState* st = P.st;
@@ -789,7 +888,7 @@ __global__ void __launch_bounds__(kK4Threads) frame_update_kernel(Problem P)
 // test hook: backward substitution of the tiled solver / the plain single-CTA solver on a standalone matrix
 __global__ void __launch_bounds__(kK5Threads) dense_backward_kernel(double* A, int n, const double* rinv, double* x, int* fail, int tiled)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     double* s_dyn = reinterpret_cast<double*>(smem_raw);
     __shared__ double s_bcast[2];
     if (tiled) chol_backward(A, n, rinv, x, s_dyn);

@@ -213,10 +213,10 @@ MC_HD void corner_accumulate(const CamParams& c, const double* R3, const double*
 #pragma unroll
     for (int i = 0; i < 6; ++i) {
 #pragma unroll
-        for (int j = i; j < 6; ++j) acc[tri6(i, j)] += j0[i] * j0[j] + j1[i] * j1[j];
-        acc[21 + i] += j0[i] * e0 + j1[i] * e1;
+        for (int j = i; j < 6; ++j) acc[tri6(i, j)] = fma(j1[i], j1[j], fma(j0[i], j0[j], acc[tri6(i, j)]));
+        acc[21 + i] = fma(j1[i], e1, fma(j0[i], e0, acc[21 + i]));
     }
-    acc[27] += e0 * e0 + e1 * e1;
+    acc[27] = fma(e1, e1, fma(e0, e0, acc[27]));
 }
 
 // Residual only: returns |e|^2 and |e| (for computeProjectError, src/multicalib.cpp:969-983).
