@@ -162,7 +162,9 @@ int enqueue_iteration(mccba_handle h, bool timed)
     if (timed)
         for (auto& e : ev) cudaEventCreate(&e);
     if (timed) cudaEventRecord(ev[0], s);
-    CUDA_TRY(h, cudaMemsetAsync(P.ar, 0, sizeof(double) * (size_t)P.ns * P.ns, s));
+    // the whole packed buffer: a rank whose frame shard never sees some camera has no record for that camera's
+    // rows, and stale (already all-reduced) values there would be summed again
+    CUDA_TRY(h, cudaMemsetAsync(P.ar, 0, sizeof(double) * (size_t)h->ar_len, s));
     frame_schur_kernel<<<(P.n_warps * 32 + kK2Threads - 1) / kK2Threads, kK2Threads, 0, s>>>(P, -1, 0.0);
     if (timed) cudaEventRecord(ev[1], s);
     reduce_records_kernel<<<(P.n_dest * 32 + 127) / 128, 128, 0, s>>>(P, 0);

@@ -1,0 +1,102 @@
+"""Generates the committed golden fixtures under tests/golden/ (run from the repo root: python tests/golden/make_golden.py).
+
+Sources of truth:
+  cv2_primitives.npz   OpenCV 4.13.0 via Python cv2: Rodrigues (+3x9 Jacobian), composeRT (all 10 outputs),
+                       projectPoints (+ Jacobian columns 0..5) for 0/4/5/8 distortion coefficients      [tier 0]
+  omni_points.npz      numpy transcription of /root/reference/src/omnidir.cpp:126-243 (oracle/dense_reenact.py),
+                       i.e. cv::omnidir::projectPoints with its 2N x 16 Jacobian                        [tier 1]
+  rig_dense.npz        dense literal re-enactment of optimizeExtrinsics (/root/reference/src/multicalib.cpp:462-514,
+                       593-703, 717-824) on seeded toy rigs: iterates in both precision policies          [tier 2]
+Nothing here reads /root/reference at run time; the reference itself cannot be built in this image.
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+import cv2  # noqa: E402
+
+from oracle import dense_reenact as dr  # noqa: E402
+from tests import rigs  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+def primitives():
+    rng = np.random.default_rng(20261018)
+    d = {}
+    oms, Rs, Js = [], [], []
+    for sc in [1e-7, 1e-3, 0.05, 0.3, 1.0, 2.0, 3.0]:
+        for _ in range(3):
+            om = rng.standard_normal(3); om *= sc / np.linalg.norm(om)
+            R, J = cv2.Rodrigues(om)
+            oms.append(om); Rs.append(R); Js.append(J)
+    d["rod_om"] = np.array(oms); d["rod_R"] = np.array(Rs); d["rod_J"] = np.array(Js)
+    ins, outs = [], []
+    for _ in range(12):
+        om1 = rng.standard_normal(3) * 0.6; t1 = rng.standard_normal(3) * 700
+        om2 = rng.standard_normal(3) * 0.6; t2 = rng.standard_normal(3) * 300
+        r = cv2.composeRT(om1, t1, om2, t2)
+        ins.append(np.concatenate([om1, t1, om2, t2]))
+        outs.append(np.concatenate([np.asarray(x).ravel() for x in r]))
+    d["compose_in"] = np.array(ins); d["compose_out"] = np.array(outs)
+    obj = rng.uniform(-250, 250, (30, 3)); obj[:, 2] *= 0.1
+    om = np.array([0.21, -0.33, 0.12]); T = np.array([35.0, -60.0, 1400.0])
+    K5 = np.array([1003.5, 998.25, 951.0, 546.5, 0.0])
+    K = np.array([[K5[0], 0, K5[2]], [0, K5[1], K5[3]], [0, 0, 1.0]])
+    dist8 = np.array([-0.21, 0.06, 1.1e-3, -0.7e-3, 0.012, 0.02, -0.01, 0.004])
+    d["pin_obj"] = obj; d["pin_om"] = om; d["pin_T"] = T; d["pin_K5"] = K5; d["pin_dist8"] = dist8
+    for nd in (0, 4, 5, 8):
+        p, j = cv2.projectPoints(obj.reshape(-1, 1, 3), om, T, K, dist8[:nd] if nd else None)
+        d["pin_proj_%d" % nd] = p.reshape(-1, 2); d["pin_jac_%d" % nd] = j[:, :6]
+    # camodocal/PinholeCamera_test.cc known answers (same 4-coefficient radtan model)
+    Kc = np.array([[712.557492, 0, 370.075592], [0, 714.825860, 244.759309], [0, 0, 1.0]])
+    Dc = np.array([-0.473, 0.273, -0.001, 0.001])
+    p, _ = cv2.projectPoints(np.array([[[0.0, 0, 1]], [[1.0, -1, 4]]]), np.zeros(3), np.zeros(3), Kc, Dc)
+    d["camodocal_K5"] = np.array([712.557492, 714.825860, 370.075592, 244.759309, 0.0]); d["camodocal_D"] = Dc
+    d["camodocal_uv"] = p.reshape(-1, 2)
+    np.savez(os.path.join(OUT, "cv2_primitives.npz"), **d)
+
+
+def omni():
+    rng = np.random.default_rng(7)
+    obj = rng.uniform(-300, 300, (25, 3)); obj[:, 2] *= 0.05
+    om = np.array([-0.15, 0.4, 0.9]); T = np.array([-80.0, 40.0, 900.0])
+    K5 = np.array([612.5, 640.25, 955.0, 530.0, 0.75]); xi = 1.25
+    K = np.array([[K5[0], K5[4], K5[2]], [0, K5[1], K5[3]], [0, 0, 1.0]])
+    D = np.array([-0.06, 0.012, 1.5e-3, -0.8e-3])
+    p, j = dr.omnidir_project_points(obj, om, T, K, xi, D)
+    np.savez(os.path.join(OUT, "omni_points.npz"), obj=obj, om=om, T=T, K5=K5, xi=xi, D=D, proj=p, jac=j)
+
+
+def rig_dense():
+    d = {}
+    for name, kw in (("pin", dict(n_cam=3, n_frame=8, cam_models=[0, 0, 0], seed=41)),
+                     ("omni", dict(n_cam=2, n_frame=7, cam_models=[1, 1], seed=42)),
+                     ("mixed", dict(n_cam=3, n_frame=9, cam_models=[0, 1, 0], seed=43, views_per_frame=3, ragged=True))):
+        rig = rigs.make_rig(**kw)
+        P = rigs.to_dense_problem(rig)
+        for pol in ("fp64", "faithful_f32"):
+            rec = []
+            p, it, ch = dr.optimize_extrinsics(P, rig["params_init"], 3, 12, 1e-7, pol, rec)
+            d["%s_%s_iters" % (name, pol)] = it
+            d["%s_%s_change" % (name, pol)] = ch
+            d["%s_%s_params" % (name, pol)] = p
+            d["%s_%s_trace" % (name, pol)] = np.array([[r["cost_before"], r["change"]] for r in rec])
+            d["%s_%s_iterates" % (name, pol)] = np.array([r["params"] for r in rec])
+            e = dr.compute_project_error(P, p, pol)
+            d["%s_%s_err" % (name, pol)] = np.array([e["mean_reproj_error"], e["rms"], e["n_points"]])
+            d["%s_%s_per_edge" % (name, pol)] = e["per_edge"]
+        x, J, E, JTJ, JTE = dr.compute_jacobian_extrinsic(P, rig["params_init"], "fp64", dense_out=True)
+        d[name + "_x0"] = x; d[name + "_JTE0"] = JTE; d[name + "_JTJ0_diag"] = np.diag(JTJ).copy()
+        d[name + "_kw"] = np.array(repr(kw))
+    np.savez_compressed(os.path.join(OUT, "rig_dense.npz"), **d)
+
+
+if __name__ == "__main__":
+    primitives()
+    omni()
+    rig_dense()
+    print("golden fixtures written to", OUT)
