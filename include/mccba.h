@@ -153,6 +153,23 @@ int mccba_solve(mccba_handle h, const mccba_solve_opts *opts, mccba_report *repo
  * per_edge_mean (optional, n_edge) = edge.reprojecterror. */
 int mccba_reproj_error(mccba_handle h, mccba_error_stats *stats, double *per_edge_mean);
 
+/* ---- single-camera Mei calibration loop ------------------------------------------------------------------------
+ * The optimisation part of cv::omnidir::calibrate (src/omnidir.cpp:1119-1147 with internal::computeJacobian :851-935,
+ * flags2idx :2031-2076, fillFixed :2138-2153): per-frame poses + 10 intrinsics, parameter vector
+ * [om_i, T_i] * n, fx, fy, s, cx, cy, xi, k1, k2, p1, p2 (encodeParameters, :1541-1568), step
+ * G = (1 - 0.99^(iter+1)) (JTJ_sub + eps 11^T)^-1 JTE_sub with eps = 0.01 * 0.9^(iter/10), fixed parameters selected
+ * by the omnidir::CALIB_FIX_* bits of `flags`.  The closed-form initialisation (initializeCalibration) is out of
+ * scope: the caller supplies the starting parameters.  Single GPU. */
+int mccba_omni_set_observations(mccba_handle h, int n_frame, const int64_t *frame_off, const float *obj_xyz,
+                                const float *img_uv);
+int mccba_omni_set_parameters(mccba_handle h, int64_t n, const double *params);   /* n = 6 n_frame + 10 */
+int mccba_omni_get_parameters(mccba_handle h, int64_t n, double *params);
+/* report->cost = sum of squared residuals at the returned parameters; rms = sqrt(cost / n_points) (:1794-1802) */
+int mccba_omni_solve(mccba_handle h, int flags, int crit_type, int max_count, double epsilon, mccba_report *report);
+/* test hook: per-frame 17x17 Gram matrices sum [J(16) | e]^T [J(16) | e] at the current parameters (Jacobian columns
+ * in the order of src/omnidir.cpp:65-73) and the total cost */
+int mccba_omni_gram(mccba_handle h, double *gram, double *cost);
+
 /* ---- utilities --------------------------------------------------------------------------------------------- */
 /* sum a small host array of doubles over all ranks (NCCL); identity when nranks == 1 */
 int mccba_allreduce_sum(mccba_handle h, double *buf, int n);

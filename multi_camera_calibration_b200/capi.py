@@ -40,7 +40,8 @@ class ErrorStats(C.Structure):
 EXPORTS = ["mccba_default_options", "mccba_default_solve_opts", "mccba_nccl_unique_id", "mccba_create", "mccba_destroy",
            "mccba_last_error", "mccba_set_cameras", "mccba_set_observations", "mccba_set_parameters",
            "mccba_get_parameters", "mccba_save_parameters", "mccba_restore_parameters", "mccba_eval", "mccba_reduced_system", "mccba_solve", "mccba_reproj_error",
-           "mccba_allreduce_sum", "mccba_last_kernel_ms", "mccba_time_eval", "mccba_debug_solve_dense"]
+           "mccba_allreduce_sum", "mccba_last_kernel_ms", "mccba_time_eval", "mccba_debug_solve_dense", "mccba_omni_set_observations",
+           "mccba_omni_set_parameters", "mccba_omni_get_parameters", "mccba_omni_solve", "mccba_omni_gram"]
 
 _lib = None
 
@@ -213,6 +214,37 @@ class Solver:
         self._check(lib().mccba_debug_solve_dense(self._h, n, _ptr(S, C.c_double), _ptr(g, C.c_double),
                                                   _ptr(x, C.c_double), int(bool(blocked))))
         return x, self.last_kernel_ms()[0]
+
+    # ---- single-camera Mei calibration loop (cv::omnidir::calibrate without its closed-form initialisation) --------
+    def omni_set_observations(self, frame_off, obj_xyz, img_uv):
+        off = np.ascontiguousarray(frame_off, dtype=np.int64)
+        obj = np.ascontiguousarray(obj_xyz, dtype=np.float32); img = np.ascontiguousarray(img_uv, dtype=np.float32)
+        self._omni_n = off.size - 1
+        self._omni_pts = int(off[-1])
+        self._check(lib().mccba_omni_set_observations(self._h, int(self._omni_n), _ptr(off, C.c_int64), _ptr(obj, C.c_float),
+                                                      _ptr(img, C.c_float)))
+
+    def omni_set_parameters(self, params):
+        p = np.ascontiguousarray(params, dtype=np.float64)
+        self._check(lib().mccba_omni_set_parameters(self._h, C.c_int64(p.size), _ptr(p, C.c_double)))
+
+    def omni_get_parameters(self):
+        p = np.zeros(6 * self._omni_n + 10)
+        self._check(lib().mccba_omni_get_parameters(self._h, C.c_int64(p.size), _ptr(p, C.c_double)))
+        return p
+
+    def omni_solve(self, flags=0, crit_type=3, max_count=200, eps=1e-8, check=True):
+        r = Report()
+        rc = lib().mccba_omni_solve(self._h, int(flags), int(crit_type), int(max_count), C.c_double(eps), C.byref(r))
+        if rc and check:
+            self._check(rc)
+        return dict(rc=rc, iterations=r.iterations, status=r.status, change=r.change, cost=r.cost,
+                    rms=float(np.sqrt(r.cost / self._omni_pts)), device_ms=r.device_ms, kernel_launches=r.kernel_launches)
+
+    def omni_gram(self):
+        g = np.zeros((self._omni_n, 17, 17)); cost = C.c_double()
+        self._check(lib().mccba_omni_gram(self._h, _ptr(g, C.c_double), C.byref(cost)))
+        return g, cost.value
 
     def time_eval(self, reps=10):
         ms = C.c_double()

@@ -13,6 +13,7 @@
 
 #include "../../include/mccba.h"
 #include "mccba_kernels.cuh"
+#include "mccba_omni.cuh"
 
 using namespace mccba;
 
@@ -93,6 +94,11 @@ struct mccba_handle_s {
     double prof_ms[6] = {0, 0, 0, 0, 0, 0};
     int profile = 0;
     double* x_saved = nullptr;        // device snapshot of the parameters (owned by the problem)
+    // single-camera Mei calibration problem (mccba_omni_*)
+    OmniProblem O;
+    std::vector<void*> omni_allocs;
+    bool omni_have = false, omni_have_params = false;
+    cudaGraphExec_t omni_graph = nullptr;
     bool have_saved = false;
 };
 
@@ -261,6 +267,7 @@ int mccba_create(const mccba_options* opts, mccba_handle* out)
     mccba_handle h = new mccba_handle_s();
     h->opts = *opts;
     memset(&h->P, 0, sizeof(h->P));
+    memset(&h->O, 0, sizeof(h->O));
     if (cudaSetDevice(opts->device) != cudaSuccess) { delete h; return MCCBA_ERR_CUDA; }
     cudaDeviceProp prop;
     cudaGetDeviceProperties(&prop, opts->device);
@@ -291,6 +298,8 @@ int mccba_destroy(mccba_handle h)
     cudaSetDevice(h->opts.device);
     cudaStreamSynchronize(h->stream);
     free_problem(h);
+    if (h->omni_graph) cudaGraphExecDestroy(h->omni_graph);
+    for (void* q : h->omni_allocs) cudaFree(q);
     if (h->d_cams) cudaFree(h->d_cams);
     if (h->comm) nccl().CommDestroy(h->comm);
     cudaFreeHost(h->h_done);
@@ -862,6 +871,204 @@ int mccba_time_eval(mccba_handle h, int reps, double* avg_ms)
     float ms = 0;
     cudaEventElapsedTime(&ms, h->ev0, h->ev1);
     *avg_ms = (double)ms / reps;
+    return MCCBA_OK;
+}
+
+}  // extern "C"
+
+// ---- single-camera Mei calibration loop (cv::omnidir::calibrate, src/omnidir.cpp:1119-1147) -------------------
+namespace {
+template <typename T>
+int omni_alloc(mccba_handle h, T** p, size_t count)
+{
+    void* q = nullptr;
+    const size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+    CUDA_TRY(h, cudaMalloc(&q, bytes));
+    CUDA_TRY(h, cudaMemsetAsync(q, 0, bytes, h->stream));
+    h->omni_allocs.push_back(q);
+    *p = (T*)q;
+    return MCCBA_OK;
+}
+int omni_enqueue_iteration(mccba_handle h)
+{
+    OmniProblem& O = h->O;
+    cudaStream_t s = h->stream;
+    omni_frame_kernel<<<O.n_frame, kOmniThreads, 0, s>>>(O, 0);
+    omni_reduce_kernel<<<kOmniRec, 256, 0, s>>>(O, 0);
+    omni_solve_kernel<<<1, 32, 0, s>>>(O);
+    omni_update_kernel<<<O.n_blocks_upd, 128, 0, s>>>(O);
+    omni_decide_kernel<<<1, 256, 0, s>>>(O);
+    CUDA_TRY(h, cudaGetLastError());
+    return MCCBA_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int mccba_omni_set_observations(mccba_handle h, int n_frame, const int64_t* frame_off, const float* obj_xyz, const float* img_uv)
+{
+    if (!h) return MCCBA_ERR_ARG;
+    if (n_frame < 1 || !frame_off || !obj_xyz || !img_uv || frame_off[0] != 0) return fail(h, MCCBA_ERR_ARG, "omni_set_observations: bad input");
+    CUDA_TRY(h, cudaSetDevice(h->opts.device));
+    const int64_t M = frame_off[n_frame];
+    if (M <= 0 || M >= (int64_t)2000000000) return fail(h, MCCBA_ERR_ARG, "omni_set_observations: corner count out of range");
+    for (int f = 0; f < n_frame; ++f)
+        if (frame_off[f + 1] <= frame_off[f]) return fail(h, MCCBA_ERR_ARG, "frame %d has no observation", f);
+    if (h->omni_graph) { cudaGraphExecDestroy(h->omni_graph); h->omni_graph = nullptr; }
+    for (void* q : h->omni_allocs) cudaFree(q);
+    h->omni_allocs.clear();
+    OmniProblem& O = h->O;
+    memset(&O, 0, sizeof(O));
+    O.n_frame = n_frame; O.n_pts = M; O.n_blocks_upd = (n_frame + 127) / 128;
+    std::vector<int> off((size_t)n_frame + 1);
+    std::vector<int64_t> src((size_t)n_frame);
+    for (int f = 0; f <= n_frame; ++f) off[f] = (int)frame_off[f];
+    for (int f = 0; f < n_frame; ++f) src[f] = frame_off[f];
+    int* d_off = nullptr; int64_t* d_src = nullptr; float* planes = nullptr;
+    int rc;
+    if ((rc = omni_alloc(h, &d_off, off.size()))) return rc;
+    if ((rc = omni_alloc(h, &d_src, src.size()))) return rc;
+    CUDA_TRY(h, cudaMemcpyAsync(d_off, off.data(), off.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(d_src, src.data(), src.size() * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
+    const size_t plane = ((size_t)M + 63) / 64 * 64;
+    if ((rc = omni_alloc(h, &planes, plane * 5))) return rc;
+    float *d_obj = nullptr, *d_img = nullptr;
+    CUDA_TRY(h, cudaMalloc((void**)&d_obj, sizeof(float) * 3 * (size_t)M));
+    CUDA_TRY(h, cudaMalloc((void**)&d_img, sizeof(float) * 2 * (size_t)M));
+    CUDA_TRY(h, cudaMemcpyAsync(d_obj, obj_xyz, sizeof(float) * 3 * (size_t)M, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(d_img, img_uv, sizeof(float) * 2 * (size_t)M, cudaMemcpyHostToDevice, h->stream));
+    gather_obs_kernel<<<h->num_sms * 8, 256, 0, h->stream>>>(n_frame, d_off, d_src, d_obj, d_img, planes, planes + plane,
+                                                            planes + 2 * plane, planes + 3 * plane, planes + 4 * plane);
+    CUDA_TRY(h, cudaGetLastError());
+    O.ox = planes; O.oy = planes + plane; O.oz = planes + 2 * plane; O.iu = planes + 3 * plane; O.iv = planes + 4 * plane;
+    O.f_off = d_off;
+    if ((rc = omni_alloc(h, &O.param, 6 * (size_t)n_frame + 10))) return rc;
+    if ((rc = omni_alloc(h, &O.rec, (size_t)kOmniRec * n_frame))) return rc;
+    if ((rc = omni_alloc(h, &O.save, (size_t)kOmniSave * n_frame))) return rc;
+    if ((rc = omni_alloc(h, &O.tot, kOmniRec))) return rc;
+    if ((rc = omni_alloc(h, &O.norm_part, 2 * (size_t)O.n_blocks_upd))) return rc;
+    if ((rc = omni_alloc(h, &O.st, 1))) return rc;
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    cudaFree(d_obj);
+    cudaFree(d_img);
+    h->omni_have = true;
+    h->omni_have_params = false;
+    return MCCBA_OK;
+}
+
+int mccba_omni_set_parameters(mccba_handle h, int64_t n, const double* params)
+{
+    if (!h) return MCCBA_ERR_ARG;
+    if (!h->omni_have) return fail(h, MCCBA_ERR_STATE, "omni_set_parameters before omni_set_observations");
+    if (!params || n != 6 * (int64_t)h->O.n_frame + 10) return fail(h, MCCBA_ERR_ARG, "omni_set_parameters: expected %lld doubles", (long long)(6 * (int64_t)h->O.n_frame + 10));
+    CUDA_TRY(h, cudaSetDevice(h->opts.device));
+    CUDA_TRY(h, cudaMemcpyAsync(h->O.param, params, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    h->omni_have_params = true;
+    return MCCBA_OK;
+}
+
+int mccba_omni_get_parameters(mccba_handle h, int64_t n, double* params)
+{
+    if (!h) return MCCBA_ERR_ARG;
+    if (!h->omni_have_params) return fail(h, MCCBA_ERR_STATE, "omni_get_parameters before omni_set_parameters");
+    if (!params || n != 6 * (int64_t)h->O.n_frame + 10) return fail(h, MCCBA_ERR_ARG, "omni_get_parameters: wrong size");
+    CUDA_TRY(h, cudaSetDevice(h->opts.device));
+    CUDA_TRY(h, cudaMemcpyAsync(params, h->O.param, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return MCCBA_OK;
+}
+
+int mccba_omni_solve(mccba_handle h, int flags, int crit_type, int max_count, double epsilon, mccba_report* rep)
+{
+    if (!h) return MCCBA_ERR_ARG;
+    if (!h->omni_have_params) return fail(h, MCCBA_ERR_STATE, "omni_solve before omni_set_parameters");
+    if (crit_type < 1 || crit_type > 3 || max_count < 0) return fail(h, MCCBA_ERR_ARG, "omni_solve: bad criteria");
+    CUDA_TRY(h, cudaSetDevice(h->opts.device));
+    OmniProblem& O = h->O;
+    cudaStream_t s = h->stream;
+    int rc;
+    CUDA_TRY(h, cudaEventRecord(h->ev0, s));
+    omni_init_state_kernel<<<1, 1, 0, s>>>(O.st, flags, crit_type, max_count, epsilon);
+    if (h->opts.use_graph && !h->omni_graph) {
+        cudaGraph_t g = nullptr;
+        CUDA_TRY(h, cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed));
+        rc = omni_enqueue_iteration(h);
+        cudaError_t ce = cudaStreamEndCapture(s, &g);
+        if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+        if (ce != cudaSuccess) return fail(h, MCCBA_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(ce));
+        ce = cudaGraphInstantiate(&h->omni_graph, g, 0);
+        cudaGraphDestroy(g);
+        if (ce != cudaSuccess) return fail(h, MCCBA_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(ce));
+    }
+    const bool exact = crit_type == 1;
+    const int64_t max_launches = (crit_type & 1) ? max_count : 200000;
+    int64_t launched = 0;
+    int slot = 0;
+    cudaEvent_t evs[2];
+    cudaEventCreateWithFlags(&evs[0], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&evs[1], cudaEventDisableTiming);
+    bool pending[2] = {false, false}, stop = false;
+    while (launched < max_launches && !stop) {
+        const int nl = (int)std::min<int64_t>(exact ? max_launches : 8, max_launches - launched);
+        for (int i = 0; i < nl; ++i) {
+            if (h->opts.use_graph) CUDA_TRY(h, cudaGraphLaunch(h->omni_graph, s));
+            else if ((rc = omni_enqueue_iteration(h))) return rc;
+        }
+        launched += nl;
+        if (exact) break;
+        CUDA_TRY(h, cudaMemcpyAsync(h->h_done + slot, &O.st->done, sizeof(int), cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(h, cudaEventRecord(evs[slot], s));
+        pending[slot] = true;
+        const int prev = slot ^ 1;
+        if (pending[prev]) {
+            CUDA_TRY(h, cudaEventSynchronize(evs[prev]));
+            if (h->h_done[prev]) stop = true;
+            pending[prev] = false;
+        }
+        slot ^= 1;
+    }
+    cudaEventDestroy(evs[0]);
+    cudaEventDestroy(evs[1]);
+    // final cost at the returned parameters (estimateUncertainties' rms, src/omnidir.cpp:1794-1802)
+    omni_frame_kernel<<<O.n_frame, kOmniThreads, 0, s>>>(O, 1);
+    omni_reduce_kernel<<<kOmniRec, 256, 0, s>>>(O, 1);
+    OmniState hs;
+    double cost = 0;
+    CUDA_TRY(h, cudaMemcpyAsync(&hs, O.st, sizeof(OmniState), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(h, cudaMemcpyAsync(&cost, O.tot + 77, sizeof(double), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(h, cudaEventRecord(h->ev1, s));
+    CUDA_TRY(h, cudaStreamSynchronize(s));
+    CUDA_TRY(h, cudaGetLastError());
+    float ms = 0;
+    cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+    if (rep) {
+        memset(rep, 0, sizeof(*rep));
+        rep->iterations = hs.iter; rep->accepted = hs.iter; rep->status = hs.status;
+        rep->graph_launches = (int)launched; rep->kernel_launches = (int)launched * 5 + 3;
+        rep->change = hs.change; rep->cost = cost; rep->lambda = hs.epsilon; rep->device_ms = ms;
+    }
+    if (hs.status) return fail(h, MCCBA_ERR_NUMERIC, "omni_solve: numeric failure at iteration %d", hs.iter);
+    if (!hs.done) return fail(h, MCCBA_ERR_NUMERIC, "omni_solve: launch budget exhausted (iter %d)", hs.iter);
+    return MCCBA_OK;
+}
+
+int mccba_omni_gram(mccba_handle h, double* gram /* n_frame x 17 x 17 */, double* cost)
+{
+    if (!h) return MCCBA_ERR_ARG;
+    if (!h->omni_have_params) return fail(h, MCCBA_ERR_STATE, "omni_gram before omni_set_parameters");
+    CUDA_TRY(h, cudaSetDevice(h->opts.device));
+    OmniProblem O = h->O;
+    double* d = nullptr;
+    const size_t cnt = (size_t)O.n_frame * 289;
+    if (gram) { CUDA_TRY(h, cudaMalloc((void**)&d, sizeof(double) * cnt)); O.dump = d; }
+    omni_frame_kernel<<<O.n_frame, kOmniThreads, 0, h->stream>>>(O, 1);
+    omni_reduce_kernel<<<kOmniRec, 256, 0, h->stream>>>(O, 1);
+    if (gram) CUDA_TRY(h, cudaMemcpyAsync(gram, d, sizeof(double) * cnt, cudaMemcpyDeviceToHost, h->stream));
+    if (cost) CUDA_TRY(h, cudaMemcpyAsync(cost, O.tot + 77, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    CUDA_TRY(h, cudaGetLastError());
+    if (d) cudaFree(d);
     return MCCBA_OK;
 }
 

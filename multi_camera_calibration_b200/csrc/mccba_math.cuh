@@ -190,6 +190,79 @@ MC_HD void omnidir_point(const CamParams& c, const double* Xc, double* uv, doubl
     }
 }
 
+// Mei model with the intrinsic block: A = d(u,v)/dXc (2x3) and Jin = d(u,v)/d(fx, fy, s, cx, cy, xi, k1, k2, p1, p2)
+// (2x10, the parameter order of omnidir::internal::encodeParameters, src/omnidir.cpp:1559-1567; same order as
+// Jacobian columns 6..15, src/omnidir.cpp:65-73, 209-241).
+MC_HD void omnidir_point_full(const CamParams& c, const double* Xc, double* uv, double* A, double* Jin)
+{
+    const double n2 = Xc[0] * Xc[0] + Xc[1] * Xc[1] + Xc[2] * Xc[2];
+    const double rn = 1.0 / sqrt(n2);
+    const double s0 = Xc[0] * rn, s1 = Xc[1] * rn, s2 = Xc[2] * rn;
+    const double id = 1.0 / (s2 + c.xi);
+    const double x = s0 * id, y = s1 * id;
+    const double r2 = x * x + y * y, r4 = r2 * r2;
+    const double rad = 1.0 + r2 * (c.k1 + r2 * c.k2);
+    const double xy2 = 2.0 * x * y;
+    const double xd = x * rad + c.p1 * xy2 + c.p2 * (r2 + 2.0 * x * x);
+    const double yd = y * rad + c.p1 * (r2 + 2.0 * y * y) + c.p2 * xy2;
+    uv[0] = c.fx * xd + c.skew * yd + c.cx;
+    uv[1] = c.fy * yd + c.cy;
+    const double dd2 = 2.0 * (c.k1 + 2.0 * c.k2 * r2);
+    const double t = 2.0 * (c.p1 * x + c.p2 * y);
+    const double dxdx = rad + dd2 * x * x + 2.0 * c.p1 * y + 6.0 * c.p2 * x;
+    const double dxdy = dd2 * x * y + t;
+    const double dydy = rad + dd2 * y * y + 6.0 * c.p1 * y + 2.0 * c.p2 * x;
+    const double m00 = c.fx * dxdx + c.skew * dxdy, m01 = c.fx * dxdy + c.skew * dydy;
+    const double m10 = c.fy * dxdy, m11 = c.fy * dydy;
+    const double k = rn * id;
+    {
+        const double g0 = m00, g1 = m01, g2 = -(m00 * x + m01 * y);
+        const double d = g0 * s0 + g1 * s1 + g2 * s2;
+        A[0] = k * (g0 - d * s0); A[1] = k * (g1 - d * s1); A[2] = k * (g2 - d * s2);
+    }
+    {
+        const double g0 = m10, g1 = m11, g2 = -(m10 * x + m11 * y);
+        const double d = g0 * s0 + g1 * s1 + g2 * s2;
+        A[3] = k * (g0 - d * s0); A[4] = k * (g1 - d * s1); A[5] = k * (g2 - d * s2);
+    }
+    // intrinsic columns
+    const double dxi0 = -x * id, dxi1 = -y * id;          // d(x,y)/dxi = -Xs.xy / (Xs.z + xi)^2
+    Jin[0] = xd;  Jin[10] = 0.0;                          // fx
+    Jin[1] = 0.0; Jin[11] = yd;                           // fy
+    Jin[2] = yd;  Jin[12] = 0.0;                          // s
+    Jin[3] = 1.0; Jin[13] = 0.0;                          // cx
+    Jin[4] = 0.0; Jin[14] = 1.0;                          // cy
+    Jin[5] = m00 * dxi0 + m01 * dxi1; Jin[15] = m10 * dxi0 + m11 * dxi1;   // xi
+    const double kx[4] = {x * r2, x * r4, xy2, r2 + 2.0 * x * x};          // d xd / d(k1,k2,p1,p2)
+    const double ky[4] = {y * r2, y * r4, r2 + 2.0 * y * y, xy2};          // d yd / d(k1,k2,p1,p2)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        Jin[6 + j] = c.fx * kx[j] + c.skew * ky[j];
+        Jin[16 + j] = c.fy * ky[j];
+    }
+}
+
+// J_l(om): left Jacobian of SO(3), psi = J_l(om) d_om (row-major 3x3).
+MC_HD void left_jacobian(const double* om, double* J)
+{
+    const double x = om[0], y = om[1], z = om[2];
+    const double th2 = x * x + y * y + z * z;
+    double B, C;
+    if (th2 < 0.0625) {
+        B = 0.5 - th2 * (1.0 / 24 - th2 * (1.0 / 720 - th2 * (1.0 / 40320 - th2 * (1.0 / 3628800))));
+        C = 1.0 / 6 - th2 * (1.0 / 120 - th2 * (1.0 / 5040 - th2 * (1.0 / 362880 - th2 * (1.0 / 39916800))));
+    } else {
+        const double th = sqrt(th2);
+        const double sh = sin(0.5 * th);
+        B = 2.0 * sh * sh / th2;
+        C = (th - sin(th)) / (th2 * th);
+    }
+    // I + B K + C K^2
+    J[0] = 1.0 - C * (y * y + z * z); J[1] = C * x * y - B * z;         J[2] = C * x * z + B * y;
+    J[3] = C * x * y + B * z;         J[4] = 1.0 - C * (x * x + z * z); J[5] = C * y * z - B * x;
+    J[6] = C * x * z - B * y;         J[7] = C * y * z + B * x;         J[8] = 1.0 - C * (x * x + y * y);
+}
+
 // One corner: Xc = R3 X + T3, residual, 2x6 Jacobian wrt the left perturbation (phi3, tau3) of the composed pose,
 // accumulated into acc[28] = upper triangle of sum J^T J (21) | sum J^T e (6) | sum |e|^2.
 // Replaces one pass of the per-corner loops inside cv::projectPoints / omnidir::projectPoints plus the rows of

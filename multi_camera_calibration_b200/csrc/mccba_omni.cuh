@@ -1,0 +1,356 @@
+// mccba_omni.cuh -- the cv::omnidir::calibrate optimisation loop (single Mei camera: per-frame poses + 10 intrinsics)
+// on the device.  Replaces src/omnidir.cpp:1119-1147 (loop), :851-935 (internal::computeJacobian: arrow-structured
+// J^T J / J^T E, flag masking, (JTJ + eps)^-1), :2031-2076 (flags2idx), :2138-2153 (fillFixed) and the RMS of
+// :1794-1802.  The reference forms a dense (6n+10)^2 matrix and inverts it; here the per-frame 6x6 blocks are
+// eliminated and the "+ eps on EVERY element" term (a rank-one eps 11^T) is carried as one extra bordered unknown, so
+// the iterates are the reference's to rounding (this path works in the reference's additive Rodrigues coordinates,
+// because the eps 11^T term is not invariant under a change of coordinates).
+//
+//   omni_frame_kernel    CTA per frame: rows a = [J(16) | e] of every corner -> shared memory; 153 threads accumulate
+//                        the 17x17 Gram matrix sum a^T a (= all arrow blocks + gradient + cost of the frame); then the
+//                        frame's 6x6 Cholesky, Y = L^-1 H_pI, z_g, z_u and its Schur record
+//   omni_reduce_kernel   fixed-order sums of the 78 record entries over the frames (no atomics)
+//   omni_solve_kernel    bordered (m+1) x (m+1) system, Gaussian elimination with partial pivoting (m <= 10)
+//   omni_update_kernel   back-substitution per frame, G = alpha * x, parameter update, norm partials
+//   omni_decide_kernel   change = |G| / |param_old| (:1141), iteration count, termination (:1125-1127)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "mccba_math.cuh"
+
+namespace mccba {
+
+constexpr int kOmniThreads = 160;   // >= 153 Gram entries
+constexpr int kOmniChunk = 64;      // corners staged per pass (128 rows x 17 doubles = 17 KB)
+constexpr int kOmniRec = 78;        // 55 (S upper) + 10 (rg) + 10 (ru) + d, c, cost
+constexpr int kOmniSave = 93;       // 21 (U) + 6 (z_g) + 6 (z_u) + 60 (Y)
+
+struct OmniState {
+    int flags, crit_type, max_count, iter, done, status;
+    double eps_crit, change, alpha, epsilon;
+    double x_intr[10];   // solution for the intrinsic block (0 at fixed parameters)
+    double t;            // bordered unknown sqrt(eps) 1^T x
+};
+
+struct OmniProblem {
+    int n_frame;
+    int n_blocks_upd;
+    int64_t n_pts;
+    const float *ox, *oy, *oz, *iu, *iv;
+    const int* f_off;     // n_frame + 1
+    double* param;        // 6 n + 10
+    double* rec;          // kOmniRec x n_frame (SoA)
+    double* save;         // kOmniSave x n_frame (SoA)
+    double* tot;          // kOmniRec
+    double* norm_part;    // 2 x n_blocks_upd
+    double* dump;         // optional: n_frame x 289 Gram matrices (tests)
+    OmniState* st;
+};
+
+__device__ __forceinline__ void omni_tri17(int t, int& i, int& j)   // t in [0,153) -> (i <= j) of a 17x17 upper triangle
+{
+    int r = 0, rem = t;
+    while (rem >= 17 - r) { rem -= 17 - r; ++r; }
+    i = r; j = r + rem;
+}
+
+__global__ void __launch_bounds__(kOmniThreads) omni_frame_kernel(OmniProblem P, int forced)
+{
+    __shared__ double rows[2 * kOmniChunk][17];
+    __shared__ double M[17][17];
+    __shared__ double sU[21], szg[6], szu[6], sY[6][10];
+    const OmniState* st = P.st;
+    if (!forced && st->done) return;
+    const int f = blockIdx.x, tid = threadIdx.x, n = P.n_frame;
+    const double* par = P.param;
+    CamParams cam;
+    cam.model = kOmnidir; cam.rational = 0;
+    cam.fx = par[6 * n]; cam.fy = par[6 * n + 1]; cam.skew = par[6 * n + 2]; cam.cx = par[6 * n + 3]; cam.cy = par[6 * n + 4];
+    cam.xi = par[6 * n + 5]; cam.k1 = par[6 * n + 6]; cam.k2 = par[6 * n + 7]; cam.p1 = par[6 * n + 8]; cam.p2 = par[6 * n + 9];
+    cam.k3 = cam.k4 = cam.k5 = cam.k6 = 0.0;
+    const double om[3] = {par[6 * f], par[6 * f + 1], par[6 * f + 2]};
+    const double T[3] = {par[6 * f + 3], par[6 * f + 4], par[6 * f + 5]};
+    double R[9], Jl[9];
+    rodrigues(om, R);
+    left_jacobian(om, Jl);
+    int gi = 0, gj = 0;
+    if (tid < 153) omni_tri17(tid, gi, gj);
+    double acc = 0.0;
+    const int b = P.f_off[f], e = P.f_off[f + 1];
+    for (int c0 = b; c0 < e; c0 += kOmniChunk) {
+        const int nc = min(kOmniChunk, e - c0);
+        if (tid < nc) {
+            const int i = c0 + tid;
+            const double X[3] = {(double)P.ox[i], (double)P.oy[i], (double)P.oz[i]};
+            double Q[3], Xc[3], uv[2], A[6], Jin[20];
+            mat3_vec(R, X, Q);
+            Xc[0] = Q[0] + T[0]; Xc[1] = Q[1] + T[1]; Xc[2] = Q[2] + T[2];
+            omnidir_point_full(cam, Xc, uv, A, Jin);
+            const double err[2] = {(double)P.iu[i] - uv[0], (double)P.iv[i] - uv[1]};
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                double jphi[3];
+                cross3(Q, A + 3 * r, jphi);
+                double* row = rows[2 * tid + r];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) row[k] = jphi[0] * Jl[k] + jphi[1] * Jl[3 + k] + jphi[2] * Jl[6 + k];   // d/d om
+#pragma unroll
+                for (int k = 0; k < 3; ++k) row[3 + k] = A[3 * r + k];
+#pragma unroll
+                for (int k = 0; k < 10; ++k) row[6 + k] = Jin[10 * r + k];
+                row[16] = err[r];
+            }
+        }
+        __syncthreads();
+        if (tid < 153)
+            for (int r = 0; r < 2 * nc; ++r) acc = fma(rows[r][gi], rows[r][gj], acc);
+        __syncthreads();
+    }
+    if (tid < 153) { M[gi][gj] = acc; M[gj][gi] = acc; }
+    __syncthreads();
+    if (P.dump)
+        for (int t = tid; t < 289; t += blockDim.x) P.dump[(int64_t)f * 289 + t] = M[t / 17][t % 17];
+    // per-frame algebra: Cholesky of H_pp, z_g, z_u (thread 0), Y columns (threads 0..9), Schur record
+    int bad = 0;
+    if (tid == 0) {
+        double U[21], zg[6], zu[6];
+#pragma unroll
+        for (int i = 0; i < 6; ++i)
+#pragma unroll
+            for (int j = i; j < 6; ++j) U[tri6(i, j)] = M[i][j];
+        if (!chol6_packed(U)) bad = 1;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) { zg[i] = M[i][16]; zu[i] = 1.0; }
+        chol6_forward(U, zg, 1);
+        chol6_forward(U, zu, 1);
+#pragma unroll
+        for (int i = 0; i < 21; ++i) sU[i] = U[i];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) { szg[i] = zg[i]; szu[i] = zu[i]; }
+    }
+    __syncthreads();
+    if (tid < 10) {
+        double U[21], col[6];
+#pragma unroll
+        for (int i = 0; i < 21; ++i) U[i] = sU[i];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) col[i] = M[i][6 + tid];
+        chol6_forward(U, col, 1);
+#pragma unroll
+        for (int i = 0; i < 6; ++i) sY[i][tid] = col[i];
+    }
+    __syncthreads();
+    const int64_t nf = n;
+    if (tid < 55) {   // S record: upper triangle of H_II - Y^T Y
+        int a = 0, rem = tid;
+        while (rem >= 10 - a) { rem -= 10 - a; ++a; }
+        const int c = a + rem;
+        double s = M[6 + a][6 + c];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) s -= sY[k][a] * sY[k][c];
+        P.rec[(int64_t)tid * nf + f] = s;
+    } else if (tid < 65) {
+        const int a = tid - 55;
+        double s = M[6 + a][16];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) s -= sY[k][a] * szg[k];
+        P.rec[(int64_t)tid * nf + f] = s;
+    } else if (tid < 75) {
+        const int a = tid - 65;
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) s -= sY[k][a] * szu[k];
+        P.rec[(int64_t)tid * nf + f] = s;
+    } else if (tid == 75) {
+        double d = 0, c = 0;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) { d += szu[k] * szu[k]; c += szu[k] * szg[k]; }
+        P.rec[(int64_t)75 * nf + f] = d;
+        P.rec[(int64_t)76 * nf + f] = c;
+        P.rec[(int64_t)77 * nf + f] = M[16][16];
+    }
+    // saved factors for the back-substitution
+    for (int t = tid; t < kOmniSave; t += blockDim.x) {
+        double v;
+        if (t < 21) v = sU[t];
+        else if (t < 27) v = szg[t - 21];
+        else if (t < 33) v = szu[t - 27];
+        else v = sY[(t - 33) / 10][(t - 33) % 10];
+        P.save[(int64_t)t * nf + f] = v;
+    }
+    if (tid == 0 && bad) P.st->status = 4;   // benign race: every writer stores the same value
+}
+
+// one block per record entry: fixed-order sum over the frames
+__global__ void __launch_bounds__(256) omni_reduce_kernel(OmniProblem P, int forced)
+{
+    if (!forced && P.st->done) return;
+    __shared__ double sm[8];
+    const int v = blockIdx.x, n = P.n_frame;
+    const double* src = P.rec + (int64_t)v * n;
+    double s = 0.0;
+    for (int f = threadIdx.x; f < n; f += blockDim.x) s += src[f];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += sm[w];
+        P.tot[v] = t;
+    }
+}
+
+// src/omnidir.cpp:2031-2076, literal >= / subtract cascade; idx[a] = 1 if intrinsic a is free
+__device__ __forceinline__ void omni_flags2free(int flags, int* fr)
+{
+    for (int a = 0; a < 10; ++a) fr[a] = 1;
+    int f = flags;
+    if (f >= 256) { fr[3] = 0; fr[4] = 0; f -= 256; }
+    if (f >= 128) { fr[0] = 0; fr[1] = 0; f -= 128; }
+    if (f >= 64) { fr[5] = 0; f -= 64; }
+    if (f >= 32) { fr[9] = 0; f -= 32; }
+    if (f >= 16) { fr[8] = 0; f -= 16; }
+    if (f >= 8) { fr[7] = 0; f -= 8; }
+    if (f >= 4) { fr[6] = 0; f -= 4; }
+    if (f >= 2) { fr[2] = 0; }
+}
+
+__global__ void omni_solve_kernel(OmniProblem P)
+{
+    if (threadIdx.x != 0) return;
+    OmniState* st = P.st;
+    if (st->done) return;
+    // schedule of this iteration (src/omnidir.cpp:1129-1131)
+    st->alpha = 1.0 - pow(1.0 - 0.01, (double)st->iter + 1.0);
+    st->epsilon = 0.01 * pow(0.9, (double)st->iter / 10.0);
+    if (st->status) { st->done = 1; return; }
+    int fr[10], map[10], m = 0;
+    omni_flags2free(st->flags, fr);
+    for (int a = 0; a < 10; ++a)
+        if (fr[a]) map[m++] = a;
+    const double* tot = P.tot;
+    const double se = sqrt(st->epsilon);
+    const int Q = m + 1;
+    double B[121], rhs[11];
+    auto Sfull = [&](int a, int c) {   // upper-triangle record index of (a, c)
+        if (a > c) { const int t = a; a = c; c = t; }
+        int idx = 0;
+        for (int r = 0; r < a; ++r) idx += 10 - r;
+        return tot[idx + (c - a)];
+    };
+    for (int a = 0; a < m; ++a) {
+        for (int c = 0; c < m; ++c) B[a * Q + c] = Sfull(map[a], map[c]);
+        const double ru = 1.0 + tot[65 + map[a]];
+        B[a * Q + m] = se * ru;
+        B[m * Q + a] = se * ru;
+        rhs[a] = tot[55 + map[a]];
+    }
+    B[m * Q + m] = -(1.0 + st->epsilon * tot[75]);
+    rhs[m] = -se * tot[76];
+    int fail = 0;
+    for (int k = 0; k < Q && !fail; ++k) {
+        int piv = k;
+        for (int i = k + 1; i < Q; ++i)
+            if (fabs(B[i * Q + k]) > fabs(B[piv * Q + k])) piv = i;
+        if (B[piv * Q + k] == 0.0 || !isfinite(B[piv * Q + k])) { fail = 1; break; }
+        if (piv != k) {
+            for (int j = 0; j < Q; ++j) { const double t = B[k * Q + j]; B[k * Q + j] = B[piv * Q + j]; B[piv * Q + j] = t; }
+            const double t = rhs[k]; rhs[k] = rhs[piv]; rhs[piv] = t;
+        }
+        for (int i = k + 1; i < Q; ++i) {
+            const double fct = B[i * Q + k] / B[k * Q + k];
+            for (int j = k; j < Q; ++j) B[i * Q + j] -= fct * B[k * Q + j];
+            rhs[i] -= fct * rhs[k];
+        }
+    }
+    if (fail) { st->status = 4; st->done = 1; return; }
+    for (int i = Q - 1; i >= 0; --i) {
+        double s = rhs[i];
+        for (int j = i + 1; j < Q; ++j) s -= B[i * Q + j] * rhs[j];
+        rhs[i] = s / B[i * Q + i];
+    }
+    for (int a = 0; a < 10; ++a) st->x_intr[a] = 0.0;
+    for (int a = 0; a < m; ++a) st->x_intr[map[a]] = rhs[a];
+    st->t = rhs[m];
+}
+
+__global__ void __launch_bounds__(128) omni_update_kernel(OmniProblem P)
+{
+    const OmniState* st = P.st;
+    if (st->done) return;
+    const int n = P.n_frame;
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    const double alpha = st->alpha, set = sqrt(st->epsilon) * st->t;
+    double g2 = 0.0, p2 = 0.0;
+    if (f < n) {
+        const int64_t nf = n;
+        double U[21], r[6];
+#pragma unroll
+        for (int k = 0; k < 21; ++k) U[k] = P.save[(int64_t)k * nf + f];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            double s = P.save[(int64_t)(21 + i) * nf + f] - set * P.save[(int64_t)(27 + i) * nf + f];
+#pragma unroll
+            for (int a = 0; a < 10; ++a) s -= P.save[(int64_t)(33 + i * 10 + a) * nf + f] * st->x_intr[a];
+            r[i] = s;
+        }
+        chol6_backward(U, r);
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            const double old = P.param[6 * (int64_t)f + i], G = alpha * r[i];
+            g2 += G * G; p2 += old * old;
+            P.param[6 * (int64_t)f + i] = old + G;
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x < 10) {   // intrinsic block (fixed parameters get G = 0, fillFixed)
+        const int a = threadIdx.x;
+        const double old = P.param[6 * (int64_t)n + a], G = alpha * st->x_intr[a];
+        g2 += G * G; p2 += old * old;
+        P.param[6 * (int64_t)n + a] = old + G;
+    }
+    __shared__ double sr[2][4];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { g2 += __shfl_xor_sync(0xffffffffu, g2, o); p2 += __shfl_xor_sync(0xffffffffu, p2, o); }
+    if ((threadIdx.x & 31) == 0) { sr[0][threadIdx.x >> 5] = g2; sr[1][threadIdx.x >> 5] = p2; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        P.norm_part[blockIdx.x] = sr[0][0] + sr[0][1] + sr[0][2] + sr[0][3];
+        P.norm_part[P.n_blocks_upd + blockIdx.x] = sr[1][0] + sr[1][1] + sr[1][2] + sr[1][3];
+    }
+}
+
+__global__ void __launch_bounds__(256) omni_decide_kernel(OmniProblem P)
+{
+    OmniState* st = P.st;
+    if (st->done) return;
+    __shared__ double sm[2][8];
+    double a = 0.0, b = 0.0;
+    for (int k = threadIdx.x; k < P.n_blocks_upd; k += blockDim.x) { a += P.norm_part[k]; b += P.norm_part[P.n_blocks_upd + k]; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+    if ((threadIdx.x & 31) == 0) { sm[0][threadIdx.x >> 5] = a; sm[1][threadIdx.x >> 5] = b; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double g2 = 0, p2 = 0;
+        for (int w = 0; w < 8; ++w) { g2 += sm[0][w]; p2 += sm[1][w]; }
+        st->change = sqrt(g2) / sqrt(p2);   // src/omnidir.cpp:1141: the norm of the parameters BEFORE the update
+        st->iter += 1;
+        const int t = st->crit_type;
+        if ((t == 1 && st->iter >= st->max_count) || (t == 2 && st->change <= st->eps_crit) ||
+            (t == 3 && (st->change <= st->eps_crit || st->iter >= st->max_count)))
+            st->done = 1;
+    }
+}
+
+__global__ void omni_init_state_kernel(OmniState* st, int flags, int crit_type, int max_count, double eps)
+{
+    st->flags = flags; st->crit_type = crit_type; st->max_count = max_count; st->iter = 0; st->status = 0;
+    st->eps_crit = eps; st->change = 1.0; st->alpha = 0; st->epsilon = 0; st->t = 0;
+    for (int a = 0; a < 10; ++a) st->x_intr[a] = 0;
+    // loop-top test of src/omnidir.cpp:1125-1127 with iter = 0, change = 1
+    st->done = (crit_type == 1 && 0 >= max_count) || (crit_type == 3 && 0 >= max_count) || (crit_type == 2 && 1.0 <= eps) ? 1 : 0;
+}
+
+}  // namespace mccba

@@ -111,7 +111,8 @@ def make_cameras(n_cam, seed, models=None, ndist=5):
 
 
 def make_rig(n_cam=8, n_frame=1000, seed=1002, models=None, views_per_frame=2, noise_px=0.3, init_rot=0.02,
-             init_trans=10.0, ndist=5, frame_stream=0, cameras=None, perturb_cameras=True):
+             init_trans=10.0, ndist=5, frame_stream=0, cameras=None, perturb_cameras=True, board_distance=(1200.0, 2000.0),
+             tilt_max_deg=30.0, lateral=120.0, min_depth=300.0):
     """Full rig in the C-ABI layout.  frame_stream selects an independent set of frames for the same cameras (used to
     give every rank its own shard in the weak-scaling benchmark)."""
     cams = cameras if cameras is not None else make_cameras(n_cam, seed, models, ndist)
@@ -139,25 +140,25 @@ def make_rig(n_cam=8, n_frame=1000, seed=1002, models=None, views_per_frame=2, n
         up = np.tile(np.array([0.0, 1.0, 0.0]), (m, 1))
         ex = np.cross(up, bis); ex /= np.linalg.norm(ex, axis=1, keepdims=True)
         ey = np.cross(bis, ex)
-        dist = rng.uniform(1200, 2000, m)
-        lat = rng.uniform(-120, 120, (m, 2))
+        dist = rng.uniform(board_distance[0], board_distance[1], m)
+        lat = rng.uniform(-lateral, lateral, (m, 2))
         pos = mid + bis * dist[:, None] + ex * lat[:, :1] + ey * lat[:, 1:]
         ax = rng.standard_normal((m, 3)); ax /= np.linalg.norm(ax, axis=1, keepdims=True)
-        tilt = rodrigues_batch(ax * rng.uniform(0, np.deg2rad(30), m)[:, None])
+        tilt = rodrigues_batch(ax * rng.uniform(0, np.deg2rad(tilt_max_deg), m)[:, None])
         inpl = rodrigues_batch(np.stack([np.zeros(m), np.zeros(m), rng.uniform(0, 2 * np.pi, m)], axis=1))
         # board z axis facing back towards the cameras: base orientation = frame of the bisector rotated by pi about x
         base = np.stack([ex, -ey, -bis], axis=2)                       # columns: board x, y, z in the reference frame
         Rw = base @ tilt @ inpl
         tw = pos - np.einsum("fij,j->fi", Rw, Bc)
         Xw = np.einsum("fij,nj->fni", Rw, B) + tw[:, None, :]          # (m, nB, 3)
-        ok = (np.linalg.norm(tw, axis=1) > 300) & (np.linalg.norm(tw, axis=1) < 3000)
+        ok = (np.linalg.norm(tw, axis=1) > min_depth) & (np.linalg.norm(tw, axis=1) < 3000)
         for v in range(V):
             c = vc[:, v]
             Xc = np.einsum("fij,fnj->fni", cR[c], Xw) + ct[c][:, None, :]
             uv = project(cams["cam_model"][c][:, None], cams["cam_K5"][c][:, None, :], cams["cam_dist8"][c][:, None, :],
                          cams["cam_xi"][c][:, None], Xc)
             T3 = np.einsum("fij,fj->fi", cR[c], tw) + ct[c]
-            ok &= (Xc[..., 2].min(axis=1) > 300) & (np.linalg.norm(T3, axis=1) < 3000)
+            ok &= (Xc[..., 2].min(axis=1) > 0.5 * min_depth) & (np.linalg.norm(T3, axis=1) < 3000)
             ok &= (uv[..., 0].min(axis=1) > MARGIN) & (uv[..., 0].max(axis=1) < IMG_W - MARGIN)
             ok &= (uv[..., 1].min(axis=1) > MARGIN) & (uv[..., 1].max(axis=1) < IMG_H - MARGIN)
         sel = todo[ok]
@@ -216,7 +217,9 @@ def make_rig(n_cam=8, n_frame=1000, seed=1002, models=None, views_per_frame=2, n
 # BASELINE.json configs
 CONFIGS = {
     2: dict(n_cam=8, n_frame=1000, seed=1002),
-    3: dict(n_cam=1, n_frame=5000, seed=1003, models="omni"),
+    # single Mei camera: boards close and strongly tilted, otherwise focal length and xi are not separately observable
+    3: dict(n_cam=1, n_frame=5000, seed=1003, models="omni", board_distance=(250.0, 600.0), tilt_max_deg=50.0,
+            lateral=250.0, min_depth=150.0),
     4: dict(n_cam=16, n_frame=10000, seed=1004, models="mixed"),
     5: dict(n_cam=64, n_frame=100000, seed=1005),
 }

@@ -1012,7 +1012,7 @@ static double omni_build(int n, const int64_t *off, const double *obj, const dou
 
 /* Solve (JTJ_sub + eps 11^T) G = JTE_sub for the arrow-structured JTJ (src/omnidir.cpp:918-934, 1135-1137).
  * dense != 0: form the dense (6n+10)^2 matrix and invert it literally (toy sizes only);
- * dense == 0: Schur complement on the intrinsic block + Sherman-Morrison for the rank-one eps 11^T term.
+ * dense == 0: Schur complement on the intrinsic block, the rank-one eps 11^T term carried as one extra bordered unknown.
  * G is returned zero-filled at fixed parameters (fillFixed). */
 static int omni_solve_step(int n, const double *Hii, const double *HiI, const double *HII, const double *gi,
                            const double *gI, int flags, double epsilon, int dense, double *G)
@@ -1072,67 +1072,107 @@ static int omni_solve_step(int n, const double *Hii, const double *HiI, const do
         }
         free(A); free(b);
     } else {
-        /* two right-hand sides through the Schur factorisation: g (JTE) and u (all ones) */
-        double S[100], rhs_g[10], rhs_u[10];
+        /* JTJ + eps 11^T is dense, but [H, sqrt(eps) u; sqrt(eps) u^T, -1] [x; t] = [g; 0] (t = sqrt(eps) u^T x) is an
+         * arrow matrix again with ONE more shared unknown.  Eliminating the per-frame 6x6 blocks leaves a symmetric
+         * indefinite (m+1) x (m+1) system, solved by Gaussian elimination with partial pivoting.  Unlike
+         * Sherman-Morrison this does not need H itself to be invertible (it is singular when focal length and xi
+         * are not separately observable -- the case the reference's "in case JTJ is singular" comment is about). */
+        double S[121], rg[11], ru[10], dsum = 0, csum = 0;
+        const double se = sqrt(epsilon);
         for (int a = 0; a < m; ++a) {
             for (int b = 0; b < m; ++b) S[a * m + b] = HII[map[a] * 10 + map[b]];
-            rhs_g[a] = gI[map[a]];
-            rhs_u[a] = 1;
+            rg[a] = gI[map[a]];
+            ru[a] = 1;
         }
         double *L = (double *)malloc(sizeof(double) * 36 * (size_t)n);
+        double *zg = (double *)malloc(sizeof(double) * 6 * (size_t)n), *zu = (double *)malloc(sizeof(double) * 6 * (size_t)n);
+        double *Y = (double *)malloc(sizeof(double) * 60 * (size_t)n); /* L^-1 H_pI, 6 x m */
         for (int i = 0; i < n && !rc; ++i) {
             double *Li = L + 36 * (size_t)i;
             memcpy(Li, Hii + 36 * (size_t)i, sizeof(double) * 36);
             if (chol_lower(Li, 6)) { rc = 1000 + i; break; }
-            double hg[6], hu[6] = {1, 1, 1, 1, 1, 1};
-            memcpy(hg, gi + 6 * (size_t)i, sizeof(hg));
-            chol_solve(Li, 6, hg);
-            chol_solve(Li, 6, hu);
+            double *g6 = zg + 6 * (size_t)i, *u6 = zu + 6 * (size_t)i;
+            for (int a = 0; a < 6; ++a) { g6[a] = gi[6 * (size_t)i + a]; u6[a] = 1; }
+            for (int a = 0; a < 6; ++a) { /* forward substitution only: z = L^-1 b */
+                double sg = g6[a], su = u6[a];
+                for (int k = 0; k < a; ++k) { sg -= Li[a * 6 + k] * g6[k]; su -= Li[a * 6 + k] * u6[k]; }
+                g6[a] = sg / Li[a * 6 + a]; u6[a] = su / Li[a * 6 + a];
+            }
+            double *Yi = Y + 60 * (size_t)i;
             for (int b = 0; b < m; ++b) {
                 double col[6];
                 for (int a = 0; a < 6; ++a) col[a] = HiI[60 * (size_t)i + a * 10 + map[b]];
-                double wg = 0, wu = 0;
-                for (int a = 0; a < 6; ++a) { wg += col[a] * hg[a]; wu += col[a] * hu[a]; }
-                rhs_g[b] -= wg;
-                rhs_u[b] -= wu;
-                chol_solve(Li, 6, col);
-                for (int a2 = 0; a2 < m; ++a2) {
-                    double s = 0;
-                    for (int a = 0; a < 6; ++a) s += HiI[60 * (size_t)i + a * 10 + map[a2]] * col[a];
-                    S[a2 * m + b] -= s;
+                for (int a = 0; a < 6; ++a) {
+                    double sv = col[a];
+                    for (int k = 0; k < a; ++k) sv -= Li[a * 6 + k] * col[k];
+                    col[a] = sv / Li[a * 6 + a];
+                }
+                for (int a = 0; a < 6; ++a) Yi[a * 10 + b] = col[a];
+            }
+            for (int a = 0; a < m; ++a) {
+                double sg = 0, su = 0;
+                for (int k = 0; k < 6; ++k) { sg += Yi[k * 10 + a] * g6[k]; su += Yi[k * 10 + a] * u6[k]; }
+                rg[a] -= sg; ru[a] -= su;
+                for (int b = 0; b < m; ++b) {
+                    double sv = 0;
+                    for (int k = 0; k < 6; ++k) sv += Yi[k * 10 + a] * Yi[k * 10 + b];
+                    S[a * m + b] -= sv;
                 }
             }
-        }
-        double *xg = (double *)calloc((size_t)P, sizeof(double)), *xu = (double *)calloc((size_t)P, sizeof(double));
-        if (!rc && m > 0) {
-            if (chol_lower(S, m)) rc = 2;
-            else { chol_solve(S, m, rhs_g); chol_solve(S, m, rhs_u); }
+            for (int k = 0; k < 6; ++k) { dsum += u6[k] * u6[k]; csum += u6[k] * g6[k]; }
         }
         if (!rc) {
-            for (int i = 0; i < n; ++i) {
-                double rg[6], ru[6];
-                for (int a = 0; a < 6; ++a) {
-                    double sg = gi[6 * (size_t)i + a], su = 1;
-                    for (int b = 0; b < m; ++b) {
-                        sg -= HiI[60 * (size_t)i + a * 10 + map[b]] * rhs_g[b];
-                        su -= HiI[60 * (size_t)i + a * 10 + map[b]] * rhs_u[b];
-                    }
-                    rg[a] = sg; ru[a] = su;
-                }
-                chol_solve(L + 36 * (size_t)i, 6, rg);
-                chol_solve(L + 36 * (size_t)i, 6, ru);
-                for (int a = 0; a < 6; ++a) { xg[6 * i + a] = rg[a]; xu[6 * i + a] = ru[a]; }
+            const int Q = m + 1;
+            double B[144], rhs[12];
+            for (int a = 0; a < m; ++a) {
+                for (int b = 0; b < m; ++b) B[a * Q + b] = S[a * m + b];
+                B[a * Q + m] = se * ru[a];
+                B[m * Q + a] = se * ru[a];
+                rhs[a] = rg[a];
             }
-            for (int b = 0; b < m; ++b) { xg[6 * n + map[b]] = rhs_g[b]; xu[6 * n + map[b]] = rhs_u[b]; }
-            /* Sherman-Morrison: (H + eps u u^T)^-1 g = xg - eps xu (u^T xg) / (1 + eps u^T xu), u = ones on free params */
-            double ug = 0, uu = 0;
-            for (int i = 0; i < P; ++i)
-                if (idx[i]) { ug += xg[i]; uu += xu[i]; }
-            double k = epsilon * ug / (1 + epsilon * uu);
-            for (int i = 0; i < P; ++i)
-                if (idx[i]) G[i] = xg[i] - k * xu[i];
+            B[m * Q + m] = -(1 + epsilon * dsum);
+            rhs[m] = -se * csum;
+            for (int k = 0; k < Q && !rc; ++k) {
+                int piv = k;
+                for (int i = k + 1; i < Q; ++i)
+                    if (fabs(B[i * Q + k]) > fabs(B[piv * Q + k])) piv = i;
+                if (B[piv * Q + k] == 0) { rc = 2; break; }
+                if (piv != k) {
+                    for (int j = 0; j < Q; ++j) { double t = B[k * Q + j]; B[k * Q + j] = B[piv * Q + j]; B[piv * Q + j] = t; }
+                    double t = rhs[k]; rhs[k] = rhs[piv]; rhs[piv] = t;
+                }
+                for (int i = k + 1; i < Q; ++i) {
+                    double f = B[i * Q + k] / B[k * Q + k];
+                    for (int j = k; j < Q; ++j) B[i * Q + j] -= f * B[k * Q + j];
+                    rhs[i] -= f * rhs[k];
+                }
+            }
+            if (!rc) {
+                for (int i = Q - 1; i >= 0; --i) {
+                    double sv = rhs[i];
+                    for (int j = i + 1; j < Q; ++j) sv -= B[i * Q + j] * rhs[j];
+                    rhs[i] = sv / B[i * Q + i];
+                }
+                const double t = rhs[m];
+                for (int b = 0; b < m; ++b) G[6 * n + map[b]] = rhs[b];
+                for (int i = 0; i < n; ++i) { /* x_p = L^-T (z_g - Y x_I - sqrt(eps) t z_u) */
+                    const double *Li = L + 36 * (size_t)i, *Yi = Y + 60 * (size_t)i;
+                    double r6[6];
+                    for (int a = 0; a < 6; ++a) {
+                        double sv = zg[6 * (size_t)i + a] - se * t * zu[6 * (size_t)i + a];
+                        for (int b = 0; b < m; ++b) sv -= Yi[a * 10 + b] * rhs[b];
+                        r6[a] = sv;
+                    }
+                    for (int a = 5; a >= 0; --a) {
+                        double sv = r6[a];
+                        for (int k = a + 1; k < 6; ++k) sv -= Li[k * 6 + a] * r6[k];
+                        r6[a] = sv / Li[a * 6 + a];
+                    }
+                    for (int a = 0; a < 6; ++a) G[6 * i + a] = r6[a];
+                }
+            }
         }
-        free(L); free(xg); free(xu);
+        free(L); free(zg); free(zu); free(Y);
     }
     free(idx);
     return rc;

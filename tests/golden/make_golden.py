@@ -95,8 +95,49 @@ def rig_dense():
     np.savez_compressed(os.path.join(OUT, "rig_dense.npz"), **d)
 
 
+
+
+def omni_fixture():
+    """tutorials/data/omni_calib_data.xml (15 frames x 54 points, 1280x960; objectPoints '3d', imagePoints '2f') through
+    the restated omnidir::calibrate loop.  The reference's closed-form initialisation (initializeCalibration) is out of
+    scope, so the start is: intrinsics guess (f=400, centre = image centre, xi=1, D=0) + per-frame PnP on the rays
+    unprojected with that guess.  Object points are rounded to float32 (the GPU path stores 20 B per corner)."""
+    src = "/root/reference/tutorials/data/omni_calib_data.xml"
+    if not os.path.exists(src):
+        print("reference fixture not available, skipping omni_fixture")
+        return
+    fs = cv2.FileStorage(src, cv2.FILE_STORAGE_READ)
+    on, im = fs.getNode("objectPoints"), fs.getNode("imagePoints")
+    objs = [on.at(i).mat().reshape(-1, 3).astype(np.float32).astype(np.float64) for i in range(on.size())]
+    imgs = [im.at(i).mat().reshape(-1, 2).astype(np.float32).astype(np.float64) for i in range(im.size())]
+    n = len(objs)
+    f0, cx, cy, xi = 400.0, 640.0, 480.0, 1.0
+    poses = []
+    for o, p in zip(objs, imgs):
+        xu, yu = (p[:, 0] - cx) / f0, (p[:, 1] - cy) / f0
+        r2 = xu * xu + yu * yu
+        z = (xi + np.sqrt(1 + (1 - xi * xi) * r2)) / (r2 + 1)
+        Xs = np.stack([z * xu, z * yu, z - xi], axis=1)
+        npix = (Xs[:, :2] / Xs[:, 2:3]).reshape(-1, 1, 2)
+        ok, rv, tv = cv2.solvePnP(o.reshape(-1, 1, 3), npix, np.eye(3), None)
+        poses.append(np.concatenate([rv.ravel(), tv.ravel()]))
+    p0 = np.concatenate([np.array(poses).ravel(), [f0, f0, 0.0, cx, cy, xi, 0, 0, 0, 0]])
+    off = np.concatenate([[0], np.cumsum([o.shape[0] for o in objs])]).astype(np.int64)
+    d = dict(off=off, obj=np.concatenate(objs).astype(np.float32), img=np.concatenate(imgs).astype(np.float32), p0=p0)
+    for flags, crit in ((0, (3, 200, 1e-8)), (0, (3, 200, 1e-4)), (2, (1, 60, 0.0))):
+        rec = []
+        p, it, ch = dr.omni_calibrate_loop(objs, imgs, p0, flags, crit[0], crit[1], crit[2], rec)
+        key = "f%d_c%d_%d" % (flags, crit[0], crit[1]) + ("_e4" if crit[2] == 1e-4 else "")
+        d[key + "_params"] = p; d[key + "_iters"] = it; d[key + "_change"] = ch
+        d[key + "_rms"] = dr.omni_rms(objs, imgs, p)
+        d[key + "_iter3"] = rec[2]["params"]
+        print("omni fixture", key, "iters", it, "rms", d[key + "_rms"], "xi", p[6 * n + 5], "f", p[6 * n], p[6 * n + 1])
+    np.savez_compressed(os.path.join(OUT, "omni_fixture.npz"), **d)
+
+
 if __name__ == "__main__":
     primitives()
     omni()
     rig_dense()
+    omni_fixture()
     print("golden fixtures written to", OUT)

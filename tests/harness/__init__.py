@@ -59,3 +59,13 @@ def left_jacobian_inv_apply(om, psi):
     lib().hm_left_jacobian_inv_apply(_p(np.ascontiguousarray(om, dtype=np.float64)),
                                      _p(np.ascontiguousarray(psi, dtype=np.float64)), _p(out))
     return out
+
+
+def omni_project(obj, om, T, K5, xi, D4):
+    obj = np.ascontiguousarray(obj, dtype=np.float64).reshape(-1, 3)
+    n = obj.shape[0]
+    proj = np.zeros((n, 2)); jac = np.zeros((2 * n, 16))
+    lib().hm_omni_project(n, _p(obj), _p(np.ascontiguousarray(om, dtype=np.float64)), _p(np.ascontiguousarray(T, dtype=np.float64)),
+                          _p(np.ascontiguousarray(K5, dtype=np.float64)), C.c_double(float(xi)),
+                          _p(np.ascontiguousarray(D4, dtype=np.float64)), _p(proj), _p(jac))
+    return proj, jac

@@ -161,6 +161,32 @@ int hm_rig_step(int n_cam, int n_frame, int n_edge, const int* edge_cam, const i
     return bad;
 }
 
+// Mei projection of n points with the reference's 2n x 16 Jacobian layout (dom dT df ds dc dxi dkp), built from the
+// product's tangent-space pieces: d/dom = (Q x a) J_l(om).
+void hm_omni_project(int n, const double* obj, const double* om, const double* T, const double* K5, double xi,
+                     const double* D4, double* proj, double* jac16)
+{
+    double d8[8] = {D4[0], D4[1], D4[2], D4[3], 0, 0, 0, 0};
+    CamParams cam = make_cam(kOmnidir, K5, d8, 4, xi);
+    double R[9], Jl[9];
+    rodrigues(om, R);
+    left_jacobian(om, Jl);
+    for (int i = 0; i < n; ++i) {
+        double Q[3], Xc[3], A[6], Jin[20];
+        mat3_vec(R, obj + 3 * i, Q);
+        for (int k = 0; k < 3; ++k) Xc[k] = Q[k] + T[k];
+        omnidir_point_full(cam, Xc, proj + 2 * i, A, Jin);
+        for (int r = 0; r < 2; ++r) {
+            double jphi[3];
+            cross3(Q, A + 3 * r, jphi);
+            double* row = jac16 + (size_t)(2 * i + r) * 16;
+            for (int k = 0; k < 3; ++k) row[k] = jphi[0] * Jl[k] + jphi[1] * Jl[3 + k] + jphi[2] * Jl[6 + k];
+            for (int k = 0; k < 3; ++k) row[3 + k] = A[3 * r + k];
+            for (int k = 0; k < 10; ++k) row[6 + k] = Jin[10 * r + k];
+        }
+    }
+}
+
 void hm_rodrigues(const double* om, double* R) { rodrigues(om, R); }
 void hm_left_jacobian_inv_apply(const double* om, const double* psi, double* out) { left_jacobian_inv_apply(om, psi, out); }
 }
