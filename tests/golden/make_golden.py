@@ -124,7 +124,7 @@ def omni_fixture():
     p0 = np.concatenate([np.array(poses).ravel(), [f0, f0, 0.0, cx, cy, xi, 0, 0, 0, 0]])
     off = np.concatenate([[0], np.cumsum([o.shape[0] for o in objs])]).astype(np.int64)
     d = dict(off=off, obj=np.concatenate(objs).astype(np.float32), img=np.concatenate(imgs).astype(np.float32), p0=p0)
-    for flags, crit in ((0, (3, 200, 1e-8)), (0, (3, 200, 1e-4)), (2, (1, 60, 0.0))):
+    for flags, crit in ((0, (3, 200, 1e-8)), (0, (3, 200, 1e-4)), (2, (3, 300, 1e-8))):
         rec = []
         p, it, ch = dr.omni_calibrate_loop(objs, imgs, p0, flags, crit[0], crit[1], crit[2], rec)
         key = "f%d_c%d_%d" % (flags, crit[0], crit[1]) + ("_e4" if crit[2] == 1e-4 else "")
