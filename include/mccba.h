@@ -179,7 +179,8 @@ int mccba_allreduce_sum(mccba_handle h, double *buf, int n);
  * out[5] resid_jac_accum (diagnostic only -- the events serialise the stream). */
 int mccba_last_kernel_ms(mccba_handle h, double out[6]);
 /* Test hook: solve the dense SPD system S x = g (n x n row-major, lower triangle read) on the device with the loop's
- * own Cholesky code (blocked != 0: the blocked shared-memory version used when it fits; 0: plain column version).
+ * own Cholesky code (blocked: 2 = one-launch tile DAG (default in the loop), 1 = panel/update kernels, 0 = plain
+ * single-CTA column version).
  * The kernel time in ms is left in mccba_last_kernel_ms()[0]. */
 int mccba_debug_solve_dense(mccba_handle h, int n, const double *S, const double *g, double *x, int blocked);
 /* time `reps` back-to-back launches of the residual+Jacobian kernel at the current parameters with CUDA events on

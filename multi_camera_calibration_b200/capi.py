@@ -212,7 +212,7 @@ class Solver:
         n = g.size
         x = np.zeros(n)
         self._check(lib().mccba_debug_solve_dense(self._h, n, _ptr(S, C.c_double), _ptr(g, C.c_double),
-                                                  _ptr(x, C.c_double), int(bool(blocked))))
+                                                  _ptr(x, C.c_double), int(blocked)))
         return x, self.last_kernel_ms()[0]
 
     # ---- single-camera Mei calibration loop (cv::omnidir::calibrate without its closed-form initialisation) --------

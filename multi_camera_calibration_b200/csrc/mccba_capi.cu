@@ -85,7 +85,7 @@ struct mccba_handle_s {
     int cur = 0;                      // host mirror of DevState::cur between calls
     int ar_len = 0;
     int obs_cap = 0;                  // floats per plane per TMA stage of the residual kernel (0: no staging)
-    int k1_grid = 0, k1_smem = 0, k5_smem = 0, k5_blocked = 0, panel_smem = 0, iter_kernels = 5;
+    int k1_grid = 0, k1_smem = 0, k5_smem = 0, k5_blocked = 0, panel_smem = 0, iter_kernels = 5, dag_grid = 0;
     cudaGraphExec_t graph = nullptr;
     int* h_done = nullptr;            // pinned
     DevState* h_state = nullptr;      // pinned
@@ -181,7 +181,12 @@ int enqueue_iteration(mccba_handle h, bool timed)
     }
     if (timed) cudaEventRecord(ev[3], s);
     decide_kernel<<<1, 32, 0, s>>>(P);
-    if (h->k5_blocked && P.ns > 0) {
+    if (h->k5_blocked == 2 && P.ns > 0) {
+        const int ntc = chol_col_tiles(P.ns), ntr = chol_row_tiles(P.ns);
+        CUDA_TRY(h, cudaMemsetAsync(P.dag_flags, 0, sizeof(int) * (size_t)(ntr * ntc + ntc), s));
+        CholDag D{P.ar, P.ns, P.dag_flags, P.rinv, P.dc, &P.st->go, &P.st->chol_fail};
+        chol_dag_kernel<<<h->dag_grid, 256, 0, s>>>(D);
+    } else if (h->k5_blocked == 1 && P.ns > 0) {
         const int ntc = chol_col_tiles(P.ns), ntr = chol_row_tiles(P.ns);
         for (int k = 0; k < ntc; ++k) {
             chol_panel_kernel<<<1, kPanelThreads, h->panel_smem, s>>>(P.ar, P.ns, k, &P.st->go, &P.st->chol_fail, P.rinv);
@@ -542,18 +547,31 @@ int mccba_set_observations(mccba_handle h, int n_frame, int n_edge, const int* e
         h->obs_cap = cap;
         h->k1_smem = (int)(fixed + (size_t)cap * 40);
     }
-    {   // tiled Cholesky when one block column fits in shared memory (n_s <= ~870), else the plain column version
+    {   // reduced-system solver: 2 = one-launch tile DAG (default), 1 = panel/update kernels per block column,
+        // 0 = plain single-CTA column Cholesky (also the fallback when a block column does not fit in shared memory)
         const size_t need = chol_panel_smem_bytes(P.ns);
-        const char* force = getenv("MCCBA_SIMPLE_CHOL");
-        h->k5_blocked = need <= 227 * 1024 && !(force && force[0] == '1');
+        const char* sel = getenv("MCCBA_CHOL");
+        int mode = 2;
+        if (sel && sel[0] >= '0' && sel[0] <= '2') mode = sel[0] - '0';
+        if (need > 227 * 1024 && mode == 1) mode = 0;
+        const int ntc = chol_col_tiles(P.ns), ntr = chol_row_tiles(P.ns);
+        int grid = 0;
+        for (int j = 0; j < ntc; ++j) grid += ntr - j;
+        if (mode == 2) {   // every diagonal CTA must be able to stay resident while it waits for the backward sweep
+            int per_sm_dag = 0;
+            CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_dag, chol_dag_kernel, 256, 0));
+            if (per_sm_dag * h->num_sms <= 2 * ntc) mode = need <= 227 * 1024 ? 1 : 0;
+        }
+        h->k5_blocked = mode;
+        h->dag_grid = grid;
         h->panel_smem = (int)need;
-        h->k5_smem = h->k5_blocked ? (int)(sizeof(double) * ((size_t)P.ns + 2 + (kK5Threads / 32) * kCLD)) : (int)(sizeof(double) * (size_t)(P.ns + 2));
-        if (h->k5_blocked && h->panel_smem > 48 * 1024)
+        h->k5_smem = mode == 0 ? (int)(sizeof(double) * (size_t)(P.ns + 2)) : (int)(sizeof(double) * ((size_t)P.ns + 2 + (kK5Threads / 32) * kCLD));
+        if (mode == 1 && h->panel_smem > 48 * 1024)
             CUDA_TRY(h, cudaFuncSetAttribute(chol_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->panel_smem));
         if (h->k5_smem > 48 * 1024)
             CUDA_TRY(h, cudaFuncSetAttribute(camera_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->k5_smem));
-        const int ntc = chol_col_tiles(P.ns);
-        h->iter_kernels = 6 + ((h->k5_blocked && P.ns > 0) ? 2 * ntc - 1 : 0);
+        h->iter_kernels = 6 + (P.ns > 0 ? (mode == 2 ? 1 : (mode == 1 ? 2 * ntc - 1 : 0)) : 0);
+        if ((rc = dev_alloc(h, &P.dag_flags, (size_t)(ntr * ntc + ntc) + 8, true))) return rc;
     }
     if (h->k1_smem > 48 * 1024)
         CUDA_TRY(h, cudaFuncSetAttribute(resid_jac_accum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->k1_smem));
@@ -826,7 +844,17 @@ int mccba_debug_solve_dense(mccba_handle h, int n, const double* S, const double
     CUDA_TRY(h, cudaFuncSetAttribute(chol_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(pneed, 1024)));
     CUDA_TRY(h, cudaFuncSetAttribute(dense_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(bneed, 1024)));
     CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));
-    if (blocked) {
+    int* dflags = nullptr;
+    if (blocked == 2) {
+        const int ntc = chol_col_tiles(n), ntr = chol_row_tiles(n);
+        int grid = 0;
+        for (int j = 0; j < ntc; ++j) grid += ntr - j;
+        CUDA_TRY(h, cudaMalloc((void**)&dflags, sizeof(int) * (size_t)(ntr * ntc + ntc)));
+        CUDA_TRY(h, cudaMemsetAsync(dflags, 0, sizeof(int) * (size_t)(ntr * ntc + ntc), h->stream));
+        CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));
+        CholDag D{dA, n, dflags, drinv, dx, nullptr, dfail};
+        chol_dag_kernel<<<grid, 256, 0, h->stream>>>(D);
+    } else if (blocked) {
         const int ntc = chol_col_tiles(n), ntr = chol_row_tiles(n);
         for (int k = 0; k < ntc; ++k) {
             chol_panel_kernel<<<1, kPanelThreads, pneed, h->stream>>>(dA, n, k, nullptr, dfail, drinv);
@@ -844,6 +872,7 @@ int mccba_debug_solve_dense(mccba_handle h, int n, const double* S, const double
     cudaEventElapsedTime(&ms, h->ev0, h->ev1);
     h->prof_ms[0] = ms;
     cudaFree(dA); cudaFree(dx); cudaFree(drinv); cudaFree(dfail);
+    if (dflags) cudaFree(dflags);
     return f ? fail(h, MCCBA_ERR_NUMERIC, "matrix is not positive definite") : MCCBA_OK;
 }
 

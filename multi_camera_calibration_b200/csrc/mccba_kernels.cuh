@@ -82,6 +82,7 @@ struct Problem {
     double* ar;          // allreduce buffer: S (ns x ns) | g (ns) | cost, step2, param2, bad
     double* dc;          // ns: camera step in tangent coordinates
     double* rinv;        // ns: reciprocal diagonal of the Cholesky factor
+    int* dag_flags;      // tile-DAG ready flags (ntr*ntc + ntc ints), zeroed before every factorisation
     double* norm_part;   // 2 x n_k4_blocks: per-block |step|^2, |trial|^2 of the frames
     double* err_sq;      // n_edge_int
     double* err_nrm;     // n_edge_int
@@ -749,6 +750,13 @@ __global__ void __launch_bounds__(kUpdThreads) chol_update_kernel(double* A, int
     chol_update_tile(A, n, k, ti, tj);
 }
 
+// the whole factorisation + both substitutions in one launch (mccba_dense.cuh, tile DAG)
+__global__ void __launch_bounds__(256) chol_dag_kernel(CholDag D)
+{
+    if (D.go && !*D.go) return;
+    chol_dag_tile(D);
+}
+
 // backward substitution + camera update (replicated on every rank) + end-of-iteration state.  Single CTA.
 __global__ void __launch_bounds__(kK5Threads) camera_update_kernel(Problem P, int tiled)
 {
@@ -760,7 +768,9 @@ __global__ void __launch_bounds__(kK5Threads) camera_update_kernel(Problem P, in
     const int ns = P.ns;
     int fail = 0;
     if (ns > 0) {
-        if (tiled) {
+        if (tiled == 2) {
+            fail = st->chol_fail;                      // chol_dag_kernel already left the solution in P.dc
+        } else if (tiled == 1) {
             chol_backward(P.ar, ns, P.rinv, P.dc, s_dyn);
             fail = st->chol_fail;
         } else {
@@ -891,6 +901,7 @@ __global__ void __launch_bounds__(kK5Threads) dense_backward_kernel(double* A, i
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* s_dyn = reinterpret_cast<double*>(smem_raw);
     __shared__ double s_bcast[2];
+    if (tiled == 2) return;
     if (tiled) chol_backward(A, n, rinv, x, s_dyn);
     else {
         const int f = chol_solve_cta(A, n, x, s_dyn, s_bcast);

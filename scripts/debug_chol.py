@@ -7,7 +7,7 @@ rng = np.random.default_rng(0)
 for n in [6, 18, 31, 32, 33, 42, 90, 127, 160, 378, 420]:
     M = rng.standard_normal((n, n)); S = M @ M.T + n * np.eye(n); g = rng.standard_normal(n)
     ref = np.linalg.solve(S, g)
-    for blocked in (True, False):
+    for blocked in (2, 1, 0):
         x, ms = s.debug_solve_dense(S, g, blocked)
         x, ms = s.debug_solve_dense(S, g, blocked)
         print("n", n, "blocked", blocked, "rel err %.2e" % (np.abs(x - ref).max() / np.abs(ref).max()), "ms %.4f" % ms)
