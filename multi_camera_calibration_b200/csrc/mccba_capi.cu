@@ -84,6 +84,7 @@ struct mccba_handle_s {
     CamParams* d_cams = nullptr;
     int cur = 0;                      // host mirror of DevState::cur between calls
     int ar_len = 0;
+    int k2_occ = 2;                   // minimum resident CTAs per SM requested from the Schur kernel (register cap)
     int obs_cap = 0;                  // floats per plane per TMA stage of the residual kernel (0: no staging)
     int k1_grid = 0, k1_smem = 0, k5_smem = 0, k5_blocked = 0, panel_smem = 0, iter_kernels = 5, dag_grid = 0;
     cudaGraphExec_t graph = nullptr;
@@ -159,6 +160,24 @@ void free_problem(mccba_handle h)
 
 int64_t n_param(mccba_handle h) { return 6 * (int64_t)(h->n_cam + h->n_frame - 1); }
 
+void launch_resid(mccba_handle h, cudaStream_t s, int forced)
+{
+    if (h->obs_cap > 0) resid_jac_accum_kernel<true><<<h->k1_grid, kK1Threads, h->k1_smem, s>>>(h->P, forced, h->obs_cap);
+    else resid_jac_accum_kernel<false><<<h->k1_grid, kK1Threads, h->k1_smem, s>>>(h->P, forced, 0);
+}
+
+void launch_schur(mccba_handle h, cudaStream_t s, int sel, double lambda)
+{
+    const Problem& P = h->P;
+    const int grid = (P.n_warps * 32 + kK2Threads - 1) / kK2Threads;
+    switch (h->k2_occ) {
+        case 2: frame_schur_kernel<2><<<grid, kK2Threads, 0, s>>>(P, sel, lambda); break;
+        case 3: frame_schur_kernel<3><<<grid, kK2Threads, 0, s>>>(P, sel, lambda); break;
+        case 4: frame_schur_kernel<4><<<grid, kK2Threads, 0, s>>>(P, sel, lambda); break;
+        default: frame_schur_kernel<1><<<grid, kK2Threads, 0, s>>>(P, sel, lambda); break;
+    }
+}
+
 // enqueue one iteration: [memset S] K2 K3a [allreduce] K5 K4 K1
 int enqueue_iteration(mccba_handle h, bool timed)
 {
@@ -171,7 +190,7 @@ int enqueue_iteration(mccba_handle h, bool timed)
     // the whole packed buffer: a rank whose frame shard never sees some camera has no record for that camera's
     // rows, and stale (already all-reduced) values there would be summed again
     CUDA_TRY(h, cudaMemsetAsync(P.ar, 0, sizeof(double) * (size_t)h->ar_len, s));
-    frame_schur_kernel<<<(P.n_warps * 32 + kK2Threads - 1) / kK2Threads, kK2Threads, 0, s>>>(P, -1, 0.0);
+    launch_schur(h, s, -1, 0.0);
     if (timed) cudaEventRecord(ev[1], s);
     reduce_records_kernel<<<(P.n_dest * 32 + 127) / 128, 128, 0, s>>>(P, 0);
     if (timed) cudaEventRecord(ev[2], s);
@@ -197,7 +216,7 @@ int enqueue_iteration(mccba_handle h, bool timed)
     if (timed) cudaEventRecord(ev[4], s);
     frame_update_kernel<<<P.n_k4_blocks, kK4Threads, 0, s>>>(P);
     if (timed) cudaEventRecord(ev[5], s);
-    resid_jac_accum_kernel<<<h->k1_grid, kK1Threads, h->k1_smem, s>>>(P, 0, h->obs_cap);
+    launch_resid(h, s, 0);
     if (timed) {
         cudaEventRecord(ev[6], s);
         cudaEventSynchronize(ev[6]);
@@ -216,7 +235,8 @@ int launch_forced_eval(mccba_handle h)
 {
     Problem& P = h->P;
     vertex_prep_kernel<<<(P.n_vertex + 127) / 128, 128, 0, h->stream>>>(P, -1);
-    resid_jac_accum_kernel<<<h->k1_grid, kK1Threads, h->k1_smem, h->stream>>>(P, 1, h->obs_cap);
+    edge_pose_kernel<<<(P.n_slots + 127) / 128, 128, 0, h->stream>>>(P, -1);
+    launch_resid(h, h->stream, 1);
     CUDA_TRY(h, cudaGetLastError());
     return MCCBA_OK;
 }
@@ -284,6 +304,7 @@ int mccba_create(const mccba_options* opts, mccba_handle* out)
     cudaMallocHost((void**)&h->h_state, sizeof(DevState));
     cudaMallocHost((void**)&h->h_small, 64 * sizeof(double));
     cudaMalloc((void**)&h->d_small, 64 * sizeof(double));
+    if (const char* occ = getenv("MCCBA_K2_OCC")) h->k2_occ = atoi(occ);
     const char* prof = getenv("MCCBA_PROFILE");
     h->profile = prof && prof[0] == '1';
     if (opts->nranks > 1) {
@@ -521,11 +542,13 @@ int mccba_set_observations(mccba_handle h, int n_frame, int n_edge, const int* e
     if ((rc = dev_alloc(h, &P.frameL, 27 * (size_t)P.n_slots, true))) return rc;
     if ((rc = dev_alloc(h, &P.edgeY, 36 * (size_t)P.n_edge_int, true))) return rc;
     if ((rc = dev_alloc(h, &P.records, (size_t)rec_total, true))) return rc;
+    if ((rc = dev_alloc(h, &P.warp_scal, 2 * (size_t)P.n_warps, true))) return rc;
     if ((rc = dev_alloc(h, &P.ar, (size_t)h->ar_len, true))) return rc;
     if ((rc = dev_alloc(h, &h->x_saved, (size_t)P.n_param, true))) return rc;
     if ((rc = dev_alloc(h, &P.dc, (size_t)std::max(P.ns, 1), true))) return rc;
     if ((rc = dev_alloc(h, &P.rinv, (size_t)std::max(P.ns, 1), true))) return rc;
     if ((rc = dev_alloc(h, &P.norm_part, 2 * (size_t)P.n_k4_blocks, true))) return rc;
+    if ((rc = dev_alloc(h, &P.erec, (size_t)P.n_edge_int, true))) return rc;
     if ((rc = dev_alloc(h, &P.err_sq, (size_t)P.n_edge_int, true))) return rc;
     if ((rc = dev_alloc(h, &P.err_nrm, (size_t)P.n_edge_int, true))) return rc;
     // launch geometry
@@ -537,7 +560,7 @@ int mccba_set_observations(mccba_handle h, int n_frame, int n_edge, const int* e
             max_chunk = std::max(max_chunk, (f1 - f0 + 3) & ~3);
         }
         const size_t off_cam = (sizeof(K1Shared) + 15) & ~(size_t)15;
-        const size_t fixed = ((off_cam + (size_t)nC * (sizeof(CamParams) + 12 * sizeof(double)) + 127) & ~(size_t)127);
+        const size_t fixed = ((off_cam + (size_t)nC * sizeof(CamParams) + 127) & ~(size_t)127);
         const size_t budget = 110 * 1024;   // per CTA, two CTAs per SM
         int cap = (max_chunk + 31) & ~31;
         const char* nostage = getenv("MCCBA_NO_TMA");
@@ -573,10 +596,16 @@ int mccba_set_observations(mccba_handle h, int n_frame, int n_edge, const int* e
         h->iter_kernels = 6 + (P.ns > 0 ? (mode == 2 ? 1 : (mode == 1 ? 2 * ntc - 1 : 0)) : 0);
         if ((rc = dev_alloc(h, &P.dag_flags, (size_t)(ntr * ntc + ntc) + 8, true))) return rc;
     }
-    if (h->k1_smem > 48 * 1024)
-        CUDA_TRY(h, cudaFuncSetAttribute(resid_jac_accum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->k1_smem));
     int per_sm = 1;
-    CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, resid_jac_accum_kernel, kK1Threads, h->k1_smem));
+    if (h->obs_cap > 0) {
+        if (h->k1_smem > 48 * 1024)
+            CUDA_TRY(h, cudaFuncSetAttribute(resid_jac_accum_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->k1_smem));
+        CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, resid_jac_accum_kernel<true>, kK1Threads, h->k1_smem));
+    } else {
+        if (h->k1_smem > 48 * 1024)
+            CUDA_TRY(h, cudaFuncSetAttribute(resid_jac_accum_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->k1_smem));
+        CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, resid_jac_accum_kernel<false>, kK1Threads, h->k1_smem));
+    }
     per_sm = std::max(per_sm, 1);
     h->k1_grid = std::max(1, std::min(P.n_edge_int / kEdgesPerBlock, h->num_sms * per_sm));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
@@ -670,7 +699,7 @@ int mccba_reduced_system(mccba_handle h, double lambda, double* S, double* gs)
     if ((rc = launch_forced_eval(h))) return rc;
     Problem& P = h->P;
     CUDA_TRY(h, cudaMemsetAsync(P.ar, 0, sizeof(double) * (size_t)h->ar_len, h->stream));
-    frame_schur_kernel<<<(P.n_warps * 32 + kK2Threads - 1) / kK2Threads, kK2Threads, 0, h->stream>>>(P, h->cur, lambda);
+    launch_schur(h, h->stream, h->cur, lambda);
     reduce_records_kernel<<<(P.n_dest * 32 + 127) / 128, 128, 0, h->stream>>>(P, 1);
     CUDA_TRY(h, cudaGetLastError());
     if (h->opts.nranks > 1) {
@@ -702,7 +731,7 @@ int mccba_solve(mccba_handle h, const mccba_solve_opts* o, mccba_report* rep)
                                       o->lambda_down, h->cur);
     CUDA_TRY(h, cudaMemsetAsync(P.norm_part, 0, sizeof(double) * 2 * (size_t)P.n_k4_blocks, s));
     if ((rc = launch_forced_eval(h))) return rc;
-    kernels += 3;
+    kernels += 4;
     // one iteration as a CUDA graph (captured once per problem)
     const bool use_graph = h->opts.use_graph && !h->profile;
     if (use_graph && !h->graph) {
@@ -893,7 +922,7 @@ int mccba_time_eval(mccba_handle h, int reps, double* avg_ms)
     if ((rc = launch_forced_eval(h))) return rc;  // warm-up, also computes the rotations
     CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));
     for (int i = 0; i < reps; ++i)
-        resid_jac_accum_kernel<<<h->k1_grid, kK1Threads, h->k1_smem, h->stream>>>(h->P, 1, h->obs_cap);
+        launch_resid(h, h->stream, 1);
     CUDA_TRY(h, cudaEventRecord(h->ev1, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     CUDA_TRY(h, cudaGetLastError());

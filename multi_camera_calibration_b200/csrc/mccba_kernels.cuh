@@ -43,6 +43,16 @@ struct DevState {
     double cam_step2, cam_param2;  // camera part of |step|^2 and |params|^2 of the current trial
 };
 
+// Per-edge record consumed by the residual kernel: composed pose of the edge at the point being evaluated + its
+// camera and corner range.  128 bytes, fetched 32 at a time by one TMA bulk copy.
+struct EdgeRec {
+    double R3[9];
+    double T3[3];
+    int cam, pad0, begin, end;
+    double pad1[2];
+};
+static_assert(sizeof(EdgeRec) == 128, "EdgeRec must be 128 bytes");
+
 struct Problem {
     int n_cam, n_frame, n_vertex, ns;
     int n_edge_int;   // internal edges (padded per group to 32-frame warps), multiple of 32
@@ -79,11 +89,13 @@ struct Problem {
     double* frameL;      // 27 x n_slots (21 packed factor + 6 z)
     double* edgeY;       // 36 x n_edge_int
     double* records;     // warp records
+    double* warp_scal;   // 2 x n_warps: [cost | bad] of every Schur warp, contiguous so that the scalar reduction is coalesced
     double* ar;          // allreduce buffer: S (ns x ns) | g (ns) | cost, step2, param2, bad
     double* dc;          // ns: camera step in tangent coordinates
     double* rinv;        // ns: reciprocal diagonal of the Cholesky factor
     int* dag_flags;      // tile-DAG ready flags (ntr*ntc + ntc ints), zeroed before every factorisation
     double* norm_part;   // 2 x n_k4_blocks: per-block |step|^2, |trial|^2 of the frames
+    EdgeRec* erec;       // n_edge_int edge records of the point the residual kernel evaluates next
     double* err_sq;      // n_edge_int
     double* err_nrm;     // n_edge_int
 };
@@ -137,6 +149,60 @@ __global__ void vertex_prep_kernel(Problem P, int which)
     for (int i = 0; i < 9; ++i) P.vR[which][9 * (int64_t)v + i] = R[i];
 }
 
+// edge records of one frame slot for parameter buffer `which` (R_p, t_p given): one record per view
+__device__ __forceinline__ void write_edge_records(const Problem& P, int which, int slot, int frame, const double* Rp,
+                                                   const double* tp)
+{
+    const int g = P.warp_group[slot >> 5];
+    const int V = P.group_V[g];
+    const int* gc = P.group_cams + P.group_cam0[g];
+    const int ls = slot - P.group_slot0[g];
+    for (int v = 0; v < V; ++v) {
+        const int c = gc[v];
+        const int64_t e = P.group_ebase[g] + (int64_t)v * P.group_stride[g] + ls;
+        EdgeRec r;
+        if (frame >= 0) {
+            double Rc[9], tc[3];
+            if (c == 0) {
+                Rc[0] = Rc[4] = Rc[8] = 1; Rc[1] = Rc[2] = Rc[3] = Rc[5] = Rc[6] = Rc[7] = 0;
+                tc[0] = tc[1] = tc[2] = 0;
+            } else {
+#pragma unroll
+                for (int i = 0; i < 9; ++i) Rc[i] = P.vR[which][9 * c + i];
+#pragma unroll
+                for (int i = 0; i < 3; ++i) tc[i] = P.x[which][6 * (c - 1) + 3 + i];
+            }
+            compose_pose(Rc, tc, Rp, tp, r.R3, r.T3);
+            r.begin = P.e_off[e]; r.end = P.e_off[e + 1];
+        } else {
+#pragma unroll
+            for (int i = 0; i < 9; ++i) r.R3[i] = 0;
+            r.T3[0] = r.T3[1] = r.T3[2] = 0;
+            r.begin = 0; r.end = 0;
+        }
+        r.cam = c; r.pad0 = 0; r.pad1[0] = r.pad1[1] = 0;
+        P.erec[e] = r;
+    }
+}
+
+// edge records for the forced evaluation of buffer `which` (-1: the state's current buffer); one thread per frame slot
+__global__ void edge_pose_kernel(Problem P, int which)
+{
+    if (which < 0) which = P.st->cur;
+    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= P.n_slots) return;
+    const int frame = P.slot_frame[slot];
+    double Rp[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, tp[3] = {0, 0, 0};
+    if (frame >= 0) {
+        const int64_t pv = P.n_cam + frame;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) Rp[i] = P.vR[which][9 * pv + i];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) tp[i] = P.x[which][6 * (pv - 1) + 3 + i];
+    }
+    write_edge_records(P, which, slot, frame, Rp, tp);
+}
+
 // --------------------------------------------------------------------------------------------------------
 // K1: residual + Jacobian + per-edge normal-equation block.  8 lanes per edge, 32 edges per CTA iteration,
 // persistent grid-stride over edge chunks.  Intrinsics and camera poses staged in shared memory once per CTA.
@@ -144,8 +210,9 @@ __global__ void vertex_prep_kernel(Problem P, int which)
 // --------------------------------------------------------------------------------------------------------
 struct K1Shared {
     double stage[kBlk][kEdgesPerBlock + 1];
-    unsigned long long bar[2];   // mbarriers of the two observation stages
-    int first[2];                // first float index (16-byte aligned) held by each stage, -1 = not staged
+    EdgeRec erec[2][kEdgesPerBlock];   // TMA destination: edge records of the two stages
+    unsigned long long bar[2];         // mbarriers of the two stages
+    int first[2];                      // first float index (16-byte aligned) held by each stage
 };
 
 // ---- TMA (1-D bulk copy) + mbarrier primitives, sm_90+/sm_100a PTX ---------------------------------------
@@ -188,17 +255,19 @@ __device__ __forceinline__ void edge_corner_loop(const float* __restrict__ ox, c
 }
 
 // forced: 0 = loop launch (evaluate the trial buffer iff the state says a step was produced), 1 = forced on `cur`.
-// Shared memory: K1Shared | camera table | camera poses | 2 stages x 5 planes x obs_cap floats.
-// The observation planes of the NEXT chunk are fetched by the TMA engine (cp.async.bulk + mbarrier) while the
-// current chunk is being evaluated; chunks whose data does not fit a stage fall back to direct global loads.
+// Shared memory: K1Shared | camera table | 2 stages x 5 planes x obs_cap floats.
+// Everything the kernel reads per chunk -- 32 edge records (composed pose, camera, corner range) and the five
+// observation planes of those edges -- is fetched by the TMA engine (cp.async.bulk + mbarrier) one chunk ahead, so
+// the arithmetic never waits on a dependent global load.  kStaged == false (a chunk does not fit a stage): the edge
+// records are still staged, the observations are read straight from global memory.
+template <bool kStaged>
 __global__ void __launch_bounds__(kK1Threads, 2) resid_jac_accum_kernel(Problem P, int forced, int obs_cap)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     K1Shared* sh = reinterpret_cast<K1Shared*>(smem_raw);
     const size_t off_cam = (sizeof(K1Shared) + 15) & ~(size_t)15;
     CamParams* s_cam = reinterpret_cast<CamParams*>(smem_raw + off_cam);
-    double* s_camR = reinterpret_cast<double*>(s_cam + P.n_cam);  // n_cam x 12: R (9) | t (3)
-    const size_t off_obs = (off_cam + (size_t)P.n_cam * (sizeof(CamParams) + 12 * sizeof(double)) + 127) & ~(size_t)127;
+    const size_t off_obs = (off_cam + (size_t)P.n_cam * sizeof(CamParams) + 127) & ~(size_t)127;
     float* s_obs = reinterpret_cast<float*>(smem_raw + off_obs);   // [2][5][obs_cap]
 
     const DevState* st = P.st;
@@ -208,17 +277,9 @@ __global__ void __launch_bounds__(kK1Threads, 2) resid_jac_accum_kernel(Problem 
         if (st->done || !st->solved) return;
         which = 1 - st->cur;
     }
-    const double* __restrict__ x = P.x[which];
-    const double* __restrict__ vR = P.vR[which];
     double* __restrict__ out = P.blocks[which];
 
-    for (int c = threadIdx.x; c < P.n_cam; c += blockDim.x) {
-        s_cam[c] = P.cams[c];
-#pragma unroll
-        for (int i = 0; i < 9; ++i) s_camR[12 * c + i] = vR[9 * c + i];
-#pragma unroll
-        for (int i = 0; i < 3; ++i) s_camR[12 * c + 9 + i] = c == 0 ? 0.0 : x[6 * (c - 1) + 3 + i];
-    }
+    for (int c = threadIdx.x; c < P.n_cam; c += blockDim.x) s_cam[c] = P.cams[c];
     if (threadIdx.x == 0) {
         mbar_init(&sh->bar[0], 1);
         mbar_init(&sh->bar[1], 1);
@@ -233,18 +294,20 @@ __global__ void __launch_bounds__(kK1Threads, 2) resid_jac_accum_kernel(Problem 
 
     // producer: one thread programs the TMA engine for chunk `chunk` into stage `stg`
     auto issue = [&](int chunk, int stg) {
-        const int f0 = P.e_off[chunk * kEdgesPerBlock] & ~3;
-        const int f1 = P.e_off[(chunk + 1) * kEdgesPerBlock];
-        const int nfl = (f1 - f0 + 3) & ~3;
-        if (obs_cap > 0 && nfl <= obs_cap && nfl > 0) {
-            sh->first[stg] = f0;
-            mbar_expect_tx(&sh->bar[stg], 5u * (unsigned)nfl * 4u);
+        unsigned bytes = (unsigned)(kEdgesPerBlock * sizeof(EdgeRec));
+        int f0 = 0, nfl = 0;
+        if (kStaged) {
+            f0 = P.e_off[chunk * kEdgesPerBlock] & ~3;
+            nfl = (P.e_off[(chunk + 1) * kEdgesPerBlock] - f0 + 3) & ~3;
+            bytes += 5u * (unsigned)nfl * 4u;
+        }
+        sh->first[stg] = f0;
+        mbar_expect_tx(&sh->bar[stg], bytes);
+        tma_load_1d(&sh->erec[stg][0], P.erec + (size_t)chunk * kEdgesPerBlock, (unsigned)(kEdgesPerBlock * sizeof(EdgeRec)), &sh->bar[stg]);
+        if (kStaged && nfl > 0) {
 #pragma unroll
             for (int pl = 0; pl < 5; ++pl)
                 tma_load_1d(s_obs + ((size_t)stg * 5 + pl) * obs_cap, planes[pl] + f0, (unsigned)nfl * 4u, &sh->bar[stg]);
-        } else {
-            sh->first[stg] = -1;
-            mbar_expect_tx(&sh->bar[stg], 0u);   // completes the phase immediately: consumers read global memory
         }
     };
 
@@ -253,40 +316,28 @@ __global__ void __launch_bounds__(kK1Threads, 2) resid_jac_accum_kernel(Problem 
     for (int chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x, ++it) {
         const int stg = it & 1;
         if (threadIdx.x == 0 && chunk + (int)gridDim.x < n_chunks) issue(chunk + gridDim.x, stg ^ 1);
-        const int e = chunk * kEdgesPerBlock + eb;
         double acc[kBlk];
 #pragma unroll
         for (int k = 0; k < kBlk; ++k) acc[k] = 0.0;
-        const int frame = P.e_frame[e];
-        double R3[9], T3[3];
-        int c = 0, b = 0, n = 0;
-        if (frame >= 0) {
-            c = P.e_cam[e];
-            const int64_t pv = P.n_cam + frame;
-            double Rp[9], tp[3];
-#pragma unroll
-            for (int i = 0; i < 9; ++i) Rp[i] = __ldg(vR + 9 * pv + i);
-#pragma unroll
-            for (int i = 0; i < 3; ++i) tp[i] = __ldg(x + 6 * (pv - 1) + 3 + i);
-            compose_pose(s_camR + 12 * c, s_camR + 12 * c + 9, Rp, tp, R3, T3);
-            b = P.e_off[e]; n = P.e_off[e + 1];
-        }
         mbar_wait(&sh->bar[stg], (unsigned)((it >> 1) & 1));
-        if (frame >= 0) {
-            const int first = sh->first[stg];
-            const float *ox, *oy, *oz, *iu, *iv;
-            if (first >= 0) {
-                const float* base = s_obs + (size_t)stg * 5 * obs_cap - first;
-                ox = base; oy = base + obs_cap; oz = base + 2 * obs_cap; iu = base + 3 * obs_cap; iv = base + 4 * obs_cap;
-            } else {
-                ox = P.ox; oy = P.oy; oz = P.oz; iu = P.iu; iv = P.iv;
-            }
-            const CamParams& cam = s_cam[c];
-            if (cam.model == kPinhole) {
-                if (cam.rational) edge_corner_loop<kPinhole, true>(ox, oy, oz, iu, iv, cam, R3, T3, b, n, sub, acc);
-                else edge_corner_loop<kPinhole, false>(ox, oy, oz, iu, iv, cam, R3, T3, b, n, sub, acc);
-            } else {
-                edge_corner_loop<kOmnidir, false>(ox, oy, oz, iu, iv, cam, R3, T3, b, n, sub, acc);
+        {
+            const EdgeRec& er = sh->erec[stg][eb];
+            const int b = er.begin, n = er.end;
+            if (n > b) {
+                const float *ox, *oy, *oz, *iu, *iv;
+                if (kStaged) {
+                    const float* base = s_obs + (size_t)stg * 5 * obs_cap - sh->first[stg];
+                    ox = base; oy = base + obs_cap; oz = base + 2 * obs_cap; iu = base + 3 * obs_cap; iv = base + 4 * obs_cap;
+                } else {
+                    ox = P.ox; oy = P.oy; oz = P.oz; iu = P.iu; iv = P.iv;
+                }
+                const CamParams& cam = s_cam[er.cam];
+                if (cam.model == kPinhole) {
+                    if (cam.rational) edge_corner_loop<kPinhole, true>(ox, oy, oz, iu, iv, cam, er.R3, er.T3, b, n, sub, acc);
+                    else edge_corner_loop<kPinhole, false>(ox, oy, oz, iu, iv, cam, er.R3, er.T3, b, n, sub, acc);
+                } else {
+                    edge_corner_loop<kOmnidir, false>(ox, oy, oz, iu, iv, cam, er.R3, er.T3, b, n, sub, acc);
+                }
             }
         }
         // transposed reduction over the 8 lanes of the edge: 28 -> 14 -> 7 -> 3(+1) values per lane, 25 adds
@@ -325,7 +376,7 @@ __global__ void __launch_bounds__(kK1Threads, 2) resid_jac_accum_kernel(Problem 
         }
 #pragma unroll
         for (int i = 0; i < 3; ++i) sh->stage[base + i][eb] = acc[i];
-        __syncthreads();   // also: every thread is done reading observation stage `stg`
+        __syncthreads();   // also: every thread is done reading stage `stg` (edge records and observations)
         for (int t = threadIdx.x; t < kBlk * kEdgesPerBlock; t += kK1Threads) {
             const int k = t / kEdgesPerBlock, col = t % kEdgesPerBlock;
             out[(int64_t)k * P.n_edge_int + chunk * kEdgesPerBlock + col] = sh->stage[k][col];
@@ -402,7 +453,8 @@ __device__ __forceinline__ void reduce_store36(const double* v, double* dst, int
 }
 
 // sel: -1 = decide from the state (loop), 0/1 = explicit buffer with explicit lambda (diagnostics)
-__global__ void __launch_bounds__(kK2Threads) frame_schur_kernel(Problem P, int sel_arg, double lambda_arg)
+template <int kMinBlocks>
+__global__ void __launch_bounds__(kK2Threads, kMinBlocks) frame_schur_kernel(Problem P, int sel_arg, double lambda_arg)
 {
     const DevState* st = P.st;
     int sel;
@@ -474,7 +526,7 @@ __global__ void __launch_bounds__(kK2Threads) frame_schur_kernel(Problem P, int 
     for (int k = 0; k < 6; ++k) P.frameL[(int64_t)(21 + k) * P.n_slots + slot] = z[k];
     {
         const double c2 = warp_sum(cost), b2 = warp_sum((double)bad);
-        if (lane == 0) { rec[0] = c2; rec[1] = b2; }
+        if (lane == 0) { rec[0] = c2; rec[1] = b2; P.warp_scal[warp] = c2; P.warp_scal[P.n_warps + warp] = b2; }
     }
     // pass 2: camera blocks of each non-gauge view
     int ai = 0;
@@ -621,9 +673,16 @@ __global__ void reduce_records_kernel(Problem P, int forced)
     } else {
         // scalars: cost and bad from every warp record; frame step / param norms from frame_update's partials
         double c = 0, b = 0, n0 = 0, n1 = 0;
-        for (int w = lane; w < P.n_warps; w += 32) {
-            c += P.records[P.warp_rec[w]];
-            b += P.records[P.warp_rec[w] + 1];
+        {
+            int w = lane;
+            for (; w + 7 * 32 < P.n_warps; w += 8 * 32) {
+                double v[8], u[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) { v[q] = P.warp_scal[w + 32 * q]; u[q] = P.warp_scal[P.n_warps + w + 32 * q]; }
+#pragma unroll
+                for (int q = 0; q < 8; ++q) { c += v[q]; b += u[q]; }
+            }
+            for (; w < P.n_warps; w += 32) { c += P.warp_scal[w]; b += P.warp_scal[P.n_warps + w]; }
         }
         for (int k = lane; k < P.n_k4_blocks; k += 32) {
             n0 += P.norm_part[k];
@@ -880,6 +939,7 @@ __global__ void __launch_bounds__(kK4Threads) frame_update_kernel(Problem P)
             rodrigues(q, R);
 #pragma unroll
             for (int i = 0; i < 9; ++i) P.vR[tr][9 * pv + i] = R[i];
+            write_edge_records(P, tr, slot, frame, R, q + 3);   // composed poses the residual kernel evaluates next
         }
     }
     __shared__ double s_red[2][kK4Threads / 32];
