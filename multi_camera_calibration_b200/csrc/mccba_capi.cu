@@ -7,7 +7,9 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <map>
+#include <unordered_map>
 #include <string>
 #include <vector>
 
@@ -81,6 +83,8 @@ struct mccba_handle_s {
     std::vector<int64_t> edge_n_h;    // corners per reference edge
     Problem P;
     std::vector<void*> allocs;        // device allocations owned by the problem
+    std::vector<size_t> alloc_bytes;  // their sizes
+    std::vector<std::pair<size_t, void*>> pool;   // allocations of the previous problem, reused when the size matches
     CamParams* d_cams = nullptr;
     int cur = 0;                      // host mirror of DevState::cur between calls
     int ar_len = 0;
@@ -130,9 +134,16 @@ int dev_alloc(mccba_handle h, T** p, size_t count, bool zero = false)
 {
     void* q = nullptr;
     const size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
-    CUDA_TRY(h, cudaMalloc(&q, bytes));
+    for (size_t i = 0; i < h->pool.size(); ++i)   // same-shape problems (outlier loop, benchmark) never touch cudaMalloc
+        if (h->pool[i].first == bytes) {
+            q = h->pool[i].second;
+            h->pool.erase(h->pool.begin() + (long)i);
+            break;
+        }
+    if (!q) CUDA_TRY(h, cudaMalloc(&q, bytes));
     if (zero) CUDA_TRY(h, cudaMemsetAsync(q, 0, bytes, h->stream));
     h->allocs.push_back(q);
+    h->alloc_bytes.push_back(bytes);
     *p = (T*)q;
     return MCCBA_OK;
 }
@@ -147,15 +158,25 @@ int dev_upload(mccba_handle h, const T** p, const std::vector<T>& v)
     return MCCBA_OK;
 }
 
-void free_problem(mccba_handle h)
+// release the problem; keep_pool: park its device allocations for the next set_observations instead of freeing them
+void free_problem(mccba_handle h, bool keep_pool = false)
 {
     if (h->graph) { cudaGraphExecDestroy(h->graph); h->graph = nullptr; }
-    for (void* p : h->allocs) cudaFree(p);
+    for (size_t i = 0; i < h->allocs.size(); ++i) {
+        if (keep_pool) h->pool.push_back({h->alloc_bytes[i], h->allocs[i]});
+        else cudaFree(h->allocs[i]);
+    }
     h->allocs.clear();
+    h->alloc_bytes.clear();
     h->have_obs = false;
     h->have_params = false;
     h->have_saved = false;
     h->x_saved = nullptr;
+}
+void drain_pool(mccba_handle h)
+{
+    for (auto& pr : h->pool) cudaFree(pr.second);
+    h->pool.clear();
 }
 
 int64_t n_param(mccba_handle h) { return 6 * (int64_t)(h->n_cam + h->n_frame - 1); }
@@ -324,6 +345,7 @@ int mccba_destroy(mccba_handle h)
     cudaSetDevice(h->opts.device);
     cudaStreamSynchronize(h->stream);
     free_problem(h);
+    drain_pool(h);
     if (h->omni_graph) cudaGraphExecDestroy(h->omni_graph);
     for (void* q : h->omni_allocs) cudaFree(q);
     if (h->d_cams) cudaFree(h->d_cams);
@@ -386,33 +408,83 @@ int mccba_set_observations(mccba_handle h, int n_frame, int n_edge, const int* e
     if (n_frame < 1 || n_edge < 1 || !edge_cam || !edge_pv || !edge_off || !obj_xyz || !img_uv)
         return fail(h, MCCBA_ERR_ARG, "set_observations: null or empty input");
     CUDA_TRY(h, cudaSetDevice(h->opts.device));
+    const bool timing = getenv("MCCBA_TIMING") != nullptr;
+    auto t_start = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!timing) return;
+        cudaStreamSynchronize(h->stream);
+        auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[set_observations] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t_start).count());
+        t_start = now;
+    };
     const int nC = h->n_cam;
     if (edge_off[0] != 0) return fail(h, MCCBA_ERR_ARG, "edge_off[0] must be 0");
     const int64_t M = edge_off[n_edge];
     if (M <= 0 || M >= (int64_t)2000000000) return fail(h, MCCBA_ERR_ARG, "corner count %lld out of range", (long long)M);
-    // per-frame view lists sorted by camera
-    std::vector<std::vector<std::pair<int, int>>> views((size_t)n_frame);
+    // the previous problem's buffers go to the pool; the big host->device copies start right away and overlap with
+    // the host-side layout work below
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    free_problem(h, true);
+    float *d_obj = nullptr, *d_img = nullptr;
+    {
+        int rc0;
+        if ((rc0 = dev_alloc(h, &d_obj, 3 * (size_t)M))) return rc0;
+        if ((rc0 = dev_alloc(h, &d_img, 2 * (size_t)M))) return rc0;
+    }
+    CUDA_TRY(h, cudaMemcpyAsync(d_obj, obj_xyz, sizeof(float) * 3 * (size_t)M, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(d_img, img_uv, sizeof(float) * 2 * (size_t)M, cudaMemcpyHostToDevice, h->stream));
+    // per-frame view lists (CSR by counting sort), each sorted by camera
+    std::vector<int> voff((size_t)n_frame + 1, 0);
     for (int e = 0; e < n_edge; ++e) {
         const int c = edge_cam[e], f = edge_pv[e] - nC;
         if (c < 0 || c >= nC) return fail(h, MCCBA_ERR_ARG, "edge %d: cameraVertex %d out of range", e, c);
         if (f < 0 || f >= n_frame) return fail(h, MCCBA_ERR_ARG, "edge %d: photoVertex %d out of range [%d,%d)", e, edge_pv[e], nC, nC + n_frame);
         if (edge_off[e + 1] < edge_off[e]) return fail(h, MCCBA_ERR_ARG, "edge_off not monotone at edge %d", e);
-        views[f].push_back({c, e});
+        voff[f + 1]++;
     }
-    std::map<std::vector<int>, std::vector<int>> groups;  // camera set -> frames (ascending)
     for (int f = 0; f < n_frame; ++f) {
-        auto& v = views[f];
-        if (v.empty()) return fail(h, MCCBA_ERR_ARG, "photo vertex %d has no observation", nC + f);
-        std::sort(v.begin(), v.end());
-        std::vector<int> key;
-        for (size_t i = 0; i < v.size(); ++i) {
-            if (i && v[i].first == v[i - 1].first)
-                return fail(h, MCCBA_ERR_ARG, "photo vertex %d is observed twice by camera %d", nC + f, v[i].first);
-            key.push_back(v[i].first);
-        }
-        groups[key].push_back(f);
+        if (voff[f + 1] == 0) return fail(h, MCCBA_ERR_ARG, "photo vertex %d has no observation", nC + f);
+        voff[f + 1] += voff[f];
     }
-    free_problem(h);
+    std::vector<std::pair<int, int>> vlist((size_t)n_edge);   // (camera, edge) per frame, CSR
+    {
+        std::vector<int> fill(voff.begin(), voff.end() - 1);
+        for (int e = 0; e < n_edge; ++e) vlist[fill[edge_pv[e] - nC]++] = {edge_cam[e], e};
+    }
+    struct ViewRef { const std::pair<int, int>* p; int n; const std::pair<int, int>& operator[](size_t i) const { return p[i]; } };
+    struct Views { const std::vector<int>* off; const std::vector<std::pair<int, int>>* l;
+                   ViewRef operator[](int f) const { return ViewRef{l->data() + (*off)[f], (*off)[f + 1] - (*off)[f]}; } };
+    Views views{&voff, &vlist};
+    std::map<std::vector<int>, std::vector<int>> groups;  // camera set -> frames (ascending)
+    {
+        // frames hashed by their (sorted) camera list; only one std::map insertion per distinct camera set
+        std::unordered_map<uint64_t, std::vector<int>*> fast;   // valid when the list packs into 64 bits
+        std::vector<int> key;
+        for (int f = 0; f < n_frame; ++f) {
+            std::pair<int, int>* b = vlist.data() + voff[f];
+            const int nv = voff[f + 1] - voff[f];
+            if (nv > 1) std::sort(b, b + nv);
+            for (int i = 1; i < nv; ++i)
+                if (b[i].first == b[i - 1].first)
+                    return fail(h, MCCBA_ERR_ARG, "photo vertex %d is observed twice by camera %d", nC + f, b[i].first);
+            if (nv <= 4 && nC < 65535) {
+                uint64_t k = 0;
+                for (int i = 0; i < nv; ++i) k = (k << 16) | (uint64_t)(b[i].first + 1);
+                auto it = fast.find(k);
+                if (it == fast.end()) {
+                    key.clear();
+                    for (int i = 0; i < nv; ++i) key.push_back(b[i].first);
+                    it = fast.emplace(k, &groups[key]).first;
+                }
+                it->second->push_back(f);
+            } else {
+                key.clear();
+                for (int i = 0; i < nv; ++i) key.push_back(b[i].first);
+                groups[key].push_back(f);
+            }
+        }
+    }
+    lap("validate + group frames");
     Problem& P = h->P;
     memset(&P, 0, sizeof(P));
     P.n_cam = nC; P.n_frame = n_frame; P.n_vertex = nC + n_frame; P.ns = 6 * (nC - 1);
@@ -492,6 +564,7 @@ int mccba_set_observations(mccba_handle h, int n_frame, int n_edge, const int* e
     dest_info.insert(dest_info.end(), {2, 0, 0, 0});
     dest_src0.push_back((int)dest_src.size());
 
+    lap("build layout tables");
     P.n_edge_int = (int)e_cam.size();
     P.n_slots = (int)slot_frame.size();
     P.n_warps = P.n_slots / 32;
@@ -512,20 +585,17 @@ int mccba_set_observations(mccba_handle h, int n_frame, int n_edge, const int* e
 #undef UP
     const int64_t* d_esrc = nullptr;
     if ((rc = dev_upload(h, &d_esrc, e_src))) return rc;
+    lap("upload tables");
     // observation planes: one allocation, each plane 256-byte aligned
     const size_t plane = ((size_t)M + 63) / 64 * 64;
     float* planes = nullptr;
     if ((rc = dev_alloc(h, &planes, plane * 5))) return rc;
     P.ox = planes; P.oy = planes + plane; P.oz = planes + 2 * plane; P.iu = planes + 3 * plane; P.iv = planes + 4 * plane;
-    float *d_obj = nullptr, *d_img = nullptr;
-    CUDA_TRY(h, cudaMalloc((void**)&d_obj, sizeof(float) * 3 * (size_t)M));
-    CUDA_TRY(h, cudaMalloc((void**)&d_img, sizeof(float) * 2 * (size_t)M));
-    CUDA_TRY(h, cudaMemcpyAsync(d_obj, obj_xyz, sizeof(float) * 3 * (size_t)M, cudaMemcpyHostToDevice, h->stream));
-    CUDA_TRY(h, cudaMemcpyAsync(d_img, img_uv, sizeof(float) * 2 * (size_t)M, cudaMemcpyHostToDevice, h->stream));
     gather_obs_kernel<<<h->num_sms * 8, 256, 0, h->stream>>>(P.n_edge_int, P.e_off, d_esrc, d_obj, d_img, planes,
                                                             planes + plane, planes + 2 * plane, planes + 3 * plane,
                                                             planes + 4 * plane);
     CUDA_TRY(h, cudaGetLastError());
+    lap("H2D observations + gather");
     // work buffers
     if ((rc = dev_alloc(h, &P.st, 1, true))) return rc;
     for (int b = 0; b < 2; ++b) {
@@ -551,6 +621,7 @@ int mccba_set_observations(mccba_handle h, int n_frame, int n_edge, const int* e
     if ((rc = dev_alloc(h, &P.erec, (size_t)P.n_edge_int, true))) return rc;
     if ((rc = dev_alloc(h, &P.err_sq, (size_t)P.n_edge_int, true))) return rc;
     if ((rc = dev_alloc(h, &P.err_nrm, (size_t)P.n_edge_int, true))) return rc;
+    lap("allocate work buffers");
     // launch geometry
     {   // shared memory of the residual kernel: fixed part + two TMA stages sized for the largest 32-edge chunk,
         // provided two CTAs still fit on an SM (otherwise no staging: direct global loads)
@@ -609,8 +680,8 @@ int mccba_set_observations(mccba_handle h, int n_frame, int n_edge, const int* e
     per_sm = std::max(per_sm, 1);
     h->k1_grid = std::max(1, std::min(P.n_edge_int / kEdgesPerBlock, h->num_sms * per_sm));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
-    cudaFree(d_obj);
-    cudaFree(d_img);
+    drain_pool(h);   // whatever the new problem did not reuse
+    lap("launch geometry");
     h->cur = 0;
     h->have_obs = true;
     h->have_params = false;
