@@ -60,7 +60,7 @@ class ClockSampler:
         self.p = None
         try:
             self.p = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                       "-i", str(gpu_index), "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+                                       "-i", str(gpu_index), "-lms", "25"], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
 
@@ -288,14 +288,14 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cams", type=int, default=64)
     ap.add_argument("--frames", type=int, default=100000)
     ap.add_argument("--iters", type=int, default=20)
-    ap.add_argument("--ref-iters", type=int, default=4, help="LM iterations per step of the CPU arm (bounded sample)")
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--ref-iters", type=int, default=10, help="LM iterations per step of the CPU arm (bounded sample)")
+    ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--seed", type=int, default=1005)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

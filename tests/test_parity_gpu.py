@@ -57,6 +57,8 @@ RIGS = {
     "rational2": dict(n_cam=2, n_frame=33, cam_models=[0, 0], seed=14, ndist=8),
     "pinhole8": dict(n_cam=8, n_frame=200, cam_models=[0] * 8, seed=15),
     "nodist5": dict(n_cam=5, n_frame=64, cam_models=[0] * 5, seed=16, ndist=4),
+    # 130 corners per image: a 32-edge chunk no longer fits a TMA stage -> observations read straight from global memory
+    "bigboard3": dict(n_cam=3, n_frame=70, cam_models=[0, 1, 0], seed=17, nx=13, ny=10),
 }
 
 
