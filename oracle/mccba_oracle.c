@@ -691,8 +691,23 @@ int orc_rig_solve_normal(orc_rig *r, const double *params, double lambda, double
         }
     }
     for (int i = 0; i < ns; ++i) S[i * ns + i] *= (1 + lambda);
-    /* frames */
-    for (int f = 0; f < F && !fail; ++f) {
+    /* frames: independent given the camera blocks; every thread accumulates its own copy of the reduced system and
+     * the copies are summed in thread order afterwards (deterministic for a fixed thread count) */
+    int nthreads = 1;
+#ifdef _OPENMP
+    nthreads = omp_get_max_threads();
+#endif
+    double *S_t = (double *)calloc((size_t)nthreads * (size_t)(ns > 0 ? ns * ns : 1), sizeof(double));
+    double *gs_t = (double *)calloc((size_t)nthreads * (size_t)(ns > 0 ? ns : 1), sizeof(double));
+#pragma omp parallel for schedule(static)
+    for (int f = 0; f < F; ++f) {
+        if (fail) continue;
+        int tidx = 0;
+#ifdef _OPENMP
+        tidx = omp_get_thread_num();
+#endif
+        double *S = S_t + (size_t)tidx * (size_t)(ns > 0 ? ns * ns : 1);
+        double *gs = gs_t + (size_t)tidx * (size_t)(ns > 0 ? ns : 1);
         double H[36], g[6], Tpi[36];
         memset(H, 0, sizeof(H));
         memset(g, 0, sizeof(g));
@@ -716,7 +731,7 @@ int orc_rig_solve_normal(orc_rig *r, const double *params, double lambda, double
             }
         }
         for (int i = 0; i < 6; ++i) H[i * 6 + i] *= (1 + lambda);
-        if (chol_lower(H, 6)) { fail = 1000 + f; break; }
+        if (chol_lower(H, 6)) { fail = 1000 + f; continue; }
         memcpy(Hpp_inv + 36 * (size_t)f, H, sizeof(H));
         memcpy(gp + 6 * (size_t)f, g, sizeof(g));
         /* Schur: S -= W_a^T H^-1 W_b, g_s -= W_a^T H^-1 g_p over the frame's non-gauge views */
@@ -751,6 +766,11 @@ int orc_rig_solve_normal(orc_rig *r, const double *params, double lambda, double
             }
         }
     }
+    for (int t = 0; t < nthreads; ++t) {
+        for (int i = 0; i < ns * ns; ++i) S[i] += S_t[(size_t)t * (size_t)(ns * ns) + i];
+        for (int i = 0; i < ns; ++i) gs[i] += gs_t[(size_t)t * (size_t)ns + i];
+    }
+    free(S_t); free(gs_t);
     if (S_out && ns > 0) memcpy(S_out, S, sizeof(double) * (size_t)ns * ns);
     if (gs_out && ns > 0) memcpy(gs_out, gs, sizeof(double) * (size_t)ns);
     double *dc = (double *)calloc((size_t)(ns > 0 ? ns : 1), sizeof(double));
@@ -764,6 +784,7 @@ int orc_rig_solve_normal(orc_rig *r, const double *params, double lambda, double
     }
     if (!fail) {
         /* back-substitution: d_p = H^-1 (g_p - sum_v W_v d_c) */
+#pragma omp parallel for schedule(static)
         for (int f = 0; f < F; ++f) {
             double rhs[6];
             memcpy(rhs, gp + 6 * (size_t)f, sizeof(rhs));
