@@ -619,6 +619,14 @@ int mccba_set_observations(mccba_handle h, int n_frame, int n_edge, const int* e
     if ((rc = dev_alloc(h, &P.rinv, (size_t)std::max(P.ns, 1), true))) return rc;
     if ((rc = dev_alloc(h, &P.norm_part, 2 * (size_t)P.n_k4_blocks, true))) return rc;
     if ((rc = dev_alloc(h, &P.erec, (size_t)P.n_edge_int, true))) return rc;
+    {
+        std::vector<EdgeMeta> meta((size_t)P.n_edge_int);
+        for (int e = 0; e < P.n_edge_int; ++e) {
+            const bool live = e_frame[e] >= 0;
+            meta[e].cam = e_cam[e]; meta[e].begin = live ? e_off[e] : 0; meta[e].end = live ? e_off[e + 1] : 0; meta[e].pad = 0;
+        }
+        if ((rc = dev_upload(h, &P.emeta, meta))) return rc;
+    }
     if ((rc = dev_alloc(h, &P.err_sq, (size_t)P.n_edge_int, true))) return rc;
     if ((rc = dev_alloc(h, &P.err_nrm, (size_t)P.n_edge_int, true))) return rc;
     lap("allocate work buffers");

@@ -45,13 +45,14 @@ struct DevState {
 
 // Per-edge record consumed by the residual kernel: composed pose of the edge at the point being evaluated + its
 // camera and corner range.  128 bytes, fetched 32 at a time by one TMA bulk copy.
-struct EdgeRec {
+struct EdgeRec {          // dynamic part, rewritten for every evaluated point: 96 bytes
     double R3[9];
     double T3[3];
-    int cam, pad0, begin, end;
-    double pad1[2];
 };
-static_assert(sizeof(EdgeRec) == 128, "EdgeRec must be 128 bytes");
+struct EdgeMeta {         // static part, written once by set_observations: 16 bytes
+    int cam, begin, end, pad;
+};
+static_assert(sizeof(EdgeRec) == 96 && sizeof(EdgeMeta) == 16, "edge record layout");
 
 struct Problem {
     int n_cam, n_frame, n_vertex, ns;
@@ -95,7 +96,8 @@ struct Problem {
     double* rinv;        // ns: reciprocal diagonal of the Cholesky factor
     int* dag_flags;      // tile-DAG ready flags (ntr*ntc + ntc ints), zeroed before every factorisation
     double* norm_part;   // 2 x n_k4_blocks: per-block |step|^2, |trial|^2 of the frames
-    EdgeRec* erec;       // n_edge_int edge records of the point the residual kernel evaluates next
+    EdgeRec* erec;       // n_edge_int composed poses of the point the residual kernel evaluates next
+    const EdgeMeta* emeta; // n_edge_int camera / corner range of every internal edge
     double* err_sq;      // n_edge_int
     double* err_nrm;     // n_edge_int
 };
@@ -149,7 +151,7 @@ __global__ void vertex_prep_kernel(Problem P, int which)
     for (int i = 0; i < 9; ++i) P.vR[which][9 * (int64_t)v + i] = R[i];
 }
 
-// edge records of one frame slot for parameter buffer `which` (R_p, t_p given): one record per view
+// composed poses of the edges of one frame slot for parameter buffer `which` (R_p, t_p given): one record per view
 __device__ __forceinline__ void write_edge_records(const Problem& P, int which, int slot, int frame, const double* Rp,
                                                    const double* tp)
 {
@@ -157,9 +159,9 @@ __device__ __forceinline__ void write_edge_records(const Problem& P, int which, 
     const int V = P.group_V[g];
     const int* gc = P.group_cams + P.group_cam0[g];
     const int ls = slot - P.group_slot0[g];
+    const int64_t ebase = P.group_ebase[g], stride = P.group_stride[g];
     for (int v = 0; v < V; ++v) {
         const int c = gc[v];
-        const int64_t e = P.group_ebase[g] + (int64_t)v * P.group_stride[g] + ls;
         EdgeRec r;
         if (frame >= 0) {
             double Rc[9], tc[3];
@@ -173,15 +175,12 @@ __device__ __forceinline__ void write_edge_records(const Problem& P, int which, 
                 for (int i = 0; i < 3; ++i) tc[i] = P.x[which][6 * (c - 1) + 3 + i];
             }
             compose_pose(Rc, tc, Rp, tp, r.R3, r.T3);
-            r.begin = P.e_off[e]; r.end = P.e_off[e + 1];
         } else {
 #pragma unroll
             for (int i = 0; i < 9; ++i) r.R3[i] = 0;
             r.T3[0] = r.T3[1] = r.T3[2] = 0;
-            r.begin = 0; r.end = 0;
         }
-        r.cam = c; r.pad0 = 0; r.pad1[0] = r.pad1[1] = 0;
-        P.erec[e] = r;
+        P.erec[ebase + v * stride + ls] = r;
     }
 }
 
@@ -210,7 +209,8 @@ __global__ void edge_pose_kernel(Problem P, int which)
 // --------------------------------------------------------------------------------------------------------
 struct K1Shared {
     double stage[kBlk][kEdgesPerBlock + 1];
-    EdgeRec erec[2][kEdgesPerBlock];   // TMA destination: edge records of the two stages
+    EdgeRec erec[2][kEdgesPerBlock];   // TMA destination: composed poses of the two stages
+    EdgeMeta emeta[2][kEdgesPerBlock]; // TMA destination: camera / corner range
     unsigned long long bar[2];         // mbarriers of the two stages
     int first[2];                      // first float index (16-byte aligned) held by each stage
 };
@@ -294,7 +294,7 @@ __global__ void __launch_bounds__(kK1Threads, 2) resid_jac_accum_kernel(Problem 
 
     // producer: one thread programs the TMA engine for chunk `chunk` into stage `stg`
     auto issue = [&](int chunk, int stg) {
-        unsigned bytes = (unsigned)(kEdgesPerBlock * sizeof(EdgeRec));
+        unsigned bytes = (unsigned)(kEdgesPerBlock * (sizeof(EdgeRec) + sizeof(EdgeMeta)));
         int f0 = 0, nfl = 0;
         if (kStaged) {
             f0 = P.e_off[chunk * kEdgesPerBlock] & ~3;
@@ -304,6 +304,7 @@ __global__ void __launch_bounds__(kK1Threads, 2) resid_jac_accum_kernel(Problem 
         sh->first[stg] = f0;
         mbar_expect_tx(&sh->bar[stg], bytes);
         tma_load_1d(&sh->erec[stg][0], P.erec + (size_t)chunk * kEdgesPerBlock, (unsigned)(kEdgesPerBlock * sizeof(EdgeRec)), &sh->bar[stg]);
+        tma_load_1d(&sh->emeta[stg][0], P.emeta + (size_t)chunk * kEdgesPerBlock, (unsigned)(kEdgesPerBlock * sizeof(EdgeMeta)), &sh->bar[stg]);
         if (kStaged && nfl > 0) {
 #pragma unroll
             for (int pl = 0; pl < 5; ++pl)
@@ -322,7 +323,8 @@ __global__ void __launch_bounds__(kK1Threads, 2) resid_jac_accum_kernel(Problem 
         mbar_wait(&sh->bar[stg], (unsigned)((it >> 1) & 1));
         {
             const EdgeRec& er = sh->erec[stg][eb];
-            const int b = er.begin, n = er.end;
+            const EdgeMeta em = sh->emeta[stg][eb];
+            const int b = em.begin, n = em.end;
             if (n > b) {
                 const float *ox, *oy, *oz, *iu, *iv;
                 if (kStaged) {
@@ -331,7 +333,7 @@ __global__ void __launch_bounds__(kK1Threads, 2) resid_jac_accum_kernel(Problem 
                 } else {
                     ox = P.ox; oy = P.oy; oz = P.oz; iu = P.iu; iv = P.iv;
                 }
-                const CamParams& cam = s_cam[er.cam];
+                const CamParams& cam = s_cam[em.cam];
                 if (cam.model == kPinhole) {
                     if (cam.rational) edge_corner_loop<kPinhole, true>(ox, oy, oz, iu, iv, cam, er.R3, er.T3, b, n, sub, acc);
                     else edge_corner_loop<kPinhole, false>(ox, oy, oz, iu, iv, cam, er.R3, er.T3, b, n, sub, acc);
@@ -897,22 +899,51 @@ __global__ void __launch_bounds__(kK4Threads) frame_update_kernel(Problem P)
     double step2 = 0, par2 = 0;
     if (slot < P.n_slots) {
         const int frame = P.slot_frame[slot];
+        const int warp = slot >> 5;
+        const int g = P.warp_group[warp];
+        const int V = P.group_V[g];
+        const int* gc = P.group_cams + P.group_cam0[g];
+        const int ls = slot - P.group_slot0[g];
+        const int64_t E = P.n_edge_int, ebase = P.group_ebase[g], stride = P.group_stride[g];
         if (frame >= 0) {
-            const int warp = slot >> 5;
-            const int g = P.warp_group[warp];
-            const int V = P.group_V[g];
-            const int* gc = P.group_cams + P.group_cam0[g];
-            const int ls = slot - P.group_slot0[g];
-            const int64_t E = P.n_edge_int;
-            double U[21], r[6];
+            // every load of the kernel is issued up front (they are independent): factor, rhs, Y of the first two
+            // views, the camera steps and the trial camera poses needed for the edge records at the end
+            const int64_t pv = P.n_cam + frame;
+            const double* p = P.x[cur] + 6 * (pv - 1);
+            double U[21], r[6], pold[6];
 #pragma unroll
             for (int k = 0; k < 21; ++k) U[k] = P.frameL[(int64_t)k * P.n_slots + slot];
 #pragma unroll
             for (int k = 0; k < 6; ++k) r[k] = P.frameL[(int64_t)(21 + k) * P.n_slots + slot];
-            for (int v = 0; v < V; ++v) {
+#pragma unroll
+            for (int k = 0; k < 6; ++k) pold[k] = p[k];
+            double Y2[2][36], d2[2][6], Rc2[2][9], tc2[2][3];
+#pragma unroll
+            for (int v = 0; v < 2; ++v) {
+                const int c = v < V ? gc[v] : 0;
+                const int64_t e = ebase + v * stride + ls;
+#pragma unroll
+                for (int k = 0; k < 36; ++k) Y2[v][k] = c != 0 ? P.edgeY[(int64_t)k * E + e] : 0.0;
+#pragma unroll
+                for (int k = 0; k < 6; ++k) d2[v][k] = c != 0 ? P.dc[6 * (c - 1) + k] : 0.0;
+#pragma unroll
+                for (int k = 0; k < 9; ++k) Rc2[v][k] = c != 0 ? P.vR[tr][9 * c + k] : ((k == 0 || k == 4 || k == 8) ? 1.0 : 0.0);
+#pragma unroll
+                for (int k = 0; k < 3; ++k) tc2[v][k] = c != 0 ? P.x[tr][6 * (c - 1) + 3 + k] : 0.0;
+            }
+#pragma unroll
+            for (int v = 0; v < 2; ++v)
+#pragma unroll
+                for (int i = 0; i < 6; ++i) {
+                    double acc = 0;
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) acc += Y2[v][i * 6 + k] * d2[v][k];
+                    r[i] -= acc;
+                }
+            for (int v = 2; v < V; ++v) {   // frames seen by more than two cameras
                 const int c = gc[v];
                 if (c == 0) continue;
-                const int64_t e = P.group_ebase[g] + (int64_t)v * P.group_stride[g] + ls;
+                const int64_t e = ebase + v * stride + ls;
                 const double* d = P.dc + 6 * (c - 1);
 #pragma unroll
                 for (int i = 0; i < 6; ++i) {
@@ -923,15 +954,13 @@ __global__ void __launch_bounds__(kK4Threads) frame_update_kernel(Problem P)
                 }
             }
             chol6_backward(U, r);
-            const int64_t pv = P.n_cam + frame;
-            const double* p = P.x[cur] + 6 * (pv - 1);
-            const double om[3] = {p[0], p[1], p[2]};
+            const double om[3] = {pold[0], pold[1], pold[2]};
             double dom[3], q[6], R[9];
             left_jacobian_inv_apply(om, r, dom);
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
                 const double s0 = alpha * dom[i], s1 = alpha * r[3 + i];
-                q[i] = p[i] + s0; q[3 + i] = p[3 + i] + s1;
+                q[i] = pold[i] + s0; q[3 + i] = pold[3 + i] + s1;
                 step2 += s0 * s0 + s1 * s1;
             }
 #pragma unroll
@@ -939,7 +968,31 @@ __global__ void __launch_bounds__(kK4Threads) frame_update_kernel(Problem P)
             rodrigues(q, R);
 #pragma unroll
             for (int i = 0; i < 9; ++i) P.vR[tr][9 * pv + i] = R[i];
-            write_edge_records(P, tr, slot, frame, R, q + 3);   // composed poses the residual kernel evaluates next
+            // composed poses the residual kernel evaluates next
+#pragma unroll
+            for (int v = 0; v < 2; ++v)
+                if (v < V) {
+                    EdgeRec er;
+                    compose_pose(Rc2[v], tc2[v], R, q + 3, er.R3, er.T3);
+                    P.erec[ebase + v * stride + ls] = er;
+                }
+            for (int v = 2; v < V; ++v) {
+                const int c = gc[v];
+                double Rc[9], tc[3];
+#pragma unroll
+                for (int k = 0; k < 9; ++k) Rc[k] = c != 0 ? P.vR[tr][9 * c + k] : ((k == 0 || k == 4 || k == 8) ? 1.0 : 0.0);
+#pragma unroll
+                for (int k = 0; k < 3; ++k) tc[k] = c != 0 ? P.x[tr][6 * (c - 1) + 3 + k] : 0.0;
+                EdgeRec er;
+                compose_pose(Rc, tc, R, q + 3, er.R3, er.T3);
+                P.erec[ebase + v * stride + ls] = er;
+            }
+        } else {
+            EdgeRec z;
+#pragma unroll
+            for (int i = 0; i < 9; ++i) z.R3[i] = 0;
+            z.T3[0] = z.T3[1] = z.T3[2] = 0;
+            for (int v = 0; v < V; ++v) P.erec[ebase + v * stride + ls] = z;
         }
     }
     __shared__ double s_red[2][kK4Threads / 32];
