@@ -20,7 +20,7 @@
 namespace mccba {
 
 constexpr int kCT = 32;        // tile
-constexpr int kCLD = kCT + 1;  // padded shared-memory row stride (doubles)
+constexpr int kCLD = kCT + 2;  // padded shared-memory row stride (doubles): 16-byte aligned rows, 2 wavefronts per fragment load
 constexpr int kPanelThreads = 512;
 constexpr int kUpdThreads = 256;
 
@@ -262,6 +262,171 @@ __device__ inline void tile_trsm_row(double* prow, const double* L, const double
     }
 }
 
+// 1/d for the pivot chain: MUFU.RCP64H seed + two Newton steps (relative error ~1e-16), ~50 cycles instead of ~80
+// for the IEEE division.  Caller guarantees d is a normal positive number well inside the double range.
+__device__ __forceinline__ double pivot_rcp(double d)
+{
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+    double r = fma(-d, y, 1.0);
+    y = fma(y, r, y);
+    r = fma(-d, y, 1.0);
+    y = fma(y, r, y);
+    return y;
+}
+
+// Warp-level Cholesky of the w x w lower triangle in C (stride kCLD), executed by ONE warp.  The SM issues in order,
+// so everything between a producer and its consumer has to be filled by hand; measured on B200: DFMA 8 cycles
+// (2-3 cycles issue), shuffle 25, shared-memory round trip 35, rsqrt() 74, 1/x 79, MUFU.RCP64H 16.
+// Lane i keeps the not yet eliminated part of row i in registers, shifted by one column per pivot (the shift is the
+// destination of the update fma, so it is free).  The pivot loop is software-pipelined: as soon as the first update
+// fma has produced the next pivot column it goes to shared memory, and its broadcast + 1/d_{j+1} overlap the
+// remaining 30 fmas of pivot j.  Columns are stored unscaled and multiplied by 1/sqrt(d_j) in one pass at the end.
+// `colbuf` = 2 x 64 doubles of shared memory.  rinv[0..w) <- 1 / L_jj.  A pivot outside [1e-200, 1e200] = failure.
+struct PotrfCol {
+    double c[kCT - 1];   // column entries below the pivot, broadcast to every lane
+    double d, t;         // pivot, a_ij / d_j
+};
+
+__device__ __forceinline__ void potrf_fetch(const double* cb, int j, double a0, PotrfCol& col)
+{
+    col.d = cb[j];
+    const double* cj = cb + j + 1;
+#pragma unroll
+    for (int k = 0; k < kCT - 1; ++k) col.c[k] = cj[k];
+    col.t = a0 * pivot_rcp(col.d);
+}
+
+__device__ __forceinline__ void potrf_step(double* C, double* colbuf, int lane, int j, int w, double (&a)[kCT], const PotrfCol& cur,
+                                           PotrfCol& nxt, int& bad)
+{
+    if (lane >= j && lane < w) C[lane * kCLD + j] = a[0];
+    if (!(cur.d > 1e-200 && cur.d < 1e200)) bad = 1;
+    const double a0n = fma(-cur.t, cur.c[0], a[1]);
+    double* cbn = colbuf + ((j + 1) & 1) * 2 * kCT;
+    cbn[lane] = a0n;
+    __syncwarp();
+    nxt.d = cbn[j + 1];
+    const double* cj = cbn + j + 2;
+#pragma unroll
+    for (int k = 0; k < kCT - 1; ++k) nxt.c[k] = cj[k];
+#pragma unroll
+    for (int k = 1; k < kCT - 1; ++k) a[k] = fma(-cur.t, cur.c[k], a[k + 1]);
+    a[0] = a0n;
+    a[kCT - 1] = 0.0;
+    nxt.t = a0n * pivot_rcp(nxt.d);
+}
+
+__device__ inline void tile_potrf_warp(double* C, int w, double* rinv, int* bad_flag, double* colbuf)
+{
+    const int lane = threadIdx.x & 31;
+    double a[kCT];   // a[k] = A[lane][j + k] at pivot j
+#pragma unroll
+    for (int k = 0; k < kCT; ++k) a[k] = (lane < w && k <= lane) ? C[lane * kCLD + k] : (k == lane ? 1.0 : 0.0);
+    colbuf[kCT + lane] = 1.0;       // what pivots past the tile read
+    colbuf[3 * kCT + lane] = 1.0;
+    colbuf[lane] = a[0];
+    __syncwarp();
+    int bad = 0;
+    PotrfCol c0, c1;
+    potrf_fetch(colbuf, 0, a[0], c0);
+#pragma unroll 1
+    for (int j = 0; j < w; j += 2) {
+        potrf_step(C, colbuf, lane, j, w, a, c0, c1, bad);
+        if (j + 1 < w) potrf_step(C, colbuf, lane, j + 1, w, a, c1, c0, bad);
+    }
+    __syncwarp();
+    double ri = 1.0;
+    if (lane < w) { ri = rsqrt(C[lane * kCLD + lane]); rinv[lane] = ri; }
+    colbuf[lane] = ri;
+    __syncwarp();
+    if (lane < w)
+        for (int k = 0; k <= lane; ++k) C[lane * kCLD + k] *= colbuf[k];
+    if (bad) *bad_flag = 1;
+}
+
+// FP64 tensor-core MMA (DMMA), D(8x8) += A(8x4, row) * B(4x8, col).  Lane = 4 g + t holds A[g][t], B[t][g] and
+// D[g][2t], D[g][2t+1].  Measured on B200: 33 cycles per dependent op; a 32^3 tile update built on it takes ~1000
+// cycles for 256 threads against ~2050 for the scalar DFMA version, which is bound by shared-memory loads.
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// C -= A * B^T for 32 x 32 tiles in shared memory (stride kCLD), 256 threads: 8 warps x two 8 x 8 output blocks.
+__device__ __forceinline__ void tile_gemm_sub(double* C, const double* A, const double* B)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const int tr = warp >> 1, tc0 = (warp & 1) * 2;
+    const double* ap = A + (8 * tr + g) * kCLD + t;
+    const double* bp0 = B + (8 * tc0 + g) * kCLD + t;
+    const double* bp1 = bp0 + 8 * kCLD;
+    double c00 = 0, c01 = 0, c10 = 0, c11 = 0, d00 = 0, d01 = 0, d10 = 0, d11 = 0;
+#pragma unroll
+    for (int ks = 0; ks < 8; ks += 2) {
+        const double a0 = ap[4 * ks], a1 = ap[4 * ks + 4];
+        dmma(c00, c01, a0, bp0[4 * ks]);
+        dmma(c10, c11, a0, bp1[4 * ks]);
+        dmma(d00, d01, a1, bp0[4 * ks + 4]);
+        dmma(d10, d11, a1, bp1[4 * ks + 4]);
+    }
+    double* cp = C + (8 * tr + g) * kCLD + 8 * tc0 + 2 * t;
+    cp[0] -= c00 + d00; cp[1] -= c01 + d01; cp[8] -= c10 + d10; cp[9] -= c11 + d11;
+}
+
+// Rows of a tile against the w x w factor L (stride kCLD): X L^T = P in place for up to 32 rows of P.  Warps 0..3
+// take 8 rows each (the other warps return); no block-wide barrier inside.  Each warp first inverts the four 8 x 8
+// diagonal blocks of L (one lane per column, `winv` = 4 x 8 x 8 doubles of shared memory -- all warps write the same
+// values), then walks the four column blocks right-looking with DMMA: X_b = S_b W_b^T, S_b' -= X_b L_b'b^T (b' > b).
+// Only the lower triangle of L is read; rows/columns of L past w must be zero below the diagonal, and rinv[c] for
+// c >= w is taken as zero, so columns past w come out as zero.
+__device__ inline void tile_trsm_dmma(double* P, int nrows, const double* L, const double* rinv, int w, double* winv)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp * 8 >= nrows) return;
+    {
+        const int b0 = (lane >> 3) * 8, q = lane & 7;
+        double acc[8], ri[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { acc[i] = (i == q) ? 1.0 : 0.0; ri[i] = (b0 + i < w) ? rinv[b0 + i] : 0.0; }
+#pragma unroll
+        for (int m = 0; m < 8; ++m) {
+            const double wm = acc[m] * ri[m];
+#pragma unroll
+            for (int i = m + 1; i < 8; ++i) acc[i] = fma(-L[(b0 + i) * kCLD + b0 + m], wm, acc[i]);
+            winv[(b0 + m) * 8 + q] = wm;   // W_b[m][q]
+        }
+    }
+    __syncwarp();
+    const int g = lane >> 2, t = lane & 3;
+    double* prow = P + (8 * warp + g) * kCLD;
+    double cf[4][2];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) { cf[b][0] = prow[8 * b + 2 * t]; cf[b][1] = prow[8 * b + 2 * t + 1]; }
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+        if (8 * b < w) {
+            // S_b: accumulator layout -> A-operand layout through shared memory
+            if (b > 0) { prow[8 * b + 2 * t] = cf[b][0]; prow[8 * b + 2 * t + 1] = cf[b][1]; __syncwarp(); }
+            const double s0 = prow[8 * b + t], s1 = prow[8 * b + 4 + t];
+            const double* wr = winv + (8 * b + g) * 8 + t;    // B(k = m, n = c) = W_b[c][m]
+            double x0 = 0.0, x1 = 0.0;
+            dmma(x0, x1, s0, wr[0]);
+            dmma(x0, x1, s1, wr[4]);
+            __syncwarp();
+            prow[8 * b + 2 * t] = x0; prow[8 * b + 2 * t + 1] = x1;
+            __syncwarp();
+            const double a0 = -prow[8 * b + t], a1 = -prow[8 * b + 4 + t];
+#pragma unroll
+            for (int b2 = b + 1; b2 < 4; ++b2) {
+                const double* lr = L + (8 * b2 + g) * kCLD + 8 * b + t;   // B(k = m, n = c) = L[8 b2 + c][8 b + m]
+                dmma(cf[b2][0], cf[b2][1], a0, lr[0]);
+                dmma(cf[b2][0], cf[b2][1], a1, lr[4]);
+            }
+        }
+    }
+}
+
 // ---- one-launch tile DAG ---------------------------------------------------------------------------------------
 // One CTA per lower-triangle tile (i, j) of the augmented matrix, launched in column-major order so that every
 // dependency points to a CTA with a smaller block index (progress is guaranteed even if not all CTAs are resident).
@@ -292,16 +457,15 @@ __device__ __forceinline__ void dag_wait(const int* flag)
 __device__ __forceinline__ void dag_publish(int* flag)
 {
     __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
+    if (threadIdx.x == 0)   // release at gpu scope is cumulative over the bar.sync: no separate fence
         asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(flag), "r"(1) : "memory");
-    }
 }
 
 __device__ inline void chol_dag_tile(const CholDag& D)
 {
-    __shared__ double C[kCT][kCLD], A1[kCT + 8][kCLD], B1[kCT + 8][kCLD];
+    __shared__ __align__(16) double C[kCT + 8][kCLD], A1[kCT + 8][kCLD], B1[kCT + 8][kCLD];
     __shared__ double s_rinv[kCT], s_part[8][kCT];
+    __shared__ __align__(16) double s_col[4 * kCT], s_winv[kCT * 8];
     __shared__ int s_bad;
     const int tid = threadIdx.x, n = D.n;
     const int ntc = chol_col_tiles(n), ntr = chol_row_tiles(n);
@@ -316,9 +480,8 @@ __device__ inline void chol_dag_tile(const CholDag& D)
         const int r = idx >> 5, c = idx & 31;
         C[r][c] = (r < h && c < w) ? D.A[(int64_t)(r0 + r) * n + c0 + c] : 0.0;
     }
-    for (int idx = tid; idx < 8 * kCLD; idx += blockDim.x) { (&A1[kCT][0])[idx] = 0.0; (&B1[kCT][0])[idx] = 0.0; }
+    for (int idx = tid; idx < 8 * kCLD; idx += blockDim.x) { (&C[kCT][0])[idx] = 0.0; (&A1[kCT][0])[idx] = 0.0; (&B1[kCT][0])[idx] = 0.0; }
     __syncthreads();
-    const int tx = tid & 15, ty = tid >> 4;
     for (int k = 0; k < j; ++k) {
         dag_wait(D.ready + i * ntc + k);
         if (i != j) dag_wait(D.ready + j * ntc + k);
@@ -329,23 +492,13 @@ __device__ inline void chol_dag_tile(const CholDag& D)
             if (i != j) B1[r][c] = (r < w) ? __ldcg(D.A + (int64_t)(c0 + r) * n + k0 + c) : 0.0;
         }
         __syncthreads();
-        const double(*Bm)[kCLD] = (i != j) ? B1 : A1;
-        double acc[2][2] = {{0, 0}, {0, 0}};
-#pragma unroll 8
-        for (int m = 0; m < kCT; ++m) {
-            const double a0 = A1[2 * ty][m], a1 = A1[2 * ty + 1][m];
-            const double b0 = Bm[tx][m], b1 = Bm[tx + 16][m];
-            acc[0][0] += a0 * b0; acc[0][1] += a0 * b1;
-            acc[1][0] += a1 * b0; acc[1][1] += a1 * b1;
-        }
-        C[2 * ty][tx] -= acc[0][0]; C[2 * ty][tx + 16] -= acc[0][1];
-        C[2 * ty + 1][tx] -= acc[1][0]; C[2 * ty + 1][tx + 16] -= acc[1][1];
+        tile_gemm_sub(&C[0][0], &A1[0][0], (i != j) ? &B1[0][0] : &A1[0][0]);
         __syncthreads();
     }
     if (i == j) {
-        tile_potrf(&C[0][0], w, s_rinv, &s_bad);
+        if (tid < 32) tile_potrf_warp(&C[0][0], w, s_rinv, &s_bad, s_col);
         __syncthreads();
-        if (h > w && tid == 0) tile_trsm_row(&C[w][0], &C[0][0], s_rinv, w);   // the g row lives in this tile (ragged last column)
+        if (h > w) tile_trsm_dmma(&C[w][0], 1, &C[0][0], s_rinv, w, s_winv);   // the g row lives in this tile (ragged last column)
         __syncthreads();
         for (int idx = tid; idx < kCT * kCT; idx += blockDim.x) {
             const int r = idx >> 5, c = idx & 31;
@@ -362,7 +515,7 @@ __device__ inline void chol_dag_tile(const CholDag& D)
         }
         if (tid < kCT) s_rinv[tid] = tid < w ? __ldcg(D.rinv + c0 + tid) : 0.0;
         __syncthreads();
-        if (tid < h) tile_trsm_row(&C[tid][0], &B1[0][0], s_rinv, w);
+        tile_trsm_dmma(&C[0][0], h, &B1[0][0], s_rinv, w, s_winv);
         __syncthreads();
         for (int idx = tid; idx < kCT * kCT; idx += blockDim.x) {
             const int r = idx >> 5, c = idx & 31;

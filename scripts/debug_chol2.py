@@ -8,4 +8,4 @@ n = 378
 M = rng.standard_normal((n, n)); S = M @ M.T + n * np.eye(n); g = rng.standard_normal(n)
 x, ms = s.debug_solve_dense(S, g, 2)
 x, ms = s.debug_solve_dense(S, g, 2)
-print("ms", ms)
+print("ms", ms, "rel err", np.abs(x - np.linalg.solve(S, g)).max() / np.abs(x).max())
