@@ -222,9 +222,8 @@ int enqueue_iteration(mccba_handle h, bool timed)
     if (timed) cudaEventRecord(ev[3], s);
     decide_kernel<<<1, 32, 0, s>>>(P);
     if (h->k5_blocked == 2 && P.ns > 0) {
-        const int ntc = chol_col_tiles(P.ns), ntr = chol_row_tiles(P.ns);
-        CUDA_TRY(h, cudaMemsetAsync(P.dag_flags, 0, sizeof(int) * (size_t)(ntr * ntc + ntc), s));
-        CholDag D{P.ar, P.ns, P.dag_flags, P.rinv, P.dc, &P.st->go, &P.st->chol_fail};
+        CUDA_TRY(h, cudaMemsetAsync(P.dag_buf, 0xFF, sizeof(double) * chol_dag_words(P.ns), s));
+        CholDag D{P.ar, P.dag_buf, P.ns, P.dc, &P.st->go, &P.st->chol_fail, nullptr};
         chol_dag_kernel<<<h->dag_grid, 256, 0, s>>>(D);
     } else if (h->k5_blocked == 1 && P.ns > 0) {
         const int ntc = chol_col_tiles(P.ns), ntr = chol_row_tiles(P.ns);
@@ -659,10 +658,10 @@ int mccba_set_observations(mccba_handle h, int n_frame, int n_edge, const int* e
         const int ntc = chol_col_tiles(P.ns), ntr = chol_row_tiles(P.ns);
         int grid = 0;
         for (int j = 0; j < ntc; ++j) grid += ntr - j;
-        if (mode == 2) {   // every diagonal CTA must be able to stay resident while it waits for the backward sweep
+        if (mode == 2) {   // every CTA of the DAG stays resident until the backward sweep has passed it
             int per_sm_dag = 0;
             CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_dag, chol_dag_kernel, 256, 0));
-            if (per_sm_dag * h->num_sms <= 2 * ntc) mode = need <= 227 * 1024 ? 1 : 0;
+            if (per_sm_dag * h->num_sms < grid) mode = need <= 227 * 1024 ? 1 : 0;
         }
         h->k5_blocked = mode;
         h->dag_grid = grid;
@@ -673,7 +672,7 @@ int mccba_set_observations(mccba_handle h, int n_frame, int n_edge, const int* e
         if (h->k5_smem > 48 * 1024)
             CUDA_TRY(h, cudaFuncSetAttribute(camera_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->k5_smem));
         h->iter_kernels = 6 + (P.ns > 0 ? (mode == 2 ? 1 : (mode == 1 ? 2 * ntc - 1 : 0)) : 0);
-        if ((rc = dev_alloc(h, &P.dag_flags, (size_t)(ntr * ntc + ntc) + 8, true))) return rc;
+        if ((rc = dev_alloc(h, &P.dag_buf, chol_dag_words(P.ns) + 8))) return rc;
     }
     int per_sm = 1;
     if (h->obs_cap > 0) {
@@ -952,16 +951,37 @@ int mccba_debug_solve_dense(mccba_handle h, int n, const double* S, const double
     CUDA_TRY(h, cudaFuncSetAttribute(chol_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(pneed, 1024)));
     CUDA_TRY(h, cudaFuncSetAttribute(dense_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(bneed, 1024)));
     CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));
-    int* dflags = nullptr;
+    double* dflags = nullptr;
     if (blocked == 2) {
         const int ntc = chol_col_tiles(n), ntr = chol_row_tiles(n);
         int grid = 0;
         for (int j = 0; j < ntc; ++j) grid += ntr - j;
-        CUDA_TRY(h, cudaMalloc((void**)&dflags, sizeof(int) * (size_t)(ntr * ntc + ntc)));
-        CUDA_TRY(h, cudaMemsetAsync(dflags, 0, sizeof(int) * (size_t)(ntr * ntc + ntc), h->stream));
+        CUDA_TRY(h, cudaMalloc((void**)&dflags, sizeof(double) * chol_dag_words(n)));
         CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));
-        CholDag D{dA, n, dflags, drinv, dx, nullptr, dfail};
+        CUDA_TRY(h, cudaMemsetAsync(dflags, 0xFF, sizeof(double) * chol_dag_words(n), h->stream));
+        unsigned long long* dtrace = nullptr;
+        if (getenv("MCCBA_DAG_TRACE")) {
+            CUDA_TRY(h, cudaMalloc((void**)&dtrace, sizeof(unsigned long long) * 8 * (size_t)grid));
+            CUDA_TRY(h, cudaMemsetAsync(dtrace, 0, sizeof(unsigned long long) * 8 * (size_t)grid, h->stream));
+        }
+        CholDag D{dA, dflags, n, dx, nullptr, dfail, dtrace};
         chol_dag_kernel<<<grid, 256, 0, h->stream>>>(D);
+        if (dtrace) {   // diagnostics: per-tile timeline in ns relative to the first stamp
+            std::vector<unsigned long long> tr(8 * (size_t)grid);
+            CUDA_TRY(h, cudaMemcpyAsync(tr.data(), dtrace, sizeof(unsigned long long) * tr.size(), cudaMemcpyDeviceToHost, h->stream));
+            CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+            unsigned long long t0 = ~0ull;
+            for (size_t b = 0; b < (size_t)grid; ++b) if (tr[8 * b]) t0 = std::min(t0, tr[8 * b]);
+            int bi = 0;
+            for (int j = 0; j < ntc; ++j)
+                for (int i = j; i < ntr; ++i, ++bi) {
+                    if (i > j + 1 && i != ntr - 1) continue;   // diagonal, first sub-diagonal and the g-row tile
+                    fprintf(stderr, "tile(%2d,%2d):", i, j);
+                    for (int k = 0; k < 7; ++k) fprintf(stderr, " %8lld", tr[8 * bi + k] ? (long long)(tr[8 * bi + k] - t0) : -1LL);
+                    fprintf(stderr, "\n");
+                }
+            cudaFree(dtrace);
+        }
     } else if (blocked) {
         const int ntc = chol_col_tiles(n), ntr = chol_row_tiles(n);
         for (int k = 0; k < ntc; ++k) {

@@ -428,132 +428,221 @@ __device__ inline void tile_trsm_dmma(double* P, int nrows, const double* L, con
 }
 
 // ---- one-launch tile DAG ---------------------------------------------------------------------------------------
-// One CTA per lower-triangle tile (i, j) of the augmented matrix, launched in column-major order so that every
-// dependency points to a CTA with a smaller block index (progress is guaranteed even if not all CTAs are resident).
-// The owner keeps its tile in shared memory, applies the updates of block columns k < j as their tiles are published,
-// finalises it (diagonal: Cholesky; below: triangular solve) and publishes it once to global memory with a
-// release flag.  The diagonal CTAs then run the backward substitution the same way.  Critical path per block column:
-// POTRF -> TRSM -> one tile update, instead of a kernel boundary per phase.
-struct CholDag {
-    double* A;        // (n+1) x n
-    int n;
-    int* ready;       // ntr x ntc tile flags, then ntc flags for the backward substitution (zeroed before the launch)
-    double* rinv;     // n
-    double* x;        // n: solution
-    const int* go;    // optional gate
-    int* fail;
-};
+// One CTA per lower-triangle tile (i, j) of the augmented matrix [S; g^T], launched in column-major order; all CTAs
+// are co-resident (checked by the host).  The input is read-only; results go to a separate buffer that the host
+// fills with an all-ones bit pattern before the launch, and THE DATA ARE THE FLAGS: a consumer polls the very words
+// it needs (relaxed gpu-scope loads) until none of them is the sentinel, so a hand-over costs one store -> L2 -> load
+// trip instead of data + fence + flag + data.  (Arithmetic never produces the all-ones NaN; stores canonicalise it.)
+//
+// Off-diagonal CTA (i, j): applies L_ik L_jk^T for k < j as the tiles appear, solves against L_jj (DMMA block solve),
+// publishes L_ij; later, when x_i appears, publishes the partial product L_ij^T x_i for the backward sweep.
+// Diagonal CTA (j, j) keeps a private copy of its left neighbour (j, j-1) as well, so that the critical path
+//   L_{j-1,j-1}  ->  solve (j, j-1)  ->  L_jj update  ->  Cholesky of the diagonal tile
+// stays inside one CTA with a single hand-over per block column; in the backward sweep it solves
+// L_jj^T x_j = y_j - sum_t part(t, j) in a fixed order (t descending: deterministic) and immediately produces
+// part(j, j-1) from its private tile for the next diagonal CTA.
+constexpr unsigned long long kDagSentinel = ~0ull;
 
-__device__ __forceinline__ void dag_wait(const int* flag)
+struct CholDag {
+    const double* A;   // (n+1) x n input: reduced matrix, then the gradient as row n (read only)
+    double* L;         // sentinel-initialised, contiguous: L (n+1) x n | part ntr x ntc x 32 | rinv n | xs n
+    int n;
+    double* xout;      // n: solution (plain copy for the kernels that follow)
+    const int* go;     // optional gate
+    int* fail;
+    unsigned long long* trace;   // optional: 8 globaltimer stamps per CTA (diagnostics), else nullptr
+};
+__host__ __device__ inline size_t chol_dag_words(int n)
 {
-    if (threadIdx.x == 0) {
-        int v;
-        do {
-            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
-        } while (v == 0);
-    }
-    __syncthreads();
+    return (size_t)(n + 1) * n + (size_t)chol_row_tiles(n) * chol_col_tiles(n) * kCT + 2 * (size_t)n;
 }
-__device__ __forceinline__ void dag_publish(int* flag)
+
+__device__ __forceinline__ void dag_stamp(const CholDag& D, int k)
 {
-    __syncthreads();
-    if (threadIdx.x == 0)   // release at gpu scope is cumulative over the bar.sync: no separate fence
-        asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(flag), "r"(1) : "memory");
+    if (D.trace && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        D.trace[blockIdx.x * 8 + k] = t;
+    }
+}
+__device__ __forceinline__ unsigned long long dag_ld(const double* p)
+{
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ double dag_poll(const double* p)
+{
+    unsigned long long v;
+    do { v = dag_ld(p); } while (v == kDagSentinel);
+    return __longlong_as_double((long long)v);
+}
+__device__ __forceinline__ void dag_st(double* p, double x)
+{
+    unsigned long long v = (unsigned long long)__double_as_longlong(x);
+    if (v == kDagSentinel) v = 0x7ff8000000000000ull;
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// rows x cols of a published tile (row stride n) into T, zero elsewhere in the 32 x 32 area; 256 threads, 4 words each
+template <bool kLower>
+__device__ __forceinline__ void dag_load_tile(double (*T)[kCLD], const double* src, int n, int rows, int cols)
+{
+    const int r = threadIdx.x >> 5, c = threadIdx.x & 31;   // rows r, r + 8, r + 16, r + 24
+    unsigned long long v[4] = {0, 0, 0, 0};
+    bool ok;
+    do {
+        ok = true;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int rr = r + 8 * q;
+            if (rr < rows && c < cols && (!kLower || c <= rr)) {
+                v[q] = dag_ld(src + (int64_t)rr * n + c);
+                ok = ok && v[q] != kDagSentinel;
+            }
+        }
+    } while (!ok);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) T[r + 8 * q][c] = __longlong_as_double((long long)v[q]);
+}
+__device__ __forceinline__ void dag_load_input(double (*T)[kCLD], const double* src, int n, int rows, int cols)
+{
+    const int r = threadIdx.x >> 5, c = threadIdx.x & 31;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int rr = r + 8 * q;
+        T[rr][c] = (rr < rows && c < cols) ? src[(int64_t)rr * n + c] : 0.0;
+    }
 }
 
 __device__ inline void chol_dag_tile(const CholDag& D)
 {
-    __shared__ __align__(16) double C[kCT + 8][kCLD], A1[kCT + 8][kCLD], B1[kCT + 8][kCLD];
-    __shared__ double s_rinv[kCT], s_part[8][kCT];
+    __shared__ __align__(16) double C[kCT + 8][kCLD], S[kCT][kCLD], A1[kCT][kCLD], B1[kCT][kCLD];
+    __shared__ double s_rinv[kCT], s_x[kCT];
     __shared__ __align__(16) double s_col[4 * kCT], s_winv[kCT * 8];
     __shared__ int s_bad;
     const int tid = threadIdx.x, n = D.n;
     const int ntc = chol_col_tiles(n), ntr = chol_row_tiles(n);
+    double* const Lg = D.L;
+    double* const part = Lg + (size_t)(n + 1) * n;
+    double* const rinvg = part + (size_t)ntr * ntc * kCT;
+    double* const xs = rinvg + n;
     // block index -> (i, j), column-major over the lower triangle
     int j = 0, rem = blockIdx.x;
     while (rem >= ntr - j) { rem -= ntr - j; ++j; }
     const int i = j + rem;
     const int r0 = i * kCT, c0 = j * kCT;
-    const int h = min(kCT, n + 1 - r0), w = min(kCT, n - c0);
+    const int h = min(kCT, n + 1 - r0), w = min(kCT, n - c0);   // rows (may include the g row), columns
+    const int hm = min(kCT, max(n - r0, 0));                     // matrix rows of this tile row
+    dag_stamp(D, 0);
     if (tid == 0) s_bad = 0;
-    for (int idx = tid; idx < kCT * kCT; idx += blockDim.x) {
-        const int r = idx >> 5, c = idx & 31;
-        C[r][c] = (r < h && c < w) ? D.A[(int64_t)(r0 + r) * n + c0 + c] : 0.0;
-    }
-    for (int idx = tid; idx < 8 * kCLD; idx += blockDim.x) { (&C[kCT][0])[idx] = 0.0; (&A1[kCT][0])[idx] = 0.0; (&B1[kCT][0])[idx] = 0.0; }
-    __syncthreads();
-    for (int k = 0; k < j; ++k) {
-        dag_wait(D.ready + i * ntc + k);
-        if (i != j) dag_wait(D.ready + j * ntc + k);
-        const int k0 = k * kCT;
-        for (int idx = tid; idx < kCT * kCT; idx += blockDim.x) {
-            const int r = idx >> 5, c = idx & 31;
-            A1[r][c] = (r < h) ? __ldcg(D.A + (int64_t)(r0 + r) * n + k0 + c) : 0.0;
-            if (i != j) B1[r][c] = (r < w) ? __ldcg(D.A + (int64_t)(c0 + r) * n + k0 + c) : 0.0;
+    dag_load_input(C, D.A + (int64_t)r0 * n + c0, n, h, w);
+    for (int idx = tid; idx < 8 * kCLD; idx += blockDim.x) (&C[kCT][0])[idx] = 0.0;
+    if (i != j) {
+        // ---------------- off-diagonal tile ----------------
+        for (int k = 0; k < j; ++k) {
+            __syncthreads();
+            dag_load_tile<false>(A1, Lg + (int64_t)r0 * n + k * kCT, n, h, kCT);
+            dag_load_tile<false>(B1, Lg + (int64_t)c0 * n + k * kCT, n, w, kCT);
+            __syncthreads();
+            tile_gemm_sub(&C[0][0], &A1[0][0], &B1[0][0]);
         }
         __syncthreads();
-        tile_gemm_sub(&C[0][0], &A1[0][0], (i != j) ? &B1[0][0] : &A1[0][0]);
+        dag_stamp(D, 1);
+        dag_load_tile<true>(B1, Lg + (int64_t)c0 * n + c0, n, w, w);
+        if (tid < kCT) s_rinv[tid] = tid < w ? dag_poll(rinvg + c0 + tid) : 0.0;
         __syncthreads();
-    }
-    if (i == j) {
-        if (tid < 32) tile_potrf_warp(&C[0][0], w, s_rinv, &s_bad, s_col);
-        __syncthreads();
-        if (h > w) tile_trsm_dmma(&C[w][0], 1, &C[0][0], s_rinv, w, s_winv);   // the g row lives in this tile (ragged last column)
-        __syncthreads();
-        for (int idx = tid; idx < kCT * kCT; idx += blockDim.x) {
-            const int r = idx >> 5, c = idx & 31;
-            if (r < h && c < w && c <= r) D.A[(int64_t)(r0 + r) * n + c0 + c] = C[r][c];
-        }
-        if (tid < w) D.rinv[c0 + tid] = s_rinv[tid];
-        if (tid == 0 && s_bad) *D.fail = 1;
-        dag_publish(D.ready + i * ntc + j);
-    } else {
-        dag_wait(D.ready + j * ntc + j);
-        for (int idx = tid; idx < kCT * kCT; idx += blockDim.x) {
-            const int r = idx >> 5, c = idx & 31;
-            B1[r][c] = (r < w && c <= r) ? __ldcg(D.A + (int64_t)(c0 + r) * n + c0 + c) : 0.0;
-        }
-        if (tid < kCT) s_rinv[tid] = tid < w ? __ldcg(D.rinv + c0 + tid) : 0.0;
-        __syncthreads();
+        dag_stamp(D, 2);
         tile_trsm_dmma(&C[0][0], h, &B1[0][0], s_rinv, w, s_winv);
         __syncthreads();
-        for (int idx = tid; idx < kCT * kCT; idx += blockDim.x) {
-            const int r = idx >> 5, c = idx & 31;
-            if (r < h && c < w) D.A[(int64_t)(r0 + r) * n + c0 + c] = C[r][c];
+        {
+            const int r = tid >> 5, c = tid & 31;
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (r + 8 * q < h && c < w) dag_st(Lg + (int64_t)(r0 + r + 8 * q) * n + c0 + c, C[r + 8 * q][c]);
         }
-        dag_publish(D.ready + i * ntc + j);
+        dag_stamp(D, 3);
+        // backward sweep: part(i, j) = L_ij^T x_i.  (i == j + 1 is produced by the diagonal CTA i from its private copy.)
+        if (i >= j + 2 && i < ntc && tid < kCT) {
+            s_x[tid] = tid < hm ? dag_poll(xs + r0 + tid) : 0.0;
+            __syncwarp();
+            double p0 = 0.0, p1 = 0.0;
+#pragma unroll 4
+            for (int r = 0; r < kCT; r += 2) {
+                p0 = fma(C[r][tid], s_x[r], p0);
+                p1 = fma(C[r + 1][tid], s_x[r + 1], p1);
+            }
+            if (tid < w) dag_st(part + ((size_t)i * ntc + j) * kCT + tid, p0 + p1);
+        }
         return;
     }
-    // ---- backward substitution, diagonal CTAs only: x_j = L_jj^-T (y_j - sum_{t>j} L_tj^T x_t) ------------------
-    int* xready = D.ready + ntr * ntc;
-    const int ig = n / kCT;                       // row tile that holds the g row (row n)
-    if (ig != j) dag_wait(D.ready + ig * ntc + j);   // y_j = A[n][c0 ..] final
-    const int lane = tid & 31, wp = tid >> 5;        // 8 warps over rows, lanes over columns
-    double sacc = 0.0;
-    for (int t = ntc - 1; t > j; --t) {
-        dag_wait(xready + t);                        // also implies tile (t, j) is final (x_t needed it... see below)
-        dag_wait(D.ready + t * ntc + j);
-        const int rt = t * kCT, ht = min(kCT, n - rt);
-        if (lane < w)
-            for (int r = wp; r < ht; r += 8) sacc += __ldcg(D.A + (int64_t)(rt + r) * n + c0 + lane) * __ldcg(D.x + rt + r);
+    // ---------------- diagonal tile ----------------
+    if (j > 0) dag_load_input(S, D.A + (int64_t)r0 * n + c0 - kCT, n, h, kCT);
+    for (int k = 0; k + 1 < j; ++k) {
+        __syncthreads();
+        dag_load_tile<false>(A1, Lg + (int64_t)r0 * n + k * kCT, n, h, kCT);
+        dag_load_tile<false>(B1, Lg + (int64_t)(c0 - kCT) * n + k * kCT, n, kCT, kCT);
+        __syncthreads();
+        tile_gemm_sub(&C[0][0], &A1[0][0], &A1[0][0]);
+        tile_gemm_sub(&S[0][0], &A1[0][0], &B1[0][0]);
     }
-    s_part[wp][lane] = sacc;
     __syncthreads();
-    if (wp == 0) {
-        double tsum = 0.0;
-#pragma unroll
-        for (int q = 0; q < 8; ++q) tsum += s_part[q][lane];
-        double yv = 0.0;
-        if (lane < w) yv = (ig == j ? C[w][lane] : __ldcg(D.A + (int64_t)n * n + c0 + lane)) - tsum;
-        const double myrinv = lane < w ? s_rinv[lane] : 1.0;
-        for (int c = w - 1; c >= 0; --c) {
-            const double xc = __shfl_sync(0xffffffffu, yv * myrinv, c);
-            if (lane == c) yv = xc;
-            if (lane < c) yv -= C[c][lane] * xc;
-        }
-        if (lane < w) D.x[c0 + lane] = yv;
+    dag_stamp(D, 1);
+    if (j > 0) {
+        dag_load_tile<true>(B1, Lg + (int64_t)(c0 - kCT) * n + c0 - kCT, n, kCT, kCT);
+        if (tid < kCT) s_rinv[tid] = dag_poll(rinvg + c0 - kCT + tid);
+        __syncthreads();
+        dag_stamp(D, 2);
+        tile_trsm_dmma(&S[0][0], h, &B1[0][0], s_rinv, kCT, s_winv);
+        __syncthreads();
+        tile_gemm_sub(&C[0][0], &S[0][0], &S[0][0]);
+        __syncthreads();
     }
-    dag_publish(xready + j);
+    if (tid < 32) tile_potrf_warp(&C[0][0], w, s_rinv, &s_bad, s_col);
+    __syncthreads();
+    if (h > w) {   // the g row lives in this tile (ragged last block column)
+        tile_trsm_dmma(&C[w][0], 1, &C[0][0], s_rinv, w, s_winv);
+        __syncthreads();
+    }
+    {
+        const int r = tid >> 5, c = tid & 31;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int rr = r + 8 * q;
+            if (rr < h && c < w && (c <= rr)) dag_st(Lg + (int64_t)(r0 + rr) * n + c0 + c, C[rr][c]);
+        }
+        if (tid < w) dag_st(rinvg + c0 + tid, s_rinv[tid]);
+        if (tid == 0 && s_bad) *D.fail = 1;
+    }
+    dag_stamp(D, 3);
+    // ---- backward substitution: x_j = L_jj^-T (y_j - sum_{t > j} part(t, j)), warp 0 ----------------------------
+    if (tid >= 32) return;
+    const int lane = tid;
+    const int ig = n / kCT;                       // row tile that holds the g row (row n)
+    double yv = 0.0;
+    if (lane < w) {
+        yv = (ig == j) ? C[w][lane] : dag_poll(Lg + (int64_t)n * n + c0 + lane);
+        for (int t = ntc - 1; t > j; --t) yv -= dag_poll(part + ((size_t)t * ntc + j) * kCT + lane);
+    }
+    dag_stamp(D, 5);
+    const double myrinv = lane < w ? s_rinv[lane] : 1.0;
+    for (int c = w - 1; c >= 0; --c) {
+        const double xc = __shfl_sync(0xffffffffu, yv * myrinv, c);
+        if (lane == c) yv = xc;
+        if (lane < c) yv -= C[c][lane] * xc;
+    }
+    s_x[lane] = lane < w ? yv : 0.0;
+    __syncwarp();
+    if (j > 0) {   // part(j, j-1) = L_{j,j-1}^T x_j from the private copy: the only hand-over on the backward chain
+        double p0 = 0.0, p1 = 0.0;
+#pragma unroll 4
+        for (int r = 0; r < kCT; r += 2) {
+            p0 = fma(S[r][lane], r < hm ? s_x[r] : 0.0, p0);
+            p1 = fma(S[r + 1][lane], r + 1 < hm ? s_x[r + 1] : 0.0, p1);
+        }
+        dag_st(part + ((size_t)j * ntc + j - 1) * kCT + lane, p0 + p1);
+    }
+    if (lane < w) { dag_st(xs + c0 + lane, yv); D.xout[c0 + lane] = yv; }
+    dag_stamp(D, 6);
 }
 
 // Trailing update of step k for tile (ti, tj): A[ti][tj] -= L[ti][k] * L[tj][k]^T.  256 threads, one tile per CTA.

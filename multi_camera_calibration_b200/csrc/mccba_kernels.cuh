@@ -94,7 +94,7 @@ struct Problem {
     double* ar;          // allreduce buffer: S (ns x ns) | g (ns) | cost, step2, param2, bad
     double* dc;          // ns: camera step in tangent coordinates
     double* rinv;        // ns: reciprocal diagonal of the Cholesky factor
-    int* dag_flags;      // tile-DAG ready flags (ntr*ntc + ntc ints), zeroed before every factorisation
+    double* dag_buf;     // tile-DAG output (chol_dag_words doubles), filled with the all-ones sentinel before every factorisation
     double* norm_part;   // 2 x n_k4_blocks: per-block |step|^2, |trial|^2 of the frames
     EdgeRec* erec;       // n_edge_int composed poses of the point the residual kernel evaluates next
     const EdgeMeta* emeta; // n_edge_int camera / corner range of every internal edge
