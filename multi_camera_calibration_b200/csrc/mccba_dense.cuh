@@ -282,67 +282,155 @@ __device__ __forceinline__ double pivot_rcp(double d)
 // destination of the update fma, so it is free).  The pivot loop is software-pipelined: as soon as the first update
 // fma has produced the next pivot column it goes to shared memory, and its broadcast + 1/d_{j+1} overlap the
 // remaining 30 fmas of pivot j.  Columns are stored unscaled and multiplied by 1/sqrt(d_j) in one pass at the end.
-// `colbuf` = 2 x 64 doubles of shared memory.  rinv[0..w) <- 1 / L_jj.  A pivot outside [1e-200, 1e200] = failure.
+// `colbuf` = 2 x 64 doubles of shared memory.  A pivot outside [1e-200, 1e200] = failure.  tile_potrf_scale() finishes.
+#ifdef MCCBA_POTRF_DBG
+__device__ long long g_potrf_ts[40];
+#endif
+template <int NW>
 struct PotrfCol {
-    double c[kCT - 1];   // column entries below the pivot, broadcast to every lane
-    double d, t;         // pivot, a_ij / d_j
+    double c[NW - 1];   // column entries below the pivot, broadcast to every lane
+    double d, t;        // pivot, a_ij / d_j
 };
 
-__device__ __forceinline__ void potrf_fetch(const double* cb, int j, double a0, PotrfCol& col)
+// Order-pinned arithmetic for the pivot step: the SM issues in order and ptxas, left alone, parks the whole update
+// block in front of the reciprocal chain; volatile asm keeps the hand-made interleave (chain op, a few independent
+// update fmas in its shadow, next chain op ...).
+__device__ __forceinline__ double pin_fma(double a, double b, double c)
 {
-    col.d = cb[j];
-    const double* cj = cb + j + 1;
-#pragma unroll
-    for (int k = 0; k < kCT - 1; ++k) col.c[k] = cj[k];
-    col.t = a0 * pivot_rcp(col.d);
+    double d;
+    asm volatile("fma.rn.f64 %0, %1, %2, %3;" : "=d"(d) : "d"(a), "d"(b), "d"(c));
+    return d;
+}
+__device__ __forceinline__ double pin_nfma(double a, double b, double c)   // c - a * b
+{
+    double d;
+    asm volatile("{ .reg .f64 na; neg.f64 na, %1; fma.rn.f64 %0, na, %2, %3; }" : "=d"(d) : "d"(a), "d"(b), "d"(c));
+    return d;
+}
+__device__ __forceinline__ double pin_nmul(double a, double b)            // -(a * b)
+{
+    double d;
+    asm volatile("{ .reg .f64 na; neg.f64 na, %1; mul.rn.f64 %0, na, %2; }" : "=d"(d) : "d"(a), "d"(b));
+    return d;
+}
+__device__ __forceinline__ double pin_rcp_seed(double a)
+{
+    double d;
+    asm volatile("rcp.approx.ftz.f64 %0, %1;" : "=d"(d) : "d"(a));
+    return d;
 }
 
-__device__ __forceinline__ void potrf_step(double* C, double* colbuf, int lane, int j, int w, double (&a)[kCT], const PotrfCol& cur,
-                                           PotrfCol& nxt, int& bad)
+// One pivot with NW live columns (a[k] = A[lane][j + k]); `t` fields hold -a_ij / d_j.  The column of pivot j + 1 is
+// broadcast with 16-byte shared-memory loads from an even offset; kNextOdd says whether j + 1 is odd (then the pivot
+// is the second word).  The NW - 2 remaining update fmas of pivot j are spread over the six latency gaps of the
+// reciprocal chain of pivot j + 1 (MUFU, four Newton fmas, the final multiply).
+template <int NW, bool kNextOdd>
+__device__ __forceinline__ void potrf_step(double* C, double* colbuf, int lane, int j, int w, double (&a)[NW],
+                                           const PotrfCol<NW>& cur, PotrfCol<NW>& nxt, int& bad)
 {
-    if (lane >= j && lane < w) C[lane * kCLD + j] = a[0];
-    if (!(cur.d > 1e-200 && cur.d < 1e200)) bad = 1;
-    const double a0n = fma(-cur.t, cur.c[0], a[1]);
+#ifdef MCCBA_POTRF_DBG
+    if (lane == 0) g_potrf_ts[j] = clock64();
+#endif
+    const double a0n = pin_fma(cur.t, cur.c[0], a[1]);
     double* cbn = colbuf + ((j + 1) & 1) * 2 * kCT;
     cbn[lane] = a0n;
     __syncwarp();
-    nxt.d = cbn[j + 1];
-    const double* cj = cbn + j + 2;
+    const unsigned vaddr = (unsigned)__cvta_generic_to_shared(cbn + ((j + 1) & ~1));
+    double v[NW];
 #pragma unroll
-    for (int k = 0; k < kCT - 1; ++k) nxt.c[k] = cj[k];
+    for (int p = 0; p < NW / 2; ++p)
+        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v[2 * p]), "=d"(v[2 * p + 1]) : "r"(vaddr + 16u * p) : "memory");
+    if (lane >= j && lane < w) C[lane * kCLD + j] = a[0];
+    if (!(cur.d > 1e-200 && cur.d < 1e200)) bad = 1;
+    const double d = kNextOdd ? v[1] : v[0];
+    constexpr int nF = NW - 2;
+    int k = 1;   // compile-time after unrolling
+    double y = pin_rcp_seed(d), r = 0.0, tn = 0.0;
 #pragma unroll
-    for (int k = 1; k < kCT - 1; ++k) a[k] = fma(-cur.t, cur.c[k], a[k + 1]);
+    for (int gap = 0; gap < 6; ++gap) {
+#pragma unroll
+        for (int f = (nF * gap) / 6; f < (nF * (gap + 1)) / 6; ++f, ++k) a[k] = pin_fma(cur.t, cur.c[k], a[k + 1]);
+        if (gap == 0) r = pin_nfma(d, y, 1.0);
+        else if (gap == 1) y = pin_fma(y, r, y);
+        else if (gap == 2) r = pin_nfma(d, y, 1.0);
+        else if (gap == 3) y = pin_fma(y, r, y);
+        else if (gap == 4) tn = pin_nmul(a0n, y);
+    }
     a[0] = a0n;
-    a[kCT - 1] = 0.0;
-    nxt.t = a0n * pivot_rcp(nxt.d);
+    a[NW - 1] = 0.0;
+    nxt.d = d;
+    nxt.t = tn;
+    if (!kNextOdd) {
+#pragma unroll
+        for (int q = 0; q < NW - 1; ++q) nxt.c[q] = v[1 + q];
+    } else {
+#pragma unroll
+        for (int q = 0; q < NW - 2; ++q) nxt.c[q] = v[2 + q];
+        nxt.c[NW - 2] = 0.0;   // column j + NW: past the tile
+    }
 }
 
-__device__ inline void tile_potrf_warp(double* C, int w, double* rinv, int* bad_flag, double* colbuf)
+__device__ inline void tile_potrf_warp(double* C, int w, int* bad_flag, double* colbuf)
 {
     const int lane = threadIdx.x & 31;
     double a[kCT];   // a[k] = A[lane][j + k] at pivot j
+    {
+        const double2* row = reinterpret_cast<const double2*>(C + lane * kCLD);   // rows are 16-byte aligned
 #pragma unroll
-    for (int k = 0; k < kCT; ++k) a[k] = (lane < w && k <= lane) ? C[lane * kCLD + k] : (k == lane ? 1.0 : 0.0);
+        for (int k = 0; k < kCT; k += 2) {
+            const double2 q = row[k >> 1];
+            a[k] = (lane < w && k <= lane) ? q.x : (k == lane ? 1.0 : 0.0);
+            a[k + 1] = (lane < w && k + 1 <= lane) ? q.y : (k + 1 == lane ? 1.0 : 0.0);
+        }
+    }
     colbuf[kCT + lane] = 1.0;       // what pivots past the tile read
     colbuf[3 * kCT + lane] = 1.0;
     colbuf[lane] = a[0];
     __syncwarp();
     int bad = 0;
-    PotrfCol c0, c1;
-    potrf_fetch(colbuf, 0, a[0], c0);
+    PotrfCol<kCT> c0, c1;
+    c0.d = colbuf[0];
+#pragma unroll
+    for (int k = 0; k < kCT - 1; ++k) c0.c[k] = colbuf[1 + k];
+    c0.t = -a[0] * pivot_rcp(c0.d);
+    const int wa = min(w, kCT / 2);
 #pragma unroll 1
-    for (int j = 0; j < w; j += 2) {
-        potrf_step(C, colbuf, lane, j, w, a, c0, c1, bad);
-        if (j + 1 < w) potrf_step(C, colbuf, lane, j + 1, w, a, c1, c0, bad);
+    for (int j = 0; j < wa; j += 2) {   // pivots 0..15: 32 live columns
+        potrf_step<kCT, true>(C, colbuf, lane, j, w, a, c0, c1, bad);
+        if (j + 1 < wa) potrf_step<kCT, false>(C, colbuf, lane, j + 1, w, a, c1, c0, bad);
     }
-    __syncwarp();
-    double ri = 1.0;
-    if (lane < w) { ri = rsqrt(C[lane * kCLD + lane]); rinv[lane] = ri; }
-    colbuf[lane] = ri;
-    __syncwarp();
-    if (lane < w)
-        for (int k = 0; k <= lane; ++k) C[lane * kCLD + k] *= colbuf[k];
+    if (w > kCT / 2) {                  // pivots 16..31: 16 live columns
+        double b[kCT / 2];
+        PotrfCol<kCT / 2> e0, e1;
+#pragma unroll
+        for (int k = 0; k < kCT / 2; ++k) b[k] = a[k];
+        e0.d = c0.d; e0.t = c0.t;
+#pragma unroll
+        for (int k = 0; k < kCT / 2 - 1; ++k) e0.c[k] = c0.c[k];
+#pragma unroll 1
+        for (int j = kCT / 2; j < w; j += 2) {
+            potrf_step<kCT / 2, true>(C, colbuf, lane, j, w, b, e0, e1, bad);
+            if (j + 1 < w) potrf_step<kCT / 2, false>(C, colbuf, lane, j + 1, w, b, e1, e0, bad);
+        }
+    }
+#ifdef MCCBA_POTRF_DBG
+    if (lane == 0) g_potrf_ts[32] = clock64();
+#endif
     if (bad) *bad_flag = 1;
+}
+
+// Second half of the factorisation, all threads (after a barrier): rinv_j = 1 / sqrt(d_j), L_ij = a_ij * rinv_j.
+// Ends with a barrier.
+__device__ __forceinline__ void tile_potrf_scale(double* C, int w, double* rinv)
+{
+    const int tid = threadIdx.x;
+    if (tid < kCT) rinv[tid] = tid < w ? rsqrt(C[tid * kCLD + tid]) : 0.0;
+    __syncthreads();
+    const int r = tid >> 5, c = tid & 31;
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+        if (r + 8 * q < w && c <= r + 8 * q) C[(r + 8 * q) * kCLD + c] *= rinv[c];
+    __syncthreads();
 }
 
 // FP64 tensor-core MMA (DMMA), D(8x8) += A(8x4, row) * B(4x8, col).  Lane = 4 g + t holds A[g][t], B[t][g] and
@@ -372,6 +460,74 @@ __device__ __forceinline__ void tile_gemm_sub(double* C, const double* A, const 
     }
     double* cp = C + (8 * tr + g) * kCLD + 8 * tc0 + 2 * t;
     cp[0] -= c00 + d00; cp[1] -= c01 + d01; cp[8] -= c10 + d10; cp[9] -= c11 + d11;
+}
+
+// Blocked Cholesky of the w x w lower triangle in C (stride kCLD), called by all 256 threads.  Per 8-column panel:
+// warp 0 eliminates the 8 pivots with lane = row and the panel in registers -- the dependent chain per pivot is
+// shuffle(d_j) -> 1/d_j -> a_ij/d_j -> fma, about 90 cycles -- then all warps apply the rank-8 update of the
+// trailing tiles with DMMA.  Columns stay unscaled (R) next to their 1/d_j-scaled copy T until one final pass
+// multiplies by 1/sqrt(d_j).  `T` = 32 x 8 doubles of shared memory.  rinv[0..w) <- 1 / L_jj; rows >= w of C are not
+// touched.  A pivot outside [1e-200, 1e200] = failure.
+__device__ inline void tile_potrf_blocked(double* C, int w, double* rinv, int* bad_flag, double* T)
+{
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t4 = lane & 3;
+    for (int p0 = 0; p0 < w; p0 += 8) {
+        if (warp == 0) {
+            double a[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) a[k] = lane < w ? C[lane * kCLD + p0 + k] : (p0 + k == lane ? 1.0 : 0.0);
+            int bad = 0;
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) {
+                const int j = p0 + jj;
+                if (j < w) {
+                    const double d = __shfl_sync(0xffffffffu, a[jj], j);
+                    double ck[8];
+#pragma unroll
+                    for (int k = jj + 1; k < 8; ++k) ck[k] = __shfl_sync(0xffffffffu, a[jj], p0 + k);
+                    const double tt = a[jj] * pivot_rcp(d);
+                    if (!(d > 1e-200 && d < 1e200)) bad = 1;
+                    T[lane * 8 + jj] = lane > j ? tt : 0.0;
+#pragma unroll
+                    for (int k = jj + 1; k < 8; ++k) a[k] = fma(-tt, ck[k], a[k]);
+                } else {
+                    T[lane * 8 + jj] = 0.0;
+                }
+            }
+            if (lane < w) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    if (p0 + k < w && lane >= p0 + k) C[lane * kCLD + p0 + k] = a[k];
+            }
+            if (bad) *bad_flag = 1;
+        }
+        __syncthreads();
+        // trailing tiles (tr >= tc > b): C_tr,tc -= T_tr R_tc^T, R = the unscaled panel columns
+        const int b = p0 >> 3, nt = 3 - b;
+        if (warp < nt * (nt + 1) / 2 && p0 + 8 < w) {
+            int tr = 0, rem = warp;
+            while (rem > tr) { rem -= tr + 1; ++tr; }
+            const int tc = rem + b + 1;
+            tr += b + 1;
+            double* cp = C + (8 * tr + g) * kCLD + 8 * tc + 2 * t4;
+            double c0 = cp[0], c1 = cp[1];
+            const double* tp = T + (8 * tr + g) * 8 + t4;
+            const double* rp = C + (8 * tc + g) * kCLD + p0 + t4;
+            dmma(c0, c1, -tp[0], rp[0]);
+            dmma(c0, c1, -tp[4], rp[4]);
+            cp[0] = c0; cp[1] = c1;
+        }
+        __syncthreads();
+    }
+    if (tid < kCT) rinv[tid] = tid < w ? rsqrt(C[tid * kCLD + tid]) : 0.0;
+    __syncthreads();
+    {
+        const int r = tid >> 5, c = tid & 31;
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (r + 8 * q < w && c <= r + 8 * q) C[(r + 8 * q) * kCLD + c] *= rinv[c];
+    }
+    __syncthreads();
 }
 
 // Rows of a tile against the w x w factor L (stride kCLD): X L^T = P in place for up to 32 rows of P.  Warps 0..3
@@ -597,8 +753,9 @@ __device__ inline void chol_dag_tile(const CholDag& D)
         tile_gemm_sub(&C[0][0], &S[0][0], &S[0][0]);
         __syncthreads();
     }
-    if (tid < 32) tile_potrf_warp(&C[0][0], w, s_rinv, &s_bad, s_col);
+    if (tid < 32) tile_potrf_warp(&C[0][0], w, &s_bad, s_col);
     __syncthreads();
+    tile_potrf_scale(&C[0][0], w, s_rinv);
     if (h > w) {   // the g row lives in this tile (ragged last block column)
         tile_trsm_dmma(&C[w][0], 1, &C[0][0], s_rinv, w, s_winv);
         __syncthreads();

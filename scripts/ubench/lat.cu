@@ -84,11 +84,11 @@ __global__ void lat_kernel(double* out, long long* cyc, double seed)
 }
 
 // POTRF variants on a 32x32 SPD tile: cold (first call) and warm (second call in the same kernel)
-__global__ void potrf_kernel(const double* A, double* L, long long* cyc, int variant)
+__global__ void potrf_kernel(const double* A, double* L, long long* cyc, int variant, int wtest)
 {
-    __shared__ double C[kCT][kCLD];
+    __shared__ __align__(16) double C[kCT][kCLD];
     __shared__ double s_rinv[kCT];
-    __shared__ __align__(16) double s_col[4 * kCT];
+    __shared__ __align__(16) double s_col[8 * kCT];
     __shared__ int s_bad;
     const int tid = threadIdx.x;
     for (int rep = 0; rep < 3; ++rep) {
@@ -96,8 +96,9 @@ __global__ void potrf_kernel(const double* A, double* L, long long* cyc, int var
         if (tid == 0) s_bad = 0;
         __syncthreads();
         const long long t0 = clock64();
-        if (variant == 0) tile_potrf(&C[0][0], kCT, s_rinv, &s_bad);
-        else if (tid < 32) tile_potrf_warp(&C[0][0], kCT, s_rinv, &s_bad, s_col);
+        if (variant == 0) tile_potrf(&C[0][0], wtest, s_rinv, &s_bad);
+        else if (variant == 1) { if (tid < 32) tile_potrf_warp(&C[0][0], wtest, &s_bad, s_col); __syncthreads(); tile_potrf_scale(&C[0][0], wtest, s_rinv); }
+        else tile_potrf_blocked(&C[0][0], wtest, s_rinv, &s_bad, s_col);
         __syncthreads();
         const long long t1 = clock64();
         if (tid == 0) cyc[rep] = t1 - t0;
@@ -159,16 +160,18 @@ int main()
     double *dA, *dL, *dP, *dX; cudaMalloc(&dA, sizeof(hA)); cudaMalloc(&dL, sizeof(hL)); cudaMalloc(&dP, sizeof(hP)); cudaMalloc(&dX, sizeof(hX));
     cudaMemcpy(dA, hA, sizeof(hA), cudaMemcpyHostToDevice);
     cudaMemcpy(dP, hP, sizeof(hP), cudaMemcpyHostToDevice);
-    for (int v = 0; v < 2; ++v) {
-        potrf_kernel<<<1, 256>>>(dA, dL, d_cyc, v);
+    for (int wt : {32, 26, 5})
+    for (int v = 0; v < 3; ++v) {
+        potrf_kernel<<<1, 256>>>(dA, dL, d_cyc, v, wt);
         cudaMemcpy(c, d_cyc, sizeof(c), cudaMemcpyDeviceToHost);
         cudaMemcpy(hL, dL, sizeof(hL), cudaMemcpyDeviceToHost);
-        double err = 0;
-        for (int i = 0; i < 32; ++i) for (int j = 0; j <= i; ++j) {
+        double err = 0, rowkeep = 0;
+        for (int i = 0; i < wt; ++i) for (int j = 0; j <= i; ++j) {
             double s = 0; for (int k = 0; k <= j; ++k) s += hL[i * 32 + k] * hL[j * 32 + k];
             err = fmax(err, fabs(s - hA[i * 32 + j]));
         }
-        printf("potrf variant %d: cold %lld, warm %lld %lld cycles, |LL^T-A| %.2e\n", v, c[0], c[1], c[2], err);
+        if (wt < 32) for (int j = 0; j < wt; ++j) rowkeep = fmax(rowkeep, fabs(hL[wt * 32 + j] - hA[wt * 32 + j]));   // the row below must survive
+        printf("potrf variant %d w %d: cold %lld, warm %lld %lld cycles, |LL^T-A| %.2e, row w changed by %.1e\n", v, wt, c[0], c[1], c[2], err, rowkeep);
     }
     for (int v = 0; v < 2; ++v) {
         trsm_kernel<<<1, 256>>>(dL, dP, dX, d_cyc, v);
