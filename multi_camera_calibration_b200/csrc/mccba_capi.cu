@@ -213,7 +213,7 @@ int enqueue_iteration(mccba_handle h, bool timed)
     CUDA_TRY(h, cudaMemsetAsync(P.ar, 0, sizeof(double) * (size_t)h->ar_len, s));
     launch_schur(h, s, -1, 0.0);
     if (timed) cudaEventRecord(ev[1], s);
-    reduce_records_kernel<<<(P.n_dest * 32 + 127) / 128, 128, 0, s>>>(P, 0);
+    reduce_records_kernel<<<P.n_dest, kK3Threads, 0, s>>>(P, 0);
     if (timed) cudaEventRecord(ev[2], s);
     if (h->opts.nranks > 1) {
         ncclResult_t r = nccl().AllReduce(P.ar, P.ar, (size_t)h->ar_len, kNcclFloat64, kNcclSum, h->comm, s);
@@ -778,7 +778,7 @@ int mccba_reduced_system(mccba_handle h, double lambda, double* S, double* gs)
     Problem& P = h->P;
     CUDA_TRY(h, cudaMemsetAsync(P.ar, 0, sizeof(double) * (size_t)h->ar_len, h->stream));
     launch_schur(h, h->stream, h->cur, lambda);
-    reduce_records_kernel<<<(P.n_dest * 32 + 127) / 128, 128, 0, h->stream>>>(P, 1);
+    reduce_records_kernel<<<P.n_dest, kK3Threads, 0, h->stream>>>(P, 1);
     CUDA_TRY(h, cudaGetLastError());
     if (h->opts.nranks > 1) {
         ncclResult_t r = nccl().AllReduce(P.ar, P.ar, (size_t)h->ar_len, kNcclFloat64, kNcclSum, h->comm, h->stream);

@@ -614,40 +614,69 @@ __global__ void __launch_bounds__(kK2Threads, kMinBlocks) frame_schur_kernel(Pro
 }
 
 // --------------------------------------------------------------------------------------------------------
-// K3a: sum the warp records into the reduced system, one warp per destination, sources in fixed order.
+// K3a: sum the warp records into the reduced system.  One CTA (8 warps) per destination: the source list is cut
+// into 8 contiguous slices (a fixed partition: the result is bit-stable run to run), every warp sums its slice in
+// order with the record offsets fetched 32 at a time and 8 gathers in flight, and warp 0 adds the 8 partial sums in
+// order.  The kernel is pure L2 latency (a few hundred dependent gathers per destination), hence the width.
 // ar must be zeroed beforehand (blocks without sources stay zero).
 // --------------------------------------------------------------------------------------------------------
-__global__ void reduce_records_kernel(Problem P, int forced)
+constexpr int kK3Threads = 256;
+__global__ void __launch_bounds__(kK3Threads) reduce_records_kernel(Problem P, int forced)
 {
     if (!forced && P.st->done) return;
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (warp >= P.n_dest) return;
-    const int kind = P.dest_info[4 * warp], A = P.dest_info[4 * warp + 1], B = P.dest_info[4 * warp + 2];
-    const int s0 = P.dest_src0[warp], s1 = P.dest_src0[warp + 1];
+    __shared__ double s_part[kK3Threads / 32][40];
+    const int dest = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int kind = P.dest_info[4 * dest], A = P.dest_info[4 * dest + 1], B = P.dest_info[4 * dest + 2];
+    const int s0 = P.dest_src0[dest], s1 = P.dest_src0[dest + 1];
     const int ns = P.ns;
     double* S = P.ar;
     double* gs = P.ar + (int64_t)ns * ns;
     double* sc = gs + ns;
-    if (kind == 0) {
-        // sources summed in a fixed order; 8 independent loads in flight (the list is a gather over warp records)
-        double a0 = 0, a1 = 0;
-        int s = s0;
-        for (; s + 8 <= s1; s += 8) {
+    if (kind == 2) {
+        // scalars: cost and bad from every warp record; frame step / param norms from frame_update's partials
+        double c = 0, b = 0, n0 = 0, n1 = 0;
+        for (int w = threadIdx.x; w < P.n_warps; w += kK3Threads) { c += P.warp_scal[w]; b += P.warp_scal[P.n_warps + w]; }
+        for (int k = threadIdx.x; k < P.n_k4_blocks; k += kK3Threads) { n0 += P.norm_part[k]; n1 += P.norm_part[P.n_k4_blocks + k]; }
+        c = warp_sum(c); b = warp_sum(b); n0 = warp_sum(n0); n1 = warp_sum(n1);
+        if (lane == 0) { s_part[warp][0] = c; s_part[warp][1] = n0; s_part[warp][2] = n1; s_part[warp][3] = b; }
+        __syncthreads();
+        if (threadIdx.x < 4) {
+            double t = 0;
+#pragma unroll
+            for (int w = 0; w < kK3Threads / 32; ++w) t += s_part[w][threadIdx.x];
+            sc[threadIdx.x] = t;
+        }
+        return;
+    }
+    const int per = (s1 - s0 + kK3Threads / 32 - 1) / (kK3Threads / 32);
+    const int b0 = min(s0 + warp * per, s1), e0 = min(b0 + per, s1);
+    const bool hi = kind == 0 && lane < 4;        // elements 32..35 of a 6 x 6 block
+    const bool lo = kind == 0 || lane < 6;        // kind 1: 6 gradient entries
+    double a0 = 0, a1 = 0;
+    for (int s = b0; s < e0; s += 32) {
+        const int cnt = min(32, e0 - s);
+        const int myoff = lane < cnt ? P.dest_src[s + lane] : 0;
+        for (int q0 = 0; q0 < cnt; q0 += 8) {
             double v[8], u[8];
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
-                const double* src = P.records + P.dest_src[s + q];
-                v[q] = src[lane];
-                u[q] = lane < 4 ? src[32 + lane] : 0.0;
+                const int off = __shfl_sync(kFull, myoff, (q0 + q) & 31);
+                const bool on = q0 + q < cnt;
+                v[q] = (on && lo) ? P.records[off + lane] : 0.0;
+                u[q] = (on && hi) ? P.records[off + 32 + lane] : 0.0;
             }
 #pragma unroll
             for (int q = 0; q < 8; ++q) { a0 += v[q]; a1 += u[q]; }
         }
-        for (; s < s1; ++s) {
-            const double* src = P.records + P.dest_src[s];
-            a0 += src[lane];
-            if (lane < 4) a1 += src[32 + lane];
-        }
+    }
+    s_part[warp][lane] = a0;
+    if (lane < 4) s_part[warp][32 + lane] = a1;
+    __syncthreads();
+    if (warp != 0) return;
+    a0 = 0; a1 = 0;
+#pragma unroll
+    for (int w = 0; w < kK3Threads / 32; ++w) { a0 += s_part[w][lane]; if (lane < 4) a1 += s_part[w][32 + lane]; }
+    if (kind == 0) {
         {
             const int i = lane / 6, j = lane % 6;
             S[(int64_t)(6 * A + i) * ns + 6 * B + j] = a0;
@@ -658,40 +687,8 @@ __global__ void reduce_records_kernel(Problem P, int forced)
             S[(int64_t)(6 * A + i) * ns + 6 * B + j] = a1;
             if (A != B) S[(int64_t)(6 * B + j) * ns + 6 * A + i] = a1;
         }
-    } else if (kind == 1) {
-        double a0 = 0;
-        if (lane < 6) {
-            int s = s0;
-            for (; s + 8 <= s1; s += 8) {
-                double v[8];
-#pragma unroll
-                for (int q = 0; q < 8; ++q) v[q] = P.records[P.dest_src[s + q] + lane];
-#pragma unroll
-                for (int q = 0; q < 8; ++q) a0 += v[q];
-            }
-            for (; s < s1; ++s) a0 += P.records[P.dest_src[s] + lane];
-            gs[6 * A + lane] = a0;
-        }
-    } else {
-        // scalars: cost and bad from every warp record; frame step / param norms from frame_update's partials
-        double c = 0, b = 0, n0 = 0, n1 = 0;
-        {
-            int w = lane;
-            for (; w + 7 * 32 < P.n_warps; w += 8 * 32) {
-                double v[8], u[8];
-#pragma unroll
-                for (int q = 0; q < 8; ++q) { v[q] = P.warp_scal[w + 32 * q]; u[q] = P.warp_scal[P.n_warps + w + 32 * q]; }
-#pragma unroll
-                for (int q = 0; q < 8; ++q) { c += v[q]; b += u[q]; }
-            }
-            for (; w < P.n_warps; w += 32) { c += P.warp_scal[w]; b += P.warp_scal[P.n_warps + w]; }
-        }
-        for (int k = lane; k < P.n_k4_blocks; k += 32) {
-            n0 += P.norm_part[k];
-            n1 += P.norm_part[P.n_k4_blocks + k];
-        }
-        c = warp_sum(c); b = warp_sum(b); n0 = warp_sum(n0); n1 = warp_sum(n1);
-        if (lane == 0) { sc[0] = c; sc[1] = n0; sc[2] = n1; sc[3] = b; }
+    } else if (lane < 6) {
+        gs[6 * A + lane] = a0;
     }
 }
 
