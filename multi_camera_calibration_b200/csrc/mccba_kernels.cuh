@@ -441,17 +441,47 @@ __global__ void __launch_bounds__(kK1Threads, 2) reproj_error_kernel(Problem P)
 // Record layout: [cost, bad] | Va x 36 diagonal blocks | Va x 6 gradient | Va(Va-1)/2 x 36 off-diagonal blocks,
 // Va = number of non-gauge views of the group.
 // --------------------------------------------------------------------------------------------------------
+// Transposed butterfly reduction of N (power of two <= 32) per-lane values over the warp: each halving step trades
+// half of the values with the partner lane, so N values cost N - 1 + (5 - log2 N) shuffles instead of 5 N.
+// On return v[0] holds the warp total of element  lane >> (5 - log2 N)  (the same in every lane of that group).
+template <int N>
+__device__ __forceinline__ void warp_tr_reduce(double (&v)[N], int lane)
+{
+    int o = 16;
+#pragma unroll
+    for (int n = N; n > 1; n >>= 1, o >>= 1) {
+        const bool up = (lane & o) != 0;
+#pragma unroll
+        for (int i = 0; i < n / 2; ++i) {
+            const double send = up ? v[i] : v[i + n / 2], keep = up ? v[i + n / 2] : v[i];
+            v[i] = keep + __shfl_xor_sync(kFull, send, o);
+        }
+    }
+#pragma unroll
+    for (; o > 0; o >>= 1) v[0] += __shfl_xor_sync(kFull, v[0], o);
+}
+
+// warp sum of a 6 x 6 block held per lane -> dst[0..36)
 __device__ __forceinline__ void reduce_store36(const double* v, double* dst, int lane)
 {
-    double o0 = 0, o1 = 0;
+    double a[32], b[4];
 #pragma unroll
-    for (int k = 0; k < 36; ++k) {
-        const double t = warp_sum(v[k]);
-        if (k < 32) { if (lane == k) o0 = t; }
-        else { if (lane == k - 32) o1 = t; }
-    }
-    dst[lane] = o0;
-    if (lane < 4) dst[32 + lane] = o1;
+    for (int k = 0; k < 32; ++k) a[k] = v[k];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) b[k] = v[32 + k];
+    warp_tr_reduce<32>(a, lane);
+    warp_tr_reduce<4>(b, lane);
+    dst[lane] = a[0];
+    if ((lane & 7) == 0) dst[32 + (lane >> 3)] = b[0];
+}
+// warp sum of 6 values -> dst[0..6)
+__device__ __forceinline__ void reduce_store6(const double* v, double* dst, int lane)
+{
+    double a[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] = k < 6 ? v[k] : 0.0;
+    warp_tr_reduce<8>(a, lane);
+    if ((lane & 3) == 0 && (lane >> 2) < 6) dst[lane >> 2] = a[0];
 }
 
 // sel: -1 = decide from the state (loop), 0/1 = explicit buffer with explicit lambda (diagnostics)
@@ -572,15 +602,7 @@ __global__ void __launch_bounds__(kK2Threads, kMinBlocks) frame_schur_kernel(Pro
             }
         }
         reduce_store36(D, rec + 2 + 36 * ai, lane);
-        {
-            double o = 0;
-#pragma unroll
-            for (int k = 0; k < 6; ++k) {
-                const double t2 = warp_sum(gd[k]);
-                if (lane == k) o = t2;
-            }
-            if (lane < 6) rec[2 + 36 * Va + 6 * ai + lane] = o;
-        }
+        reduce_store6(gd, rec + 2 + 36 * Va + 6 * ai, lane);
         ++ai;
     }
     // pass 3: off-diagonal blocks  -Y_a^T Y_b  for non-gauge views a < b
