@@ -234,7 +234,7 @@ int enqueue_iteration(mccba_handle h, bool timed)
     }
     camera_update_kernel<<<1, kK5Threads, h->k5_smem, s>>>(P, h->k5_blocked);
     if (timed) cudaEventRecord(ev[4], s);
-    frame_update_kernel<<<P.n_k4_blocks, kK4Threads, 0, s>>>(P);
+    frame_update_kernel<<<P.n_k4_blocks, kK4Threads, kK4SmemBytes, s>>>(P);
     if (timed) cudaEventRecord(ev[5], s);
     launch_resid(h, s, 0);
     if (timed) {
@@ -569,6 +569,7 @@ int mccba_set_observations(mccba_handle h, int n_frame, int n_edge, const int* e
     P.n_warps = P.n_slots / 32;
     P.n_dest = (int)dest_info.size() / 4;
     P.n_k4_blocks = (P.n_slots + kK4Threads - 1) / kK4Threads;
+    CUDA_TRY(h, cudaFuncSetAttribute(frame_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kK4SmemBytes));
     h->n_frame = n_frame; h->n_edge = n_edge; h->n_pts = M;
     h->edge_cam_h.assign(edge_cam, edge_cam + n_edge);
     h->edge_n_h.resize((size_t)n_edge);
@@ -749,19 +750,23 @@ int mccba_eval(mccba_handle h, double* cost, double* edge_H6, double* edge_g6, d
     const size_t E = (size_t)P.n_edge_int;
     const bool full = edge_H6 || edge_g6;
     std::vector<double> buf(full ? kBlk * E : E);
-    const double* src = P.blocks[h->cur] + (full ? 0 : 27 * E);
-    CUDA_TRY(h, cudaMemcpyAsync(buf.data(), src, sizeof(double) * buf.size(), cudaMemcpyDeviceToHost, h->stream));
+    if (full) {
+        CUDA_TRY(h, cudaMemcpyAsync(buf.data(), P.blocks[h->cur], sizeof(double) * buf.size(), cudaMemcpyDeviceToHost, h->stream));
+    } else {   // cost only: row 27 of every tile (tile-major records, see tile_idx)
+        CUDA_TRY(h, cudaMemcpy2DAsync(buf.data(), 32 * sizeof(double), P.blocks[h->cur] + 27 * 32, kBlk * 32 * sizeof(double),
+                                      32 * sizeof(double), E / 32, cudaMemcpyDeviceToHost, h->stream));
+    }
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     double total = 0;
     for (int e = 0; e < h->n_edge; ++e) {
         const size_t ie = (size_t)h->int_of_edge[e];
-        const double c = full ? buf[27 * E + ie] : buf[ie];
+        const double c = full ? buf[tile_idx(kBlk, ie, 27)] : buf[ie];
         total += c;
         if (edge_cost) edge_cost[e] = c;
         if (edge_H6)
-            for (int k = 0; k < 21; ++k) edge_H6[21 * (size_t)e + k] = buf[k * E + ie];
+            for (int k = 0; k < 21; ++k) edge_H6[21 * (size_t)e + k] = buf[tile_idx(kBlk, ie, k)];
         if (edge_g6)
-            for (int k = 0; k < 6; ++k) edge_g6[6 * (size_t)e + k] = buf[(21 + k) * E + ie];
+            for (int k = 0; k < 6; ++k) edge_g6[6 * (size_t)e + k] = buf[tile_idx(kBlk, ie, 21 + k)];
     }
     if (cost) *cost = total;
     return MCCBA_OK;

@@ -102,6 +102,11 @@ struct Problem {
     double* err_nrm;     // n_edge_int
 };
 
+// Tile-major record layout: the K values of 32 consecutive edges (frame slots) form one contiguous tile [k][32], so
+// everything a warp of 32 frames touches per view is a single K x 256-byte block (one TMA/bulk-copy sized unit)
+// instead of K segments spread over K planes.
+__host__ __device__ __forceinline__ int64_t tile_idx(int K, int64_t e, int k) { return ((e >> 5) * K + k) * 32 + (e & 31); }
+
 __device__ __forceinline__ double warp_sum(double v)
 {
 #pragma unroll
@@ -244,6 +249,19 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, unsigned
                  "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+// shared -> global bulk copy (TMA engine): make generic-proxy writes to shared memory visible to the async proxy,
+// issue, and wait until the source has been read (the CTA may then reuse or release the buffer)
+__device__ __forceinline__ void tma_store_fence() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_1d(void* dst, const void* src, unsigned bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit_wait()
+{
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
 template <int kModel, bool kRational>
 __device__ __forceinline__ void edge_corner_loop(const float* __restrict__ ox, const float* __restrict__ oy,
                                                  const float* __restrict__ oz, const float* __restrict__ iu,
@@ -381,7 +399,7 @@ __global__ void __launch_bounds__(kK1Threads, 2) resid_jac_accum_kernel(Problem 
         __syncthreads();   // also: every thread is done reading stage `stg` (edge records and observations)
         for (int t = threadIdx.x; t < kBlk * kEdgesPerBlock; t += kK1Threads) {
             const int k = t / kEdgesPerBlock, col = t % kEdgesPerBlock;
-            out[(int64_t)k * P.n_edge_int + chunk * kEdgesPerBlock + col] = sh->stage[k][col];
+            out[(int64_t)chunk * (kBlk * kEdgesPerBlock) + t] = sh->stage[k][col];   // tile-major: one contiguous 7 KB tile per chunk
         }
         __syncthreads();
     }
@@ -533,7 +551,7 @@ __global__ void __launch_bounds__(kK2Threads, kMinBlocks) frame_schur_kernel(Pro
         const int64_t e = ebase + (int64_t)v * stride + ls;
         double t[kBlk], H[36], Rc[9];
 #pragma unroll
-        for (int k = 0; k < kBlk; ++k) t[k] = blk[k * E + e];
+        for (int k = 0; k < kBlk; ++k) t[k] = blk[tile_idx(kBlk, e, k)];
         cost += t[27];
         unpack_sym6(t, H);
         if (c != 0) {
@@ -553,9 +571,9 @@ __global__ void __launch_bounds__(kK2Threads, kMinBlocks) frame_schur_kernel(Pro
         for (int i = 0; i < 6; ++i) U[tri6(i, i)] = 1.0;
     }
 #pragma unroll
-    for (int k = 0; k < 21; ++k) P.frameL[(int64_t)k * P.n_slots + slot] = U[k];
+    for (int k = 0; k < 21; ++k) P.frameL[tile_idx(27, slot, k)] = U[k];
 #pragma unroll
-    for (int k = 0; k < 6; ++k) P.frameL[(int64_t)(21 + k) * P.n_slots + slot] = z[k];
+    for (int k = 0; k < 6; ++k) P.frameL[tile_idx(27, slot, 21 + k)] = z[k];
     {
         const double c2 = warp_sum(cost), b2 = warp_sum((double)bad);
         if (lane == 0) { rec[0] = c2; rec[1] = b2; P.warp_scal[warp] = c2; P.warp_scal[P.n_warps + warp] = b2; }
@@ -574,7 +592,7 @@ __global__ void __launch_bounds__(kK2Threads, kMinBlocks) frame_schur_kernel(Pro
         if (active) {
             double t[kBlk], H[36], Rc[9], s[3], Y[36], gcv[6];
 #pragma unroll
-            for (int k = 0; k < kBlk; ++k) t[k] = blk[k * E + e];
+            for (int k = 0; k < kBlk; ++k) t[k] = blk[tile_idx(kBlk, e, k)];
             unpack_sym6(t, H);
 #pragma unroll
             for (int i = 0; i < 9; ++i) Rc[i] = vR[9 * c + i];
@@ -583,7 +601,7 @@ __global__ void __launch_bounds__(kK2Threads, kMinBlocks) frame_schur_kernel(Pro
 #pragma unroll
             for (int j = 0; j < 6; ++j) chol6_forward(U, Y + j, 6);  // Y = L^-1 W, column by column
 #pragma unroll
-            for (int k = 0; k < 36; ++k) P.edgeY[k * E + e] = Y[k];
+            for (int k = 0; k < 36; ++k) P.edgeY[tile_idx(36, e, k)] = Y[k];
 #pragma unroll
             for (int i = 0; i < 6; ++i) D[i * 6 + i] *= (1.0 + lambda);
 #pragma unroll
@@ -618,7 +636,7 @@ __global__ void __launch_bounds__(kK2Threads, kMinBlocks) frame_schur_kernel(Pro
                 const int64_t ea = ebase + (int64_t)va * stride + ls, ebx = ebase + (int64_t)vb * stride + ls;
                 double Ya[36], Yb[36];
 #pragma unroll
-                for (int k = 0; k < 36; ++k) { Ya[k] = P.edgeY[k * E + ea]; Yb[k] = P.edgeY[k * E + ebx]; }
+                for (int k = 0; k < 36; ++k) { Ya[k] = P.edgeY[tile_idx(36, ea, k)]; Yb[k] = P.edgeY[tile_idx(36, ebx, k)]; }
 #pragma unroll
                 for (int i = 0; i < 6; ++i)
 #pragma unroll
@@ -908,48 +926,73 @@ __global__ void __launch_bounds__(kK5Threads) camera_update_kernel(Problem P, in
 // K4: back-substitution of the pattern-pose steps + trial parameters + rotations of the trial point.
 // One thread per frame slot.  d_p = L^-T (z - sum_v Y_v dc_v).
 // --------------------------------------------------------------------------------------------------------
+// Shared memory per warp: the frame-factor tile (27 x 32 doubles) and the Y tiles of the first two views (36 x 32
+// doubles each), fetched by the TMA engine (tile-major records: each is one contiguous block) while the lanes load the
+// camera steps and poses; 4 mbarriers behind the tiles.
+constexpr int kK4WarpDoubles = (27 + 2 * 36) * 32;
+constexpr int kK4SmemBytes = (kK4Threads / 32) * kK4WarpDoubles * 8 + (kK4Threads / 32) * 8;
 __global__ void __launch_bounds__(kK4Threads) frame_update_kernel(Problem P)
 {
+    extern __shared__ __align__(128) unsigned char k4_smem[];
     const DevState* st = P.st;
     if (st->done || !st->solved) return;
     const int cur = st->cur, tr = 1 - cur;
     const double alpha = st->alpha;
     const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    const int wic = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double* fl = reinterpret_cast<double*>(k4_smem) + wic * kK4WarpDoubles;
+    double* ey = fl + 27 * 32;
+    unsigned long long* bar = reinterpret_cast<unsigned long long*>(k4_smem + (kK4Threads / 32) * kK4WarpDoubles * 8) + wic;
     double step2 = 0, par2 = 0;
-    if (slot < P.n_slots) {
+    if (slot < P.n_slots) {   // n_slots is a multiple of 32: whole warps
         const int frame = P.slot_frame[slot];
         const int warp = slot >> 5;
         const int g = P.warp_group[warp];
         const int V = P.group_V[g];
         const int* gc = P.group_cams + P.group_cam0[g];
         const int ls = slot - P.group_slot0[g];
-        const int64_t E = P.n_edge_int, ebase = P.group_ebase[g], stride = P.group_stride[g];
+        const int64_t ebase = P.group_ebase[g], stride = P.group_stride[g];
+        const int c0v = gc[0], c1v = V > 1 ? gc[1] : 0;
+        if (lane == 0) {
+            mbar_init(bar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            const unsigned bytes = 27u * 256u + (c0v != 0 ? 36u * 256u : 0u) + (c1v != 0 ? 36u * 256u : 0u);
+            mbar_expect_tx(bar, bytes);
+            tma_load_1d(fl, P.frameL + (int64_t)warp * 27 * 32, 27u * 256u, bar);
+            if (c0v != 0) tma_load_1d(ey, P.edgeY + ((ebase + ls) >> 5) * 36 * 32, 36u * 256u, bar);
+            if (c1v != 0) tma_load_1d(ey + 36 * 32, P.edgeY + ((ebase + stride + ls) >> 5) * 36 * 32, 36u * 256u, bar);
+        }
+        __syncwarp();
+        // everything else the thread needs is loaded while the tiles are in flight
+        const int64_t pv = P.n_cam + (frame >= 0 ? frame : 0);
+        double pold[6], d2[2][6], Rc2[2][9], tc2[2][3];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) pold[k] = frame >= 0 ? P.x[cur][6 * (pv - 1) + k] : 0.0;
+#pragma unroll
+        for (int v = 0; v < 2; ++v) {
+            const int c = v == 0 ? c0v : c1v;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) d2[v][k] = c != 0 ? P.dc[6 * (c - 1) + k] : 0.0;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) Rc2[v][k] = c != 0 ? P.vR[tr][9 * c + k] : ((k == 0 || k == 4 || k == 8) ? 1.0 : 0.0);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) tc2[v][k] = c != 0 ? P.x[tr][6 * (c - 1) + 3 + k] : 0.0;
+        }
+        mbar_wait(bar, 0);
+        double U[21], r[6], Y2[2][36];
+#pragma unroll
+        for (int k = 0; k < 21; ++k) U[k] = fl[k * 32 + lane];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) r[k] = fl[(21 + k) * 32 + lane];
+#pragma unroll
+        for (int v = 0; v < 2; ++v) {
+            const int c = v == 0 ? c0v : c1v;
+#pragma unroll
+            for (int k = 0; k < 36; ++k) Y2[v][k] = c != 0 ? ey[(v * 36 + k) * 32 + lane] : 0.0;
+        }
+        __syncwarp();   // every lane has taken its columns out of `ey`, which now stages the outgoing edge records
+        EdgeRec* stage = reinterpret_cast<EdgeRec*>(ey);
         if (frame >= 0) {
-            // every load of the kernel is issued up front (they are independent): factor, rhs, Y of the first two
-            // views, the camera steps and the trial camera poses needed for the edge records at the end
-            const int64_t pv = P.n_cam + frame;
-            const double* p = P.x[cur] + 6 * (pv - 1);
-            double U[21], r[6], pold[6];
-#pragma unroll
-            for (int k = 0; k < 21; ++k) U[k] = P.frameL[(int64_t)k * P.n_slots + slot];
-#pragma unroll
-            for (int k = 0; k < 6; ++k) r[k] = P.frameL[(int64_t)(21 + k) * P.n_slots + slot];
-#pragma unroll
-            for (int k = 0; k < 6; ++k) pold[k] = p[k];
-            double Y2[2][36], d2[2][6], Rc2[2][9], tc2[2][3];
-#pragma unroll
-            for (int v = 0; v < 2; ++v) {
-                const int c = v < V ? gc[v] : 0;
-                const int64_t e = ebase + v * stride + ls;
-#pragma unroll
-                for (int k = 0; k < 36; ++k) Y2[v][k] = c != 0 ? P.edgeY[(int64_t)k * E + e] : 0.0;
-#pragma unroll
-                for (int k = 0; k < 6; ++k) d2[v][k] = c != 0 ? P.dc[6 * (c - 1) + k] : 0.0;
-#pragma unroll
-                for (int k = 0; k < 9; ++k) Rc2[v][k] = c != 0 ? P.vR[tr][9 * c + k] : ((k == 0 || k == 4 || k == 8) ? 1.0 : 0.0);
-#pragma unroll
-                for (int k = 0; k < 3; ++k) tc2[v][k] = c != 0 ? P.x[tr][6 * (c - 1) + 3 + k] : 0.0;
-            }
 #pragma unroll
             for (int v = 0; v < 2; ++v)
 #pragma unroll
@@ -968,7 +1011,7 @@ __global__ void __launch_bounds__(kK4Threads) frame_update_kernel(Problem P)
                 for (int i = 0; i < 6; ++i) {
                     double acc = 0;
 #pragma unroll
-                    for (int k = 0; k < 6; ++k) acc += P.edgeY[(int64_t)(i * 6 + k) * E + e] * d[k];
+                    for (int k = 0; k < 6; ++k) acc += P.edgeY[tile_idx(36, e, i * 6 + k)] * d[k];
                     r[i] -= acc;
                 }
             }
@@ -987,14 +1030,11 @@ __global__ void __launch_bounds__(kK4Threads) frame_update_kernel(Problem P)
             rodrigues(q, R);
 #pragma unroll
             for (int i = 0; i < 9; ++i) P.vR[tr][9 * pv + i] = R[i];
-            // composed poses the residual kernel evaluates next
+            // composed poses the residual kernel evaluates next: the first two views go out through shared memory as
+            // one 3 KB bulk store per view (32 consecutive edge records), the rest straight from registers
 #pragma unroll
             for (int v = 0; v < 2; ++v)
-                if (v < V) {
-                    EdgeRec er;
-                    compose_pose(Rc2[v], tc2[v], R, q + 3, er.R3, er.T3);
-                    P.erec[ebase + v * stride + ls] = er;
-                }
+                if (v < V) compose_pose(Rc2[v], tc2[v], R, q + 3, stage[v * 32 + lane].R3, stage[v * 32 + lane].T3);
             for (int v = 2; v < V; ++v) {
                 const int c = gc[v];
                 double Rc[9], tc[3];
@@ -1011,7 +1051,17 @@ __global__ void __launch_bounds__(kK4Threads) frame_update_kernel(Problem P)
 #pragma unroll
             for (int i = 0; i < 9; ++i) z.R3[i] = 0;
             z.T3[0] = z.T3[1] = z.T3[2] = 0;
-            for (int v = 0; v < V; ++v) P.erec[ebase + v * stride + ls] = z;
+            for (int v = 0; v < V; ++v) {
+                if (v < 2) stage[v * 32 + lane] = z;
+                else P.erec[ebase + v * stride + ls] = z;
+            }
+        }
+        tma_store_fence();
+        __syncwarp();
+        if (lane == 0) {
+            tma_store_1d(P.erec + ebase + ls, ey, 32u * (unsigned)sizeof(EdgeRec));
+            if (V > 1) tma_store_1d(P.erec + ebase + stride + ls, reinterpret_cast<EdgeRec*>(ey) + 32, 32u * (unsigned)sizeof(EdgeRec));
+            tma_store_commit_wait();
         }
     }
     __shared__ double s_red[2][kK4Threads / 32];
