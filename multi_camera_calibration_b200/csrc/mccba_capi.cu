@@ -68,7 +68,11 @@ struct mccba_handle_s {
     mccba_options opts;
     std::string err;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaStream_t copy_stream = nullptr;   // bulk observation upload, so that table uploads and memsets do not queue behind it
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_copy = nullptr;
+    // pinned staging arena for the layout tables: their uploads must not block the host behind the observation copy
+    char* pin_buf = nullptr;
+    size_t pin_cap = 0, pin_used = 0, pin_want = 0;
     ncclComm_t comm = nullptr;
     int num_sms = 148;
     // cameras
@@ -153,7 +157,17 @@ int dev_upload(mccba_handle h, const T** p, const std::vector<T>& v)
     T* q = nullptr;
     int rc = dev_alloc(h, &q, v.size());
     if (rc) return rc;
-    if (!v.empty()) CUDA_TRY(h, cudaMemcpyAsync(q, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+    if (!v.empty()) {
+        const size_t bytes = v.size() * sizeof(T), padded = (bytes + 255) & ~(size_t)255;
+        h->pin_want += padded;
+        const void* src = v.data();
+        if (h->pin_used + padded <= h->pin_cap) {   // staged: the copy is asynchronous for the host
+            memcpy(h->pin_buf + h->pin_used, v.data(), bytes);
+            src = h->pin_buf + h->pin_used;
+            h->pin_used += padded;
+        }
+        CUDA_TRY(h, cudaMemcpyAsync(q, src, bytes, cudaMemcpyHostToDevice, h->stream));
+    }
     *p = q;
     return MCCBA_OK;
 }
@@ -318,8 +332,10 @@ int mccba_create(const mccba_options* opts, mccba_handle* out)
     cudaGetDeviceProperties(&prop, opts->device);
     h->num_sms = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return MCCBA_ERR_CUDA; }
+    if (cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { cudaStreamDestroy(h->stream); delete h; return MCCBA_ERR_CUDA; }
     cudaEventCreate(&h->ev0);
     cudaEventCreate(&h->ev1);
+    cudaEventCreateWithFlags(&h->ev_copy, cudaEventDisableTiming);
     cudaMallocHost((void**)&h->h_done, 64 * sizeof(int));
     cudaMallocHost((void**)&h->h_state, sizeof(DevState));
     cudaMallocHost((void**)&h->h_small, 64 * sizeof(double));
@@ -356,6 +372,9 @@ int mccba_destroy(mccba_handle h)
     cudaEventDestroy(h->ev0);
     cudaEventDestroy(h->ev1);
     cudaStreamDestroy(h->stream);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    if (h->pin_buf) cudaFreeHost(h->pin_buf);
+    if (h->ev_copy) cudaEventDestroy(h->ev_copy);
     delete h;
     return MCCBA_OK;
 }
@@ -407,11 +426,12 @@ int mccba_set_observations(mccba_handle h, int n_frame, int n_edge, const int* e
     if (n_frame < 1 || n_edge < 1 || !edge_cam || !edge_pv || !edge_off || !obj_xyz || !img_uv)
         return fail(h, MCCBA_ERR_ARG, "set_observations: null or empty input");
     CUDA_TRY(h, cudaSetDevice(h->opts.device));
-    const bool timing = getenv("MCCBA_TIMING") != nullptr;
+    const char* timing_env = getenv("MCCBA_TIMING");
+    const bool timing = timing_env != nullptr, timing_sync = timing && timing_env[0] != '2';   // "2": host laps only, no stream sync
     auto t_start = std::chrono::steady_clock::now();
     auto lap = [&](const char* what) {
         if (!timing) return;
-        cudaStreamSynchronize(h->stream);
+        if (timing_sync) cudaStreamSynchronize(h->stream);
         auto now = std::chrono::steady_clock::now();
         fprintf(stderr, "[set_observations] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t_start).count());
         t_start = now;
@@ -424,14 +444,29 @@ int mccba_set_observations(mccba_handle h, int n_frame, int n_edge, const int* e
     // the host-side layout work below
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     free_problem(h, true);
+    if (h->pin_want > h->pin_cap) {   // the previous call did not fit: grow the staging arena (nothing is in flight here)
+        if (h->pin_buf) cudaFreeHost(h->pin_buf);
+        h->pin_buf = nullptr;
+        h->pin_cap = 0;
+        const size_t want = h->pin_want + h->pin_want / 4 + 4096;
+        if (cudaHostAlloc((void**)&h->pin_buf, want, cudaHostAllocDefault) == cudaSuccess) h->pin_cap = want;
+        else cudaGetLastError();   // no arena: plain pageable uploads
+    }
+    h->pin_used = 0;
+    h->pin_want = 0;
     float *d_obj = nullptr, *d_img = nullptr;
     {
         int rc0;
         if ((rc0 = dev_alloc(h, &d_obj, 3 * (size_t)M))) return rc0;
         if ((rc0 = dev_alloc(h, &d_img, 2 * (size_t)M))) return rc0;
     }
-    CUDA_TRY(h, cudaMemcpyAsync(d_obj, obj_xyz, sizeof(float) * 3 * (size_t)M, cudaMemcpyHostToDevice, h->stream));
-    CUDA_TRY(h, cudaMemcpyAsync(d_img, img_uv, sizeof(float) * 2 * (size_t)M, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(d_obj, obj_xyz, sizeof(float) * 3 * (size_t)M, cudaMemcpyHostToDevice, h->copy_stream));
+    CUDA_TRY(h, cudaMemcpyAsync(d_img, img_uv, sizeof(float) * 2 * (size_t)M, cudaMemcpyHostToDevice, h->copy_stream));
+    CUDA_TRY(h, cudaEventRecord(h->ev_copy, h->copy_stream));
+    struct CopyGuard {   // an early error return must not leave the engine reading the caller's buffers
+        cudaStream_t s;
+        ~CopyGuard() { cudaStreamSynchronize(s); }
+    } copy_guard{h->copy_stream};
     // per-frame view lists (CSR by counting sort), each sorted by camera
     std::vector<int> voff((size_t)n_frame + 1, 0);
     for (int e = 0; e < n_edge; ++e) {
@@ -450,32 +485,54 @@ int mccba_set_observations(mccba_handle h, int n_frame, int n_edge, const int* e
         std::vector<int> fill(voff.begin(), voff.end() - 1);
         for (int e = 0; e < n_edge; ++e) vlist[fill[edge_pv[e] - nC]++] = {edge_cam[e], e};
     }
-    struct ViewRef { const std::pair<int, int>* p; int n; const std::pair<int, int>& operator[](size_t i) const { return p[i]; } };
-    struct Views { const std::vector<int>* off; const std::vector<std::pair<int, int>>* l;
-                   ViewRef operator[](int f) const { return ViewRef{l->data() + (*off)[f], (*off)[f + 1] - (*off)[f]}; } };
-    Views views{&voff, &vlist};
     std::map<std::vector<int>, std::vector<int>> groups;  // camera set -> frames (ascending)
     {
-        // frames hashed by their (sorted) camera list; only one std::map insertion per distinct camera set
-        std::unordered_map<uint64_t, std::vector<int>*> fast;   // valid when the list packs into 64 bits
+        // frames hashed by their (sorted) camera list: a flat open-addressing table keyed by the list packed into 64
+        // bits (up to 4 views), with the previous frame's group tried first; one std::map insertion per distinct set
+        struct Slot { uint64_t key; std::vector<int>* grp; };
+        std::vector<Slot> table(4096, Slot{0, nullptr});
+        size_t used = 0;
+        auto probe = [&](uint64_t k) -> Slot& {
+            size_t m = table.size() - 1, i = (size_t)((k * 0x9E3779B97F4A7C15ull) >> 20) & m;
+            while (table[i].grp && table[i].key != k) i = (i + 1) & m;
+            return table[i];
+        };
         std::vector<int> key;
+        uint64_t last_k = 0;
+        std::vector<int>* last_grp = nullptr;
         for (int f = 0; f < n_frame; ++f) {
             std::pair<int, int>* b = vlist.data() + voff[f];
             const int nv = voff[f + 1] - voff[f];
-            if (nv > 1) std::sort(b, b + nv);
+            if (nv == 2) { if (b[1] < b[0]) std::swap(b[0], b[1]); }
+            else if (nv > 2) std::sort(b, b + nv);
             for (int i = 1; i < nv; ++i)
                 if (b[i].first == b[i - 1].first)
                     return fail(h, MCCBA_ERR_ARG, "photo vertex %d is observed twice by camera %d", nC + f, b[i].first);
             if (nv <= 4 && nC < 65535) {
                 uint64_t k = 0;
                 for (int i = 0; i < nv; ++i) k = (k << 16) | (uint64_t)(b[i].first + 1);
-                auto it = fast.find(k);
-                if (it == fast.end()) {
-                    key.clear();
-                    for (int i = 0; i < nv; ++i) key.push_back(b[i].first);
-                    it = fast.emplace(k, &groups[key]).first;
+                if (k != last_k || !last_grp) {
+                    Slot* sl = &probe(k);
+                    if (!sl->grp) {
+                        if (2 * (used + 1) > table.size()) {   // grow and rehash
+                            std::vector<Slot> old;
+                            old.swap(table);
+                            table.assign(old.size() * 4, Slot{0, nullptr});
+                            for (const Slot& o : old)
+                                if (o.grp) probe(o.key) = o;
+                            sl = &probe(k);
+                        }
+                        key.clear();
+                        for (int i = 0; i < nv; ++i) key.push_back(b[i].first);
+                        sl->key = k;
+                        sl->grp = &groups[key];
+                        sl->grp->reserve(64);
+                        ++used;
+                    }
+                    last_k = k;
+                    last_grp = sl->grp;
                 }
-                it->second->push_back(f);
+                last_grp->push_back(f);
             } else {
                 key.clear();
                 for (int i = 0; i < nv; ++i) key.push_back(b[i].first);
@@ -497,36 +554,47 @@ int mccba_set_observations(mccba_handle h, int n_frame, int n_edge, const int* e
     std::map<std::pair<int, int>, std::vector<int>> dest_blocks;  // (A,B) -> record offsets
     std::map<int, std::vector<int>> dest_g;
     int64_t rec_total = 0;
-    e_off.push_back(0);
+    {
+        size_t n_int = 0, n_sl = 0;
+        for (auto& kv : groups) {
+            const size_t st = (kv.second.size() + 31) / 32 * 32;
+            n_int += st * kv.first.size();
+            n_sl += st;
+        }
+        if (n_int >= (size_t)2000000000) return fail(h, MCCBA_ERR_ARG, "too many edges");
+        e_cam.resize(n_int); e_frame.resize(n_int); e_src.resize(n_int); e_off.resize(n_int + 1);
+        slot_frame.resize(n_sl);
+    }
+    e_off[0] = 0;
     int gi = 0;
+    size_t ne = 0, nsl = 0;
     for (auto& kv : groups) {
         const std::vector<int>& cams = kv.first;
         const std::vector<int>& frames = kv.second;
-        const int V = (int)cams.size();
-        const int nw = ((int)frames.size() + 31) / 32, stride = nw * 32;
+        const int V = (int)cams.size(), nf = (int)frames.size();
+        const int nw = (nf + 31) / 32, stride = nw * 32;
         group_V.push_back(V);
         group_cam0.push_back((int)group_cams.size());
         for (int c : cams) group_cams.push_back(c);
-        group_ebase.push_back((int)e_cam.size());
+        group_ebase.push_back((int)ne);
         group_stride.push_back(stride);
-        group_slot0.push_back((int)slot_frame.size());
-        for (int ls = 0; ls < stride; ++ls) slot_frame.push_back(ls < (int)frames.size() ? frames[ls] : -1);
-        for (int v = 0; v < V; ++v)
-            for (int ls = 0; ls < stride; ++ls) {
-                int frame = -1;
-                int64_t src = 0, cnt = 0;
-                if (ls < (int)frames.size()) {
-                    frame = frames[ls];
-                    const int oe = views[frame][v].second;
-                    src = edge_off[oe];
-                    cnt = edge_off[oe + 1] - edge_off[oe];
-                    h->int_of_edge[oe] = (int)e_cam.size();
-                }
-                e_cam.push_back(cams[v]);
-                e_frame.push_back(frame);
-                e_src.push_back(src);
-                e_off.push_back(e_off.back() + (int)cnt);
+        group_slot0.push_back((int)nsl);
+        for (int ls = 0; ls < stride; ++ls) slot_frame[nsl + ls] = ls < nf ? frames[ls] : -1;
+        nsl += stride;
+        for (int v = 0; v < V; ++v) {
+            const int cam = cams[v];
+            int off = e_off[ne];
+            for (int ls = 0; ls < nf; ++ls, ++ne) {
+                const int frame = frames[ls];
+                const int oe = vlist[(size_t)voff[frame] + v].second;
+                const int64_t src = edge_off[oe];
+                h->int_of_edge[oe] = (int)ne;
+                e_cam[ne] = cam; e_frame[ne] = frame; e_src[ne] = src;
+                off += (int)(edge_off[oe + 1] - src);
+                e_off[ne + 1] = off;
             }
+            for (int ls = nf; ls < stride; ++ls, ++ne) { e_cam[ne] = cam; e_frame[ne] = -1; e_src[ne] = 0; e_off[ne + 1] = off; }
+        }
         std::vector<int> act;
         for (int c : cams)
             if (c != 0) act.push_back(c);
@@ -586,16 +654,6 @@ int mccba_set_observations(mccba_handle h, int n_frame, int n_edge, const int* e
     const int64_t* d_esrc = nullptr;
     if ((rc = dev_upload(h, &d_esrc, e_src))) return rc;
     lap("upload tables");
-    // observation planes: one allocation, each plane 256-byte aligned
-    const size_t plane = ((size_t)M + 63) / 64 * 64;
-    float* planes = nullptr;
-    if ((rc = dev_alloc(h, &planes, plane * 5))) return rc;
-    P.ox = planes; P.oy = planes + plane; P.oz = planes + 2 * plane; P.iu = planes + 3 * plane; P.iv = planes + 4 * plane;
-    gather_obs_kernel<<<h->num_sms * 8, 256, 0, h->stream>>>(P.n_edge_int, P.e_off, d_esrc, d_obj, d_img, planes,
-                                                            planes + plane, planes + 2 * plane, planes + 3 * plane,
-                                                            planes + 4 * plane);
-    CUDA_TRY(h, cudaGetLastError());
-    lap("H2D observations + gather");
     // work buffers
     if ((rc = dev_alloc(h, &P.st, 1, true))) return rc;
     for (int b = 0; b < 2; ++b) {
@@ -604,10 +662,9 @@ int mccba_set_observations(mccba_handle h, int n_frame, int n_edge, const int* e
         if ((rc = dev_alloc(h, &P.blocks[b], (size_t)kBlk * P.n_edge_int, true))) return rc;
     }
     {   // vertex 0 is the gauge: identity rotation in both rotation buffers (never rewritten by the update kernels)
-        const double I9[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+        static const double I9[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
         for (int b = 0; b < 2; ++b)
             CUDA_TRY(h, cudaMemcpyAsync(P.vR[b], I9, sizeof(I9), cudaMemcpyHostToDevice, h->stream));
-        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     }
     if ((rc = dev_alloc(h, &P.frameL, 27 * (size_t)P.n_slots, true))) return rc;
     if ((rc = dev_alloc(h, &P.edgeY, 36 * (size_t)P.n_edge_int, true))) return rc;
@@ -687,9 +744,21 @@ int mccba_set_observations(mccba_handle h, int n_frame, int n_edge, const int* e
     }
     per_sm = std::max(per_sm, 1);
     h->k1_grid = std::max(1, std::min(P.n_edge_int / kEdgesPerBlock, h->num_sms * per_sm));
-    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
-    drain_pool(h);   // whatever the new problem did not reuse
     lap("launch geometry");
+    // last: everything above ran while the observation upload was in flight on its own stream
+    // observation planes: one allocation, each plane 256-byte aligned
+    const size_t plane = ((size_t)M + 63) / 64 * 64;
+    float* planes = nullptr;
+    if ((rc = dev_alloc(h, &planes, plane * 5))) return rc;
+    P.ox = planes; P.oy = planes + plane; P.oz = planes + 2 * plane; P.iu = planes + 3 * plane; P.iv = planes + 4 * plane;
+    CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_copy, 0));
+    gather_obs_kernel<<<h->num_sms * 8, 256, 0, h->stream>>>(P.n_edge_int, P.e_off, d_esrc, d_obj, d_img, planes,
+                                                            planes + plane, planes + 2 * plane, planes + 3 * plane,
+                                                            planes + 4 * plane);
+    CUDA_TRY(h, cudaGetLastError());
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));   // also: the caller's buffers are no longer read
+    drain_pool(h);   // whatever the new problem did not reuse
+    lap("H2D observations + gather");
     h->cur = 0;
     h->have_obs = true;
     h->have_params = false;
@@ -1097,8 +1166,13 @@ int mccba_omni_set_observations(mccba_handle h, int n_frame, const int64_t* fram
     float *d_obj = nullptr, *d_img = nullptr;
     CUDA_TRY(h, cudaMalloc((void**)&d_obj, sizeof(float) * 3 * (size_t)M));
     CUDA_TRY(h, cudaMalloc((void**)&d_img, sizeof(float) * 2 * (size_t)M));
-    CUDA_TRY(h, cudaMemcpyAsync(d_obj, obj_xyz, sizeof(float) * 3 * (size_t)M, cudaMemcpyHostToDevice, h->stream));
-    CUDA_TRY(h, cudaMemcpyAsync(d_img, img_uv, sizeof(float) * 2 * (size_t)M, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(d_obj, obj_xyz, sizeof(float) * 3 * (size_t)M, cudaMemcpyHostToDevice, h->copy_stream));
+    CUDA_TRY(h, cudaMemcpyAsync(d_img, img_uv, sizeof(float) * 2 * (size_t)M, cudaMemcpyHostToDevice, h->copy_stream));
+    CUDA_TRY(h, cudaEventRecord(h->ev_copy, h->copy_stream));
+    struct CopyGuard {   // an early error return must not leave the engine reading the caller's buffers
+        cudaStream_t s;
+        ~CopyGuard() { cudaStreamSynchronize(s); }
+    } copy_guard{h->copy_stream};
     gather_obs_kernel<<<h->num_sms * 8, 256, 0, h->stream>>>(n_frame, d_off, d_src, d_obj, d_img, planes, planes + plane,
                                                             planes + 2 * plane, planes + 3 * plane, planes + 4 * plane);
     CUDA_TRY(h, cudaGetLastError());

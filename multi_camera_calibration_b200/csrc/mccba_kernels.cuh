@@ -528,7 +528,6 @@ __global__ void __launch_bounds__(kK2Threads, kMinBlocks) frame_schur_kernel(Pro
     const double* __restrict__ x = P.x[sel];
     const double* __restrict__ vR = P.vR[sel];
     const double* __restrict__ blk = P.blocks[sel];
-    const int64_t E = P.n_edge_int;
     double* rec = P.records + P.warp_rec[warp];
 
     double tp[3] = {0, 0, 0};
