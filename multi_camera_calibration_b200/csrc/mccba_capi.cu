@@ -206,10 +206,10 @@ void launch_schur(mccba_handle h, cudaStream_t s, int sel, double lambda)
     const Problem& P = h->P;
     const int grid = (P.n_warps * 32 + kK2Threads - 1) / kK2Threads;
     switch (h->k2_occ) {
-        case 2: frame_schur_kernel<2><<<grid, kK2Threads, 0, s>>>(P, sel, lambda); break;
-        case 3: frame_schur_kernel<3><<<grid, kK2Threads, 0, s>>>(P, sel, lambda); break;
-        case 4: frame_schur_kernel<4><<<grid, kK2Threads, 0, s>>>(P, sel, lambda); break;
-        default: frame_schur_kernel<1><<<grid, kK2Threads, 0, s>>>(P, sel, lambda); break;
+        case 2: frame_schur_kernel<2><<<grid, kK2Threads, kK2SmemBytes, s>>>(P, sel, lambda); break;
+        case 3: frame_schur_kernel<3><<<grid, kK2Threads, kK2SmemBytes, s>>>(P, sel, lambda); break;
+        case 4: frame_schur_kernel<4><<<grid, kK2Threads, kK2SmemBytes, s>>>(P, sel, lambda); break;
+        default: frame_schur_kernel<1><<<grid, kK2Threads, kK2SmemBytes, s>>>(P, sel, lambda); break;
     }
 }
 
@@ -638,6 +638,10 @@ int mccba_set_observations(mccba_handle h, int n_frame, int n_edge, const int* e
     P.n_dest = (int)dest_info.size() / 4;
     P.n_k4_blocks = (P.n_slots + kK4Threads - 1) / kK4Threads;
     CUDA_TRY(h, cudaFuncSetAttribute(frame_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kK4SmemBytes));
+    CUDA_TRY(h, cudaFuncSetAttribute(frame_schur_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kK2SmemBytes));
+    CUDA_TRY(h, cudaFuncSetAttribute(frame_schur_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kK2SmemBytes));
+    CUDA_TRY(h, cudaFuncSetAttribute(frame_schur_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kK2SmemBytes));
+    CUDA_TRY(h, cudaFuncSetAttribute(frame_schur_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kK2SmemBytes));
     h->n_frame = n_frame; h->n_edge = n_edge; h->n_pts = M;
     h->edge_cam_h.assign(edge_cam, edge_cam + n_edge);
     h->edge_n_h.resize((size_t)n_edge);

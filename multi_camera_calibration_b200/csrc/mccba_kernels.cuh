@@ -503,6 +503,8 @@ __device__ __forceinline__ void reduce_store6(const double* v, double* dst, int 
 }
 
 // sel: -1 = decide from the state (loop), 0/1 = explicit buffer with explicit lambda (diagnostics)
+constexpr int kK2WarpDoubles = 2 * 36 * 32;
+constexpr int kK2SmemBytes = (kK2Threads / 32) * kK2WarpDoubles * 8 + (kK2Threads / 32) * 8;
 template <int kMinBlocks>
 __global__ void __launch_bounds__(kK2Threads, kMinBlocks) frame_schur_kernel(Problem P, int sel_arg, double lambda_arg)
 {
@@ -515,7 +517,8 @@ __global__ void __launch_bounds__(kK2Threads, kMinBlocks) frame_schur_kernel(Pro
         if (st->phase == kPhaseDecide) { sel = 1 - st->cur; lambda = st->lambda_spec; }
         else { sel = st->cur; lambda = st->lambda; }
     }
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    extern __shared__ __align__(128) unsigned char k2_smem[];
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
     if (warp >= P.n_warps) return;
     const int g = P.warp_group[warp];
     const int V = P.group_V[g];
@@ -523,11 +526,23 @@ __global__ void __launch_bounds__(kK2Threads, kMinBlocks) frame_schur_kernel(Pro
     const int slot = warp * 32 + lane;
     const int ls = slot - P.group_slot0[g];
     const int ebase = P.group_ebase[g], stride = P.group_stride[g];
+    const double* __restrict__ blk = P.blocks[sel];
+    // per warp: two 36 x 32 tiles.  A tile first receives the 28 x 32 edge-block tile of view 0 / 1 from the TMA
+    // engine (tile-major records: one contiguous 7 KB block), later the lanes overwrite their own column with Y.
+    double* stage = reinterpret_cast<double*>(k2_smem) + wic * kK2WarpDoubles;
+    unsigned long long* bar = reinterpret_cast<unsigned long long*>(k2_smem + (kK2Threads / 32) * kK2WarpDoubles * 8) + wic;
+    if (lane == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_expect_tx(bar, (V > 1 ? 2u : 1u) * kBlk * 256u);
+        tma_load_1d(stage, blk + (int64_t)((ebase + ls) >> 5) * kBlk * 32, kBlk * 256u, bar);
+        if (V > 1) tma_load_1d(stage + 36 * 32, blk + (int64_t)((ebase + stride + ls) >> 5) * kBlk * 32, kBlk * 256u, bar);
+    }
+    __syncwarp();
     const int frame = P.slot_frame[slot];
     const bool active = frame >= 0;
     const double* __restrict__ x = P.x[sel];
     const double* __restrict__ vR = P.vR[sel];
-    const double* __restrict__ blk = P.blocks[sel];
     double* rec = P.records + P.warp_rec[warp];
 
     double tp[3] = {0, 0, 0};
@@ -542,6 +557,7 @@ __global__ void __launch_bounds__(kK2Threads, kMinBlocks) frame_schur_kernel(Pro
 #pragma unroll
     for (int i = 0; i < 6; ++i) z[i] = 0;
     int Va = 0;
+    mbar_wait(bar, 0);
     // pass 1: pattern-pose block
     for (int v = 0; v < V; ++v) {
         const int c = gc[v];
@@ -549,8 +565,13 @@ __global__ void __launch_bounds__(kK2Threads, kMinBlocks) frame_schur_kernel(Pro
         if (!active) continue;
         const int64_t e = ebase + (int64_t)v * stride + ls;
         double t[kBlk], H[36], Rc[9];
+        if (v < 2) {
 #pragma unroll
-        for (int k = 0; k < kBlk; ++k) t[k] = blk[tile_idx(kBlk, e, k)];
+            for (int k = 0; k < kBlk; ++k) t[k] = stage[(v * 36 + k) * 32 + lane];
+        } else {
+#pragma unroll
+            for (int k = 0; k < kBlk; ++k) t[k] = blk[tile_idx(kBlk, e, k)];
+        }
         cost += t[27];
         unpack_sym6(t, H);
         if (c != 0) {
@@ -590,8 +611,13 @@ __global__ void __launch_bounds__(kK2Threads, kMinBlocks) frame_schur_kernel(Pro
         for (int i = 0; i < 6; ++i) gd[i] = 0;
         if (active) {
             double t[kBlk], H[36], Rc[9], s[3], Y[36], gcv[6];
+            if (v < 2) {
 #pragma unroll
-            for (int k = 0; k < kBlk; ++k) t[k] = blk[tile_idx(kBlk, e, k)];
+                for (int k = 0; k < kBlk; ++k) t[k] = stage[(v * 36 + k) * 32 + lane];
+            } else {
+#pragma unroll
+                for (int k = 0; k < kBlk; ++k) t[k] = blk[tile_idx(kBlk, e, k)];
+            }
             unpack_sym6(t, H);
 #pragma unroll
             for (int i = 0; i < 9; ++i) Rc[i] = vR[9 * c + i];
@@ -601,6 +627,10 @@ __global__ void __launch_bounds__(kK2Threads, kMinBlocks) frame_schur_kernel(Pro
             for (int j = 0; j < 6; ++j) chol6_forward(U, Y + j, 6);  // Y = L^-1 W, column by column
 #pragma unroll
             for (int k = 0; k < 36; ++k) P.edgeY[tile_idx(36, e, k)] = Y[k];
+            if (v < 2) {   // keep Y for the off-diagonal pass (own column only: no other lane reads it)
+#pragma unroll
+                for (int k = 0; k < 36; ++k) stage[(v * 36 + k) * 32 + lane] = Y[k];
+            }
 #pragma unroll
             for (int i = 0; i < 6; ++i) D[i * 6 + i] *= (1.0 + lambda);
 #pragma unroll
@@ -634,8 +664,13 @@ __global__ void __launch_bounds__(kK2Threads, kMinBlocks) frame_schur_kernel(Pro
             if (active) {
                 const int64_t ea = ebase + (int64_t)va * stride + ls, ebx = ebase + (int64_t)vb * stride + ls;
                 double Ya[36], Yb[36];
+                if (vb < 2) {   // va = 0, vb = 1: both still in shared memory
 #pragma unroll
-                for (int k = 0; k < 36; ++k) { Ya[k] = P.edgeY[tile_idx(36, ea, k)]; Yb[k] = P.edgeY[tile_idx(36, ebx, k)]; }
+                    for (int k = 0; k < 36; ++k) { Ya[k] = stage[k * 32 + lane]; Yb[k] = stage[(36 + k) * 32 + lane]; }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 36; ++k) { Ya[k] = P.edgeY[tile_idx(36, ea, k)]; Yb[k] = P.edgeY[tile_idx(36, ebx, k)]; }
+                }
 #pragma unroll
                 for (int i = 0; i < 6; ++i)
 #pragma unroll
