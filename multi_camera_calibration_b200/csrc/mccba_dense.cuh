@@ -673,7 +673,7 @@ __device__ __forceinline__ void dag_load_input(double (*T)[kCLD], const double* 
 __device__ inline void chol_dag_tile(const CholDag& D)
 {
     __shared__ __align__(16) double C[kCT + 8][kCLD], S[kCT][kCLD], A1[kCT][kCLD], B1[kCT][kCLD];
-    __shared__ double s_rinv[kCT], s_x[kCT];
+    __shared__ __align__(16) double s_rinv[kCT], s_x[kCT];
     __shared__ __align__(16) double s_col[4 * kCT], s_winv[kCT * 8];
     __shared__ int s_bad;
     const int tid = threadIdx.x, n = D.n;
@@ -771,6 +771,18 @@ __device__ inline void chol_dag_tile(const CholDag& D)
         if (tid == 0 && s_bad) *D.fail = 1;
     }
     dag_stamp(D, 3);
+    // While the factorisation moves on, invert the factor for the backward sweep: X = L_jj^-T (X L^T = I, same block
+    // solve as the off-diagonal tiles), so that x_j is one 32 x 32 matrix-vector product instead of a 32-step
+    // dependent chain.  Not for the last block column, whose backward step starts right away.
+    const bool use_inv = j != ntc - 1;
+    if (use_inv) {
+        const int r = tid >> 5, c = tid & 31;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) A1[r + 8 * q][c] = (r + 8 * q == c) ? 1.0 : 0.0;
+        __syncthreads();
+        tile_trsm_dmma(&A1[0][0], kCT, &C[0][0], s_rinv, w, s_winv);
+        __syncthreads();
+    }
     // ---- backward substitution: x_j = L_jj^-T (y_j - sum_{t > j} part(t, j)), warp 0 ----------------------------
     if (tid >= 32) return;
     const int lane = tid;
@@ -781,11 +793,27 @@ __device__ inline void chol_dag_tile(const CholDag& D)
         for (int t = ntc - 1; t > j; --t) yv -= dag_poll(part + ((size_t)t * ntc + j) * kCT + lane);
     }
     dag_stamp(D, 5);
-    const double myrinv = lane < w ? s_rinv[lane] : 1.0;
-    for (int c = w - 1; c >= 0; --c) {
-        const double xc = __shfl_sync(0xffffffffu, yv * myrinv, c);
-        if (lane == c) yv = xc;
-        if (lane < c) yv -= C[c][lane] * xc;
+    if (use_inv) {
+        s_x[lane] = yv;
+        __syncwarp();
+        const double2* xr = reinterpret_cast<const double2*>(&A1[lane][0]);
+        const double2* yr = reinterpret_cast<const double2*>(s_x);
+        double x0 = 0.0, x1 = 0.0;
+#pragma unroll
+        for (int c = 0; c < kCT / 2; ++c) {
+            const double2 a = xr[c], b = yr[c];
+            x0 = fma(a.x, b.x, x0);
+            x1 = fma(a.y, b.y, x1);
+        }
+        yv = x0 + x1;
+        __syncwarp();
+    } else {
+        const double myrinv = lane < w ? s_rinv[lane] : 1.0;
+        for (int c = w - 1; c >= 0; --c) {
+            const double xc = __shfl_sync(0xffffffffu, yv * myrinv, c);
+            if (lane == c) yv = xc;
+            if (lane < c) yv -= C[c][lane] * xc;
+        }
     }
     s_x[lane] = lane < w ? yv : 0.0;
     __syncwarp();
