@@ -1034,6 +1034,14 @@ int mccba_debug_solve_dense(mccba_handle h, int n, const double* S, const double
         const int ntc = chol_col_tiles(n), ntr = chol_row_tiles(n);
         int grid = 0;
         for (int j = 0; j < ntc; ++j) grid += ntr - j;
+        {   // every CTA of the DAG must be resident at once (see chol_dag_tile)
+            int per_sm_dag = 0;
+            CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_dag, chol_dag_kernel, 256, 0));
+            if (per_sm_dag * h->num_sms < grid) {
+                cudaFree(dA); cudaFree(dx); cudaFree(drinv); cudaFree(dfail);
+                return fail(h, MCCBA_ERR_ARG, "n = %d needs %d co-resident CTAs for the tile DAG, the device holds %d", n, grid, per_sm_dag * h->num_sms);
+            }
+        }
         CUDA_TRY(h, cudaMalloc((void**)&dflags, sizeof(double) * chol_dag_words(n)));
         CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));
         CUDA_TRY(h, cudaMemsetAsync(dflags, 0xFF, sizeof(double) * chol_dag_words(n), h->stream));

@@ -1,0 +1,60 @@
+"""Reduced-system solver in isolation (mccba_debug_solve_dense): every size class of the tile DAG -- single tile, ragged
+last block column, g row in its own tile row (n % 32 == 0), the config #5 size -- against numpy, for all three modes
+(0 single-CTA column Cholesky, 1 panel/update kernels, 2 one-launch tile DAG).  Replaces the Eigen CG of
+src/multicalib.cpp:565-592 on the Schur-reduced system."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+SIZES = [1, 5, 6, 12, 31, 32, 33, 63, 64, 65, 96, 127, 128, 200, 378, 384]
+
+
+@pytest.fixture(scope="module")
+def solver():
+    import multi_camera_calibration_b200 as m
+    s = m.Solver(device=0)
+    yield s
+    s.close()
+
+
+def _spd(n, seed):
+    rng = np.random.default_rng(seed)
+    M = rng.standard_normal((n, n))
+    return M @ M.T + n * np.eye(n), rng.standard_normal(n)
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("n", SIZES)
+def test_dense_solve_matches_numpy(solver, n, mode):
+    S, g = _spd(n, 100 + n)
+    x, _ = solver.debug_solve_dense(S, g, mode)
+    ref = np.linalg.solve(S, g)
+    assert np.abs(x - ref).max() <= 1e-11 * max(np.abs(ref).max(), 1e-300) * n      # fp64, cond ~ 10
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_dense_solve_ill_conditioned(solver, mode):
+    """Reduced camera systems of real rigs have condition numbers ~1e9: the factorisation must stay backward stable."""
+    n = 190
+    rng = np.random.default_rng(7)
+    Q, _ = np.linalg.qr(rng.standard_normal((n, n)))
+    S = (Q * np.logspace(0, 9, n)) @ Q.T
+    S = 0.5 * (S + S.T)
+    g = rng.standard_normal(n)
+    x, _ = solver.debug_solve_dense(S, g, mode)
+    assert np.linalg.norm(S @ x - g) <= 1e-9 * (np.linalg.norm(S, 2) * np.linalg.norm(x) + np.linalg.norm(g))
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("n", [7, 40, 100])
+def test_dense_solve_rejects_indefinite(solver, n, mode):
+    import multi_camera_calibration_b200 as m
+    S, g = _spd(n, 5)
+    S[n // 2, n // 2] = -1.0
+    with pytest.raises(m.MccbaError):
+        solver.debug_solve_dense(S, g, mode)
+    # the handle stays usable
+    S2, g2 = _spd(n, 6)
+    x, _ = solver.debug_solve_dense(S2, g2, mode)
+    assert np.allclose(x, np.linalg.solve(S2, g2), rtol=1e-9, atol=1e-12)
