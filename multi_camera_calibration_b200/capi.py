@@ -37,7 +37,7 @@ class ErrorStats(C.Structure):
                 ("n_points", C.c_int64)]
 
 
-EXPORTS = ["mccba_default_options", "mccba_default_solve_opts", "mccba_nccl_unique_id", "mccba_create", "mccba_destroy",
+EXPORTS = ["mccba_exchange_mode", "mccba_default_options", "mccba_default_solve_opts", "mccba_nccl_unique_id", "mccba_create", "mccba_destroy",
            "mccba_last_error", "mccba_set_cameras", "mccba_set_observations", "mccba_set_parameters",
            "mccba_get_parameters", "mccba_save_parameters", "mccba_restore_parameters", "mccba_eval", "mccba_reduced_system", "mccba_solve", "mccba_reproj_error",
            "mccba_allreduce_sum", "mccba_last_kernel_ms", "mccba_time_eval", "mccba_debug_solve_dense", "mccba_omni_set_observations",
@@ -206,6 +206,10 @@ class Solver:
         out = np.zeros(6)
         self._check(lib().mccba_last_kernel_ms(self._h, _ptr(out, C.c_double)))
         return out
+
+    def exchange_mode(self):
+        """0 single rank, 1 ncclAllReduce, 2 NVLink peer-memory windows (include/mccba.h: mccba_exchange_mode)."""
+        return int(lib().mccba_exchange_mode(self._h))
 
     def debug_solve_dense(self, S, g, blocked=True):
         S = np.ascontiguousarray(S, dtype=np.float64); g = np.ascontiguousarray(g, dtype=np.float64)

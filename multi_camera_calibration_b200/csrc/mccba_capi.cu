@@ -32,6 +32,7 @@ struct NcclApi {
     ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
     bool ok = false;
 };
@@ -51,6 +52,7 @@ NcclApi& nccl()
             api.CommInitRank = (decltype(api.CommInitRank))dlsym(api.lib, "ncclCommInitRank");
             api.CommDestroy = (decltype(api.CommDestroy))dlsym(api.lib, "ncclCommDestroy");
             api.AllReduce = (decltype(api.AllReduce))dlsym(api.lib, "ncclAllReduce");
+            api.AllGather = (decltype(api.AllGather))dlsym(api.lib, "ncclAllGather");
             api.GetErrorString = (decltype(api.GetErrorString))dlsym(api.lib, "ncclGetErrorString");
             api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllReduce;
         }
@@ -59,6 +61,8 @@ NcclApi& nccl()
 }
 constexpr int kNcclFloat64 = 8;  // ncclDouble
 constexpr int kNcclSum = 0;
+constexpr int kNcclMin = 3;
+constexpr int kNcclInt8 = 0, kNcclInt32 = 2;
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------------------
@@ -71,6 +75,13 @@ struct mccba_handle_s {
     cudaStream_t copy_stream = nullptr;   // bulk observation upload, so that table uploads and memsets do not queue behind it
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_copy = nullptr;
     // pinned staging arena for the layout tables: their uploads must not block the host behind the observation copy
+    // peer-memory exchange (N > 1): own window + the windows of the peers opened through CUDA IPC
+    double* p2p_win = nullptr;
+    void* p2p_open[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    double* p2p_peer[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    unsigned long long* p2p_epoch = nullptr;
+    int64_t p2p_stride = 0;
+    bool p2p_ok = false;
     char* pin_buf = nullptr;
     size_t pin_cap = 0, pin_used = 0, pin_want = 0;
     ncclComm_t comm = nullptr;
@@ -229,7 +240,11 @@ int enqueue_iteration(mccba_handle h, bool timed)
     if (timed) cudaEventRecord(ev[1], s);
     reduce_records_kernel<<<P.n_dest, kK3Threads, 0, s>>>(P, 0);
     if (timed) cudaEventRecord(ev[2], s);
-    if (h->opts.nranks > 1) {
+    if (h->opts.nranks > 1 && h->p2p_ok) {
+        const int grid = std::max(1, std::min(h->num_sms, (int)((h->ar_len / 2 + kP2pThreads - 1) / kP2pThreads)));
+        p2p_push_kernel<<<grid, kP2pThreads, 0, s>>>(P, (int64_t)h->ar_len);
+        p2p_sum_kernel<<<grid, kP2pThreads, 0, s>>>(P, (int64_t)h->ar_len);
+    } else if (h->opts.nranks > 1) {
         ncclResult_t r = nccl().AllReduce(P.ar, P.ar, (size_t)h->ar_len, kNcclFloat64, kNcclSum, h->comm, s);
         if (r != 0) return fail(h, MCCBA_ERR_NCCL, "ncclAllReduce failed: %s", nccl().GetErrorString ? nccl().GetErrorString(r) : "?");
     }
@@ -354,6 +369,7 @@ int mccba_create(const mccba_options* opts, mccba_handle* out)
     return MCCBA_OK;
 }
 
+static void p2p_teardown(mccba_handle h);
 int mccba_destroy(mccba_handle h)
 {
     if (!h) return MCCBA_OK;
@@ -364,6 +380,7 @@ int mccba_destroy(mccba_handle h)
     if (h->omni_graph) cudaGraphExecDestroy(h->omni_graph);
     for (void* q : h->omni_allocs) cudaFree(q);
     if (h->d_cams) cudaFree(h->d_cams);
+    p2p_teardown(h);
     if (h->comm) nccl().CommDestroy(h->comm);
     cudaFreeHost(h->h_done);
     cudaFreeHost(h->h_state);
@@ -415,6 +432,84 @@ int mccba_set_cameras(mccba_handle h, int n_cam, const int* model, const double*
     h->n_cam = n_cam;
     h->have_cams = true;
     if (h->have_obs) h->P.cams = h->d_cams;
+    return MCCBA_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// peer-memory windows for the per-iteration exchange (N > 1).  Collective: every rank calls it from the same
+// set_observations.  Any failure on any rank (no IPC, no peer access, more than 8 ranks, MCCBA_P2P=0) makes ALL
+// ranks fall back to ncclAllReduce -- the decision itself is all-reduced.  Enabled with MCCBA_P2P=1 (on every rank).
+// ---------------------------------------------------------------------------------------------------------
+static void p2p_teardown(mccba_handle h)
+{
+    for (int r = 0; r < 8; ++r) {
+        if (h->p2p_open[r]) cudaIpcCloseMemHandle(h->p2p_open[r]);
+        h->p2p_open[r] = nullptr;
+        h->p2p_peer[r] = nullptr;
+    }
+    if (h->p2p_win) cudaFree(h->p2p_win);
+    if (h->p2p_epoch) cudaFree(h->p2p_epoch);
+    h->p2p_win = nullptr;
+    h->p2p_epoch = nullptr;
+    h->p2p_ok = false;
+    h->p2p_stride = 0;
+    cudaGetLastError();
+}
+
+static int p2p_setup(mccba_handle h)
+{
+    const int n = h->opts.nranks, me = h->opts.rank;
+    const int64_t stride = ((int64_t)h->ar_len + 31) & ~(int64_t)31;
+    if (h->p2p_stride == stride) return MCCBA_OK;   // same reduced-system size as the previous problem: nothing to do
+    p2p_teardown(h);
+    h->p2p_stride = stride;                         // remembered even on fallback, so the decision is taken once per size
+    const char* env = getenv("MCCBA_P2P");
+    struct Msg { cudaIpcMemHandle_t hdl; int ok; int pad[15]; };
+    static_assert(sizeof(Msg) == 128, "message layout");
+    Msg mine;
+    memset(&mine, 0, sizeof(mine));
+    // opt-in: measured on 8 x B200 (NVSwitch, NCCL 2.28 with NVLS) the plain push/sum exchange costs 436 us per LM
+    // iteration against 421 us with ncclAllReduce (2 GPUs: 391 vs 389), see profiles/r1_summary.md
+    mine.ok = (n <= 8 && nccl().AllGather && env && env[0] == '1') ? 1 : 0;
+    const size_t words = (size_t)kP2pFlagWords + 2 * (size_t)n * (size_t)stride;
+    if (mine.ok && cudaMalloc((void**)&h->p2p_win, words * sizeof(double)) != cudaSuccess) { mine.ok = 0; h->p2p_win = nullptr; cudaGetLastError(); }
+    if (mine.ok) {
+        CUDA_TRY(h, cudaMemsetAsync(h->p2p_win, 0, words * sizeof(double), h->stream));
+        if (cudaIpcGetMemHandle(&mine.hdl, h->p2p_win) != cudaSuccess) { mine.ok = 0; cudaGetLastError(); }
+    }
+    if (!nccl().AllGather) { p2p_teardown(h); h->p2p_stride = stride; return MCCBA_OK; }   // same on every rank
+    char* d_msg = nullptr;
+    CUDA_TRY(h, cudaMalloc((void**)&d_msg, sizeof(Msg) * (size_t)(n + 1) + 256));
+    std::vector<Msg> all((size_t)n);
+    CUDA_TRY(h, cudaMemcpyAsync(d_msg, &mine, sizeof(Msg), cudaMemcpyHostToDevice, h->stream));
+    ncclResult_t r = nccl().AllGather(d_msg, d_msg + sizeof(Msg), sizeof(Msg), kNcclInt8, h->comm, h->stream);
+    if (r != 0) { cudaFree(d_msg); return fail(h, MCCBA_ERR_NCCL, "ncclAllGather failed: %d", r); }
+    CUDA_TRY(h, cudaMemcpyAsync(all.data(), d_msg + sizeof(Msg), sizeof(Msg) * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    int ok = 1;
+    for (int q = 0; q < n; ++q) ok = ok && all[(size_t)q].ok;
+    if (ok) {
+        for (int q = 0; q < n && ok; ++q) {
+            if (q == me) { h->p2p_peer[q] = h->p2p_win; continue; }
+            void* ptr = nullptr;
+            if (cudaIpcOpenMemHandle(&ptr, all[(size_t)q].hdl, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; cudaGetLastError(); break; }
+            h->p2p_open[q] = ptr;
+            h->p2p_peer[q] = (double*)ptr;
+        }
+        if (ok && cudaMalloc((void**)&h->p2p_epoch, 256) != cudaSuccess) { ok = 0; h->p2p_epoch = nullptr; cudaGetLastError(); }
+        if (ok) CUDA_TRY(h, cudaMemsetAsync(h->p2p_epoch, 0, 256, h->stream));
+    }
+    // second round: did every rank manage to open every window?  (also the barrier behind the window memsets)
+    int* d_ok = (int*)(d_msg + sizeof(Msg) * (size_t)(n + 1));
+    CUDA_TRY(h, cudaMemcpyAsync(d_ok, &ok, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    r = nccl().AllReduce(d_ok, d_ok, 1, kNcclInt32, kNcclMin, h->comm, h->stream);
+    if (r != 0) { cudaFree(d_msg); return fail(h, MCCBA_ERR_NCCL, "ncclAllReduce failed: %d", r); }
+    CUDA_TRY(h, cudaMemcpyAsync(&ok, d_ok, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    cudaFree(d_msg);
+    if (!ok) { p2p_teardown(h); h->p2p_stride = stride; }
+    else h->p2p_ok = true;
+    if (h->opts.verbose) fprintf(stderr, "[mccba] rank %d: reduced-system exchange over %s\n", me, h->p2p_ok ? "NVLink peer memory" : "ncclAllReduce");
     return MCCBA_OK;
 }
 
@@ -647,6 +742,16 @@ int mccba_set_observations(mccba_handle h, int n_frame, int n_edge, const int* e
     h->edge_n_h.resize((size_t)n_edge);
     for (int e = 0; e < n_edge; ++e) h->edge_n_h[e] = edge_off[e + 1] - edge_off[e];
     h->ar_len = P.ns * P.ns + P.ns + 4;
+    if (h->opts.nranks > 1) {
+        int rc_p2p = p2p_setup(h);
+        if (rc_p2p) return rc_p2p;
+    }
+    for (int q = 0; q < 8; ++q) P.p2p_peer[q] = h->p2p_peer[q];
+    P.p2p_n = h->p2p_ok ? h->opts.nranks : 0;
+    P.p2p_rank = h->opts.rank;
+    P.p2p_stride = h->p2p_stride;
+    P.p2p_epoch = h->p2p_epoch;
+    P.p2p_count = h->p2p_epoch ? reinterpret_cast<unsigned*>(h->p2p_epoch + 8) : nullptr;
 
     int rc;
 #define UP(field, vec) if ((rc = dev_upload(h, &P.field, vec))) return rc
@@ -1088,6 +1193,12 @@ int mccba_debug_solve_dense(mccba_handle h, int n, const double* S, const double
     cudaFree(dA); cudaFree(dx); cudaFree(drinv); cudaFree(dfail);
     if (dflags) cudaFree(dflags);
     return f ? fail(h, MCCBA_ERR_NUMERIC, "matrix is not positive definite") : MCCBA_OK;
+}
+
+int mccba_exchange_mode(mccba_handle h)
+{
+    if (!h || h->opts.nranks <= 1) return 0;
+    return h->p2p_ok ? 2 : 1;
 }
 
 int mccba_last_kernel_ms(mccba_handle h, double out[6])

@@ -94,6 +94,13 @@ struct Problem {
     double* ar;          // allreduce buffer: S (ns x ns) | g (ns) | cost, step2, param2, bad
     double* dc;          // ns: camera step in tangent coordinates
     double* rinv;        // ns: reciprocal diagonal of the Cholesky factor
+    // peer-memory exchange of the packed reduced system (N > 1, see p2p_push_kernel): every rank's window is
+    // [64 epoch flags (u64) | parity 0: n ranks x p2p_stride doubles | parity 1: ...], mapped into every process by CUDA IPC
+    double* p2p_peer[8];
+    unsigned long long* p2p_epoch;   // local: number of completed exchanges
+    unsigned* p2p_count;             // local: CTA completion counter of the push kernel
+    int p2p_n, p2p_rank;
+    int64_t p2p_stride;
     double* dag_buf;     // tile-DAG output (chol_dag_words doubles), filled with the all-ones sentinel before every factorisation
     double* norm_part;   // 2 x n_k4_blocks: per-block |step|^2, |trial|^2 of the frames
     EdgeRec* erec;       // n_edge_int composed poses of the point the residual kernel evaluates next
@@ -818,10 +825,70 @@ __device__ int chol_solve_cta(double* A, int n, double* xout, double* s_col, dou
 }
 
 // loop control (single warp): accept/reject of the trial point, damping, termination; sets st->go
+// --------------------------------------------------------------------------------------------------------
+// C1 (N > 1): the per-iteration exchange of the packed buffer [S | g | scalars] over NVLink peer memory.
+// push: every rank stores its partial buffer into slot[rank] of EVERY rank's window (plain stores to IPC-mapped
+// peer memory, 16 bytes per thread), the last CTA to finish releases an epoch flag in every window (system scope).
+// sum: waits for all epoch flags of its own window, then adds the n slots in rank order -- every rank performs the
+// identical additions, so the reduced system and therefore the camera parameters are bit-identical on all ranks.
+// Windows are double-buffered by epoch parity: a rank can only be one exchange ahead of its slowest peer.
+// --------------------------------------------------------------------------------------------------------
+constexpr int kP2pFlagWords = 64;
+constexpr int kP2pThreads = 256;
+__global__ void __launch_bounds__(kP2pThreads) p2p_push_kernel(Problem P, int64_t len)
+{
+    const unsigned long long e = *P.p2p_epoch + 1;
+    const int n = P.p2p_n, me = P.p2p_rank;
+    const int64_t slot = (int64_t)((e & 1) * n + me) * P.p2p_stride + kP2pFlagWords;
+    const double2* src = reinterpret_cast<const double2*>(P.ar);
+    const int64_t n2 = len / 2, tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, step = (int64_t)gridDim.x * blockDim.x;
+    for (int r = 0; r < n; ++r) {
+        const int peer = (me + r) % n;   // spread the traffic: start with the own window, then the next rank ...
+        double* base = P.p2p_peer[peer] + slot;
+        double2* dst = reinterpret_cast<double2*>(base);
+        for (int64_t i = tid; i < n2; i += step) dst[i] = src[i];
+        if ((len & 1) && tid == 0) base[len - 1] = P.ar[len - 1];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned done = atomicAdd(P.p2p_count, 1u) + 1u;
+        if (done == gridDim.x) {
+            *P.p2p_count = 0;
+            __threadfence_system();
+            for (int r = 0; r < n; ++r) {
+                unsigned long long* flag = reinterpret_cast<unsigned long long*>(P.p2p_peer[r]) + me;
+                asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag), "l"(e) : "memory");
+            }
+        }
+    }
+}
+__global__ void __launch_bounds__(kP2pThreads) p2p_sum_kernel(Problem P, int64_t len)
+{
+    const unsigned long long e = *P.p2p_epoch + 1;
+    const int n = P.p2p_n, me = P.p2p_rank;
+    if (threadIdx.x < n) {
+        const unsigned long long* flag = reinterpret_cast<const unsigned long long*>(P.p2p_peer[me]) + threadIdx.x;
+        unsigned long long v;
+        do {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory");
+        } while (v < e);
+    }
+    __syncthreads();
+    const double* win = P.p2p_peer[me] + kP2pFlagWords + (int64_t)((e & 1) * n) * P.p2p_stride;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, step = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = tid; i < len; i += step) {
+        double acc = __ldcg(win + i);
+        for (int r = 1; r < n; ++r) acc += __ldcg(win + (int64_t)r * P.p2p_stride + i);
+        P.ar[i] = acc;
+    }
+}
+
 __global__ void decide_kernel(Problem P)
 {
     if (threadIdx.x != 0) return;
     DevState* st = P.st;
+    if (P.p2p_n > 1) *P.p2p_epoch += 1;   // the exchange of this launch is complete (both kernels ran before this one)
     const int ns = P.ns;
     const double* sc = P.ar + (int64_t)ns * ns + ns;
     int go = 0;

@@ -39,6 +39,7 @@ def main():
         s.set_parameters(sh["params_init"])
         S, gs = s.reduced_system(1e-3)
         rep = s.solve(mode=mode, crit_type=1, max_count=6)
+        xmode = s.exchange_mode()
         p_local = s.get_parameters()
         err = s.reproj_error()
         s.close()
@@ -67,8 +68,8 @@ def main():
             rs = float(np.abs(S - So).max() / np.abs(So).max())
             same_cams = all(torch.equal(cam_all[0], c) for c in cam_all)
             eo = O.error(ref["params"])
-            line = "%s world=%d iters=%d param_rel=%.2e S_rel=%.2e cams_bit_identical=%s rms=%.9f/%.9f cost=%.9e/%.9e" % (
-                name, world, rep["iterations"], rel, rs, same_cams, err["rms"], eo["rms"], rep["cost"], ref["cost"])
+            line = "%s world=%d exchange=%s iters=%d param_rel=%.2e S_rel=%.2e cams_bit_identical=%s rms=%.9f/%.9f cost=%.9e/%.9e" % (
+                name, world, {0: "none", 1: "nccl", 2: "peer"}[xmode], rep["iterations"], rel, rs, same_cams, err["rms"], eo["rms"], rep["cost"], ref["cost"])
             print(line, flush=True)
             ok = ok and rel < 1e-6 and rs < 1e-9 and same_cams and abs(err["rms"] - eo["rms"]) < 1e-9 * eo["rms"] \
                 and abs(rep["cost"] - ref["cost"]) < 1e-9 * ref["cost"] and rep["iterations"] == 6

@@ -15,5 +15,14 @@ def test_two_rank_parity():
         pytest.skip("needs 2 GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
            "127.0.0.1", "--master-port", "29517", os.path.join(ROOT, "scripts", "mgpu_parity.py")]
-    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    env = dict(os.environ)
+    env.pop("MCCBA_P2P", None)
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     assert "MGPU_PARITY_OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
+    assert "exchange=nccl" in out.stdout
+    # the same run with the opt-in NVLink peer-memory exchange (falls back to NCCL when the windows cannot be mapped)
+    env["MCCBA_P2P"] = "1"
+    cmd[cmd.index("29517")] = "29518"
+    out2 = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
+    assert "MGPU_PARITY_OK" in out2.stdout, out2.stdout[-3000:] + out2.stderr[-3000:]
+    print(out.stdout[-1500:], out2.stdout[-1500:])
