@@ -233,9 +233,10 @@ int enqueue_iteration(mccba_handle h, bool timed)
     if (timed)
         for (auto& e : ev) cudaEventCreate(&e);
     if (timed) cudaEventRecord(ev[0], s);
-    // the whole packed buffer: a rank whose frame shard never sees some camera has no record for that camera's
-    // rows, and stale (already all-reduced) values there would be summed again
-    CUDA_TRY(h, cudaMemsetAsync(P.ar, 0, sizeof(double) * (size_t)h->ar_len, s));
+    // reduce_records rewrites every block that has a source and nothing else writes into its buffer (the collective
+    // is out of place, the tile DAG does not factor in place), so blocks without sources stay zero from allocation;
+    // only the in-place factorisations (MCCBA_CHOL=0/1) on a single rank need the buffer cleared again
+    if (h->opts.nranks == 1 && h->k5_blocked != 2) CUDA_TRY(h, cudaMemsetAsync(P.ar, 0, sizeof(double) * (size_t)h->ar_len, s));
     launch_schur(h, s, -1, 0.0);
     if (timed) cudaEventRecord(ev[1], s);
     reduce_records_kernel<<<P.n_dest, kK3Threads, 0, s>>>(P, 0);
@@ -245,14 +246,13 @@ int enqueue_iteration(mccba_handle h, bool timed)
         p2p_push_kernel<<<grid, kP2pThreads, 0, s>>>(P, (int64_t)h->ar_len);
         p2p_sum_kernel<<<grid, kP2pThreads, 0, s>>>(P, (int64_t)h->ar_len);
     } else if (h->opts.nranks > 1) {
-        ncclResult_t r = nccl().AllReduce(P.ar, P.ar, (size_t)h->ar_len, kNcclFloat64, kNcclSum, h->comm, s);
+        ncclResult_t r = nccl().AllReduce(P.ar_part, P.ar, (size_t)h->ar_len, kNcclFloat64, kNcclSum, h->comm, s);
         if (r != 0) return fail(h, MCCBA_ERR_NCCL, "ncclAllReduce failed: %s", nccl().GetErrorString ? nccl().GetErrorString(r) : "?");
     }
     if (timed) cudaEventRecord(ev[3], s);
     decide_kernel<<<1, 32, 0, s>>>(P);
     if (h->k5_blocked == 2 && P.ns > 0) {
-        CUDA_TRY(h, cudaMemsetAsync(P.dag_buf, 0xFF, sizeof(double) * chol_dag_words(P.ns), s));
-        CholDag D{P.ar, P.dag_buf, P.ns, P.dc, &P.st->go, &P.st->chol_fail, nullptr};
+        CholDag D{P.ar, P.dag_buf, P.ns, P.dc, &P.st->go, &P.st->chol_fail, nullptr};   // sentinel fill: reduce_records
         chol_dag_kernel<<<h->dag_grid, 256, 0, s>>>(D);
     } else if (h->k5_blocked == 1 && P.ns > 0) {
         const int ntc = chol_col_tiles(P.ns), ntr = chol_row_tiles(P.ns);
@@ -780,6 +780,8 @@ int mccba_set_observations(mccba_handle h, int n_frame, int n_edge, const int* e
     if ((rc = dev_alloc(h, &P.records, (size_t)rec_total, true))) return rc;
     if ((rc = dev_alloc(h, &P.warp_scal, 2 * (size_t)P.n_warps, true))) return rc;
     if ((rc = dev_alloc(h, &P.ar, (size_t)h->ar_len, true))) return rc;
+    P.ar_part = P.ar;
+    if (h->opts.nranks > 1 && (rc = dev_alloc(h, &P.ar_part, (size_t)h->ar_len, true))) return rc;
     if ((rc = dev_alloc(h, &h->x_saved, (size_t)P.n_param, true))) return rc;
     if ((rc = dev_alloc(h, &P.dc, (size_t)std::max(P.ns, 1), true))) return rc;
     if ((rc = dev_alloc(h, &P.rinv, (size_t)std::max(P.ns, 1), true))) return rc;
@@ -840,6 +842,7 @@ int mccba_set_observations(mccba_handle h, int n_frame, int n_edge, const int* e
             CUDA_TRY(h, cudaFuncSetAttribute(camera_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->k5_smem));
         h->iter_kernels = 6 + (P.ns > 0 ? (mode == 2 ? 1 : (mode == 1 ? 2 * ntc - 1 : 0)) : 0);
         if ((rc = dev_alloc(h, &P.dag_buf, chol_dag_words(P.ns) + 8))) return rc;
+        P.dag_words = (mode == 2 && P.ns > 0) ? (int64_t)chol_dag_words(P.ns) : 0;
     }
     int per_sm = 1;
     if (h->obs_cap > 0) {
@@ -964,7 +967,7 @@ int mccba_reduced_system(mccba_handle h, double lambda, double* S, double* gs)
     reduce_records_kernel<<<P.n_dest, kK3Threads, 0, h->stream>>>(P, 1);
     CUDA_TRY(h, cudaGetLastError());
     if (h->opts.nranks > 1) {
-        ncclResult_t r = nccl().AllReduce(P.ar, P.ar, (size_t)h->ar_len, kNcclFloat64, kNcclSum, h->comm, h->stream);
+        ncclResult_t r = nccl().AllReduce(P.ar_part, P.ar, (size_t)h->ar_len, kNcclFloat64, kNcclSum, h->comm, h->stream);
         if (r != 0) return fail(h, MCCBA_ERR_NCCL, "ncclAllReduce failed: %d", r);
     }
     const size_t ns = (size_t)P.ns;

@@ -101,6 +101,8 @@ struct Problem {
     unsigned* p2p_count;             // local: CTA completion counter of the push kernel
     int p2p_n, p2p_rank;
     int64_t p2p_stride;
+    double* ar_part;     // rank-local packed buffer written by reduce_records (== ar on a single rank)
+    int64_t dag_words;   // chol_dag_words(ns) when the tile DAG is in use, else 0
     double* dag_buf;     // tile-DAG output (chol_dag_words doubles), filled with the all-ones sentinel before every factorisation
     double* norm_part;   // 2 x n_k4_blocks: per-block |step|^2, |trial|^2 of the frames
     EdgeRec* erec;       // n_edge_int composed poses of the point the residual kernel evaluates next
@@ -710,9 +712,19 @@ __global__ void __launch_bounds__(kK3Threads) reduce_records_kernel(Problem P, i
     const int kind = P.dest_info[4 * dest], A = P.dest_info[4 * dest + 1], B = P.dest_info[4 * dest + 2];
     const int s0 = P.dest_src0[dest], s1 = P.dest_src0[dest + 1];
     const int ns = P.ns;
-    double* S = P.ar;
-    double* gs = P.ar + (int64_t)ns * ns;
+    double* S = P.ar_part;
+    double* gs = P.ar_part + (int64_t)ns * ns;
     double* sc = gs + ns;
+    if (P.dag_words > 0) {
+        // the solve that follows wants its output buffer filled with the all-ones sentinel (mccba_dense.cuh); this
+        // kernel is pure gather latency, so its CTAs write the 1.2 MB on the side instead of a separate memset node
+        const int64_t per = (P.dag_words / 2 + gridDim.x - 1) / gridDim.x;
+        const int64_t b2 = (int64_t)blockIdx.x * per, e2 = min(b2 + per, P.dag_words / 2);
+        double2* d2 = reinterpret_cast<double2*>(P.dag_buf);
+        const double sent = __longlong_as_double(-1LL);
+        for (int64_t i = b2 + threadIdx.x; i < e2; i += kK3Threads) d2[i] = make_double2(sent, sent);
+        if ((P.dag_words & 1) && blockIdx.x == 0 && threadIdx.x == 0) P.dag_buf[P.dag_words - 1] = sent;
+    }
     if (kind == 2) {
         // scalars: cost and bad from every warp record; frame step / param norms from frame_update's partials
         double c = 0, b = 0, n0 = 0, n1 = 0;
@@ -840,14 +852,14 @@ __global__ void __launch_bounds__(kP2pThreads) p2p_push_kernel(Problem P, int64_
     const unsigned long long e = *P.p2p_epoch + 1;
     const int n = P.p2p_n, me = P.p2p_rank;
     const int64_t slot = (int64_t)((e & 1) * n + me) * P.p2p_stride + kP2pFlagWords;
-    const double2* src = reinterpret_cast<const double2*>(P.ar);
+    const double2* src = reinterpret_cast<const double2*>(P.ar_part);
     const int64_t n2 = len / 2, tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, step = (int64_t)gridDim.x * blockDim.x;
     for (int r = 0; r < n; ++r) {
         const int peer = (me + r) % n;   // spread the traffic: start with the own window, then the next rank ...
         double* base = P.p2p_peer[peer] + slot;
         double2* dst = reinterpret_cast<double2*>(base);
         for (int64_t i = tid; i < n2; i += step) dst[i] = src[i];
-        if ((len & 1) && tid == 0) base[len - 1] = P.ar[len - 1];
+        if ((len & 1) && tid == 0) base[len - 1] = P.ar_part[len - 1];
     }
     __threadfence_system();
     __syncthreads();
