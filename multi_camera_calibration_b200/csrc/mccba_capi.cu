@@ -253,7 +253,7 @@ int enqueue_iteration(mccba_handle h, bool timed)
     decide_kernel<<<1, 32, 0, s>>>(P);
     if (h->k5_blocked == 2 && P.ns > 0) {
         CholDag D{P.ar, P.dag_buf, P.ns, P.dc, &P.st->go, &P.st->chol_fail, nullptr};   // sentinel fill: reduce_records
-        chol_dag_kernel<<<h->dag_grid, 256, 0, s>>>(D);
+        chol_dag_kernel<<<h->dag_grid, 256, 0, s>>>(D, P, P.ns <= 512 ? 1 : 0);
     } else if (h->k5_blocked == 1 && P.ns > 0) {
         const int ntc = chol_col_tiles(P.ns), ntr = chol_row_tiles(P.ns);
         for (int k = 0; k < ntc; ++k) {
@@ -261,7 +261,8 @@ int enqueue_iteration(mccba_handle h, bool timed)
             if (k + 1 < ntc) chol_update_kernel<<<dim3(ntc - k - 1, ntr - k - 1), kUpdThreads, 0, s>>>(P.ar, P.ns, k, &P.st->go);
         }
     }
-    camera_update_kernel<<<1, kK5Threads, h->k5_smem, s>>>(P, h->k5_blocked);
+    if (!(h->k5_blocked == 2 && P.ns > 0 && P.ns <= 512))   // otherwise fused into the tail of chol_dag_kernel
+        camera_update_kernel<<<1, kK5Threads, h->k5_smem, s>>>(P, h->k5_blocked);
     if (timed) cudaEventRecord(ev[4], s);
     frame_update_kernel<<<P.n_k4_blocks, kK4Threads, kK4SmemBytes, s>>>(P);
     if (timed) cudaEventRecord(ev[5], s);
@@ -840,7 +841,7 @@ int mccba_set_observations(mccba_handle h, int n_frame, int n_edge, const int* e
             CUDA_TRY(h, cudaFuncSetAttribute(chol_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->panel_smem));
         if (h->k5_smem > 48 * 1024)
             CUDA_TRY(h, cudaFuncSetAttribute(camera_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->k5_smem));
-        h->iter_kernels = 6 + (P.ns > 0 ? (mode == 2 ? 1 : (mode == 1 ? 2 * ntc - 1 : 0)) : 0);
+        h->iter_kernels = 6 + (P.ns > 0 ? (mode == 2 ? (P.ns <= 512 ? 0 : 1) : (mode == 1 ? 2 * ntc - 1 : 0)) : 0);
         if ((rc = dev_alloc(h, &P.dag_buf, chol_dag_words(P.ns) + 8))) return rc;
         P.dag_words = (mode == 2 && P.ns > 0) ? (int64_t)chol_dag_words(P.ns) : 0;
     }
@@ -1159,7 +1160,7 @@ int mccba_debug_solve_dense(mccba_handle h, int n, const double* S, const double
             CUDA_TRY(h, cudaMemsetAsync(dtrace, 0, sizeof(unsigned long long) * 8 * (size_t)grid, h->stream));
         }
         CholDag D{dA, dflags, n, dx, nullptr, dfail, dtrace};
-        chol_dag_kernel<<<grid, 256, 0, h->stream>>>(D);
+        chol_dag_kernel<<<grid, 256, 0, h->stream>>>(D, h->P, 0);
         if (dtrace) {   // diagnostics: per-tile timeline in ns relative to the first stamp
             std::vector<unsigned long long> tr(8 * (size_t)grid);
             CUDA_TRY(h, cudaMemcpyAsync(tr.data(), dtrace, sizeof(unsigned long long) * tr.size(), cudaMemcpyDeviceToHost, h->stream));

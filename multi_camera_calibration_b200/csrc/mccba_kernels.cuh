@@ -962,33 +962,39 @@ __global__ void __launch_bounds__(kUpdThreads) chol_update_kernel(double* A, int
 }
 
 // the whole factorisation + both substitutions in one launch (mccba_dense.cuh, tile DAG)
-__global__ void __launch_bounds__(256) chol_dag_kernel(CholDag D)
+__device__ __forceinline__ void camera_update_body(const Problem& P, const double* dc, int fail);
+
+// fused != 0: the CTA of tile (0, 0) -- the last one to finish, the backward sweep ends there -- also runs the camera
+// update (one kernel boundary less per iteration).  It reads the solution from the sentinel buffer, where every word
+// validates itself, and treats a non-finite entry as a failed factorisation (a bad pivot turns its column into NaN).
+__global__ void __launch_bounds__(256) chol_dag_kernel(CholDag D, Problem P, int fused)
 {
     if (D.go && !*D.go) return;
     chol_dag_tile(D);
+    if (!fused || blockIdx.x != 0) return;
+    __shared__ double s_dx[512];
+    __shared__ int s_nonfinite;
+    const int n = D.n;
+    if (threadIdx.x == 0) s_nonfinite = 0;
+    __syncthreads();   // also: warp 0 is back from the backward sweep
+    const double* xs = D.L + (size_t)(n + 1) * n + (size_t)chol_row_tiles(n) * chol_col_tiles(n) * kCT + n;
+    int bad = 0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const double v = dag_poll(xs + i);
+        s_dx[i] = v;
+        if (!isfinite(v)) bad = 1;
+    }
+    if (bad) s_nonfinite = 1;
+    __syncthreads();
+    const int fail = s_nonfinite || *reinterpret_cast<volatile int*>(D.fail);
+    camera_update_body(P, s_dx, fail);
 }
 
-// backward substitution + camera update (replicated on every rank) + end-of-iteration state.  Single CTA.
-__global__ void __launch_bounds__(kK5Threads) camera_update_kernel(Problem P, int tiled)
+// camera step (tangent -> additive Rodrigues step, scaled), trial camera parameters and rotations, end-of-iteration
+// state.  Called by one whole CTA (any multiple of 32 threads); dc = solution of the reduced system.
+__device__ __forceinline__ void camera_update_body(const Problem& P, const double* dc, int fail)
 {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    double* s_dyn = reinterpret_cast<double*>(smem_raw);
-    __shared__ double s_bcast[2];
     DevState* st = P.st;
-    if (!st->go) return;
-    const int ns = P.ns;
-    int fail = 0;
-    if (ns > 0) {
-        if (tiled == 2) {
-            fail = st->chol_fail;                      // chol_dag_kernel already left the solution in P.dc
-        } else if (tiled == 1) {
-            chol_backward(P.ar, ns, P.rinv, P.dc, s_dyn);
-            fail = st->chol_fail;
-        } else {
-            fail = chol_solve_cta(P.ar, ns, P.dc, s_dyn, s_bcast);
-        }
-    }
-    __syncthreads();
     // tangent step -> additive Rodrigues step, scaled, trial parameters
     const int cur = st->cur, tr = 1 - cur;
     const double alpha = st->mode == 0 ? pow(0.95, (double)st->iter + 1.0) : 1.0;
@@ -996,7 +1002,7 @@ __global__ void __launch_bounds__(kK5Threads) camera_update_kernel(Problem P, in
     for (int c = 1 + threadIdx.x; c < P.n_cam; c += blockDim.x) {
         const double* p = P.x[cur] + 6 * (c - 1);
         const double om[3] = {p[0], p[1], p[2]};
-        const double* d = P.dc + 6 * (c - 1);
+        const double* d = dc + 6 * (c - 1);
         double dom[3], R[9];
         left_jacobian_inv_apply(om, d, dom);
         double q[6];
@@ -1033,6 +1039,30 @@ __global__ void __launch_bounds__(kK5Threads) camera_update_kernel(Problem P, in
             }
         }
     }
+}
+
+// backward substitution + camera update (replicated on every rank) + end-of-iteration state.  Single CTA.
+__global__ void __launch_bounds__(kK5Threads) camera_update_kernel(Problem P, int tiled)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double* s_dyn = reinterpret_cast<double*>(smem_raw);
+    __shared__ double s_bcast[2];
+    DevState* st = P.st;
+    if (!st->go) return;
+    const int ns = P.ns;
+    int fail = 0;
+    if (ns > 0) {
+        if (tiled == 2) {
+            fail = st->chol_fail;                      // chol_dag_kernel already left the solution in P.dc
+        } else if (tiled == 1) {
+            chol_backward(P.ar, ns, P.rinv, P.dc, s_dyn);
+            fail = st->chol_fail;
+        } else {
+            fail = chol_solve_cta(P.ar, ns, P.dc, s_dyn, s_bcast);
+        }
+    }
+    __syncthreads();
+    camera_update_body(P, P.dc, fail);
 }
 
 // --------------------------------------------------------------------------------------------------------
