@@ -253,7 +253,15 @@ int enqueue_iteration(mccba_handle h, bool timed)
     decide_kernel<<<1, 32, 0, s>>>(P);
     if (h->k5_blocked == 2 && P.ns > 0) {
         CholDag D{P.ar, P.dag_buf, P.ns, P.dc, &P.st->go, &P.st->chol_fail, nullptr};   // sentinel fill: reduce_records
-        chol_dag_kernel<<<h->dag_grid, 256, 0, s>>>(D, P, P.ns <= 512 ? 1 : 0);
+        // cooperative launch: the CTAs of the DAG spin on each other, so the runtime must place all of them at once
+        // (or fail) -- a second context or stream sharing the GPU can then delay the solve but never deadlock it
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)h->dag_grid); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = s;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeCooperative;
+        attr[0].val.cooperative = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        CUDA_TRY(h, cudaLaunchKernelEx(&cfg, chol_dag_kernel, D, P, P.ns <= 512 ? 1 : 0));
     } else if (h->k5_blocked == 1 && P.ns > 0) {
         const int ntc = chol_col_tiles(P.ns), ntr = chol_row_tiles(P.ns);
         for (int k = 0; k < ntc; ++k) {
