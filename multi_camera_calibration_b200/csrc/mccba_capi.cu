@@ -652,6 +652,7 @@ int mccba_set_observations(mccba_handle h, int n_frame, int n_edge, const int* e
     P.cams = h->d_cams;
 
     std::vector<int> slot_frame, warp_group, group_V, group_cam0, group_cams, group_ebase, group_stride, group_slot0, warp_rec;
+    std::vector<int> wmeta;   // 8 ints per warp, see Problem::wmeta
     std::vector<int> e_cam, e_frame, e_off;
     std::vector<int64_t> e_src;
     h->int_of_edge.assign((size_t)n_edge, -1);
@@ -709,6 +710,8 @@ int mccba_set_observations(mccba_handle h, int n_frame, int n_edge, const int* e
             if (rec_total + rec_len >= (int64_t)2000000000) return fail(h, MCCBA_ERR_ARG, "record buffer too large");
             const int ro = (int)rec_total;
             warp_rec.push_back(ro);
+            const int meta[8] = {V, group_cam0.back(), group_ebase.back(), stride, 32 * w, ro, gi, 0};
+            wmeta.insert(wmeta.end(), meta, meta + 8);
             for (int i = 0; i < Va; ++i) {
                 dest_blocks[{act[i] - 1, act[i] - 1}].push_back(ro + 2 + 36 * i);
                 dest_g[act[i] - 1].push_back(ro + 2 + 36 * Va + 6 * i);
@@ -767,6 +770,11 @@ int mccba_set_observations(mccba_handle h, int n_frame, int n_edge, const int* e
     UP(e_off, e_off); UP(e_cam, e_cam); UP(e_frame, e_frame);
     UP(slot_frame, slot_frame); UP(warp_group, warp_group); UP(group_V, group_V); UP(group_cam0, group_cam0);
     UP(group_cams, group_cams); UP(group_ebase, group_ebase); UP(group_stride, group_stride); UP(group_slot0, group_slot0);
+    {
+        const int* d_wmeta = nullptr;
+        if ((rc = dev_upload(h, &d_wmeta, wmeta))) return rc;
+        P.wmeta = reinterpret_cast<const int4*>(d_wmeta);
+    }
     UP(warp_rec, warp_rec); UP(dest_info, dest_info); UP(dest_src0, dest_src0); UP(dest_src, dest_src);
 #undef UP
     const int64_t* d_esrc = nullptr;

@@ -78,6 +78,8 @@ struct Problem {
     const int* group_stride; // per group: slots (multiple of 32); edge(v, ls) = ebase + v*stride + ls
     const int* group_slot0;  // per group: first slot
     const int* warp_rec;     // per warp: offset of its record (in doubles)
+    const int4* wmeta;       // per warp, 2 x int4: {V, first index into group_cams, ebase, stride}, {first local slot, record
+                             // offset, group, 0} -- everything a frame warp needs in ONE load instead of a three-level chain
     // reduce destinations
     const int* dest_info;    // n_dest x 4: kind (0 block, 1 g, 2 scalars), A (cam-1), B (cam-1), unused
     const int* dest_src0;    // n_dest + 1
@@ -529,12 +531,12 @@ __global__ void __launch_bounds__(kK2Threads, kMinBlocks) frame_schur_kernel(Pro
     extern __shared__ __align__(128) unsigned char k2_smem[];
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
     if (warp >= P.n_warps) return;
-    const int g = P.warp_group[warp];
-    const int V = P.group_V[g];
-    const int* gc = P.group_cams + P.group_cam0[g];
+    const int4 m0 = P.wmeta[2 * warp], m1 = P.wmeta[2 * warp + 1];
+    const int V = m0.x;
+    const int* gc = P.group_cams + m0.y;
     const int slot = warp * 32 + lane;
-    const int ls = slot - P.group_slot0[g];
-    const int ebase = P.group_ebase[g], stride = P.group_stride[g];
+    const int ls = m1.x + lane;
+    const int ebase = m0.z, stride = m0.w;
     const double* __restrict__ blk = P.blocks[sel];
     // per warp: two 36 x 32 tiles.  A tile first receives the 28 x 32 edge-block tile of view 0 / 1 from the TMA
     // engine (tile-major records: one contiguous 7 KB block), later the lanes overwrite their own column with Y.
@@ -552,7 +554,7 @@ __global__ void __launch_bounds__(kK2Threads, kMinBlocks) frame_schur_kernel(Pro
     const bool active = frame >= 0;
     const double* __restrict__ x = P.x[sel];
     const double* __restrict__ vR = P.vR[sel];
-    double* rec = P.records + P.warp_rec[warp];
+    double* rec = P.records + m1.y;
 
     double tp[3] = {0, 0, 0};
     if (active) {
@@ -1090,11 +1092,11 @@ __global__ void __launch_bounds__(kK4Threads) frame_update_kernel(Problem P)
     if (slot < P.n_slots) {   // n_slots is a multiple of 32: whole warps
         const int frame = P.slot_frame[slot];
         const int warp = slot >> 5;
-        const int g = P.warp_group[warp];
-        const int V = P.group_V[g];
-        const int* gc = P.group_cams + P.group_cam0[g];
-        const int ls = slot - P.group_slot0[g];
-        const int64_t ebase = P.group_ebase[g], stride = P.group_stride[g];
+        const int4 m0 = P.wmeta[2 * warp], m1 = P.wmeta[2 * warp + 1];
+        const int V = m0.x;
+        const int* gc = P.group_cams + m0.y;
+        const int ls = m1.x + lane;
+        const int64_t ebase = m0.z, stride = m0.w;
         const int c0v = gc[0], c1v = V > 1 ? gc[1] : 0;
         if (lane == 0) {
             mbar_init(bar, 1);
