@@ -279,8 +279,13 @@ __device__ __forceinline__ void edge_corner_loop(const float* __restrict__ ox, c
                                                  const float* __restrict__ iv, const CamParams& cam, const double* R3,
                                                  const double* T3, int begin, int end, int sub, double* acc)
 {
-    for (int i = begin + sub; i < end; i += kLanesPerEdge)
+    for (int i = begin + sub; i < end; i += kLanesPerEdge) {
+        // The pose and the intrinsics live in shared memory; the barrier keeps the compiler from hoisting those ~25
+        // loads out of the loop into registers it does not have (it spilled the accumulators to local memory instead:
+        // 6 LDL/STL per corner).  Re-reading them per corner costs broadcast LDS only.
+        asm volatile("" ::: "memory");
         corner_accumulate<kModel, kRational>(cam, R3, T3, ox[i], oy[i], oz[i], iu[i], iv[i], acc);
+    }
 }
 
 // forced: 0 = loop launch (evaluate the trial buffer iff the state says a step was produced), 1 = forced on `cur`.
