@@ -106,6 +106,7 @@ struct mccba_handle_s {
     int k2_occ = 2;                   // minimum resident CTAs per SM requested from the Schur kernel (register cap)
     int obs_cap = 0;                  // floats per plane per TMA stage of the residual kernel (0: no staging)
     int k1_grid = 0, k1_smem = 0, k5_smem = 0, k5_blocked = 0, panel_smem = 0, iter_kernels = 5, dag_grid = 0;
+    int band_nw = 0;                  // 6 (block bandwidth + 1) of the reduced system (agreed over the ranks)
     cudaGraphExec_t graph = nullptr;
     int* h_done = nullptr;            // pinned
     DevState* h_state = nullptr;      // pinned
@@ -224,6 +225,29 @@ void launch_schur(mccba_handle h, cudaStream_t s, int sel, double lambda)
     }
 }
 
+// banded LDL^T solve of the reduced system (mode 3): NW = 6 (m + 1) live columns, m = block bandwidth
+template <int NW>
+static cudaError_t launch_band_nw(const double* A, int n, double* xout, int* fail, const int* go, const Problem& P, int fused, cudaStream_t s)
+{
+    const size_t smem = chol_band_smem_bytes(n, NW);
+    cudaError_t e = cudaFuncSetAttribute(chol_band_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    chol_band_kernel<NW><<<1, kBandThreads, smem, s>>>(A, n, xout, fail, go, P, fused);
+    return cudaGetLastError();
+}
+static cudaError_t launch_band(int nw, const double* A, int n, double* xout, int* fail, const int* go, const Problem& P, int fused, cudaStream_t s)
+{
+    switch (nw) {
+        case 6: return launch_band_nw<6>(A, n, xout, fail, go, P, fused, s);
+        case 12: return launch_band_nw<12>(A, n, xout, fail, go, P, fused, s);
+        case 18: return launch_band_nw<18>(A, n, xout, fail, go, P, fused, s);
+        case 24: return launch_band_nw<24>(A, n, xout, fail, go, P, fused, s);
+        case 30: return launch_band_nw<30>(A, n, xout, fail, go, P, fused, s);
+        default: return cudaErrorInvalidValue;
+    }
+}
+static bool band_fits(int nw, int n) { return nw >= 6 && nw <= 30 && chol_band_smem_bytes(n, nw) <= 200 * 1024; }
+
 // enqueue one iteration: [memset S] K2 K3a [allreduce] K5 K4 K1
 int enqueue_iteration(mccba_handle h, bool timed)
 {
@@ -236,7 +260,7 @@ int enqueue_iteration(mccba_handle h, bool timed)
     // reduce_records rewrites every block that has a source and nothing else writes into its buffer (the collective
     // is out of place, the tile DAG does not factor in place), so blocks without sources stay zero from allocation;
     // only the in-place factorisations (MCCBA_CHOL=0/1) on a single rank need the buffer cleared again
-    if (h->opts.nranks == 1 && h->k5_blocked != 2) CUDA_TRY(h, cudaMemsetAsync(P.ar, 0, sizeof(double) * (size_t)h->ar_len, s));
+    if (h->opts.nranks == 1 && h->k5_blocked < 2) CUDA_TRY(h, cudaMemsetAsync(P.ar, 0, sizeof(double) * (size_t)h->ar_len, s));
     launch_schur(h, s, -1, 0.0);
     if (timed) cudaEventRecord(ev[1], s);
     reduce_records_kernel<<<P.n_dest, kK3Threads, 0, s>>>(P, 0);
@@ -251,7 +275,9 @@ int enqueue_iteration(mccba_handle h, bool timed)
     }
     if (timed) cudaEventRecord(ev[3], s);
     decide_kernel<<<1, 32, 0, s>>>(P);
-    if (h->k5_blocked == 2 && P.ns > 0) {
+    if (h->k5_blocked == 3 && P.ns > 0) {
+        CUDA_TRY(h, launch_band(h->band_nw, P.ar, P.ns, P.dc, &P.st->chol_fail, &P.st->go, P, 1, s));
+    } else if (h->k5_blocked == 2 && P.ns > 0) {
         CholDag D{P.ar, P.dag_buf, P.ns, P.dc, &P.st->go, &P.st->chol_fail, nullptr};   // sentinel fill: reduce_records
         // cooperative launch: the CTAs of the DAG spin on each other, so the runtime must place all of them at once
         // (or fail) -- a second context or stream sharing the GPU can then delay the solve but never deadlock it
@@ -269,7 +295,7 @@ int enqueue_iteration(mccba_handle h, bool timed)
             if (k + 1 < ntc) chol_update_kernel<<<dim3(ntc - k - 1, ntr - k - 1), kUpdThreads, 0, s>>>(P.ar, P.ns, k, &P.st->go);
         }
     }
-    if (!(h->k5_blocked == 2 && P.ns > 0 && P.ns <= 512))   // otherwise fused into the tail of chol_dag_kernel
+    if (!((h->k5_blocked == 3 && P.ns > 0) || (h->k5_blocked == 2 && P.ns > 0 && P.ns <= 512)))   // otherwise fused into the solve
         camera_update_kernel<<<1, kK5Threads, h->k5_smem, s>>>(P, h->k5_blocked);
     if (timed) cudaEventRecord(ev[4], s);
     frame_update_kernel<<<P.n_k4_blocks, kK4Threads, kK4SmemBytes, s>>>(P);
@@ -723,6 +749,18 @@ int mccba_set_observations(mccba_handle h, int n_frame, int n_edge, const int* e
         }
         ++gi;
     }
+    {   // block bandwidth of the reduced system under the camera numbering (over all ranks)
+        int m = 0;
+        for (auto& kv : dest_blocks) m = std::max(m, std::abs(kv.first.first - kv.first.second));
+        if (h->opts.nranks > 1) {
+            CUDA_TRY(h, cudaMemcpyAsync(h->d_small, &m, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+            ncclResult_t r = nccl().AllReduce(h->d_small, h->d_small, 1, kNcclInt32, 2 /* ncclMax */, h->comm, h->stream);
+            if (r != 0) return fail(h, MCCBA_ERR_NCCL, "ncclAllReduce failed: %d", r);
+            CUDA_TRY(h, cudaMemcpyAsync(&m, h->d_small, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+            CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+        }
+        h->band_nw = 6 * (m + 1);
+    }
     std::vector<int> dest_info, dest_src0, dest_src;
     dest_src0.push_back(0);
     for (auto& kv : dest_blocks) {
@@ -838,8 +876,10 @@ int mccba_set_observations(mccba_handle h, int n_frame, int n_edge, const int* e
         // 0 = plain single-CTA column Cholesky (also the fallback when a block column does not fit in shared memory)
         const size_t need = chol_panel_smem_bytes(P.ns);
         const char* sel = getenv("MCCBA_CHOL");
-        int mode = 2;
-        if (sel && sel[0] >= '0' && sel[0] <= '2') mode = sel[0] - '0';
+        // 3 = banded LDL^T by one warp when the camera graph is banded (block bandwidth <= 4), else the tile DAG
+        int mode = band_fits(h->band_nw, P.ns) ? 3 : 2;
+        if (sel && sel[0] >= '0' && sel[0] <= '3') mode = sel[0] - '0';
+        if (mode == 3 && !band_fits(h->band_nw, P.ns)) mode = 2;
         if (need > 227 * 1024 && mode == 1) mode = 0;
         const int ntc = chol_col_tiles(P.ns), ntr = chol_row_tiles(P.ns);
         int grid = 0;
@@ -857,7 +897,7 @@ int mccba_set_observations(mccba_handle h, int n_frame, int n_edge, const int* e
             CUDA_TRY(h, cudaFuncSetAttribute(chol_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->panel_smem));
         if (h->k5_smem > 48 * 1024)
             CUDA_TRY(h, cudaFuncSetAttribute(camera_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->k5_smem));
-        h->iter_kernels = 6 + (P.ns > 0 ? (mode == 2 ? (P.ns <= 512 ? 0 : 1) : (mode == 1 ? 2 * ntc - 1 : 0)) : 0);
+        h->iter_kernels = 6 + (P.ns > 0 ? (mode == 3 ? 0 : mode == 2 ? (P.ns <= 512 ? 0 : 1) : (mode == 1 ? 2 * ntc - 1 : 0)) : 0);
         if ((rc = dev_alloc(h, &P.dag_buf, chol_dag_words(P.ns) + 8))) return rc;
         P.dag_words = (mode == 2 && P.ns > 0) ? (int64_t)chol_dag_words(P.ns) : 0;
     }
@@ -1155,7 +1195,19 @@ int mccba_debug_solve_dense(mccba_handle h, int n, const double* S, const double
     CUDA_TRY(h, cudaFuncSetAttribute(dense_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(bneed, 1024)));
     CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));
     double* dflags = nullptr;
-    if (blocked == 2) {
+    if (blocked == 3) {   // banded LDL^T: the half bandwidth is measured on the host copy
+        int wmax = 0;
+        for (int i = 0; i < n; ++i)
+            for (int j = 0; j < i; ++j)
+                if (S[(size_t)i * n + j] != 0.0) wmax = std::max(wmax, i - j);
+        int nw = 6;
+        while (nw < wmax + 1) nw += 6;
+        if (!band_fits(nw, n)) { cudaFree(dA); cudaFree(dx); cudaFree(drinv); cudaFree(dfail); return fail(h, MCCBA_ERR_ARG, "half bandwidth %d is too wide for the banded solver", wmax); }
+        Problem none;
+        memset(&none, 0, sizeof(none));
+        CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));
+        CUDA_TRY(h, launch_band(nw, dA, n, dx, dfail, nullptr, none, 0, h->stream));
+    } else if (blocked == 2) {
         const int ntc = chol_col_tiles(n), ntr = chol_row_tiles(n);
         int grid = 0;
         for (int j = 0; j < ntc; ++j) grid += ntr - j;
@@ -1200,7 +1252,7 @@ int mccba_debug_solve_dense(mccba_handle h, int n, const double* S, const double
             if (k + 1 < ntc) chol_update_kernel<<<dim3(ntc - k - 1, ntr - k - 1), kUpdThreads, 0, h->stream>>>(dA, n, k, nullptr);
         }
     }
-    dense_backward_kernel<<<1, kK5Threads, bneed, h->stream>>>(dA, n, drinv, dx, dfail, blocked);
+    if (blocked != 3) dense_backward_kernel<<<1, kK5Threads, bneed, h->stream>>>(dA, n, drinv, dx, dfail, blocked);
     CUDA_TRY(h, cudaEventRecord(h->ev1, h->stream));
     int f = 0;
     CUDA_TRY(h, cudaMemcpyAsync(x, dx, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
@@ -1316,6 +1368,7 @@ int mccba_omni_set_observations(mccba_handle h, int n_frame, const int64_t* fram
         cudaStream_t s;
         ~CopyGuard() { cudaStreamSynchronize(s); }
     } copy_guard{h->copy_stream};
+    CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_copy, 0));   // the gather reads what the copy stream uploads
     gather_obs_kernel<<<h->num_sms * 8, 256, 0, h->stream>>>(n_frame, d_off, d_src, d_obj, d_img, planes, planes + plane,
                                                             planes + 2 * plane, planes + 3 * plane, planes + 4 * plane);
     CUDA_TRY(h, cudaGetLastError());

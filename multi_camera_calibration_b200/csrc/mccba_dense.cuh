@@ -830,6 +830,173 @@ __device__ inline void chol_dag_tile(const CholDag& D)
     dag_stamp(D, 6);
 }
 
+// ---- banded solver ----------------------------------------------------------------------------------------------
+// Camera rigs overlap with their neighbours only, so under the camera numbering the reduced system is banded: block
+// (A, B) is structurally zero unless |A - B| <= m.  The host measures m from the record layout (and agrees on the
+// maximum over the ranks); for 6 (m + 1) <= 32 the solve is an LDL^T factorisation of the band by ONE warp -- the
+// pivot chain is the cost either way (n dependent pivots), but the band needs no tile hand-overs and touches
+// (w + 1) n numbers instead of n^2 / 2.
+//   * lane = row mod 32; an active row keeps its window  a[k] = A[row][j + k]  in registers, shifted by one column
+//     per pivot exactly like tile_potrf_warp; rows enter from the shared-memory band w pivots before they become the
+//     pivot row and retire after it;
+//   * the right-hand side rides along as one more column (rhs_i -= (a_ij / d_j) rhs_j);
+//   * no square roots: with u_ij the unscaled entries,  x_j = (rhs_j - sum_{i>j} u_ij x_i) / d_j;
+//   * the backward sweep keeps one accumulator per lane (= row) and adds u_ij x_i for the whole column of x_i at once.
+// band: n x NW doubles, band[r][k] = A[r][r - w + k] (zero for negative columns), w = NW - 1; overwritten with the
+// unscaled factor (same positions, d_j on the diagonal).  rhs: n doubles, overwritten with the solution x.
+// Returns non-zero (in every lane) if a pivot is outside [1e-200, 1e200].
+#ifdef MCCBA_BAND_DBG
+__device__ long long g_band_ts[4];
+#endif
+// predicated shared-memory loads (no branch: a divergent branch per pivot costs the whole warp ~30 cycles)
+__device__ __forceinline__ void lds_v2_if(double& x0, double& x1, unsigned addr, int pred)
+{
+    asm volatile("{ .reg .pred p; setp.ne.s32 p, %3, 0; @p ld.shared.v2.f64 {%0, %1}, [%2]; }" : "+d"(x0), "+d"(x1) : "r"(addr), "r"(pred) : "memory");
+}
+__device__ __forceinline__ void lds_if(double& x0, unsigned addr, int pred)
+{
+    asm volatile("{ .reg .pred p; setp.ne.s32 p, %2, 0; @p ld.shared.f64 %0, [%1]; }" : "+d"(x0) : "r"(addr), "r"(pred) : "memory");
+}
+
+// One pivot of the banded factorisation; kOdd = parity of j (static so that the column broadcast can use 16-byte
+// loads from an even offset).  colbuf layout per parity buffer: [64 column entries | 64 right-hand sides], indexed by
+// row & 31 and duplicated at +32 so that a window never wraps.  The window a[] has one spare element: the row that
+// becomes active at pivot j + 2 is fetched during pivot j, one position to the right, and the idle shift of pivot
+// j + 1 moves it into place -- its load latency never meets the pivot chain.
+template <int NW, bool kOdd>
+__device__ __forceinline__ void band_step(double* band, double* rhs, double* colbuf, int lane, int j, int n, double (&a)[NW + 2],
+                                          double& r, int& row, int& bad)
+{
+    constexpr int w = NW - 1;
+    double* cb = colbuf + (kOdd ? 128 : 0);
+    double* rb = cb + 64;
+    const double a0 = a[0];
+    cb[lane] = a0; cb[lane + 32] = a0;
+    rb[lane] = r;
+    __syncwarp();
+    const int pj = j & 31;
+    // 16-byte loads from the even offset at or below pj: v[0 | 1] is the pivot, the column follows
+    const unsigned vaddr = (unsigned)__cvta_generic_to_shared(cb + (pj & ~1));
+    double v[NW + 2];
+#pragma unroll
+    for (int p = 0; p < (NW + 2) / 2; ++p)
+        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v[2 * p]), "=d"(v[2 * p + 1]) : "r"(vaddr + 16u * p) : "memory");
+    const double d = kOdd ? v[1] : v[0];
+    const double rp = rb[pj];
+    double y = pin_rcp_seed(d);
+    const bool in_band = row >= j && row <= j + w && row < n;      // the pivot row and the rows below it inside the band
+    if (in_band) band[row * NW + (j - (row - w))] = a0;             // unscaled factor entry u_{row, j}; d_j for row == j
+    double e = pin_nfma(d, y, 1.0);
+    if (!(d > 1e-200 && d < 1e200)) bad = 1;
+    y = pin_fma(y, e, y);
+    e = pin_nfma(d, y, 1.0);
+    const bool below = in_band && row != j;
+    y = pin_fma(y, e, y);
+    const double t = below ? -a0 * y : 0.0;
+    const bool piv = row == j;
+    if (piv) rhs[j] = fma(t, rp, r);          // the pivot row retires: its right-hand side is final (t = 0 there)
+#pragma unroll
+    for (int k = 0; k < w + 1; ++k) a[k] = fma(t, v[(kOdd ? 2 : 1) + k], a[k + 1]);
+    a[w + 1] = 0.0;
+    r = fma(t, rp, r);
+    row += piv ? 32 : 0;
+    // prefetch the row that becomes active at pivot j + 2, shifted right by one
+    const int re = j + 2 + w;
+    const int ent = (lane == (re & 31) && re < n) ? 1 : 0;
+    const unsigned baddr = (unsigned)__cvta_generic_to_shared(band + (ent ? re : 0) * NW);
+    {
+        double q0 = a[1], q1 = a[2];
+#pragma unroll
+        for (int p = 0; p < NW / 2; ++p) {
+            q0 = a[2 * p + 1]; q1 = a[2 * p + 2];
+            lds_v2_if(q0, q1, baddr + 16u * p, ent);
+            a[2 * p + 1] = q0; a[2 * p + 2] = q1;
+        }
+        if (ent) a[0] = 0.0;
+        lds_if(r, (unsigned)__cvta_generic_to_shared(rhs + (ent ? re : 0)), ent);
+        row = ent ? re : row;
+    }
+}
+
+template <int NW>
+__device__ inline int band_ldlt_solve_warp(double* band, double* rhs, int n, double* colbuf /* 256 doubles, 16-byte aligned */)
+{
+    constexpr int w = NW - 1;
+    const int lane = threadIdx.x & 31;
+#ifdef MCCBA_BAND_DBG
+    if (lane == 0) g_band_ts[0] = clock64();
+#endif
+    double a[NW + 2];
+    double r = 0.0;
+    int row = lane;   // the row this lane holds (or will hold next)
+    // rows 0 .. w enter before pivot 0 (window starts at column 0); row w + 1 waits one position to the right
+    {
+        const bool in = row <= w && row < n;
+        const bool nxt = row == w + 1 && row < n;
+#pragma unroll
+        for (int k = 0; k < NW + 2; ++k) {
+            double x = 0.0;
+            if (in && k <= row) x = band[row * NW + (w - row) + k];
+            if (nxt && k >= 1 && k <= NW) x = band[row * NW + k - 1];
+            a[k] = x;
+        }
+        r = (in || nxt) ? rhs[row] : 0.0;
+        if (!in && !nxt && row <= w + 1) row += 32;   // n too small: nothing to hold
+    }
+    colbuf[lane] = 0.0; colbuf[32 + lane] = 0.0; colbuf[64 + lane] = 0.0; colbuf[96 + lane] = 0.0;
+    colbuf[128 + lane] = 0.0; colbuf[160 + lane] = 0.0; colbuf[192 + lane] = 0.0; colbuf[224 + lane] = 0.0;
+    __syncwarp();
+    int bad = 0;
+#pragma unroll 1
+    for (int j = 0; j < n; j += 2) {
+        band_step<NW, false>(band, rhs, colbuf, lane, j, n, a, r, row, bad);
+        if (j + 1 < n) band_step<NW, true>(band, rhs, colbuf, lane, j + 1, n, a, r, row, bad);
+    }
+    __syncwarp();
+#ifdef MCCBA_BAND_DBG
+    if (lane == 0) g_band_ts[1] = clock64();
+#endif
+    for (int q = lane; q < n; q += 32) band[q * NW + w] = 1.0 / band[q * NW + w];   // 1 / d_q, off the chain
+    __syncwarp();
+    // backward sweep, branch-free: lane = row & 31 owns row rj with accumulator acc = rhs_rj - sum_{i > rj} u_{i,rj} x_i and
+    // has 1 / d_rj in a register; every step each lane offers acc / d, the owner of row i wins the shuffle, and the
+    // rows i-w .. i-1 subtract u_{i,row} x_i.  The next row of a lane (rj - 32) and the factor entry of the next step
+    // are fetched ahead, so the loop carries  mul -> shuffle -> fma -> select  only.
+    const int last = n - 1;
+    int rj = last - ((last - lane) & 31);          // the largest row <= last in this lane (negative: none)
+    double acc = rj >= 0 ? rhs[rj] : 0.0, inv = rj >= 0 ? band[rj * NW + w] : 0.0;
+    int rn = rj - 32;
+    double nacc = rn >= 0 ? rhs[rn] : 0.0, ninv = rn >= 0 ? band[rn * NW + w] : 0.0;
+    double u = 0.0;
+    {
+        const int off = rj - (last - w);
+        if (off >= 0 && off < w && rj >= 0) u = band[last * NW + off];
+    }
+#pragma unroll 1
+    for (int i = last; i >= 0; --i) {
+        const double xi = __shfl_sync(0xffffffffu, acc * inv, i & 31);
+        const bool own = rj == i;
+        const double upd = fma(-u, xi, acc);
+        if (own) rhs[i] = xi;
+        acc = own ? nacc : upd;
+        inv = own ? ninv : inv;
+        rj = own ? rn : rj;
+        rn -= own ? 32 : 0;
+        const int ok = (own && rn >= 0) ? 1 : 0;   // (a lane whose rows are exhausted never owns again: stale values are fine)
+        lds_if(nacc, (unsigned)__cvta_generic_to_shared(rhs + (ok ? rn : 0)), ok);
+        lds_if(ninv, (unsigned)__cvta_generic_to_shared(band + (ok ? rn : 0) * NW + w), ok);
+        const int off = rj - (i - 1 - w);          // factor entry for the next step
+        const int ul = (off >= 0 && off < w && rj >= 0 && i > 0) ? 1 : 0;
+        u = 0.0;
+        lds_if(u, (unsigned)__cvta_generic_to_shared(band + (ul ? (i - 1) * NW + off : 0)), ul);
+    }
+    __syncwarp();
+#ifdef MCCBA_BAND_DBG
+    if (lane == 0) g_band_ts[2] = clock64();
+#endif
+    return bad;
+}
+
 // Trailing update of step k for tile (ti, tj): A[ti][tj] -= L[ti][k] * L[tj][k]^T.  256 threads, one tile per CTA.
 __device__ inline void chol_update_tile(double* __restrict__ A, int n, int k, int ti, int tj)
 {

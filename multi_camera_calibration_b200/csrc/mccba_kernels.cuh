@@ -1048,6 +1048,43 @@ __device__ __forceinline__ void camera_update_body(const Problem& P, const doubl
     }
 }
 
+// Banded reduced system (see band_ldlt_solve_warp): one CTA stages the band, warp 0 factors and solves, and -- in the
+// iteration (fused != 0) -- the whole CTA runs the camera update.  Dynamic shared memory: n x NW + n + 256 doubles.
+constexpr int kBandThreads = 256;
+__host__ __device__ inline size_t chol_band_smem_bytes(int n, int NW) { return sizeof(double) * ((size_t)n * NW + (size_t)n + 256 + 8); }
+template <int NW>
+__global__ void __launch_bounds__(kBandThreads) chol_band_kernel(const double* A, int n, double* xout, int* fail_out,
+                                                                 const int* go, Problem P, int fused)
+{
+    extern __shared__ __align__(16) unsigned char band_smem[];
+    if (go && !*go) return;
+    double* colbuf = reinterpret_cast<double*>(band_smem);     // 256 doubles
+    double* rhs = colbuf + 256;
+    double* band = rhs + ((n + 1) & ~1);
+    __shared__ int s_fail;
+    constexpr int w = NW - 1;
+    for (int idx = threadIdx.x; idx < n * NW; idx += kBandThreads) {
+        const int r = idx / NW, k = idx - r * NW, c = r - w + k;
+        band[idx] = c >= 0 ? A[(int64_t)r * n + c] : 0.0;
+    }
+    for (int idx = threadIdx.x; idx < n; idx += kBandThreads) rhs[idx] = A[(int64_t)n * n + idx];
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const int bad = band_ldlt_solve_warp<NW>(band, rhs, n, colbuf);
+        if (threadIdx.x == 0) s_fail = bad;
+    }
+    __syncthreads();
+    int fail = s_fail;
+    for (int idx = threadIdx.x; idx < n; idx += kBandThreads) {
+        const double v = rhs[idx];
+        xout[idx] = v;
+        if (!isfinite(v)) fail = 1;
+    }
+    fail = __syncthreads_or(fail);
+    if (fused) camera_update_body(P, rhs, fail);
+    else if (threadIdx.x == 0 && fail) *fail_out = 1;
+}
+
 // backward substitution + camera update (replicated on every rank) + end-of-iteration state.  Single CTA.
 __global__ void __launch_bounds__(kK5Threads) camera_update_kernel(Problem P, int tiled)
 {

@@ -58,3 +58,33 @@ def test_dense_solve_rejects_indefinite(solver, n, mode):
     S2, g2 = _spd(n, 6)
     x, _ = solver.debug_solve_dense(S2, g2, mode)
     assert np.allclose(x, np.linalg.solve(S2, g2), rtol=1e-9, atol=1e-12)
+
+
+def _banded_spd(n, w, seed):
+    rng = np.random.default_rng(seed)
+    M = rng.standard_normal((n, n))
+    S = M @ M.T
+    i, j = np.indices((n, n))
+    S[np.abs(i - j) > w] = 0.0
+    S += (np.abs(S).sum(axis=1).max() + 1.0) * np.eye(n)      # diagonally dominant: SPD
+    return S, rng.standard_normal(n)
+
+
+@pytest.mark.parametrize("n,w", [(1, 0), (5, 4), (6, 5), (12, 11), (12, 5), (37, 11), (64, 17), (200, 23), (378, 11), (378, 29), (400, 5)])
+def test_banded_solve_matches_numpy(solver, n, w):
+    """mode 3: banded LDL^T by one warp (block-banded camera graphs), every supported band width."""
+    S, g = _banded_spd(n, w, 300 + n + w)
+    x, _ = solver.debug_solve_dense(S, g, 3)
+    ref = np.linalg.solve(S, g)
+    assert np.abs(x - ref).max() <= 1e-11 * max(np.abs(ref).max(), 1e-300) * n
+
+
+def test_banded_solve_rejects_indefinite_and_wide(solver):
+    import multi_camera_calibration_b200 as m
+    S, g = _banded_spd(50, 11, 1)
+    S[20, 20] = -3.0
+    with pytest.raises(m.MccbaError):
+        solver.debug_solve_dense(S, g, 3)
+    S, g = _spd(64, 2)            # dense: half bandwidth 63 does not fit
+    with pytest.raises(m.MccbaError):
+        solver.debug_solve_dense(S, g, 3)
