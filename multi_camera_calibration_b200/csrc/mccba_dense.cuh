@@ -858,64 +858,85 @@ __device__ __forceinline__ void lds_if(double& x0, unsigned addr, int pred)
     asm volatile("{ .reg .pred p; setp.ne.s32 p, %2, 0; @p ld.shared.f64 %0, [%1]; }" : "+d"(x0) : "r"(addr), "r"(pred) : "memory");
 }
 
-// One pivot of the banded factorisation; kOdd = parity of j (static so that the column broadcast can use 16-byte
-// loads from an even offset).  colbuf layout per parity buffer: [64 column entries | 64 right-hand sides], indexed by
-// row & 31 and duplicated at +32 so that a window never wraps.  The window a[] has one spare element: the row that
-// becomes active at pivot j + 2 is fetched during pivot j, one position to the right, and the idle shift of pivot
-// j + 1 moves it into place -- its load latency never meets the pivot chain.
+// Column j of the active rows as every lane sees it: pivot d, right-hand side of the pivot row, the entries of the w
+// rows below the pivot, and this lane's multiplier t = -a_ij / d_j (0 unless its row lies below the pivot in the band).
+template <int NW>
+struct BandCol {
+    double c[NW - 1];
+    double d, rp, t;
+};
+
+// colbuf layout per parity buffer: [64 column entries | 64 right-hand sides], indexed by row & 31 and duplicated at +32
+// so that a window never wraps; 16-byte loads from the even offset at or below the pivot slot.
 template <int NW, bool kOdd>
-__device__ __forceinline__ void band_step(double* band, double* rhs, double* colbuf, int lane, int j, int n, double (&a)[NW + 2],
-                                          double& r, int& row, int& bad)
+__device__ __forceinline__ void band_fetch(const double* cb, int pj, BandCol<NW>& col)
 {
-    constexpr int w = NW - 1;
-    double* cb = colbuf + (kOdd ? 128 : 0);
-    double* rb = cb + 64;
-    const double a0 = a[0];
-    cb[lane] = a0; cb[lane + 32] = a0;
-    rb[lane] = r;
-    __syncwarp();
-    const int pj = j & 31;
-    // 16-byte loads from the even offset at or below pj: v[0 | 1] is the pivot, the column follows
     const unsigned vaddr = (unsigned)__cvta_generic_to_shared(cb + (pj & ~1));
     double v[NW + 2];
 #pragma unroll
     for (int p = 0; p < (NW + 2) / 2; ++p)
         asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v[2 * p]), "=d"(v[2 * p + 1]) : "r"(vaddr + 16u * p) : "memory");
-    const double d = kOdd ? v[1] : v[0];
-    const double rp = rb[pj];
-    double y = pin_rcp_seed(d);
+    col.d = kOdd ? v[1] : v[0];
+#pragma unroll
+    for (int k = 0; k < NW - 1; ++k) col.c[k] = v[(kOdd ? 2 : 1) + k];
+    col.rp = cb[64 + pj];
+}
+
+// One pivot of the banded factorisation, software-pipelined like potrf_step: the column of pivot j + 1 is published as
+// soon as its first update fma is done, and its broadcast and reciprocal chain overlap the remaining work of pivot j
+// (w - 1 update fmas, the factor store, retiring the pivot row, fetching the row that becomes active at pivot j + 2
+// one position to the right so that the idle shift of pivot j + 1 moves it into place).  kOdd = parity of j + 1.
+template <int NW, bool kOdd>
+__device__ __forceinline__ void band_step(double* band, double* rhs, double* colbuf, int lane, int j, int n, double (&a)[NW + 1],
+                                          double& r, int& row, const BandCol<NW>& cur, BandCol<NW>& nxt, int& bad)
+{
+    constexpr int w = NW - 1;
+    const double a0 = a[0];
+    const double a0n = pin_fma(cur.t, cur.c[0], a[1]);
+    const double rn = pin_fma(cur.t, cur.rp, r);
+    double* cbn = colbuf + (kOdd ? 128 : 0);
+    cbn[lane] = a0n; cbn[lane + 32] = a0n;
+    cbn[64 + lane] = rn;
+    __syncwarp();
+    band_fetch<NW, kOdd>(cbn, (j + 1) & 31, nxt);
+    double y = pin_rcp_seed(nxt.d);
+    // ---- work of pivot j in the shadow of the chain ----
     const bool in_band = row >= j && row <= j + w && row < n;      // the pivot row and the rows below it inside the band
     if (in_band) band[row * NW + (j - (row - w))] = a0;             // unscaled factor entry u_{row, j}; d_j for row == j
-    double e = pin_nfma(d, y, 1.0);
-    if (!(d > 1e-200 && d < 1e200)) bad = 1;
-    y = pin_fma(y, e, y);
-    e = pin_nfma(d, y, 1.0);
-    const bool below = in_band && row != j;
-    y = pin_fma(y, e, y);
-    const double t = below ? -a0 * y : 0.0;
     const bool piv = row == j;
-    if (piv) rhs[j] = fma(t, rp, r);          // the pivot row retires: its right-hand side is final (t = 0 there)
+    if (piv) rhs[j] = rn;                                           // the pivot row retires with its final right-hand side
+    if (!(cur.d > 1e-200 && cur.d < 1e200)) bad = 1;
+    double e = pin_nfma(nxt.d, y, 1.0);
+    constexpr int nF = w - 1;
 #pragma unroll
-    for (int k = 0; k < w + 1; ++k) a[k] = fma(t, v[(kOdd ? 2 : 1) + k], a[k + 1]);
+    for (int k = 1; k <= nF / 3; ++k) a[k] = pin_fma(cur.t, cur.c[k], a[k + 1]);
+    y = pin_fma(y, e, y);
+#pragma unroll
+    for (int k = nF / 3 + 1; k <= (2 * nF) / 3; ++k) a[k] = pin_fma(cur.t, cur.c[k], a[k + 1]);
+    e = pin_nfma(nxt.d, y, 1.0);
+#pragma unroll
+    for (int k = (2 * nF) / 3 + 1; k <= nF; ++k) a[k] = pin_fma(cur.t, cur.c[k], a[k + 1]);
+    y = pin_fma(y, e, y);
+    a[0] = a0n;
+    a[w] = a[w + 1];     // the spare slot only shifts
     a[w + 1] = 0.0;
-    r = fma(t, rp, r);
+    r = rn;
     row += piv ? 32 : 0;
-    // prefetch the row that becomes active at pivot j + 2, shifted right by one
     const int re = j + 2 + w;
     const int ent = (lane == (re & 31) && re < n) ? 1 : 0;
+    row = ent ? re : row;
+    const bool below = row > j + 1 && row <= j + 1 + w && row < n;
+    nxt.t = below ? -a0n * y : 0.0;
+    // fetch row re one position to the right: a[1 .. NW] <- band[re][0 .. w]  (used one step from now)
     const unsigned baddr = (unsigned)__cvta_generic_to_shared(band + (ent ? re : 0) * NW);
-    {
-        double q0 = a[1], q1 = a[2];
 #pragma unroll
-        for (int p = 0; p < NW / 2; ++p) {
-            q0 = a[2 * p + 1]; q1 = a[2 * p + 2];
-            lds_v2_if(q0, q1, baddr + 16u * p, ent);
-            a[2 * p + 1] = q0; a[2 * p + 2] = q1;
-        }
-        if (ent) a[0] = 0.0;
-        lds_if(r, (unsigned)__cvta_generic_to_shared(rhs + (ent ? re : 0)), ent);
-        row = ent ? re : row;
+    for (int p = 0; p < NW / 2; ++p) {
+        double q0 = a[2 * p + 1], q1 = a[2 * p + 2];
+        lds_v2_if(q0, q1, baddr + 16u * p, ent);
+        a[2 * p + 1] = q0;
+        a[2 * p + 2] = q1;
     }
+    lds_if(r, (unsigned)__cvta_generic_to_shared(rhs + (ent ? re : 0)), ent);
 }
 
 template <int NW>
@@ -926,31 +947,39 @@ __device__ inline int band_ldlt_solve_warp(double* band, double* rhs, int n, dou
 #ifdef MCCBA_BAND_DBG
     if (lane == 0) g_band_ts[0] = clock64();
 #endif
-    double a[NW + 2];
+    double a[NW + 1];   // a[k] = A[row][j + k] at pivot j, plus one spare slot for the row waiting to become active
     double r = 0.0;
-    int row = lane;   // the row this lane holds (or will hold next)
+    int row = lane;     // the row this lane holds (or will hold next)
     // rows 0 .. w enter before pivot 0 (window starts at column 0); row w + 1 waits one position to the right
     {
         const bool in = row <= w && row < n;
-        const bool nxt = row == w + 1 && row < n;
+        const bool nx = row == w + 1 && row < n;
 #pragma unroll
-        for (int k = 0; k < NW + 2; ++k) {
+        for (int k = 0; k < NW + 1; ++k) {
             double x = 0.0;
             if (in && k <= row) x = band[row * NW + (w - row) + k];
-            if (nxt && k >= 1 && k <= NW) x = band[row * NW + k - 1];
+            if (nx && k >= 1) x = band[row * NW + k - 1];
             a[k] = x;
         }
-        r = (in || nxt) ? rhs[row] : 0.0;
-        if (!in && !nxt && row <= w + 1) row += 32;   // n too small: nothing to hold
+        r = (in || nx) ? rhs[row] : 0.0;
+        if (!in && !nx && row <= w + 1) row += 32;   // n too small: nothing to hold
     }
-    colbuf[lane] = 0.0; colbuf[32 + lane] = 0.0; colbuf[64 + lane] = 0.0; colbuf[96 + lane] = 0.0;
-    colbuf[128 + lane] = 0.0; colbuf[160 + lane] = 0.0; colbuf[192 + lane] = 0.0; colbuf[224 + lane] = 0.0;
+    for (int q = lane; q < 256; q += 32) colbuf[q] = 0.0;
     __syncwarp();
     int bad = 0;
+    BandCol<NW> c0, c1;
+    {   // prologue: publish and fetch column 0
+        colbuf[lane] = a[0]; colbuf[lane + 32] = a[0];
+        colbuf[64 + lane] = r;
+        __syncwarp();
+        band_fetch<NW, false>(colbuf, 0, c0);
+        const bool below = row > 0 && row <= w && row < n;
+        c0.t = below ? -a[0] * pivot_rcp(c0.d) : 0.0;
+    }
 #pragma unroll 1
     for (int j = 0; j < n; j += 2) {
-        band_step<NW, false>(band, rhs, colbuf, lane, j, n, a, r, row, bad);
-        if (j + 1 < n) band_step<NW, true>(band, rhs, colbuf, lane, j + 1, n, a, r, row, bad);
+        band_step<NW, true>(band, rhs, colbuf, lane, j, n, a, r, row, c0, c1, bad);
+        if (j + 1 < n) band_step<NW, false>(band, rhs, colbuf, lane, j + 1, n, a, r, row, c1, c0, bad);
     }
     __syncwarp();
 #ifdef MCCBA_BAND_DBG
