@@ -209,6 +209,27 @@ def test_lm_rejections(solver, oracle_lib):
         assert _param_rel(solver.get_parameters(), ref["params"]) < 1e-7, k
 
 
+@pytest.mark.parametrize("chol", ["0", "1", "2", "3"])
+def test_every_reduced_solver_matches(case, chol, monkeypatch):
+    """The reduced camera system has four interchangeable solvers (MCCBA_CHOL, read when the observations are set):
+    0 single-CTA column Cholesky, 1 panel/update kernels, 2 one-launch tile DAG, 3 banded LDL^T (the default when the
+    camera graph is banded, which every small rig here is).  All of them must reproduce the oracle's LM iterates."""
+    import multi_camera_calibration_b200 as m
+    name, rig, O = case
+    monkeypatch.setenv("MCCBA_CHOL", chol)
+    s = m.Solver(device=0)
+    try:
+        s.set_rig(rig)
+        s.set_parameters(rig["params_init"])
+        rep = s.solve(mode=1, crit_type=1, max_count=5)
+        ref = O.solve(rig["params_init"], mode=1, crit_type=1, max_count=5)
+        assert rep["iterations"] == 5 == ref["iters"]
+        assert _param_rel(s.get_parameters(), ref["params"]) < 1e-8
+        assert abs(rep["cost"] - ref["cost"]) <= 1e-9 * ref["cost"]
+    finally:
+        s.close()
+
+
 def test_no_graph_path_matches(case):
     import multi_camera_calibration_b200 as m
     name, rig, O = case
