@@ -227,22 +227,22 @@ void launch_schur(mccba_handle h, cudaStream_t s, int sel, double lambda)
 
 // banded LDL^T solve of the reduced system (mode 3): NW = 6 (m + 1) live columns, m = block bandwidth
 template <int NW>
-static cudaError_t launch_band_nw(const double* A, int n, double* xout, int* fail, const int* go, const Problem& P, int fused, cudaStream_t s)
+static cudaError_t launch_band_nw(const double* A, int n, double* xout, int* fail, const int* go, const Problem& P, int fused, int packed, cudaStream_t s)
 {
     const size_t smem = chol_band_smem_bytes(n, NW);
     cudaError_t e = cudaFuncSetAttribute(chol_band_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    chol_band_kernel<NW><<<1, kBandThreads, smem, s>>>(A, n, xout, fail, go, P, fused);
+    chol_band_kernel<NW><<<1, kBandThreads, smem, s>>>(A, n, xout, fail, go, P, fused, packed);
     return cudaGetLastError();
 }
-static cudaError_t launch_band(int nw, const double* A, int n, double* xout, int* fail, const int* go, const Problem& P, int fused, cudaStream_t s)
+static cudaError_t launch_band(int nw, const double* A, int n, double* xout, int* fail, const int* go, const Problem& P, int fused, int packed, cudaStream_t s)
 {
     switch (nw) {
-        case 6: return launch_band_nw<6>(A, n, xout, fail, go, P, fused, s);
-        case 12: return launch_band_nw<12>(A, n, xout, fail, go, P, fused, s);
-        case 18: return launch_band_nw<18>(A, n, xout, fail, go, P, fused, s);
-        case 24: return launch_band_nw<24>(A, n, xout, fail, go, P, fused, s);
-        case 30: return launch_band_nw<30>(A, n, xout, fail, go, P, fused, s);
+        case 6: return launch_band_nw<6>(A, n, xout, fail, go, P, fused, packed, s);
+        case 12: return launch_band_nw<12>(A, n, xout, fail, go, P, fused, packed, s);
+        case 18: return launch_band_nw<18>(A, n, xout, fail, go, P, fused, packed, s);
+        case 24: return launch_band_nw<24>(A, n, xout, fail, go, P, fused, packed, s);
+        case 30: return launch_band_nw<30>(A, n, xout, fail, go, P, fused, packed, s);
         default: return cudaErrorInvalidValue;
     }
 }
@@ -276,7 +276,7 @@ int enqueue_iteration(mccba_handle h, bool timed)
     if (timed) cudaEventRecord(ev[3], s);
     decide_kernel<<<1, 32, 0, s>>>(P);
     if (h->k5_blocked == 3 && P.ns > 0) {
-        CUDA_TRY(h, launch_band(h->band_nw, P.ar, P.ns, P.dc, &P.st->chol_fail, &P.st->go, P, 1, s));
+        CUDA_TRY(h, launch_band(h->band_nw, P.ar, P.ns, P.dc, &P.st->chol_fail, &P.st->go, P, 1, 1, s));
     } else if (h->k5_blocked == 2 && P.ns > 0) {
         CholDag D{P.ar, P.dag_buf, P.ns, P.dc, &P.st->go, &P.st->chol_fail, nullptr};   // sentinel fill: reduce_records
         // cooperative launch: the CTAs of the DAG spin on each other, so the runtime must place all of them at once
@@ -791,7 +791,17 @@ int mccba_set_observations(mccba_handle h, int n_frame, int n_edge, const int* e
     h->edge_cam_h.assign(edge_cam, edge_cam + n_edge);
     h->edge_n_h.resize((size_t)n_edge);
     for (int e = 0; e < n_edge; ++e) h->edge_n_h[e] = edge_off[e + 1] - edge_off[e];
-    h->ar_len = P.ns * P.ns + P.ns + 4;
+    {   // reduced-system solver: 3 = banded LDL^T by one warp when the camera graph is banded (block bandwidth <= 4),
+        // 2 = one-launch tile DAG, 1 = panel/update kernels per block column, 0 = plain single-CTA column Cholesky
+        const char* sel = getenv("MCCBA_CHOL");
+        int mode = band_fits(h->band_nw, P.ns) ? 3 : 2;
+        if (sel && sel[0] >= '0' && sel[0] <= '3') mode = sel[0] - '0';
+        if (mode == 3 && !band_fits(h->band_nw, P.ns)) mode = 2;
+        h->k5_blocked = mode;
+    }
+    P.band_nw = (h->k5_blocked == 3 && P.ns > 0) ? h->band_nw : 0;
+    P.ar_goff = P.band_nw > 0 ? (int64_t)P.ns * P.band_nw : (int64_t)P.ns * P.ns;
+    h->ar_len = (int)P.ar_goff + P.ns + 4;
     if (h->opts.nranks > 1) {
         int rc_p2p = p2p_setup(h);
         if (rc_p2p) return rc_p2p;
@@ -875,11 +885,7 @@ int mccba_set_observations(mccba_handle h, int n_frame, int n_edge, const int* e
     {   // reduced-system solver: 2 = one-launch tile DAG (default), 1 = panel/update kernels per block column,
         // 0 = plain single-CTA column Cholesky (also the fallback when a block column does not fit in shared memory)
         const size_t need = chol_panel_smem_bytes(P.ns);
-        const char* sel = getenv("MCCBA_CHOL");
-        // 3 = banded LDL^T by one warp when the camera graph is banded (block bandwidth <= 4), else the tile DAG
-        int mode = band_fits(h->band_nw, P.ns) ? 3 : 2;
-        if (sel && sel[0] >= '0' && sel[0] <= '3') mode = sel[0] - '0';
-        if (mode == 3 && !band_fits(h->band_nw, P.ns)) mode = 2;
+        int mode = h->k5_blocked;   // chosen above, before the packed buffer was sized
         if (need > 227 * 1024 && mode == 1) mode = 0;
         const int ntc = chol_col_tiles(P.ns), ntr = chol_row_tiles(P.ns);
         int grid = 0;
@@ -1028,8 +1034,23 @@ int mccba_reduced_system(mccba_handle h, double lambda, double* S, double* gs)
         if (r != 0) return fail(h, MCCBA_ERR_NCCL, "ncclAllReduce failed: %d", r);
     }
     const size_t ns = (size_t)P.ns;
-    if (S && ns) CUDA_TRY(h, cudaMemcpyAsync(S, P.ar, sizeof(double) * ns * ns, cudaMemcpyDeviceToHost, h->stream));
-    if (gs && ns) CUDA_TRY(h, cudaMemcpyAsync(gs, P.ar + ns * ns, sizeof(double) * ns, cudaMemcpyDeviceToHost, h->stream));
+    if (P.band_nw > 0 && S && ns) {   // packed band -> dense symmetric matrix for the caller
+        const size_t NW = (size_t)P.band_nw, w = NW - 1;
+        std::vector<double> band(ns * NW);
+        CUDA_TRY(h, cudaMemcpyAsync(band.data(), P.ar, sizeof(double) * ns * NW, cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+        std::fill(S, S + ns * ns, 0.0);
+        for (size_t r = 0; r < ns; ++r)
+            for (size_t k = 0; k < NW; ++k) {
+                if (r + k < w) continue;
+                const size_t c = r + k - w;
+                S[r * ns + c] = band[r * NW + k];
+                S[c * ns + r] = band[r * NW + k];
+            }
+    } else if (S && ns) {
+        CUDA_TRY(h, cudaMemcpyAsync(S, P.ar, sizeof(double) * ns * ns, cudaMemcpyDeviceToHost, h->stream));
+    }
+    if (gs && ns) CUDA_TRY(h, cudaMemcpyAsync(gs, P.ar + P.ar_goff, sizeof(double) * ns, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     return MCCBA_OK;
 }
@@ -1206,7 +1227,7 @@ int mccba_debug_solve_dense(mccba_handle h, int n, const double* S, const double
         Problem none;
         memset(&none, 0, sizeof(none));
         CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));
-        CUDA_TRY(h, launch_band(nw, dA, n, dx, dfail, nullptr, none, 0, h->stream));
+        CUDA_TRY(h, launch_band(nw, dA, n, dx, dfail, nullptr, none, 0, 0, h->stream));
     } else if (blocked == 2) {
         const int ntc = chol_col_tiles(n), ntr = chol_row_tiles(n);
         int grid = 0;

@@ -104,6 +104,9 @@ struct Problem {
     int p2p_n, p2p_rank;
     int64_t p2p_stride;
     double* ar_part;     // rank-local packed buffer written by reduce_records (== ar on a single rank)
+    int band_nw;         // 0: ar = [S (ns x ns) | g | 4 scalars]; NW > 0: ar = [band (ns x NW, band[r][c - r + NW - 1], lower
+                         // triangle only) | g | 4 scalars] -- what the banded solver reads and all the collective has to move
+    int64_t ar_goff;     // offset of g in ar (ns * ns or ns * band_nw); the scalars follow at ar_goff + ns
     int64_t dag_words;   // chol_dag_words(ns) when the tile DAG is in use, else 0
     double* dag_buf;     // tile-DAG output (chol_dag_words doubles), filled with the all-ones sentinel before every factorisation
     double* norm_part;   // 2 x n_k4_blocks: per-block |step|^2, |trial|^2 of the frames
@@ -720,7 +723,7 @@ __global__ void __launch_bounds__(kK3Threads) reduce_records_kernel(Problem P, i
     const int s0 = P.dest_src0[dest], s1 = P.dest_src0[dest + 1];
     const int ns = P.ns;
     double* S = P.ar_part;
-    double* gs = P.ar_part + (int64_t)ns * ns;
+    double* gs = P.ar_part + P.ar_goff;
     double* sc = gs + ns;
     if (P.dag_words > 0) {
         // the solve that follows wants its output buffer filled with the all-ones sentinel (mccba_dense.cuh); this
@@ -776,7 +779,19 @@ __global__ void __launch_bounds__(kK3Threads) reduce_records_kernel(Problem P, i
     a0 = 0; a1 = 0;
 #pragma unroll
     for (int w = 0; w < kK3Threads / 32; ++w) { a0 += s_part[w][lane]; if (lane < 4) a1 += s_part[w][32 + lane]; }
-    if (kind == 0) {
+    if (kind == 0 && P.band_nw > 0) {
+        // packed band, lower triangle: element (row, col), row >= col, at band[row][col - row + w]
+        const int NW = P.band_nw, w = NW - 1;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const int k = half ? 32 + lane : lane;
+            if (half && lane >= 4) break;
+            const int i = k / 6, j = k % 6;
+            int row = 6 * A + i, col = 6 * B + j;
+            if (row < col) { const int t = row; row = col; col = t; }   // (A, B) with A < B holds the transpose
+            if (A != B || i >= j) S[(int64_t)row * NW + (col - row + w)] = half ? a1 : a0;
+        }
+    } else if (kind == 0) {
         {
             const int i = lane / 6, j = lane % 6;
             S[(int64_t)(6 * A + i) * ns + 6 * B + j] = a0;
@@ -909,7 +924,7 @@ __global__ void decide_kernel(Problem P)
     DevState* st = P.st;
     if (P.p2p_n > 1) *P.p2p_epoch += 1;   // the exchange of this launch is complete (both kernels ran before this one)
     const int ns = P.ns;
-    const double* sc = P.ar + (int64_t)ns * ns + ns;
+    const double* sc = P.ar + P.ar_goff + ns;
     int go = 0;
     if (!st->done) {
         st->launches += 1;
@@ -1054,7 +1069,7 @@ constexpr int kBandThreads = 256;
 __host__ __device__ inline size_t chol_band_smem_bytes(int n, int NW) { return sizeof(double) * ((size_t)n * NW + (size_t)n + 256 + 8); }
 template <int NW>
 __global__ void __launch_bounds__(kBandThreads) chol_band_kernel(const double* A, int n, double* xout, int* fail_out,
-                                                                 const int* go, Problem P, int fused)
+                                                                 const int* go, Problem P, int fused, int packed)
 {
     extern __shared__ __align__(16) unsigned char band_smem[];
     if (go && !*go) return;
@@ -1063,11 +1078,16 @@ __global__ void __launch_bounds__(kBandThreads) chol_band_kernel(const double* A
     double* band = rhs + ((n + 1) & ~1);
     __shared__ int s_fail;
     constexpr int w = NW - 1;
-    for (int idx = threadIdx.x; idx < n * NW; idx += kBandThreads) {
-        const int r = idx / NW, k = idx - r * NW, c = r - w + k;
-        band[idx] = c >= 0 ? A[(int64_t)r * n + c] : 0.0;
+    if (packed) {   // A = [band | g] already (reduce_records wrote it that way)
+        for (int idx = threadIdx.x; idx < n * NW; idx += kBandThreads) band[idx] = A[idx];
+        for (int idx = threadIdx.x; idx < n; idx += kBandThreads) rhs[idx] = A[(int64_t)n * NW + idx];
+    } else {
+        for (int idx = threadIdx.x; idx < n * NW; idx += kBandThreads) {
+            const int r = idx / NW, k = idx - r * NW, c = r - w + k;
+            band[idx] = c >= 0 ? A[(int64_t)r * n + c] : 0.0;
+        }
+        for (int idx = threadIdx.x; idx < n; idx += kBandThreads) rhs[idx] = A[(int64_t)n * n + idx];
     }
-    for (int idx = threadIdx.x; idx < n; idx += kBandThreads) rhs[idx] = A[(int64_t)n * n + idx];
     __syncthreads();
     if (threadIdx.x < 32) {
         const int bad = band_ldlt_solve_warp<NW>(band, rhs, n, colbuf);
