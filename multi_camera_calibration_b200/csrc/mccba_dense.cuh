@@ -1004,20 +1004,25 @@ __device__ inline int band_ldlt_solve_warp(double* band, double* rhs, int n, dou
 #pragma unroll 1
     for (int i = last; i >= 0; --i) {
         const double xi = __shfl_sync(0xffffffffu, acc * inv, i & 31);
+        // bookkeeping of the next step, independent of xi: it issues in the shadow of the shuffle
         const bool own = rj == i;
-        const double upd = fma(-u, xi, acc);
+        const double acc_own = nacc, inv_own = ninv;          // fetched when this lane took its current row
+        const int rj_new = own ? rn : rj;
+        const int rn_new = rn - (own ? 32 : 0);
+        const int ok = (own && rn_new >= 0) ? 1 : 0;          // (a lane whose rows are exhausted never owns again)
+        lds_if(nacc, (unsigned)__cvta_generic_to_shared(rhs + (ok ? rn_new : 0)), ok);
+        lds_if(ninv, (unsigned)__cvta_generic_to_shared(band + (ok ? rn_new : 0) * NW + w), ok);
+        const int off = rj_new - (i - 1 - w);                 // factor entry for the next step
+        const int ul = (off >= 0 && off < w && rj_new >= 0 && i > 0) ? 1 : 0;
+        double un = 0.0;
+        lds_if(un, (unsigned)__cvta_generic_to_shared(band + (ul ? (i - 1) * NW + off : 0)), ul);
+        // consume xi
         if (own) rhs[i] = xi;
-        acc = own ? nacc : upd;
-        inv = own ? ninv : inv;
-        rj = own ? rn : rj;
-        rn -= own ? 32 : 0;
-        const int ok = (own && rn >= 0) ? 1 : 0;   // (a lane whose rows are exhausted never owns again: stale values are fine)
-        lds_if(nacc, (unsigned)__cvta_generic_to_shared(rhs + (ok ? rn : 0)), ok);
-        lds_if(ninv, (unsigned)__cvta_generic_to_shared(band + (ok ? rn : 0) * NW + w), ok);
-        const int off = rj - (i - 1 - w);          // factor entry for the next step
-        const int ul = (off >= 0 && off < w && rj >= 0 && i > 0) ? 1 : 0;
-        u = 0.0;
-        lds_if(u, (unsigned)__cvta_generic_to_shared(band + (ul ? (i - 1) * NW + off : 0)), ul);
+        acc = own ? acc_own : fma(-u, xi, acc);
+        inv = own ? inv_own : inv;
+        rj = rj_new;
+        rn = rn_new;
+        u = un;
     }
     __syncwarp();
 #ifdef MCCBA_BAND_DBG
