@@ -22,6 +22,37 @@
 
 namespace mccba {
 
+// 1/x and 1/sqrt(x) for the per-corner projection (depths, distortion denominators: positive, far from the ends of the
+// double range).  On the device: MUFU seed + Newton steps, ~1 ulp, no special-case branch -- the IEEE division and
+// sqrt() carry a slow-path call that costs the residual kernel a divergence check per corner.  The host build of this
+// header (tests/harness) keeps the library operations; the two agree to a few ulp.
+MC_HD double proj_rcp(double d)
+{
+#if defined(__CUDA_ARCH__)
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+    double e = fma(-d, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-d, y, 1.0);   // seed error e0 -> e0^4 after two steps
+    return fma(y, e, y);
+#else
+    return 1.0 / d;
+#endif
+}
+MC_HD double proj_rsqrt(double d)
+{
+#if defined(__CUDA_ARCH__)
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+    const double hd = 0.5 * d;
+    y = y * fma(-hd * y, y, 1.5);
+    y = y * fma(-hd * y, y, 1.5);
+    return y * fma(-hd * y, y, 1.5);
+#else
+    return 1.0 / sqrt(d);
+#endif
+}
+
 constexpr int kPinhole = 0;
 constexpr int kOmnidir = 1;
 constexpr int kBlk = 28;  // per-edge block record: 21 (upper triangle of H6) + 6 (g6) + 1 (sum sq residual)
@@ -120,7 +151,7 @@ MC_HD void mat3t_vec(const double* A, const double* x, double* y)  // A^T x
 template <bool kRational, bool kJac>
 MC_HD void pinhole_point(const CamParams& c, const double* Xc, double* uv, double* A)
 {
-    const double iz = 1.0 / Xc[2];
+    const double iz = proj_rcp(Xc[2]);
     const double x = Xc[0] * iz, y = Xc[1] * iz;
     const double r2 = x * x + y * y;
     double rad = 1.0 + r2 * (c.k1 + r2 * (c.k2 + r2 * c.k3));
@@ -128,7 +159,7 @@ MC_HD void pinhole_point(const CamParams& c, const double* Xc, double* uv, doubl
     if (kRational) {
         const double den = 1.0 + r2 * (c.k4 + r2 * (c.k5 + r2 * c.k6));
         const double dden = c.k4 + r2 * (2.0 * c.k5 + 3.0 * c.k6 * r2);
-        const double iden = 1.0 / den;
+        const double iden = proj_rcp(den);
         drad = (drad - rad * iden * dden) * iden;
         rad = rad * iden;
     }
@@ -154,9 +185,9 @@ template <bool kJac>
 MC_HD void omnidir_point(const CamParams& c, const double* Xc, double* uv, double* A)
 {
     const double n2 = Xc[0] * Xc[0] + Xc[1] * Xc[1] + Xc[2] * Xc[2];
-    const double rn = 1.0 / sqrt(n2);
+    const double rn = proj_rsqrt(n2);
     const double s0 = Xc[0] * rn, s1 = Xc[1] * rn, s2 = Xc[2] * rn;
-    const double id = 1.0 / (s2 + c.xi);
+    const double id = proj_rcp(s2 + c.xi);
     const double x = s0 * id, y = s1 * id;
     const double r2 = x * x + y * y;
     const double rad = 1.0 + r2 * (c.k1 + r2 * c.k2);
