@@ -228,11 +228,13 @@ def run_ours(args):
     d2h = pin["params_init"].nbytes
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
 
+    p_host = torch.empty(pin["params_init"].size, dtype=torch.float64).pin_memory().numpy()   # result lands in pinned memory
+
     def e2e_step():
         s.set_observations(rig["n_frame"], rig["edge_cam"], rig["edge_pv"], rig["edge_off"], pin["obj"], pin["img"])
         s.set_parameters(pin["params_init"])
         r = s.solve(**kw)
-        p = s.get_parameters()
+        p = s.get_parameters(out=p_host)
         return r, p
 
     e2e_step()

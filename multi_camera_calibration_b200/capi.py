@@ -152,8 +152,11 @@ class Solver:
         p = np.ascontiguousarray(params, dtype=np.float64)
         self._check(lib().mccba_set_parameters(self._h, C.c_int64(p.size), _ptr(p, C.c_double)))
 
-    def get_parameters(self):
-        p = np.zeros(self.n_param)
+    def get_parameters(self, out=None):
+        """Current parameters [rvec|tvec] per vertex 1..; `out` (float64, C-contiguous, n_param long, e.g. pinned memory)
+        receives them without an intermediate allocation."""
+        p = np.empty(self.n_param) if out is None else out
+        assert p.dtype == np.float64 and p.flags["C_CONTIGUOUS"] and p.size == self.n_param
         self._check(lib().mccba_get_parameters(self._h, C.c_int64(p.size), _ptr(p, C.c_double)))
         return p
 
