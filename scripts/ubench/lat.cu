@@ -2,6 +2,7 @@
 #include <cstdio>
 #include <cuda_runtime.h>
 #include "../../multi_camera_calibration_b200/csrc/mccba_dense.cuh"
+#include "tile_variants.cuh"
 using namespace mccba;
 
 __global__ void lat_kernel(double* out, long long* cyc, double seed)

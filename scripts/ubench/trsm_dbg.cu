@@ -75,7 +75,7 @@ template <int kVar> __global__ void k(const double* Lg, const double* Pg, double
 }
 int main()
 {
-    static double hA[1024], hL[1024], hP[1024];
+    static double hL[1024], hP[1024];
     for (int i = 0; i < 32; ++i) for (int j = 0; j < 32; ++j) hL[i * 32 + j] = j < i ? 0.1 / (1 + i + j) : (i == j ? 3.0 : 0.0);
     for (int i = 0; i < 1024; ++i) hP[i] = sin(0.37 * i) + 0.1;
     double *dL, *dP, *dX; long long* dc; long long c[16];
