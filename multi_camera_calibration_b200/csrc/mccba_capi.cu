@@ -265,7 +265,10 @@ int enqueue_iteration(mccba_handle h, bool timed)
     if (timed) cudaEventRecord(ev[1], s);
     reduce_records_kernel<<<P.n_dest, kK3Threads, 0, s>>>(P, 0);
     if (timed) cudaEventRecord(ev[2], s);
-    if (h->opts.nranks > 1 && h->p2p_ok) {
+    static const bool no_exchange = getenv("MCCBA_NO_EXCHANGE") != nullptr;   // diagnosis only: wrong results for N > 1
+    if (h->opts.nranks > 1 && no_exchange) {
+        CUDA_TRY(h, cudaMemcpyAsync(P.ar, P.ar_part, sizeof(double) * (size_t)h->ar_len, cudaMemcpyDeviceToDevice, s));
+    } else if (h->opts.nranks > 1 && h->p2p_ok) {
         const int grid = std::max(1, std::min(h->num_sms, (int)((h->ar_len / 2 + kP2pThreads - 1) / kP2pThreads)));
         p2p_push_kernel<<<grid, kP2pThreads, 0, s>>>(P, (int64_t)h->ar_len);
         p2p_sum_kernel<<<grid, kP2pThreads, 0, s>>>(P, (int64_t)h->ar_len);
