@@ -255,13 +255,17 @@ def run_ours(args):
     if rank == 0 and world == 1 and not args.no_cpu:
         orc, O = _oracle_rig(rig)
         ci = args.ref_iters
-        t0 = time.perf_counter()
-        ref = O.solve(rig["params_init"], mode=1, crit_type=1, max_count=ci, lambda0=1e-3, lambda_up=10.0,
-                      lambda_down=1.0 / 3.0)
-        cdt = time.perf_counter() - t0
-        cpu = {"value": M * ci / cdt, "unit": UNIT, "cores": orc.num_threads(), "kind": "port",
-               "sample": "full rig (%d corners), %d LM iterations (%.1f s of CPU work)" % (M, ci, cdt),
-               "lm_iters_per_sec": ci / cdt}
+        ckw = dict(mode=1, crit_type=1, max_count=ci, lambda0=1e-3, lambda_up=10.0, lambda_down=1.0 / 3.0)
+        O.solve(rig["params_init"], **ckw)                       # warm-up (page faults, thread pool)
+        reps, cdt = 0, 0.0
+        while cdt < 10.0 and reps < 50:                          # about 10 s of CPU work
+            t0 = time.perf_counter()
+            O.solve(rig["params_init"], **ckw)
+            cdt += time.perf_counter() - t0
+            reps += 1
+        cpu = {"value": M * ci * reps / cdt, "unit": UNIT, "cores": orc.num_threads(), "kind": "port",
+               "sample": "full rig (%d corners), %d solves of %d LM iterations (%.1f s of CPU work)" % (M, reps, ci, cdt),
+               "lm_iters_per_sec": ci * reps / cdt}
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
