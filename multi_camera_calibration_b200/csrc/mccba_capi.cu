@@ -277,9 +277,10 @@ int enqueue_iteration(mccba_handle h, bool timed)
         if (r != 0) return fail(h, MCCBA_ERR_NCCL, "ncclAllReduce failed: %s", nccl().GetErrorString ? nccl().GetErrorString(r) : "?");
     }
     if (timed) cudaEventRecord(ev[3], s);
-    decide_kernel<<<1, 32, 0, s>>>(P);
-    if (h->k5_blocked == 3 && P.ns > 0) {
-        CUDA_TRY(h, launch_band(h->band_nw, P.ar, P.ns, P.dc, &P.st->chol_fail, &P.st->go, P, 1, 1, s));
+    const bool band = h->k5_blocked == 3 && P.ns > 0;
+    if (!band) decide_kernel<<<1, 32, 0, s>>>(P);   // banded mode: the single-CTA solver does the loop control itself
+    if (band) {
+        CUDA_TRY(h, launch_band(h->band_nw, P.ar, P.ns, P.dc, &P.st->chol_fail, &P.st->go, P, 2, 1, s));
     } else if (h->k5_blocked == 2 && P.ns > 0) {
         CholDag D{P.ar, P.dag_buf, P.ns, P.dc, &P.st->go, &P.st->chol_fail, nullptr};   // sentinel fill: reduce_records
         // cooperative launch: the CTAs of the DAG spin on each other, so the runtime must place all of them at once
@@ -906,7 +907,7 @@ int mccba_set_observations(mccba_handle h, int n_frame, int n_edge, const int* e
             CUDA_TRY(h, cudaFuncSetAttribute(chol_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->panel_smem));
         if (h->k5_smem > 48 * 1024)
             CUDA_TRY(h, cudaFuncSetAttribute(camera_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->k5_smem));
-        h->iter_kernels = 6 + (P.ns > 0 ? (mode == 3 ? 0 : mode == 2 ? (P.ns <= 512 ? 0 : 1) : (mode == 1 ? 2 * ntc - 1 : 0)) : 0);
+        h->iter_kernels = 6 + (P.ns > 0 ? (mode == 3 ? -1 : mode == 2 ? (P.ns <= 512 ? 0 : 1) : (mode == 1 ? 2 * ntc - 1 : 0)) : 0);
         if ((rc = dev_alloc(h, &P.dag_buf, chol_dag_words(P.ns) + 8))) return rc;
         P.dag_words = (mode == 2 && P.ns > 0) ? (int64_t)chol_dag_words(P.ns) : 0;
     }

@@ -918,9 +918,9 @@ __global__ void __launch_bounds__(kP2pThreads) p2p_sum_kernel(Problem P, int64_t
     }
 }
 
-__global__ void decide_kernel(Problem P)
+// loop control of one launch (single thread): accept/reject of the trial point, damping, termination
+__device__ __forceinline__ void decide_body(const Problem& P)
 {
-    if (threadIdx.x != 0) return;
     DevState* st = P.st;
     if (P.p2p_n > 1) *P.p2p_epoch += 1;   // the exchange of this launch is complete (both kernels ran before this one)
     const int ns = P.ns;
@@ -966,6 +966,10 @@ __global__ void decide_kernel(Problem P)
     }
     st->go = go;
     st->chol_fail = 0;
+}
+__global__ void decide_kernel(Problem P)
+{
+    if (threadIdx.x == 0) decide_body(P);
 }
 
 // Cholesky of the reduced system, one block column per launch pair (mccba_dense.cuh).  go == nullptr: always run.
@@ -1072,7 +1076,11 @@ __global__ void __launch_bounds__(kBandThreads) chol_band_kernel(const double* A
                                                                  const int* go, Problem P, int fused, int packed)
 {
     extern __shared__ __align__(16) unsigned char band_smem[];
-    if (go && !*go) return;
+    if (fused == 2) {   // the loop control runs here instead of in its own launch (this kernel is a single CTA)
+        if (threadIdx.x == 0) decide_body(P);
+        __syncthreads();
+    }
+    if (go && !*reinterpret_cast<const volatile int*>(go)) return;
     double* colbuf = reinterpret_cast<double*>(band_smem);     // 256 doubles
     double* rhs = colbuf + 256;
     double* band = rhs + ((n + 1) & ~1);
