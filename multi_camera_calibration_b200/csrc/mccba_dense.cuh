@@ -666,9 +666,9 @@ __device__ inline void chol_dag_tile(const CholDag& D)
 //     pivot row and retire after it;
 //   * the right-hand side rides along as one more column (rhs_i -= (a_ij / d_j) rhs_j);
 //   * no square roots: with u_ij the unscaled entries,  x_j = (rhs_j - sum_{i>j} u_ij x_i) / d_j;
-//   * the backward sweep keeps one accumulator per lane (= row) and adds u_ij x_i for the whole column of x_i at once.
-// band: n x NW doubles, band[r][k] = A[r][r - w + k] (zero for negative columns), w = NW - 1; overwritten with the
-// unscaled factor (same positions, d_j on the diagonal).  rhs: n doubles, overwritten with the solution x.
+//   * the backward sweep keeps one accumulator per lane (= row) and handles two rows per shuffle round trip.
+// band: (n + 1) x NW doubles, band[r][k] = A[r][r - w + k] (zero for negative columns), w = NW - 1; overwritten with the
+// unscaled factor (same positions, d_j on the diagonal).  rhs: n + 1 doubles, overwritten with the solution x.
 // Returns non-zero (in every lane) if a pivot is outside [1e-200, 1e200].
 #ifdef MCCBA_BAND_DBG
 __device__ long long g_band_ts[4];
@@ -765,7 +765,8 @@ __device__ __forceinline__ void band_step(double* band, double* rhs, double* col
 }
 
 template <int NW>
-__device__ inline int band_ldlt_solve_warp(double* band, double* rhs, int n, double* colbuf /* 256 doubles, 16-byte aligned */)
+__device__ inline int band_ldlt_solve_warp(double* band, double* rhs, const int n, double* colbuf /* 256 doubles, 16-byte aligned */,
+                                           double* pinv /* 3 * ((n + 1) / 2) doubles */)
 {
     constexpr int w = NW - 1;
     const int lane = threadIdx.x & 31;
@@ -810,44 +811,62 @@ __device__ inline int band_ldlt_solve_warp(double* band, double* rhs, int n, dou
 #ifdef MCCBA_BAND_DBG
     if (lane == 0) g_band_ts[1] = clock64();
 #endif
+    // Backward sweep, two rows per step.  With inv_q = 1 / d_q and acc_q = rhs_q - sum_{i > pair} u_iq x_i, the pair
+    // (j, j+1) is a 2 x 2 back-substitution   x_j+1 = inv_j+1 acc_j+1,  x_j = inv_j acc_j - (u_j+1,j inv_j inv_j+1) acc_j+1,
+    // so one round of shuffles serves two rows and the dependent chain is halved.  The row count is padded to even with
+    // an identity row (band and rhs have room for it).
+    const int ne = n + (n & 1);
+    if (ne != n && lane == 0) {
+        for (int k = 0; k < NW; ++k) band[n * NW + k] = k == w ? 1.0 : 0.0;
+        rhs[n] = 0.0;
+    }
+    __syncwarp();
     for (int q = lane; q < n; q += 32) band[q * NW + w] = 1.0 / band[q * NW + w];   // 1 / d_q, off the chain
     __syncwarp();
-    // backward sweep, branch-free: lane = row & 31 owns row rj with accumulator acc = rhs_rj - sum_{i > rj} u_{i,rj} x_i and
-    // has 1 / d_rj in a register; every step each lane offers acc / d, the owner of row i wins the shuffle, and the
-    // rows i-w .. i-1 subtract u_{i,row} x_i.  The next row of a lane (rj - 32) and the factor entry of the next step
-    // are fetched ahead, so the loop carries  mul -> shuffle -> fma -> select  only.
-    const int last = n - 1;
-    int rj = last - ((last - lane) & 31);          // the largest row <= last in this lane (negative: none)
-    double acc = rj >= 0 ? rhs[rj] : 0.0, inv = rj >= 0 ? band[rj * NW + w] : 0.0;
-    int rn = rj - 32;
-    double nacc = rn >= 0 ? rhs[rn] : 0.0, ninv = rn >= 0 ? band[rn * NW + w] : 0.0;
-    double u = 0.0;
-    {
-        const int off = rj - (last - w);
-        if (off >= 0 && off < w && rj >= 0) u = band[last * NW + off];
+    for (int q = lane; 2 * q < ne; q += 32) {
+        const double i0 = band[(2 * q) * NW + w], i1 = band[(2 * q + 1) * NW + w];
+        pinv[3 * q] = i0;
+        pinv[3 * q + 1] = -band[(2 * q + 1) * NW + w - 1] * i0 * i1;
+        pinv[3 * q + 2] = i1;
     }
+    __syncwarp();
+    const int last = ne - 1;
+    int rj = last - ((last - lane) & 31);
+    double acc = rj >= 0 ? rhs[rj] : 0.0;
+    int rn = rj - 32;
+    double nacc = rn >= 0 ? rhs[rn] : 0.0;
+    auto fetch_u = [&](int j, int rrow, double& uu0, double& uu1) {
+        const int o0 = rrow - (j - w), o1 = rrow - (j + 1 - w);
+        const int l0 = (j >= 0 && rrow >= 0 && rrow < j && o0 >= 0) ? 1 : 0;
+        const int l1 = (j >= 0 && rrow >= 0 && rrow < j && o1 >= 0) ? 1 : 0;
+        uu0 = 0.0; uu1 = 0.0;
+        lds_if(uu0, (unsigned)__cvta_generic_to_shared(band + (l0 ? j * NW + o0 : 0)), l0);
+        lds_if(uu1, (unsigned)__cvta_generic_to_shared(band + (l1 ? (j + 1) * NW + o1 : 0)), l1);
+    };
+    double u0 = 0.0, u1 = 0.0, p00 = 0.0, p01 = 0.0, p11 = 0.0;
+    fetch_u(ne - 2, rj, u0, u1);
+    if (ne >= 2) { p00 = pinv[3 * ((ne - 2) >> 1)]; p01 = pinv[3 * ((ne - 2) >> 1) + 1]; p11 = pinv[3 * ((ne - 2) >> 1) + 2]; }
 #pragma unroll 1
-    for (int i = last; i >= 0; --i) {
-        const double xi = __shfl_sync(0xffffffffu, acc * inv, i & 31);
-        // bookkeeping of the next step, independent of xi: it issues in the shadow of the shuffle
-        const bool own = rj == i;
-        const double acc_own = nacc, inv_own = ninv;          // fetched when this lane took its current row
+    for (int j = ne - 2; j >= 0; j -= 2) {
+        const double A0 = __shfl_sync(0xffffffffu, acc, j & 31);
+        const double A1 = __shfl_sync(0xffffffffu, acc, (j + 1) & 31);
+        // bookkeeping for the next pair in the shadow of the shuffles
+        const bool own0 = rj == j, own1 = rj == j + 1, own = own0 || own1;
+        const double acc_own = nacc;
         const int rj_new = own ? rn : rj;
         const int rn_new = rn - (own ? 32 : 0);
-        const int ok = (own && rn_new >= 0) ? 1 : 0;          // (a lane whose rows are exhausted never owns again)
+        const int ok = (own && rn_new >= 0) ? 1 : 0;
         lds_if(nacc, (unsigned)__cvta_generic_to_shared(rhs + (ok ? rn_new : 0)), ok);
-        lds_if(ninv, (unsigned)__cvta_generic_to_shared(band + (ok ? rn_new : 0) * NW + w), ok);
-        const int off = rj_new - (i - 1 - w);                 // factor entry for the next step
-        const int ul = (off >= 0 && off < w && rj_new >= 0 && i > 0) ? 1 : 0;
-        double un = 0.0;
-        lds_if(un, (unsigned)__cvta_generic_to_shared(band + (ul ? (i - 1) * NW + off : 0)), ul);
-        // consume xi
-        if (own) rhs[i] = xi;
-        acc = own ? acc_own : fma(-u, xi, acc);
-        inv = own ? inv_own : inv;
-        rj = rj_new;
-        rn = rn_new;
-        u = un;
+        double nu0, nu1;
+        fetch_u(j - 2, rj_new, nu0, nu1);
+        double q00 = 0.0, q01 = 0.0, q11 = 0.0;
+        if (j >= 2) { q00 = pinv[3 * ((j - 2) >> 1)]; q01 = pinv[3 * ((j - 2) >> 1) + 1]; q11 = pinv[3 * ((j - 2) >> 1) + 2]; }
+        // consume
+        const double x0 = fma(p00, A0, p01 * A1), x1 = p11 * A1;
+        if (own0) rhs[j] = x0;
+        if (own1) rhs[j + 1] = x1;
+        acc = own ? acc_own : fma(-u1, x1, fma(-u0, x0, acc));
+        rj = rj_new; rn = rn_new; u0 = nu0; u1 = nu1; p00 = q00; p01 = q01; p11 = q11;
     }
     __syncwarp();
 #ifdef MCCBA_BAND_DBG

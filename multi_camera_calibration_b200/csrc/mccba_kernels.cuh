@@ -1068,9 +1068,12 @@ __device__ __forceinline__ void camera_update_body(const Problem& P, const doubl
 }
 
 // Banded reduced system (see band_ldlt_solve_warp): one CTA stages the band, warp 0 factors and solves, and -- in the
-// iteration (fused != 0) -- the whole CTA runs the camera update.  Dynamic shared memory: n x NW + n + 256 doubles.
+// iteration (fused != 0) -- the whole CTA runs the camera update.  Dynamic shared memory: chol_band_smem_bytes().
 constexpr int kBandThreads = 256;
-__host__ __device__ inline size_t chol_band_smem_bytes(int n, int NW) { return sizeof(double) * ((size_t)n * NW + (size_t)n + 256 + 8); }
+__host__ __device__ inline size_t chol_band_smem_bytes(int n, int NW)
+{
+    return sizeof(double) * ((size_t)(n + 1) * NW + (size_t)(n + 2) + 3 * (size_t)((n + 1) / 2) + 2 + 256 + 8);
+}
 template <int NW>
 __global__ void __launch_bounds__(kBandThreads) chol_band_kernel(const double* A, int n, double* xout, int* fail_out,
                                                                  const int* go, Problem P, int fused, int packed)
@@ -1082,8 +1085,9 @@ __global__ void __launch_bounds__(kBandThreads) chol_band_kernel(const double* A
     }
     if (go && !*reinterpret_cast<const volatile int*>(go)) return;
     double* colbuf = reinterpret_cast<double*>(band_smem);     // 256 doubles
-    double* rhs = colbuf + 256;
-    double* band = rhs + ((n + 1) & ~1);
+    double* rhs = colbuf + 256;                                // n + 1
+    double* band = rhs + ((n + 1) & ~1) + 2;                   // (n + 1) x NW
+    double* pinv = band + (size_t)(n + 1) * NW;                // 3 per pair of rows (behind the band: the band keeps its place)
     __shared__ int s_fail;
     constexpr int w = NW - 1;
     if (packed) {   // A = [band | g] already (reduce_records wrote it that way)
@@ -1098,7 +1102,7 @@ __global__ void __launch_bounds__(kBandThreads) chol_band_kernel(const double* A
     }
     __syncthreads();
     if (threadIdx.x < 32) {
-        const int bad = band_ldlt_solve_warp<NW>(band, rhs, n, colbuf);
+        const int bad = band_ldlt_solve_warp<NW>(band, rhs, n, colbuf, pinv);
         if (threadIdx.x == 0) s_fail = bad;
     }
     __syncthreads();

@@ -12,7 +12,8 @@ __global__ void k(const double* A, int n, double* x, long long* out)
     extern __shared__ __align__(16) unsigned char sm[];
     double* colbuf = reinterpret_cast<double*>(sm);
     double* rhs = colbuf + 256;
-    double* band = rhs + ((n + 1) & ~1);
+    double* band = rhs + ((n + 1) & ~1) + 2;
+    double* pinv = band + (size_t)(n + 1) * NW;
     constexpr int w = NW - 1;
     for (int idx = threadIdx.x; idx < n * NW; idx += blockDim.x) {
         const int r = idx / NW, kk = idx - r * NW, c = r - w + kk;
@@ -20,7 +21,7 @@ __global__ void k(const double* A, int n, double* x, long long* out)
     }
     for (int idx = threadIdx.x; idx < n; idx += blockDim.x) rhs[idx] = A[(long long)n * n + idx];
     __syncthreads();
-    if (threadIdx.x < 32) band_ldlt_solve_warp<NW>(band, rhs, n, colbuf);
+    if (threadIdx.x < 32) band_ldlt_solve_warp<NW>(band, rhs, n, colbuf, pinv);
     __syncthreads();
     for (int idx = threadIdx.x; idx < n; idx += blockDim.x) x[idx] = rhs[idx];
     if (threadIdx.x == 0) { out[0] = g_band_ts[1] - g_band_ts[0]; out[1] = g_band_ts[2] - g_band_ts[1]; }
@@ -34,7 +35,7 @@ int main()
     double *dA, *dx; long long* dc; long long c[2];
     cudaMalloc(&dA, A.size() * 8); cudaMalloc(&dx, n * 8); cudaMalloc(&dc, 16);
     cudaMemcpy(dA, A.data(), A.size() * 8, cudaMemcpyHostToDevice);
-    const size_t smem = 8 * ((size_t)n * NW + n + 256 + 8);
+    const size_t smem = 8 * ((size_t)(n + 1) * NW + (n + 2) + 3 * ((n + 1) / 2) + 2 + 256 + 8);
     cudaFuncSetAttribute(k<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     for (int rep = 0; rep < 2; ++rep) {
         k<NW><<<1, 256, smem>>>(dA, n, dx, dc);
