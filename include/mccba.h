@@ -179,11 +179,11 @@ int mccba_allreduce_sum(mccba_handle h, double *buf, int n);
  * out[5] resid_jac_accum (diagnostic only -- the events serialise the stream). */
 int mccba_last_kernel_ms(mccba_handle h, double out[6]);
 /* How the packed reduced system [S | g | scalars] is summed over the ranks in every iteration (replaces nothing in the
- * reference, which is single-process): 0 = single rank, 1 = ncclAllReduce, 2 = stores into every rank's CUDA-IPC
- * mapped window over NVLink followed by a rank-ordered sum (p2p_push_kernel / p2p_sum_kernel; bit-identical result on
- * every rank).  Mode 2 is opt-in (MCCBA_P2P=1 in the environment of every rank; measured slower than NCCL's in-switch
- * reduction on 8 x B200) and is chosen collectively in mccba_set_observations when all ranks can map all windows
- * (<= 8 ranks on one NVLink domain); otherwise mode 1. */
+ * reference, which is single-process): 0 = single rank, 1 = ncclAllReduce, 2 = low-latency exchange over NVLink peer
+ * memory: every rank stores {data, epoch} words into every rank's CUDA-IPC mapped window and sums the slots in rank order
+ * (p2p_exchange_kernel; bit-identical result on every rank).  Mode 2 is chosen collectively in mccba_set_observations
+ * when all ranks can map all windows (<= 8 ranks on one NVLink domain); MCCBA_P2P=0 in the environment of every rank
+ * forces mode 1. */
 int mccba_exchange_mode(mccba_handle h);
 
 /* Test hook: solve the dense SPD system S x = g (n x n row-major, lower triangle read) on the device with the loop's

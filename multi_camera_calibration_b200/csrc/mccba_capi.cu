@@ -269,9 +269,8 @@ int enqueue_iteration(mccba_handle h, bool timed)
     if (h->opts.nranks > 1 && no_exchange) {
         CUDA_TRY(h, cudaMemcpyAsync(P.ar, P.ar_part, sizeof(double) * (size_t)h->ar_len, cudaMemcpyDeviceToDevice, s));
     } else if (h->opts.nranks > 1 && h->p2p_ok) {
-        const int grid = std::max(1, std::min(h->num_sms, (int)((h->ar_len / 2 + kP2pThreads - 1) / kP2pThreads)));
-        p2p_push_kernel<<<grid, kP2pThreads, 0, s>>>(P, (int64_t)h->ar_len);
-        p2p_sum_kernel<<<grid, kP2pThreads, 0, s>>>(P, (int64_t)h->ar_len);
+        const int grid = std::max(1, std::min(h->num_sms, (h->ar_len + 4 * kP2pThreads - 1) / (4 * kP2pThreads)));
+        p2p_exchange_kernel<<<grid, kP2pThreads, 0, s>>>(P, (int64_t)h->ar_len);
     } else if (h->opts.nranks > 1) {
         ncclResult_t r = nccl().AllReduce(P.ar_part, P.ar, (size_t)h->ar_len, kNcclFloat64, kNcclSum, h->comm, s);
         if (r != 0) return fail(h, MCCBA_ERR_NCCL, "ncclAllReduce failed: %s", nccl().GetErrorString ? nccl().GetErrorString(r) : "?");
@@ -477,7 +476,7 @@ int mccba_set_cameras(mccba_handle h, int n_cam, const int* model, const double*
 // ---------------------------------------------------------------------------------------------------------
 // peer-memory windows for the per-iteration exchange (N > 1).  Collective: every rank calls it from the same
 // set_observations.  Any failure on any rank (no IPC, no peer access, more than 8 ranks, MCCBA_P2P=0) makes ALL
-// ranks fall back to ncclAllReduce -- the decision itself is all-reduced.  Enabled with MCCBA_P2P=1 (on every rank).
+// ranks fall back to ncclAllReduce -- the decision itself is all-reduced.
 // ---------------------------------------------------------------------------------------------------------
 static void p2p_teardown(mccba_handle h)
 {
@@ -498,7 +497,7 @@ static void p2p_teardown(mccba_handle h)
 static int p2p_setup(mccba_handle h)
 {
     const int n = h->opts.nranks, me = h->opts.rank;
-    const int64_t stride = ((int64_t)h->ar_len + 31) & ~(int64_t)31;
+    const int64_t stride = (2 * (int64_t)h->ar_len + 31) & ~(int64_t)31;   // LL protocol: two 8-byte words per element
     if (h->p2p_stride == stride) return MCCBA_OK;   // same reduced-system size as the previous problem: nothing to do
     p2p_teardown(h);
     h->p2p_stride = stride;                         // remembered even on fallback, so the decision is taken once per size
@@ -507,9 +506,8 @@ static int p2p_setup(mccba_handle h)
     static_assert(sizeof(Msg) == 128, "message layout");
     Msg mine;
     memset(&mine, 0, sizeof(mine));
-    // opt-in: measured on 8 x B200 (NVSwitch, NCCL 2.28 with NVLS) the plain push/sum exchange costs 436 us per LM
-    // iteration against 421 us with ncclAllReduce (2 GPUs: 391 vs 389), see profiles/r1_summary.md
-    mine.ok = (n <= 8 && nccl().AllGather && env && env[0] == '1') ? 1 : 0;
+    // default when every rank can map every window; MCCBA_P2P=0 (on every rank) forces ncclAllReduce
+    mine.ok = (n <= 8 && nccl().AllGather && !(env && env[0] == '0')) ? 1 : 0;
     const size_t words = (size_t)kP2pFlagWords + 2 * (size_t)n * (size_t)stride;
     if (mine.ok && cudaMalloc((void**)&h->p2p_win, words * sizeof(double)) != cudaSuccess) { mine.ok = 0; h->p2p_win = nullptr; cudaGetLastError(); }
     if (mine.ok) {
@@ -815,7 +813,6 @@ int mccba_set_observations(mccba_handle h, int n_frame, int n_edge, const int* e
     P.p2p_rank = h->opts.rank;
     P.p2p_stride = h->p2p_stride;
     P.p2p_epoch = h->p2p_epoch;
-    P.p2p_count = h->p2p_epoch ? reinterpret_cast<unsigned*>(h->p2p_epoch + 8) : nullptr;
 
     int rc;
 #define UP(field, vec) if ((rc = dev_upload(h, &P.field, vec))) return rc

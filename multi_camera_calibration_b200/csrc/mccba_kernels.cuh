@@ -96,11 +96,11 @@ struct Problem {
     double* ar;          // allreduce buffer: S (ns x ns) | g (ns) | cost, step2, param2, bad
     double* dc;          // ns: camera step in tangent coordinates
     double* rinv;        // ns: reciprocal diagonal of the Cholesky factor
-    // peer-memory exchange of the packed reduced system (N > 1, see p2p_push_kernel): every rank's window is
-    // [64 epoch flags (u64) | parity 0: n ranks x p2p_stride doubles | parity 1: ...], mapped into every process by CUDA IPC
+    // peer-memory exchange of the packed reduced system (N > 1, see p2p_exchange_kernel): every rank's window is
+    // [header | parity 0: n ranks x p2p_stride doubles | parity 1: ...] (a slot holds 2 words per element, LL protocol),
+    // mapped into every process by CUDA IPC
     double* p2p_peer[8];
     unsigned long long* p2p_epoch;   // local: number of completed exchanges
-    unsigned* p2p_count;             // local: CTA completion counter of the push kernel
     int p2p_n, p2p_rank;
     int64_t p2p_stride;
     double* ar_part;     // rank-local packed buffer written by reduce_records (== ar on a single rank)
@@ -861,59 +861,49 @@ __device__ int chol_solve_cta(double* A, int n, double* xout, double* s_col, dou
 // loop control (single warp): accept/reject of the trial point, damping, termination; sets st->go
 // --------------------------------------------------------------------------------------------------------
 // C1 (N > 1): the per-iteration exchange of the packed buffer [S | g | scalars] over NVLink peer memory.
-// push: every rank stores its partial buffer into slot[rank] of EVERY rank's window (plain stores to IPC-mapped
-// peer memory, 16 bytes per thread), the last CTA to finish releases an epoch flag in every window (system scope).
-// sum: waits for all epoch flags of its own window, then adds the n slots in rank order -- every rank performs the
-// identical additions, so the reduced system and therefore the camera parameters are bit-identical on all ranks.
+// Every rank stores its partial buffer into slot[rank] of EVERY rank's window (IPC-mapped peer memory) and adds the n
+// slots of its own window in rank order -- every rank performs the identical additions, so the reduced system and
+// therefore the camera parameters are bit-identical on all ranks.
 // Windows are double-buffered by epoch parity: a rank can only be one exchange ahead of its slowest peer.
 // --------------------------------------------------------------------------------------------------------
-constexpr int kP2pFlagWords = 64;
+constexpr int kP2pFlagWords = 32;   // header of a window (unused by the LL protocol, keeps the slots 256-byte aligned)
 constexpr int kP2pThreads = 256;
-__global__ void __launch_bounds__(kP2pThreads) p2p_push_kernel(Problem P, int64_t len)
+// Low-latency protocol (the one NCCL calls LL): every double travels as two 8-byte words {32 data bits | 32-bit epoch},
+// so the data carry their own arrival flag -- no fence, no separate flag, no grid-wide step.  A thread stores its
+// elements into slot[rank] of every window, then spins on the n slots of its own window until both words of an
+// element carry this launch's epoch, and adds them in rank order.  8-byte stores are single-copy atomic, which is all
+// the protocol needs; slots are double-buffered by epoch parity (a rank can be at most one exchange ahead of a peer).
+__device__ __forceinline__ void p2p_ll_store(unsigned long long* dst, double x, unsigned flag)
 {
-    const unsigned long long e = *P.p2p_epoch + 1;
-    const int n = P.p2p_n, me = P.p2p_rank;
-    const int64_t slot = (int64_t)((e & 1) * n + me) * P.p2p_stride + kP2pFlagWords;
-    const double2* src = reinterpret_cast<const double2*>(P.ar_part);
-    const int64_t n2 = len / 2, tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, step = (int64_t)gridDim.x * blockDim.x;
-    for (int r = 0; r < n; ++r) {
-        const int peer = (me + r) % n;   // spread the traffic: start with the own window, then the next rank ...
-        double* base = P.p2p_peer[peer] + slot;
-        double2* dst = reinterpret_cast<double2*>(base);
-        for (int64_t i = tid; i < n2; i += step) dst[i] = src[i];
-        if ((len & 1) && tid == 0) base[len - 1] = P.ar_part[len - 1];
-    }
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const unsigned done = atomicAdd(P.p2p_count, 1u) + 1u;
-        if (done == gridDim.x) {
-            *P.p2p_count = 0;
-            __threadfence_system();
-            for (int r = 0; r < n; ++r) {
-                unsigned long long* flag = reinterpret_cast<unsigned long long*>(P.p2p_peer[r]) + me;
-                asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag), "l"(e) : "memory");
-            }
-        }
-    }
+    const unsigned long long v = (unsigned long long)__double_as_longlong(x);
+    const unsigned long long w0 = (v & 0xffffffffull) | ((unsigned long long)flag << 32);
+    const unsigned long long w1 = (v >> 32) | ((unsigned long long)flag << 32);
+    asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(dst), "l"(w0), "l"(w1) : "memory");
 }
-__global__ void __launch_bounds__(kP2pThreads) p2p_sum_kernel(Problem P, int64_t len)
+__device__ __forceinline__ double p2p_ll_load(const unsigned long long* src, unsigned flag)
+{
+    unsigned long long w0, w1;
+    do {
+        asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(src) : "memory");
+    } while ((unsigned)(w0 >> 32) != flag || (unsigned)(w1 >> 32) != flag);
+    return __longlong_as_double((long long)((w0 & 0xffffffffull) | (w1 << 32)));
+}
+__global__ void __launch_bounds__(kP2pThreads) p2p_exchange_kernel(Problem P, int64_t len)
 {
     const unsigned long long e = *P.p2p_epoch + 1;
+    const unsigned flag = (unsigned)e;
     const int n = P.p2p_n, me = P.p2p_rank;
-    if (threadIdx.x < n) {
-        const unsigned long long* flag = reinterpret_cast<const unsigned long long*>(P.p2p_peer[me]) + threadIdx.x;
-        unsigned long long v;
-        do {
-            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory");
-        } while (v < e);
-    }
-    __syncthreads();
-    const double* win = P.p2p_peer[me] + kP2pFlagWords + (int64_t)((e & 1) * n) * P.p2p_stride;
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, step = (int64_t)gridDim.x * blockDim.x;
+    const int64_t par = (int64_t)((e & 1) * n) * P.p2p_stride;          // slots of this parity (in doubles)
+    for (int r = 0; r < n; ++r) {
+        const int peer = (me + r) % n;      // spread the traffic: own window first, then the next rank ...
+        unsigned long long* dst = reinterpret_cast<unsigned long long*>(P.p2p_peer[peer] + kP2pFlagWords + par + (int64_t)me * P.p2p_stride);
+        for (int64_t i = tid; i < len; i += step) p2p_ll_store(dst + 2 * i, P.ar_part[i], flag);
+    }
+    const unsigned long long* win = reinterpret_cast<const unsigned long long*>(P.p2p_peer[me] + kP2pFlagWords + par);
     for (int64_t i = tid; i < len; i += step) {
-        double acc = __ldcg(win + i);
-        for (int r = 1; r < n; ++r) acc += __ldcg(win + (int64_t)r * P.p2p_stride + i);
+        double acc = p2p_ll_load(win + 2 * i, flag);
+        for (int r = 1; r < n; ++r) acc += p2p_ll_load(win + (int64_t)r * P.p2p_stride + 2 * i, flag);
         P.ar[i] = acc;
     }
 }

@@ -19,10 +19,12 @@ def test_two_rank_parity():
     env.pop("MCCBA_P2P", None)
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     assert "MGPU_PARITY_OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
-    assert "exchange=nccl" in out.stdout
-    # the same run with the opt-in NVLink peer-memory exchange (falls back to NCCL when the windows cannot be mapped)
-    env["MCCBA_P2P"] = "1"
+    # default: the NVLink peer-memory exchange when the windows can be mapped, else NCCL
+    assert "exchange=peer" in out.stdout or "exchange=nccl" in out.stdout
+    # the same run with the peer-memory exchange switched off: ncclAllReduce
+    env["MCCBA_P2P"] = "0"
     cmd[cmd.index("29517")] = "29518"
     out2 = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     assert "MGPU_PARITY_OK" in out2.stdout, out2.stdout[-3000:] + out2.stderr[-3000:]
+    assert "exchange=nccl" in out2.stdout
     print(out.stdout[-1500:], out2.stdout[-1500:])
