@@ -6,7 +6,8 @@ residual+Jacobian evals/sec at 1/2/4/8 B200 vs host CPU).
 
 Workload (config.workload): BASELINE.json configs[4] -- synthetic 64-camera pinhole rig, 100k frames, 9x6 board,
 2 views per frame = 10.8 M corner observations PER GPU (frames shard across ranks; every rank holds the 64 cameras and
-its own 100k frames: weak scaling, one NCCL all-reduce of the 378x378 reduced camera system per iteration).
+its own 100k frames: weak scaling, one exchange of the packed reduced camera system per iteration -- the library's
+NVLink peer-memory kernel, or ncclAllReduce as its fallback; `exchange` in the JSON line says which).
 A "step" = one optimizeExtrinsics call = `iters` (default 20, the reference's TermCriteria(COUNT, 20)) full LM
 iterations on that rig.  value = corner observations processed per second through full LM iterations, whole job.
 """
@@ -280,6 +281,7 @@ def run_ours(args):
                              "algorithmic_bytes_per_launch": 20.0 * M,
                              "whole_iteration_gbs": iter_gbs, "whole_iteration_frac": iter_gbs / peak,
                              "note": "fp64 arithmetic: the kernel is FP64-pipe-bound, see DESIGN.md"},
+                "exchange": {0: "none", 1: "ncclAllReduce", 2: "nvlink-peer-memory"}[s.exchange_mode()],
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                         "ms_per_step": e2e_ms, "steps": e2e_steps},
                 "gpu_launches": int(launches), "clocks": clocks}
