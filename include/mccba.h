@@ -186,9 +186,11 @@ int mccba_last_kernel_ms(mccba_handle h, double out[6]);
  * forces mode 1. */
 int mccba_exchange_mode(mccba_handle h);
 
-/* Test hook: solve the dense SPD system S x = g (n x n row-major, lower triangle read) on the device with the loop's
- * own Cholesky code (blocked: 2 = one-launch tile DAG (default in the loop), 1 = panel/update kernels, 0 = plain
- * single-CTA column version).
+/* Test hook: solve the SPD system S x = g (n x n row-major, lower triangle read) on the device with the loop's own
+ * solvers (blocked: 3 = banded LDL^T by one warp -- the half bandwidth is measured from S and must be <= 29; this is
+ * what the loop uses when the camera graph is banded -- 2 = one-launch tile DAG (the loop's choice for dense camera
+ * graphs), 1 = panel/update kernels, 0 = plain single-CTA column version).  Replaces the Eigen conjugate-gradient
+ * solve of src/multicalib.cpp:565-592 on the Schur-reduced system.
  * The kernel time in ms is left in mccba_last_kernel_ms()[0]. */
 int mccba_debug_solve_dense(mccba_handle h, int n, const double *S, const double *g, double *x, int blocked);
 /* time `reps` back-to-back launches of the residual+Jacobian kernel at the current parameters with CUDA events on
