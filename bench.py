@@ -122,15 +122,29 @@ def config_dict(args, world):
             "seed": args.seed}
 
 
+def _cpu_threads(orc):
+    """torchrun exports OMP_NUM_THREADS=1: the CPU arm asks for every host core explicitly and reports what it got."""
+    want = os.cpu_count() or 1
+    try:
+        want = len(os.sched_getaffinity(0))
+    except Exception:
+        pass
+    orc.set_num_threads(want)
+    return orc.num_threads()
+
+
 def run_reference(args):
     """CPU arm: the restated reference algorithm (oracle port -- the reference itself needs OpenCV C++ and Eigen and
-    cannot be built in this image) with all host threads, on a bounded sample of the same workload."""
+    cannot be built in this image) with all host threads, on a bounded sample of the same workload: rank 0's shard of
+    the rig (the per-GPU unit of the weak-scaling job; corner observations/s does not depend on how many such shards
+    the job holds), `--ref-iters` LM iterations per step."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
     rig = _rig(args, 0)
     orc, O = _oracle_rig(rig)
-    cores = orc.num_threads()
+    cores = _cpu_threads(orc)
     iters = args.ref_iters
     M = rig["n_points"]
     kw = dict(mode=1, crit_type=1, max_count=iters, lambda0=1e-3, lambda_up=10.0, lambda_down=1.0 / 3.0)
@@ -141,14 +155,104 @@ def run_reference(args):
         O.solve(rig["params_init"], **kw)
     dt = (time.perf_counter() - t0) / args.steps
     value = M * iters / dt
-    sample = "full rig (%d corners), %d LM iterations per step instead of %d" % (M, iters, args.iters)
+    sample = "one %d-frame shard (%d corners), %d LM iterations per step instead of %d" % (args.frames, M, iters, args.iters)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": config_dict(args, 1), "lm_iters_per_sec": iters / dt,
+            "config": config_dict(args, world), "lm_iters_per_sec": iters / dt,
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
+
+
+def _time_solves(s, kw, steps, warmup, world, barrier):
+    """(ms per solve, max over ranks, timed by the library with CUDA events on its own stream; last report)"""
+    import torch
+    import torch.distributed as dist
+    rep = None
+    for _ in range(warmup):
+        s.restore_parameters()
+        rep = s.solve(**kw)
+    barrier()
+    ms = 0.0
+    for _ in range(steps):
+        s.restore_parameters()
+        rep = s.solve(**kw)
+        ms += rep["device_ms"]
+    barrier()
+    t = torch.tensor([ms / steps], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t[0]), rep
+
+
+def _sharded_leg(m, dist, rig_local, kw, world, rank, local, barrier, steps=10, warmup=3):
+    from scripts import mgpu_parity
+    nccl_id = mgpu_parity._fresh_id(m, dist, rank) if world > 1 else None
+    s2 = m.Solver(device=local, rank=rank, nranks=world, nccl_id=nccl_id)
+    s2.set_rig(rig_local)
+    s2.set_parameters(rig_local["params_init"])
+    s2.save_parameters()
+    ms, rep = _time_solves(s2, kw, steps, warmup, world, barrier)
+    err = s2.reproj_error()
+    s2.close()
+    return ms, rep, err
+
+
+def _extra_legs(args, m, s, rig, pin, kw, world, rank, local, barrier):
+    """Secondary measurements, each one a few solves: (a) the dense-graph reduced solver (tile DAG, MCCBA_CHOL=2) on the
+    headline rig, (b) strong scaling of config #5 as written (args.frames frames in TOTAL, split over the ranks),
+    (c) BASELINE configs[3] (16-camera mixed rig, 10k frames in total, split over the ranks), (d) at N > 1 the
+    multi-GPU parity check against the whole-rig oracle (checker only, outside every timed region)."""
+    import torch.distributed as dist
+    from multi_camera_calibration_b200 import synth
+    out = {}
+    M = rig["n_points"]
+    # (a) dense-graph solver on the same rig: what a rig without the ring topology would pay per iteration
+    old = os.environ.get("MCCBA_CHOL")
+    os.environ["MCCBA_CHOL"] = "2"
+    try:
+        s.set_observations(rig["n_frame"], rig["edge_cam"], rig["edge_pv"], rig["edge_off"], pin["obj"], pin["img"])
+        s.set_parameters(pin["params_init"])
+        s.save_parameters()
+        ms, rep = _time_solves(s, kw, 5, 3, world, barrier)
+        out["dense_graph_solver"] = {"us_per_lm_iteration": ms * 1e3 / max(rep["iterations"], 1),
+                                     "note": "same rig, reduced system solved by the dense tile-DAG Cholesky (MCCBA_CHOL=2)"}
+    finally:
+        if old is None:
+            os.environ.pop("MCCBA_CHOL", None)
+        else:
+            os.environ["MCCBA_CHOL"] = old
+    # (b) strong scaling: BASELINE configs[4] as written -- args.frames frames in total
+    if world > 1:
+        fr = args.frames // world
+        cams = synth.make_cameras(args.cams, args.seed)
+        rl = synth.make_rig(n_cam=args.cams, n_frame=fr, seed=args.seed, cameras=cams, frame_stream=100 + rank)
+        ms, rep, err = _sharded_leg(m, dist, rl, kw, world, rank, local, barrier)
+        it = max(rep["iterations"], 1)
+        out["strong"] = {"workload": "%d-camera rig, %d frames in TOTAL split over %d GPUs (%d per GPU)" % (args.cams, fr * world, world, fr),
+                         "us_per_lm_iteration": ms * 1e3 / it, "lm_iters_per_sec": it / (ms * 1e-3),
+                         "corner_obs_per_s": world * rl["n_points"] * it / (ms * 1e-3), "rms_px": err["rms"]}
+    # (c) config #4: 16-camera mixed pinhole / Mei rig, 10k frames in total
+    fr4 = 10000 // world
+    models = [1 if c % 2 else 0 for c in range(16)]
+    cams4 = synth.make_cameras(16, 1004, models)
+    r4 = synth.make_rig(n_cam=16, n_frame=fr4, seed=1004, cameras=cams4, frame_stream=rank)
+    ms, rep, err = _sharded_leg(m, dist, r4, kw, world, rank, local, barrier)
+    it = max(rep["iterations"], 1)
+    out["config4"] = {"workload": "BASELINE configs[3]: 16-camera mixed pinhole/omnidir rig, %d frames in total over %d GPU(s)" % (fr4 * world, world),
+                      "us_per_lm_iteration": ms * 1e3 / it, "lm_iters_per_sec": it / (ms * 1e-3),
+                      "corner_obs_per_s": world * r4["n_points"] * it / (ms * 1e-3), "rms_px": err["rms"]}
+    # (d) parity of the sharded path (both exchanges) against the oracle on the whole rig
+    if world > 1:
+        from scripts import mgpu_parity
+        res = mgpu_parity.check(dist, rank, world, local, verbose=False)
+        if rank == 0:
+            out["parity"] = {"ok": res["ok"], "param_rel": res["param_rel"], "S_rel": res["S_rel"], "cost_rel": res["cost_rel"],
+                             "cams_bit_identical": res["cams_bit_identical"], "exchange": res["exchange"],
+                             "cases": [c["case"] + ":" + c["exchange"] for c in res["cases"]],
+                             "checker": "oracle/ on the whole rig (rank 0), tolerance 1e-6"}
+    return out
 
 
 def run_ours(args):
@@ -252,9 +356,14 @@ def run_ours(args):
     e2e_value = world * M * r2["iterations"] / (e2e_ms * 1e-3)
     err = s.reproj_error()
 
+    # ---- secondary legs (extra keys, not the headline): other BASELINE configs and solver variants ------------------
+    extra = {}
+    if not args.no_extra:
+        extra = _extra_legs(args, m, s, rig, pin, kw, world, rank, local, barrier)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         orc, O = _oracle_rig(rig)
+        cores = _cpu_threads(orc)
         ci = args.ref_iters
         ckw = dict(mode=1, crit_type=1, max_count=ci, lambda0=1e-3, lambda_up=10.0, lambda_down=1.0 / 3.0)
         O.solve(rig["params_init"], **ckw)                       # warm-up (page faults, thread pool)
@@ -264,7 +373,7 @@ def run_ours(args):
             O.solve(rig["params_init"], **ckw)
             cdt += time.perf_counter() - t0
             reps += 1
-        cpu = {"value": M * ci * reps / cdt, "unit": UNIT, "cores": orc.num_threads(), "kind": "port",
+        cpu = {"value": M * ci * reps / cdt, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": "full rig (%d corners), %d solves of %d LM iterations (%.1f s of CPU work)" % (M, reps, ci, cdt),
                "lm_iters_per_sec": ci * reps / cdt}
     if rank == 0:
@@ -285,6 +394,7 @@ def run_ours(args):
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                         "ms_per_step": e2e_ms, "steps": e2e_steps},
                 "gpu_launches": int(launches), "clocks": clocks}
+        line.update(extra)
         if cpu:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)
@@ -306,6 +416,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--seed", type=int, default=1005)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the secondary legs (dense solver, strong scaling, config #4, parity)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 0)
     if args.impl == "reference":

@@ -11,7 +11,7 @@ LIB_DEVICE = os.path.join(HERE, "libmccba.so")
 LIB_HOST = os.path.join(HERE, "libmccba_host.so")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
-              "-shared"]
+              "-shared", "-cudart", "shared", "-Xlinker", "-rpath=/usr/local/cuda/lib64"]
 
 
 def _stale(target, sources):

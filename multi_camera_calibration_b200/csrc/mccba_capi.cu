@@ -82,6 +82,7 @@ struct mccba_handle_s {
     unsigned long long* p2p_epoch = nullptr;
     int64_t p2p_stride = 0;
     bool p2p_ok = false;
+    unsigned long long p2p_budget_ns = 30000000000ull;   // spin budget of one exchange (MCCBA_P2P_TIMEOUT_MS), then MCCBA_ERR_NCCL
     char* pin_buf = nullptr;
     size_t pin_cap = 0, pin_used = 0, pin_want = 0;
     ncclComm_t comm = nullptr;
@@ -270,7 +271,7 @@ int enqueue_iteration(mccba_handle h, bool timed)
         CUDA_TRY(h, cudaMemcpyAsync(P.ar, P.ar_part, sizeof(double) * (size_t)h->ar_len, cudaMemcpyDeviceToDevice, s));
     } else if (h->opts.nranks > 1 && h->p2p_ok) {
         const int grid = std::max(1, std::min(h->num_sms, (h->ar_len + 4 * kP2pThreads - 1) / (4 * kP2pThreads)));
-        p2p_exchange_kernel<<<grid, kP2pThreads, 0, s>>>(P, (int64_t)h->ar_len);
+        p2p_exchange_kernel<<<grid, kP2pThreads, 0, s>>>(P, (int64_t)h->ar_len, h->p2p_budget_ns);
     } else if (h->opts.nranks > 1) {
         ncclResult_t r = nccl().AllReduce(P.ar_part, P.ar, (size_t)h->ar_len, kNcclFloat64, kNcclSum, h->comm, s);
         if (r != 0) return fail(h, MCCBA_ERR_NCCL, "ncclAllReduce failed: %s", nccl().GetErrorString ? nccl().GetErrorString(r) : "?");
@@ -494,14 +495,32 @@ static void p2p_teardown(mccba_handle h)
     cudaGetLastError();
 }
 
+// all-rank barrier on the library's own communicator (tiny all-reduce + host wait)
+static int p2p_barrier(mccba_handle h)
+{
+    if (!h->comm || !nccl().AllReduce) return MCCBA_OK;
+    ncclResult_t r = nccl().AllReduce(h->d_small, h->d_small, 1, kNcclInt32, kNcclMin, h->comm, h->stream);
+    if (r != 0) return fail(h, MCCBA_ERR_NCCL, "ncclAllReduce (barrier) failed: %d", r);
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return MCCBA_OK;
+}
+
 static int p2p_setup(mccba_handle h)
 {
     const int n = h->opts.nranks, me = h->opts.rank;
     const int64_t stride = (2 * (int64_t)h->ar_len + 31) & ~(int64_t)31;   // LL protocol: two 8-byte words per element
     if (h->p2p_stride == stride) return MCCBA_OK;   // same reduced-system size as the previous problem: nothing to do
+    if (h->p2p_win) {   // a peer may still have the old window mapped: nobody frees before everybody is here
+        int rcb = p2p_barrier(h);
+        if (rcb) return rcb;
+    }
     p2p_teardown(h);
     h->p2p_stride = stride;                         // remembered even on fallback, so the decision is taken once per size
     const char* env = getenv("MCCBA_P2P");
+    if (const char* tmo = getenv("MCCBA_P2P_TIMEOUT_MS")) {
+        const long long ms = atoll(tmo);
+        if (ms > 0) h->p2p_budget_ns = (unsigned long long)ms * 1000000ull;
+    }
     struct Msg { cudaIpcMemHandle_t hdl; int ok; int pad[15]; };
     static_assert(sizeof(Msg) == 128, "message layout");
     Msg mine;
@@ -510,21 +529,23 @@ static int p2p_setup(mccba_handle h)
     mine.ok = (n <= 8 && nccl().AllGather && !(env && env[0] == '0')) ? 1 : 0;
     const size_t words = (size_t)kP2pFlagWords + 2 * (size_t)n * (size_t)stride;
     if (mine.ok && cudaMalloc((void**)&h->p2p_win, words * sizeof(double)) != cudaSuccess) { mine.ok = 0; h->p2p_win = nullptr; cudaGetLastError(); }
-    if (mine.ok) {
-        CUDA_TRY(h, cudaMemsetAsync(h->p2p_win, 0, words * sizeof(double), h->stream));
-        if (cudaIpcGetMemHandle(&mine.hdl, h->p2p_win) != cudaSuccess) { mine.ok = 0; cudaGetLastError(); }
-    }
+    if (mine.ok && cudaMemsetAsync(h->p2p_win, 0, words * sizeof(double), h->stream) != cudaSuccess) { mine.ok = 0; cudaGetLastError(); }
+    if (mine.ok && cudaIpcGetMemHandle(&mine.hdl, h->p2p_win) != cudaSuccess) { mine.ok = 0; cudaGetLastError(); }
     if (!nccl().AllGather) { p2p_teardown(h); h->p2p_stride = stride; return MCCBA_OK; }   // same on every rank
+    // From here on every rank must reach both collectives whatever happens locally: a local failure only clears `ok`.
     char* d_msg = nullptr;
-    CUDA_TRY(h, cudaMalloc((void**)&d_msg, sizeof(Msg) * (size_t)(n + 1) + 256));
+    if (cudaMalloc((void**)&d_msg, sizeof(Msg) * (size_t)(n + 1) + 256) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(h, MCCBA_ERR_CUDA, "p2p_setup: cudaMalloc of the %d-byte handshake buffer failed", (int)(sizeof(Msg) * (size_t)(n + 1) + 256));
+    }
     std::vector<Msg> all((size_t)n);
-    CUDA_TRY(h, cudaMemcpyAsync(d_msg, &mine, sizeof(Msg), cudaMemcpyHostToDevice, h->stream));
+    bool local_ok = cudaMemcpyAsync(d_msg, &mine, sizeof(Msg), cudaMemcpyHostToDevice, h->stream) == cudaSuccess;
     ncclResult_t r = nccl().AllGather(d_msg, d_msg + sizeof(Msg), sizeof(Msg), kNcclInt8, h->comm, h->stream);
     if (r != 0) { cudaFree(d_msg); return fail(h, MCCBA_ERR_NCCL, "ncclAllGather failed: %d", r); }
-    CUDA_TRY(h, cudaMemcpyAsync(all.data(), d_msg + sizeof(Msg), sizeof(Msg) * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
-    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
-    int ok = 1;
-    for (int q = 0; q < n; ++q) ok = ok && all[(size_t)q].ok;
+    local_ok = local_ok && cudaMemcpyAsync(all.data(), d_msg + sizeof(Msg), sizeof(Msg) * (size_t)n, cudaMemcpyDeviceToHost, h->stream) == cudaSuccess;
+    local_ok = local_ok && cudaStreamSynchronize(h->stream) == cudaSuccess;
+    int ok = local_ok ? 1 : 0;
+    for (int q = 0; q < n && ok; ++q) ok = ok && all[(size_t)q].ok;
     if (ok) {
         for (int q = 0; q < n && ok; ++q) {
             if (q == me) { h->p2p_peer[q] = h->p2p_win; continue; }
@@ -534,17 +555,22 @@ static int p2p_setup(mccba_handle h)
             h->p2p_peer[q] = (double*)ptr;
         }
         if (ok && cudaMalloc((void**)&h->p2p_epoch, 256) != cudaSuccess) { ok = 0; h->p2p_epoch = nullptr; cudaGetLastError(); }
-        if (ok) CUDA_TRY(h, cudaMemsetAsync(h->p2p_epoch, 0, 256, h->stream));
+        if (ok && cudaMemsetAsync(h->p2p_epoch, 0, 256, h->stream) != cudaSuccess) { ok = 0; cudaGetLastError(); }
     }
     // second round: did every rank manage to open every window?  (also the barrier behind the window memsets)
     int* d_ok = (int*)(d_msg + sizeof(Msg) * (size_t)(n + 1));
-    CUDA_TRY(h, cudaMemcpyAsync(d_ok, &ok, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    if (cudaMemcpyAsync(d_ok, &ok, sizeof(int), cudaMemcpyHostToDevice, h->stream) != cudaSuccess) {
+        cudaGetLastError();
+        ok = 0;
+        cudaMemsetAsync(d_ok, 0, sizeof(int), h->stream);   // the collective still runs, with "not ok"
+    }
     r = nccl().AllReduce(d_ok, d_ok, 1, kNcclInt32, kNcclMin, h->comm, h->stream);
     if (r != 0) { cudaFree(d_msg); return fail(h, MCCBA_ERR_NCCL, "ncclAllReduce failed: %d", r); }
-    CUDA_TRY(h, cudaMemcpyAsync(&ok, d_ok, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    int all_ok = 0;
+    if (cudaMemcpyAsync(&all_ok, d_ok, sizeof(int), cudaMemcpyDeviceToHost, h->stream) != cudaSuccess ||
+        cudaStreamSynchronize(h->stream) != cudaSuccess) { cudaGetLastError(); all_ok = 0; }
     cudaFree(d_msg);
-    if (!ok) { p2p_teardown(h); h->p2p_stride = stride; }
+    if (!all_ok || !ok) { p2p_teardown(h); h->p2p_stride = stride; }
     else h->p2p_ok = true;
     if (h->opts.verbose) fprintf(stderr, "[mccba] rank %d: reduced-system exchange over %s\n", me, h->p2p_ok ? "NVLink peer memory" : "ncclAllReduce");
     return MCCBA_OK;
@@ -803,6 +829,7 @@ int mccba_set_observations(mccba_handle h, int n_frame, int n_edge, const int* e
     }
     P.band_nw = (h->k5_blocked == 3 && P.ns > 0) ? h->band_nw : 0;
     P.ar_goff = P.band_nw > 0 ? (int64_t)P.ns * P.band_nw : (int64_t)P.ns * P.ns;
+    if (P.ar_goff + P.ns + 4 >= (int64_t)2000000000) return fail(h, MCCBA_ERR_ARG, "reduced camera system too large (%d x %d)", P.ns, P.ns);
     h->ar_len = (int)P.ar_goff + P.ns + 4;
     if (h->opts.nranks > 1) {
         int rc_p2p = p2p_setup(h);
@@ -1069,6 +1096,12 @@ int mccba_solve(mccba_handle h, const mccba_solve_opts* o, mccba_report* rep)
     cudaStream_t s = h->stream;
     int rc;
     int kernels = 0;
+    if (h->p2p_ok) {
+        // re-agree the exchange epoch: after an error on one rank (or unequal launch counts) the per-rank counters may
+        // differ; the maximum is newer than every flag word any rank has written so far
+        ncclResult_t r = nccl().AllReduce(h->p2p_epoch, h->p2p_epoch, 1, 5 /* ncclUint64 */, 2 /* ncclMax */, h->comm, s);
+        if (r != 0) return fail(h, MCCBA_ERR_NCCL, "ncclAllReduce (epoch) failed: %d", r);
+    }
     CUDA_TRY(h, cudaEventRecord(h->ev0, s));
     init_state_kernel<<<1, 1, 0, s>>>(P.st, o->mode, o->crit_type, o->max_count, o->epsilon, o->lambda0, o->lambda_up,
                                       o->lambda_down, h->cur);
@@ -1138,6 +1171,8 @@ int mccba_solve(mccba_handle h, const mccba_solve_opts* o, mccba_report* rep)
         rep->status = st.status; rep->graph_launches = (int)launched; rep->kernel_launches = kernels;
         rep->change = st.change; rep->cost = st.cost_cur; rep->lambda = st.lambda; rep->device_ms = ms;
     }
+    if (st.status == 5)
+        return fail(h, MCCBA_ERR_NCCL, "solve: the peer-memory exchange timed out at iteration %d (a peer rank is gone or out of step)", st.iter);
     if (st.status != 0)
         return fail(h, MCCBA_ERR_NUMERIC, "solve: numeric failure at iteration %d (non-finite cost or a block that is not positive definite)", st.iter);
     if (!st.done)

@@ -880,15 +880,30 @@ __device__ __forceinline__ void p2p_ll_store(unsigned long long* dst, double x, 
     const unsigned long long w1 = (v >> 32) | ((unsigned long long)flag << 32);
     asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(dst), "l"(w0), "l"(w1) : "memory");
 }
-__device__ __forceinline__ double p2p_ll_load(const unsigned long long* src, unsigned flag)
+// Bounded spin (a peer that died, returned early from mccba_solve or launched a different number of graphs must not
+// hang the GPU): the wall clock is sampled every 1024 polls; on expiry the caller gets *timed_out = 1 and zeros.
+__device__ __forceinline__ unsigned long long p2p_now_ns()
 {
-    unsigned long long w0, w1;
-    do {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ double p2p_ll_load(const unsigned long long* src, unsigned flag, unsigned long long budget_ns, int* timed_out)
+{
+    unsigned long long w0, w1, t0 = 0;
+    unsigned polls = 0;
+    for (;;) {
         asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(src) : "memory");
-    } while ((unsigned)(w0 >> 32) != flag || (unsigned)(w1 >> 32) != flag);
+        if ((unsigned)(w0 >> 32) == flag && (unsigned)(w1 >> 32) == flag) break;
+        if ((++polls & 1023u) == 0) {
+            const unsigned long long now = p2p_now_ns();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > budget_ns) { *timed_out = 1; return 0.0; }
+        }
+    }
     return __longlong_as_double((long long)((w0 & 0xffffffffull) | (w1 << 32)));
 }
-__global__ void __launch_bounds__(kP2pThreads) p2p_exchange_kernel(Problem P, int64_t len)
+__global__ void __launch_bounds__(kP2pThreads) p2p_exchange_kernel(Problem P, int64_t len, unsigned long long budget_ns)
 {
     const unsigned long long e = *P.p2p_epoch + 1;
     const unsigned flag = (unsigned)e;
@@ -901,10 +916,16 @@ __global__ void __launch_bounds__(kP2pThreads) p2p_exchange_kernel(Problem P, in
         for (int64_t i = tid; i < len; i += step) p2p_ll_store(dst + 2 * i, P.ar_part[i], flag);
     }
     const unsigned long long* win = reinterpret_cast<const unsigned long long*>(P.p2p_peer[me] + kP2pFlagWords + par);
+    int timed_out = 0;
     for (int64_t i = tid; i < len; i += step) {
-        double acc = p2p_ll_load(win + 2 * i, flag);
-        for (int r = 1; r < n; ++r) acc += p2p_ll_load(win + (int64_t)r * P.p2p_stride + 2 * i, flag);
-        P.ar[i] = acc;
+        double acc = p2p_ll_load(win + 2 * i, flag, budget_ns, &timed_out);
+        for (int r = 1; r < n && !timed_out; ++r) acc += p2p_ll_load(win + (int64_t)r * P.p2p_stride + 2 * i, flag, budget_ns, &timed_out);
+        P.ar[i] = timed_out ? 0.0 : acc;
+        if (timed_out) break;
+    }
+    if (timed_out) {   // sticky: the loop control of this launch (decide_body) sees done and does nothing else
+        P.st->status = 5;
+        P.st->done = 1;
     }
 }
 

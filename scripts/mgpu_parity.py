@@ -1,80 +1,145 @@
-"""Multi-GPU parity: frames shard across ranks (one process per GPU, torchrun), the library sums the reduced camera
-system with one ncclAllReduce per iteration, every rank solves it redundantly.  Rank 0 gathers the parameters and
-checks them against the CPU oracle run on the WHOLE rig.
+"""Multi-GPU parity: frames shard across ranks (one process per GPU, torchrun), the library exchanges the packed reduced
+camera system once per iteration (NVLink peer-memory kernel, or ncclAllReduce with MCCBA_P2P=0), every rank solves it
+redundantly.  Rank 0 gathers the parameters and checks them against the CPU oracle run on the WHOLE rig (checker only).
 
-Tolerance: 1e-6 relative (the north star gate).  The all-reduce changes the summation order of S, and the undamped
-Gauss-Newton system has condition ~1e9, so parameters agree to ~1e-8..1e-7 rather than the 1e-12 of one GPU."""
+`check(dist, rank, world, local)` is what `bench.py` (N > 1), `__graft_entry__.smoke()` (>= 2 GPUs) and
+`tests/test_multi_gpu.py` run; `python -m torch.distributed.run ... scripts/mgpu_parity.py` prints its result.
+
+Tolerance: 1e-6 relative (the north star gate).  The exchange changes the summation order of S, and the undamped
+Gauss-Newton system has condition ~1e9, so parameters agree to ~1e-8..1e-7 rather than the 1e-12 of one GPU.  Camera
+parameters must be BIT-identical across ranks (every rank adds the same slots in the same order)."""
+import json
 import os
 import sys
 
 import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT)
-import torch
-import torch.distributed as dist
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
 
-import multi_camera_calibration_b200 as m
-from multi_camera_calibration_b200 import synth
+XNAME = {0: "none", 1: "nccl", 2: "peer"}
+
+# name, rig kwargs, solve kwargs.  "lm40": >= 40 LM iterations with the EPS criterion (chunked host loop, reject
+# launches, many epochs of the double-buffered windows); every case is solved twice on the same handle with a second
+# set_observations in between (window reuse across problems of the same reduced size).
+CASES = (
+    ("pinhole8_gn6", dict(n_cam=8, n_frame=400, seed=1002), dict(mode=0, crit_type=1, max_count=6)),
+    ("mixed6_v3_lm6", dict(n_cam=6, n_frame=301, seed=77, models=[0, 1, 0, 1, 0, 1], views_per_frame=3),
+     dict(mode=1, crit_type=1, max_count=6)),
+    ("pinhole8_lm45_eps", dict(n_cam=8, n_frame=400, seed=1002, init_rot=0.05, init_trans=40.0),
+     dict(mode=1, crit_type=3, max_count=45, eps=0.0, lambda0=1e-6)),
+)
+
+
+def _fresh_id(m, dist, rank):
+    """every communicator needs its own ncclUniqueId"""
+    import torch
+    idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        idt = torch.tensor(list(m.capi.nccl_unique_id()), dtype=torch.uint8, device="cuda")
+    dist.broadcast(idt, 0)
+    return bytes(idt.cpu().tolist())
+
+
+def _gather_params(dist, world, p_local, nC):
+    """(full parameter vector in global vertex order, camera blocks of every rank)"""
+    import torch
+    fr = torch.from_numpy(p_local[6 * (nC - 1):].copy()).cuda()
+    sizes = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(world)]
+    dist.all_gather(sizes, torch.tensor([fr.numel()], dtype=torch.int64, device="cuda"))
+    mx = int(max(int(x) for x in sizes))
+    pad = torch.zeros(mx, dtype=torch.float64, device="cuda")
+    pad[:fr.numel()] = fr
+    parts = [torch.zeros(mx, dtype=torch.float64, device="cuda") for _ in range(world)]
+    dist.all_gather(parts, pad)
+    cams = torch.from_numpy(p_local[:6 * (nC - 1)].copy()).cuda()
+    cam_all = [torch.zeros_like(cams) for _ in range(world)]
+    dist.all_gather(cam_all, cams)
+    full = np.concatenate([p_local[:6 * (nC - 1)]] + [parts[r][:int(sizes[r])].cpu().numpy() for r in range(world)])
+    same = all(torch.equal(cam_all[0], c) for c in cam_all)
+    return full, same
+
+
+def check(dist, rank, world, local, cases=CASES, verbose=True):
+    """Runs every case with the default exchange and with MCCBA_P2P=0.  Returns (on rank 0; None elsewhere)
+    {"ok", "param_rel", "S_rel", "cams_bit_identical", "exchange": [...], "cases": [...]}."""
+    import multi_camera_calibration_b200 as m
+    from multi_camera_calibration_b200 import synth
+    out = dict(ok=True, param_rel=0.0, S_rel=0.0, cost_rel=0.0, cams_bit_identical=True, exchange=[], cases=[])
+    prev_env = os.environ.get("MCCBA_P2P")
+    for setting in (None, "0"):
+        if setting is None:
+            os.environ.pop("MCCBA_P2P", None)
+        else:
+            os.environ["MCCBA_P2P"] = setting
+        for name, kw, skw in cases:
+            rig = synth.make_rig(**kw)
+            sh = synth.shard_rig(rig, rank, world)
+            s = m.Solver(device=local, rank=rank, nranks=world, nccl_id=_fresh_id(m, dist, rank))
+            s.set_rig(sh)
+            s.set_parameters(sh["params_init"])
+            S, gs = s.reduced_system(1e-3)
+            rep = s.solve(**skw)
+            xmode = s.exchange_mode()
+            p_local = s.get_parameters()
+            err = s.reproj_error()
+            # the same problem again on the same handle: second set_observations, windows and epochs carried over
+            s.set_rig(sh)
+            s.set_parameters(sh["params_init"])
+            rep2 = s.solve(**skw)
+            p_again = s.get_parameters()
+            s.close()
+            again_same = bool(np.array_equal(p_local, p_again)) and rep2["iterations"] == rep["iterations"]
+            nC = rig["n_cam"]
+            full, same_cams = _gather_params(dist, world, p_local, nC)
+            if rank == 0:
+                from tests import rigs          # oracle: checker only
+                O = rigs.to_oracle_rig(rig)
+                okw = dict(skw)
+                ref = O.solve(rig["params_init"], **okw)
+                scale = np.maximum(np.abs(ref["params"]), 1.0)
+                rel = float(np.max(np.abs(full - ref["params"]) / scale))
+                O.eval(rig["params_init"])
+                _, _, So, gso = O.solve_normal(rig["params_init"], 1e-3)
+                rs = float(np.abs(S - So).max() / np.abs(So).max())
+                eo = O.error(ref["params"])
+                crel = abs(rep["cost"] - ref["cost"]) / ref["cost"]
+                # LM with the EPS criterion: the accept/reject sequence must coincide for the counts to coincide
+                iters_ok = rep["iterations"] == ref["iters"]
+                case_ok = (rel < 1e-6 and rs < 1e-9 and same_cams and abs(err["rms"] - eo["rms"]) < 1e-8 * eo["rms"]
+                           and crel < 1e-8 and iters_ok and again_same)
+                line = dict(case=name, world=world, exchange=XNAME[xmode], iters=rep["iterations"], oracle_iters=ref["iters"],
+                            rejected=rep["rejected"], param_rel=rel, S_rel=rs, cost_rel=crel, cams_bit_identical=bool(same_cams),
+                            resolve_bit_identical=again_same, rms=err["rms"], oracle_rms=eo["rms"], ok=bool(case_ok))
+                if verbose:
+                    print("mgpu_parity " + json.dumps(line), flush=True)
+                out["cases"].append(line)
+                out["ok"] = out["ok"] and case_ok
+                out["param_rel"] = max(out["param_rel"], rel)
+                out["S_rel"] = max(out["S_rel"], rs)
+                out["cost_rel"] = max(out["cost_rel"], crel)
+                out["cams_bit_identical"] = out["cams_bit_identical"] and bool(same_cams)
+                if XNAME[xmode] not in out["exchange"]:
+                    out["exchange"].append(XNAME[xmode])
+    if prev_env is None:
+        os.environ.pop("MCCBA_P2P", None)
+    else:
+        os.environ["MCCBA_P2P"] = prev_env
+    dist.barrier()
+    return out if rank == 0 else None
 
 
 def main():
+    import torch
+    import torch.distributed as dist
     rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); local = int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    def fresh_id():
-        """every communicator needs its own ncclUniqueId"""
-        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
-        if rank == 0:
-            idt = torch.tensor(list(m.capi.nccl_unique_id()), dtype=torch.uint8, device="cuda")
-        dist.broadcast(idt, 0)
-        return bytes(idt.cpu().tolist())
-    ok = True
-    for name, kw, mode in (("pinhole8", dict(n_cam=8, n_frame=400, seed=1002), 0),
-                           ("mixed6", dict(n_cam=6, n_frame=301, seed=77, models=[0, 1, 0, 1, 0, 1], views_per_frame=3), 1)):
-        rig = synth.make_rig(**kw)
-        sh = synth.shard_rig(rig, rank, world)
-        s = m.Solver(device=local, rank=rank, nranks=world, nccl_id=fresh_id())
-        s.set_rig(sh)
-        s.set_parameters(sh["params_init"])
-        S, gs = s.reduced_system(1e-3)
-        rep = s.solve(mode=mode, crit_type=1, max_count=6)
-        xmode = s.exchange_mode()
-        p_local = s.get_parameters()
-        err = s.reproj_error()
-        s.close()
-        # gather frame parameters (cameras are replicated)
-        nC = rig["n_cam"]
-        fr = torch.from_numpy(p_local[6 * (nC - 1):]).cuda()
-        sizes = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(world)]
-        dist.all_gather(sizes, torch.tensor([fr.numel()], dtype=torch.int64, device="cuda"))
-        mx = int(max(int(x) for x in sizes))
-        pad = torch.zeros(mx, dtype=torch.float64, device="cuda"); pad[:fr.numel()] = fr
-        parts = [torch.zeros(mx, dtype=torch.float64, device="cuda") for _ in range(world)]
-        dist.all_gather(parts, pad)
-        cams = torch.from_numpy(p_local[:6 * (nC - 1)]).cuda()
-        cam_all = [torch.zeros_like(cams) for _ in range(world)]
-        dist.all_gather(cam_all, cams)
-        if rank == 0:
-            from oracle import oracle as orc    # checker only
-            from tests import rigs
-            O = rigs.to_oracle_rig(rig)
-            ref = O.solve(rig["params_init"], mode=mode, crit_type=1, max_count=6)
-            full = np.concatenate([p_local[:6 * (nC - 1)]] + [parts[r][:int(sizes[r])].cpu().numpy() for r in range(world)])
-            scale = np.maximum(np.abs(ref["params"]), 1.0)
-            rel = float(np.max(np.abs(full - ref["params"]) / scale))
-            O.eval(rig["params_init"])
-            _, _, So, gso = O.solve_normal(rig["params_init"], 1e-3)
-            rs = float(np.abs(S - So).max() / np.abs(So).max())
-            same_cams = all(torch.equal(cam_all[0], c) for c in cam_all)
-            eo = O.error(ref["params"])
-            line = "%s world=%d exchange=%s iters=%d param_rel=%.2e S_rel=%.2e cams_bit_identical=%s rms=%.9f/%.9f cost=%.9e/%.9e" % (
-                name, world, {0: "none", 1: "nccl", 2: "peer"}[xmode], rep["iterations"], rel, rs, same_cams, err["rms"], eo["rms"], rep["cost"], ref["cost"])
-            print(line, flush=True)
-            ok = ok and rel < 1e-6 and rs < 1e-9 and same_cams and abs(err["rms"] - eo["rms"]) < 1e-9 * eo["rms"] \
-                and abs(rep["cost"] - ref["cost"]) < 1e-9 * ref["cost"] and rep["iterations"] == 6
+    res = check(dist, rank, world, local)
     if rank == 0:
-        print("MGPU_PARITY_OK" if ok else "MGPU_PARITY_FAIL", flush=True)
+        print("mgpu_parity_summary " + json.dumps({k: v for k, v in res.items() if k != "cases"}), flush=True)
+        print("MGPU_PARITY_OK" if res["ok"] else "MGPU_PARITY_FAIL", flush=True)
     dist.barrier()
     dist.destroy_process_group()
 

@@ -1,5 +1,5 @@
-"""Parity at BASELINE.json's full sizes: the oracle still finishes in seconds for configs #2 and
-#4; config #5 (10.8 M corners) is covered through size-independent properties."""
+"""Parity at BASELINE.json's full sizes: configs #2, #4 and #5 (10.8 M corners; the OpenMP oracle
+needs about a second per LM iteration) against the oracle, plus size-independent properties of config #5."""
 import numpy as np
 import pytest
 
@@ -51,6 +51,24 @@ def test_config4_mixed_full(solver, oracle_lib):
     e, eo = solver.reproj_error(), O.error(ref["params"])
     assert abs(e["rms"] - eo["rms"]) <= 1e-6 * eo["rms"] and e["n_points"] == 1080000
     assert abs(e["mean_reproj_error"] - eo["mean_reproj_error"]) <= 1e-6 * eo["mean_reproj_error"]
+
+
+def test_config5_vs_oracle(solver, oracle_lib):
+    """The headline workload itself -- 64 cameras x 100k frames, 10.8 M corners -- against the oracle: 8 LM iterations
+    (the bench's solver settings) and 8 iterations of the reference schedule; every parameter, the cost and the fp64 RMS
+    within the north star's 1e-6 (observed ~1e-11)."""
+    rig = synth.make_config(5)
+    O = rigs.to_oracle_rig(rig)
+    solver.set_rig(rig)
+    for mode, kw in ((1, dict(lambda0=1e-3, lambda_up=10.0, lambda_down=1.0 / 3.0)), (0, {})):
+        solver.set_parameters(rig["params_init"])
+        rep = solver.solve(mode=mode, crit_type=1, max_count=8, **kw)
+        ref = O.solve(rig["params_init"], mode=mode, crit_type=1, max_count=8, **kw)
+        assert rep["iterations"] == 8 == ref["iters"]
+        assert _prel(solver.get_parameters(), ref["params"]) < 1e-6
+        assert abs(rep["cost"] - ref["cost"]) <= 1e-8 * ref["cost"]
+    e, eo = solver.reproj_error(), O.error(ref["params"])
+    assert abs(e["rms"] - eo["rms"]) <= 1e-6 * eo["rms"] and e["n_points"] == 10800000
 
 
 def test_config5_properties(solver):

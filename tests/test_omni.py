@@ -145,3 +145,29 @@ def test_gpu_config3_converges(solver, oracle_lib):
     assert rep["status"] == 0 and 0.40 < rep["rms"] < 0.44          # 0.3 px noise per axis
     assert abs(p[6 * n + 5] - ptrue[6 * n + 5]) < 0.02              # xi recovered
     assert abs(p[6 * n] - ptrue[6 * n]) / ptrue[6 * n] < 0.01
+
+
+@pytest.mark.gpu
+def test_gpu_config3_vs_oracle(solver, oracle_lib):
+    """BASELINE configs[2] at its full size (1 Mei camera, 5k frames, 270k corners, 30 010 parameters): the CUDA path
+    against the oracle's Schur-mode loop (omni_solve(dense=False)) -- iterate parity after 1, 5 and 30 iterations of the
+    reference schedule, then the run to the reference's termination criterion."""
+    rig, off, p0, ptrue = _synthetic(5000, seed_pert=3)
+    obj, img = rig["obj"].astype(np.float64), rig["img"].astype(np.float64)
+    solver.omni_set_observations(off, rig["obj"], rig["img"])
+    for k in (1, 5, 30):
+        solver.omni_set_parameters(p0)
+        rep = solver.omni_solve(0, 1, k, 0.0)
+        ref = oracle_lib.omni_solve(off, obj, img, p0, 0, 1, k, 0.0, dense=False)
+        p = solver.omni_get_parameters()
+        scale = np.maximum(np.abs(ref["params"]), 1.0)
+        assert rep["iterations"] == k == ref["iters"]
+        assert np.max(np.abs(p - ref["params"]) / scale) < 1e-6, k          # north star gate; observed ~1e-10
+        assert abs(rep["rms"] - ref["rms"]) <= 1e-6 * ref["rms"]
+    solver.omni_set_parameters(p0)
+    rep = solver.omni_solve(0, 3, 300, 1e-7)
+    ref = oracle_lib.omni_solve(off, obj, img, p0, 0, 3, 300, 1e-7, dense=False)
+    p = solver.omni_get_parameters()
+    assert abs(rep["iterations"] - ref["iters"]) <= 1
+    assert np.max(np.abs(p - ref["params"]) / np.maximum(np.abs(ref["params"]), 1.0)) < 1e-6
+    assert abs(rep["rms"] - ref["rms"]) <= 1e-6 * ref["rms"]
