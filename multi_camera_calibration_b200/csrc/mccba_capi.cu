@@ -226,28 +226,28 @@ void launch_schur(mccba_handle h, cudaStream_t s, int sel, double lambda)
     }
 }
 
-// banded LDL^T solve of the reduced system (mode 3): NW = 6 (m + 1) live columns, m = block bandwidth
-template <int NW>
-static cudaError_t launch_band_nw(const double* A, int n, double* xout, int* fail, const int* go, const Problem& P, int fused, int packed, cudaStream_t s)
+// banded reduced system (mode 3): block cyclic reduction with super-blocks of B = 6 m rows, m = block bandwidth;
+// nw = 6 (m + 1) is the width of the packed band
+template <int B>
+static cudaError_t launch_bcr_b(const double* A, int n, double* xout, int* fail, const int* go, const Problem& P, int fused, int packed, cudaStream_t s)
 {
-    const size_t smem = chol_band_smem_bytes(n, NW);
-    cudaError_t e = cudaFuncSetAttribute(chol_band_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const size_t smem = bcr_smem_bytes(n, B);
+    cudaError_t e = cudaFuncSetAttribute(chol_bcr_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    chol_band_kernel<NW><<<1, kBandThreads, smem, s>>>(A, n, xout, fail, go, P, fused, packed);
+    chol_bcr_kernel<B><<<1, BcrCfg<B>::kThreads, smem, s>>>(A, n, xout, fail, go, P, fused, packed);
     return cudaGetLastError();
 }
 static cudaError_t launch_band(int nw, const double* A, int n, double* xout, int* fail, const int* go, const Problem& P, int fused, int packed, cudaStream_t s)
 {
     switch (nw) {
-        case 6: return launch_band_nw<6>(A, n, xout, fail, go, P, fused, packed, s);
-        case 12: return launch_band_nw<12>(A, n, xout, fail, go, P, fused, packed, s);
-        case 18: return launch_band_nw<18>(A, n, xout, fail, go, P, fused, packed, s);
-        case 24: return launch_band_nw<24>(A, n, xout, fail, go, P, fused, packed, s);
-        case 30: return launch_band_nw<30>(A, n, xout, fail, go, P, fused, packed, s);
+        case 12: return launch_bcr_b<6>(A, n, xout, fail, go, P, fused, packed, s);
+        case 18: return launch_bcr_b<12>(A, n, xout, fail, go, P, fused, packed, s);
+        case 24: return launch_bcr_b<18>(A, n, xout, fail, go, P, fused, packed, s);
+        case 30: return launch_bcr_b<24>(A, n, xout, fail, go, P, fused, packed, s);
         default: return cudaErrorInvalidValue;
     }
 }
-static bool band_fits(int nw, int n) { return nw >= 6 && nw <= 30 && chol_band_smem_bytes(n, nw) <= 200 * 1024; }
+static bool band_fits(int nw, int n) { return nw >= 12 && nw <= 30 && nw % 6 == 0 && bcr_smem_bytes(n, nw - 6) <= 220 * 1024; }
 
 // enqueue one iteration: [memset S] K2 K3a [allreduce] K5 K4 K1
 int enqueue_iteration(mccba_handle h, bool timed)
@@ -787,7 +787,7 @@ int mccba_set_observations(mccba_handle h, int n_frame, int n_edge, const int* e
             CUDA_TRY(h, cudaMemcpyAsync(&m, h->d_small, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
             CUDA_TRY(h, cudaStreamSynchronize(h->stream));
         }
-        h->band_nw = 6 * (m + 1);
+        h->band_nw = 6 * (std::max(m, 1) + 1);   // at least one off-diagonal block: the solver wants super-blocks of >= 6 rows
     }
     std::vector<int> dest_info, dest_src0, dest_src;
     dest_src0.push_back(0);
@@ -1252,14 +1252,13 @@ int mccba_debug_solve_dense(mccba_handle h, int n, const double* S, const double
     CUDA_TRY(h, cudaFuncSetAttribute(dense_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(bneed, 1024)));
     CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));
     double* dflags = nullptr;
-    if (blocked == 3) {   // banded LDL^T: the half bandwidth is measured on the host copy
-        int wmax = 0;
+    if (blocked == 3) {   // block cyclic reduction: the bandwidth in 6 x 6 blocks is measured on the host copy
+        int m = 1;
         for (int i = 0; i < n; ++i)
             for (int j = 0; j < i; ++j)
-                if (S[(size_t)i * n + j] != 0.0) wmax = std::max(wmax, i - j);
-        int nw = 6;
-        while (nw < wmax + 1) nw += 6;
-        if (!band_fits(nw, n)) { cudaFree(dA); cudaFree(dx); cudaFree(drinv); cudaFree(dfail); return fail(h, MCCBA_ERR_ARG, "half bandwidth %d is too wide for the banded solver", wmax); }
+                if (S[(size_t)i * n + j] != 0.0) m = std::max(m, i / 6 - j / 6);
+        const int nw = 6 * (m + 1);
+        if (!band_fits(nw, n)) { cudaFree(dA); cudaFree(dx); cudaFree(drinv); cudaFree(dfail); return fail(h, MCCBA_ERR_ARG, "block bandwidth %d is too wide for the banded solver", m); }
         Problem none;
         memset(&none, 0, sizeof(none));
         CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));

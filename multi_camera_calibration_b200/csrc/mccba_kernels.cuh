@@ -18,6 +18,7 @@
 
 #include "mccba_math.cuh"
 #include "mccba_dense.cuh"
+#include "mccba_bcr.cuh"
 
 namespace mccba {
 
@@ -1078,47 +1079,28 @@ __device__ __forceinline__ void camera_update_body(const Problem& P, const doubl
     }
 }
 
-// Banded reduced system (see band_ldlt_solve_warp): one CTA stages the band, warp 0 factors and solves, and -- in the
-// iteration (fused != 0) -- the whole CTA runs the camera update.  Dynamic shared memory: chol_band_smem_bytes().
-constexpr int kBandThreads = 256;
-__host__ __device__ inline size_t chol_band_smem_bytes(int n, int NW)
+// Banded reduced system (block cyclic reduction, mccba_bcr.cuh): one CTA stages the packed band as super-blocks, solves,
+// and -- in the iteration (fused != 0) -- runs the camera update; fused == 2: the loop control (decide_body) runs here
+// too, so the whole serial part of an iteration is ONE launch.  Dynamic shared memory: bcr_smem_bytes(n, B).
+template <int B>
+__global__ void __launch_bounds__(BcrCfg<B>::kThreads) chol_bcr_kernel(const double* A, int n, double* xout, int* fail_out,
+                                                                       const int* go, Problem P, int fused, int packed)
 {
-    return sizeof(double) * ((size_t)(n + 1) * NW + (size_t)(n + 2) + 3 * (size_t)((n + 1) / 2) + 2 + 256 + 8);
-}
-template <int NW>
-__global__ void __launch_bounds__(kBandThreads) chol_band_kernel(const double* A, int n, double* xout, int* fail_out,
-                                                                 const int* go, Problem P, int fused, int packed)
-{
-    extern __shared__ __align__(16) unsigned char band_smem[];
-    if (fused == 2) {   // the loop control runs here instead of in its own launch (this kernel is a single CTA)
+    extern __shared__ __align__(16) unsigned char bcr_smem[];
+    if (fused == 2) {
         if (threadIdx.x == 0) decide_body(P);
         __syncthreads();
     }
     if (go && !*reinterpret_cast<const volatile int*>(go)) return;
-    double* colbuf = reinterpret_cast<double*>(band_smem);     // 256 doubles
-    double* rhs = colbuf + 256;                                // n + 1
-    double* band = rhs + ((n + 1) & ~1) + 2;                   // (n + 1) x NW
-    double* pinv = band + (size_t)(n + 1) * NW;                // 3 per pair of rows (behind the band: the band keeps its place)
-    __shared__ int s_fail;
-    constexpr int w = NW - 1;
-    if (packed) {   // A = [band | g] already (reduce_records wrote it that way)
-        for (int idx = threadIdx.x; idx < n * NW; idx += kBandThreads) band[idx] = A[idx];
-        for (int idx = threadIdx.x; idx < n; idx += kBandThreads) rhs[idx] = A[(int64_t)n * NW + idx];
-    } else {
-        for (int idx = threadIdx.x; idx < n * NW; idx += kBandThreads) {
-            const int r = idx / NW, k = idx - r * NW, c = r - w + k;
-            band[idx] = c >= 0 ? A[(int64_t)r * n + c] : 0.0;
-        }
-        for (int idx = threadIdx.x; idx < n; idx += kBandThreads) rhs[idx] = A[(int64_t)n * n + idx];
-    }
+    const int Nb = bcr_blocks(n, B);
+    double* Dg = reinterpret_cast<double*>(bcr_smem);
+    double* Lo = Dg + (size_t)Nb * B * B;
+    double* Tmp = Lo + (size_t)Nb * B * B;
+    double* rhs = Tmp + (size_t)((Nb + 1) / 2) * B * B;
+    bcr_stage<B>(A, n, packed, Dg, Lo, rhs, Nb);
     __syncthreads();
-    if (threadIdx.x < 32) {
-        const int bad = band_ldlt_solve_warp<NW>(band, rhs, n, colbuf, pinv);
-        if (threadIdx.x == 0) s_fail = bad;
-    }
-    __syncthreads();
-    int fail = s_fail;
-    for (int idx = threadIdx.x; idx < n; idx += kBandThreads) {
+    int fail = bcr_solve_cta<B>(Dg, Lo, Tmp, rhs, Nb);
+    for (int idx = threadIdx.x; idx < n; idx += blockDim.x) {
         const double v = rhs[idx];
         xout[idx] = v;
         if (!isfinite(v)) fail = 1;
