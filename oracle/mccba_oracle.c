@@ -35,7 +35,16 @@
  *
  * Precision policy: policy 0 = fp64 everywhere; policy 1 = "faithful_f32", the
  * reference's float32 round trips (parameters stored float32, composed pose rounded to float32, projected
- * points rounded to float32, float32 residual, float32 step and update).
+ * points rounded to float32, float32 residual, float32 step and update); policy 2 = "fp64_direct": fp64 like
+ * policy 0, except that the composed rotation R3 = R2 R1 reaches the projection AS A MATRIX instead of through the
+ * reference's Rodrigues(R3) -> om3 -> Rodrigues(om3) round trip (src/multicalib.cpp:1035 followed by the
+ * projectPoints call at :771/:787).  That round trip is inexact for edges whose composed rotation angle is close to
+ * pi: for sin(theta3) < 1e-5 the axis is read off the diagonal of R3 (as cv::Rodrigues does), an approximation with
+ * relative error ~(pi - theta3)^2 / (8 a_i^2), and just outside that branch the axis comes from R - R^T with error
+ * eps / sin(theta3).  Among 200k edges some fall there and the reference's own residuals carry ~1e-9 relative noise,
+ * which the weakly damped 64-camera system amplifies to ~1e-6..1e-5 in the parameters.  Policy 2 removes exactly that
+ * noise and nothing else (the chain
+ * rule still runs in Rodrigues-vector coordinates); tests use it to separate reference noise from build error.
  */
 #include <float.h>
 #include <math.h>
@@ -173,10 +182,18 @@ int orc_rodrigues_inv(const double *R, double *om)
  * The reference chains dom3dR3 * dR3dR1 * dR1dom1 (9x9 products); because dR3dR1*dR1dom1 maps into the
  * tangent space of SO(3) at R3 the product equals J_l(om3)^-1 R2 J_l(om1) (verified
  * against cv2.composeRT in tests/test_oracle_primitives.py). */
+static int compose_motion_ex(const double *om1, const double *T1, const double *om2, const double *T2,
+                             double *om3, double *T3, double *d, double *R3);
 int orc_compose_motion(const double *om1, const double *T1, const double *om2, const double *T2,
                        double *om3, double *T3, double *d)
 {
-    double R1[9], R2[9], R3[9], t[3];
+    double R3[9];
+    return compose_motion_ex(om1, T1, om2, T2, om3, T3, d, R3);
+}
+static int compose_motion_ex(const double *om1, const double *T1, const double *om2, const double *T2,
+                             double *om3, double *T3, double *d, double *R3)
+{
+    double R1[9], R2[9], t[3];
     orc_rodrigues(om1, R1, 0);
     orc_rodrigues(om2, R2, 0);
     mat3_mul(R2, R1, R3);
@@ -506,8 +523,8 @@ static void get_pose(const orc_rig *r, const double *params, int vertex, int pol
     }
     const double *p = params + 6 * (size_t)(vertex - 1);
     for (int i = 0; i < 3; ++i) {
-        om[i] = policy ? (double)(float)p[i] : p[i];
-        T[i] = policy ? (double)(float)p[3 + i] : p[3 + i];
+        om[i] = policy == 1 ? (double)(float)p[i] : p[i];
+        T[i] = policy == 1 ? (double)(float)p[3 + i] : p[3 + i];
     }
     (void)r;
 }
@@ -522,12 +539,26 @@ static void eval_edge(orc_rig *r, int e, const double *params, int policy, int w
     double omP[3], TP[3], omC[3], TC[3], om3[3], T3[3], d[72];
     get_pose(r, params, pv, policy, omP, TP);
     get_pose(r, params, cam, policy, omC, TC);
-    orc_compose_motion(omP, TP, omC, TC, om3, T3, want_blocks ? d : 0); /* call order of :734 */
-    if (policy) { /* :742-749 */
+    double R3direct[9];
+    compose_motion_ex(omP, TP, omC, TC, om3, T3, want_blocks ? d : 0, R3direct); /* call order of :734 */
+    if (policy == 1) { /* :742-749 */
         for (int i = 0; i < 3; ++i) { om3[i] = (double)(float)om3[i]; T3[i] = (double)(float)T3[i]; }
     }
     double R3[9], dRdom[27];
     orc_rodrigues(om3, R3, want_blocks ? dRdom : 0);
+    if (policy == 2) { /* fp64_direct: R3 = R2 R1 itself; dR/dom3_k = [J_l(om3) e_k]_x R3 with that R3 */
+        memcpy(R3, R3direct, sizeof(R3));
+        if (want_blocks) {
+            double Jl[9];
+            so3_left_jacobian(om3, Jl);
+            for (int k = 0; k < 3; ++k) {
+                double colk[3] = {Jl[k], Jl[3 + k], Jl[6 + k]}, S[9], dR[9];
+                skew3(colk, S);
+                mat3_mul(S, R3, dR);
+                for (int i = 0; i < 9; ++i) dRdom[k * 9 + i] = dR[i];
+            }
+        }
+    }
     double H[36], g[6], cost = 0, sumnorm = 0;
     memset(H, 0, sizeof(H));
     memset(g, 0, sizeof(g));
@@ -538,7 +569,7 @@ static void eval_edge(orc_rig *r, int e, const double *params, int policy, int w
         Xc[0] += T3[0]; Xc[1] += T3[1]; Xc[2] += T3[2];
         if (c->model == ORC_PINHOLE) pinhole_point(c, Xc, uv, want_blocks ? A : 0);
         else omnidir_point(c, Xc, uv, want_blocks ? A : 0, 0);
-        if (policy) { /* projected points come back as float32 and the subtraction is float32 (:789-792) */
+        if (policy == 1) { /* projected points come back as float32 and the subtraction is float32 (:789-792) */
             E0 = (double)(float)(r->img[2 * i] - (float)uv[0]);
             E1 = (double)(float)(r->img[2 * i + 1] - (float)uv[1]);
         } else {
@@ -851,7 +882,7 @@ int orc_rig_solve(orc_rig *r, double *params, int mode, int crit_type, int max_c
     double *trial = (double *)malloc(sizeof(double) * P);
     double change = 1, lambda = mode ? lambda0 : 0, cost = 0;
     int iter = 0, status = 0;
-    if (policy)
+    if (policy == 1)
         for (size_t i = 0; i < P; ++i) params[i] = (double)(float)params[i]; /* CV_32F storage :426 */
     if (mode == 1) cost = orc_rig_eval(r, params, policy, 1);
     for (;; ++iter) {
@@ -865,7 +896,7 @@ int orc_rig_solve(orc_rig *r, double *params, int mode, int crit_type, int max_c
             if (status) break;
             for (size_t i = 0; i < P; ++i) {
                 double G = alpha * step[i];
-                if (policy) { /* :493-501 */
+                if (policy == 1) { /* :493-501 */
                     float Gf = (float)G;
                     step[i] = (double)Gf;
                     params[i] = (double)(float)((float)params[i] + Gf);
@@ -936,7 +967,7 @@ int orc_rig_error(orc_rig *r, const double *params, int policy, double *out, dou
         npts += n;
         cnt_ref += (r->cam[r->edge_cam[e]].model == ORC_PINHOLE) ? 2 * n : n;
     }
-    out[0] = (policy ? (double)totf : tot) / (double)cnt_ref;
+    out[0] = (policy == 1 ? (double)totf : tot) / (double)cnt_ref;
     out[1] = sqrt(sq / (double)npts);
     out[2] = tot; out[3] = sq; out[4] = (double)npts;
     return 0;

@@ -6,9 +6,10 @@ from oracle import oracle as orc
 rig = synth.make_config(5)
 O = rigs.to_oracle_rig(rig)
 p = rig["params_init"]
-for lam in (1e-3, 0.0):
+POL = int(sys.argv[1]) if len(sys.argv) > 1 else 0
+for lam in (1e-3,):
     t = time.time(); out = harness.rig_step(rig, p, lam); print("harness", time.time() - t)
-    O.eval(p); rc, step, S, gs = O.solve_normal(p, lam)
+    O.eval(p, policy=POL); rc, step, S, gs = O.solve_normal(p, lam)
     r = np.abs(out["step"] - step) / np.maximum(np.abs(p), 1.0)
     ncp = 6 * 63
     print("lam", lam, "cam rel", r[:ncp].max(), "frame rel", r[ncp:].max(), "n>1e-9", (r > 1e-9).sum(), "n>1e-7", (r > 1e-7).sum())

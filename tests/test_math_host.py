@@ -45,3 +45,34 @@ def test_rodrigues_and_left_jacobian_inverse(oracle_lib):
             ((th - np.sin(th)) / th ** 3 if th > 1e-4 else 1 / 6) * (K @ K)
         back = harness.left_jacobian_inv_apply(om, Jl @ delta)
         assert np.abs(back - delta).max() < 1e-7 * max(1.0, 1.0)
+
+
+def test_oracle_direct_policy_only_removes_the_log_exp_round_trip(oracle_lib):
+    """Oracle policy 2 (fp64_direct, oracle/mccba_oracle.c header) differs from policy 0 only by skipping
+    Rodrigues(R3) -> om3 -> Rodrigues(om3).  Away from theta3 = pi the two agree to rounding; with an edge whose composed
+    rotation is 1e-6 from pi, policy 0 picks up the eps / sin(theta3) noise of the reference formulation while the
+    product arithmetic (tangent space, no log map) keeps agreeing with policy 2."""
+    rig = rigs.make_rig(**CASES[0])
+    O = rigs.to_oracle_rig(rig)
+    p = rig["params_init"].copy()
+    c0, c2 = O.eval(p, policy=0), O.eval(p, policy=2)
+    assert abs(c0 - c2) <= 1e-13 * c0
+    r0 = O.solve(p, mode=1, crit_type=1, max_count=5, policy=0)
+    r2 = O.solve(p, mode=1, crit_type=1, max_count=5, policy=2)
+    assert np.abs(r0["params"] - r2["params"]).max() <= 1e-10 * np.abs(r2["params"]).max()
+    # turn one photo pose so that its edge with camera 0 (identity: R3 = R_photo) is 9e-6 from pi: just inside the
+    # branch (sin(theta3) < 1e-5) where the matrix -> vector conversion reads the axis off the diagonal of R3, an
+    # approximation with relative error ~(pi - theta3)^2 / (8 a_i^2)
+    e = int(np.nonzero(rig["edge_cam"] == 0)[0][0])
+    pv = int(rig["edge_pv"][e])
+    om = p[6 * (pv - 1):6 * (pv - 1) + 3]
+    a = om / np.linalg.norm(om) * 0.98 + 0.02 * np.array([0.02, 0.7, 0.7139])
+    p[6 * (pv - 1):6 * (pv - 1) + 3] = a / np.linalg.norm(a) * (np.pi - 9e-6)
+    out = harness.rig_step(rig, p, 1e-3)
+    O.eval(p, policy=2)
+    _, step2, S2, g2 = O.solve_normal(p, 1e-3)
+    O.eval(p, policy=0)
+    _, step0, S0, g0 = O.solve_normal(p, 1e-3)
+    rel = lambda a, b: np.abs(a - b).max() / np.abs(b).max()
+    assert rel(out["step"], step2) < 1e-12 and rel(out["gs"], g2) < 1e-12
+    assert rel(step0, step2) > 1e-11                              # the reference formulation's own noise floor
