@@ -61,6 +61,17 @@ extern "C" {
 #define MCCBA_MODE_REFERENCE_GN 0 /* step-scaled Gauss-Newton, G = 0.95^(iter+1) x (src/multicalib.cpp:482-504) */
 #define MCCBA_MODE_LM 1           /* Levenberg-Marquardt: damping, accept/reject on device (north star) */
 
+/* precision policy of the residual / Jacobian pass (mccba_set_precision).  Everything summed over many observations
+ * (per-edge blocks onwards: Schur complement, reduced solve, update, cost test, the reported RMS) is fp64 in both. */
+#define MCCBA_PRECISION_FP64 0  /* per-corner projection, Jacobian and accumulation in double */
+#define MCCBA_PRECISION_MIXED 1 /* default: residual (projection) in double, Jacobian and the per-corner products in packed
+                                   float32 (two corners per lane), per-edge sums promoted to double.  Final parameters
+                                   agree with FP64 to ~1e-8 relative (tests/test_precision_gpu.py, tests/test_math_host.py) */
+#define MCCBA_PRECISION_FAST32 2 /* everything per corner in packed float32, like the reference, which evaluates the
+                                   projection through float32 (src/multicalib.cpp:742-749, 789-792): RMS agrees to 1e-9,
+                                   but the tilt of boards that face a camera squarely moves by ~2e-6 -- outside the 1e-6
+                                   parity gate, hence opt-in */
+
 typedef struct mccba_handle_s *mccba_handle;
 
 typedef struct {
@@ -111,6 +122,12 @@ int mccba_nccl_unique_id(unsigned char out[128]);
 int mccba_create(const mccba_options *opts, mccba_handle *out);
 int mccba_destroy(mccba_handle h);
 const char *mccba_last_error(mccba_handle h);
+/* Precision policy of the residual / Jacobian pass (MCCBA_PRECISION_*; default MIXED, or the environment variable
+ * MCCBA_PRECISION=fp64|mixed|fast32 read at mccba_create).  The observation layout on the device depends on it: changing the
+ * policy discards the current problem (set_observations / set_parameters have to be called again).
+ * Replaces the float32 conversions of src/multicalib.cpp:742-749. */
+int mccba_set_precision(mccba_handle h, int policy);
+int mccba_get_precision(mccba_handle h);
 
 /* ---- problem ----------------------------------------------------------------------------------------------- */
 /* Replaces _cameraMatrix / _distortCoeffs / _xi (multicalib.hpp:211-213).  K5 = fx fy cx cy skew per camera

@@ -14,6 +14,7 @@ OK, ERR_ARG, ERR_CUDA, ERR_STATE, ERR_NUMERIC, ERR_NCCL = 0, 1, 2, 3, 4, 5
 PINHOLE, OMNIDIRECTIONAL = 0, 1
 CRIT_COUNT, CRIT_EPS = 1, 2
 MODE_REFERENCE_GN, MODE_LM = 0, 1
+PRECISION_FP64, PRECISION_MIXED, PRECISION_FAST32 = 0, 1, 2
 
 
 class Options(C.Structure):
@@ -41,7 +42,8 @@ EXPORTS = ["mccba_exchange_mode", "mccba_default_options", "mccba_default_solve_
            "mccba_last_error", "mccba_set_cameras", "mccba_set_observations", "mccba_set_parameters",
            "mccba_get_parameters", "mccba_save_parameters", "mccba_restore_parameters", "mccba_eval", "mccba_reduced_system", "mccba_solve", "mccba_reproj_error",
            "mccba_allreduce_sum", "mccba_last_kernel_ms", "mccba_time_eval", "mccba_debug_solve_dense", "mccba_omni_set_observations",
-           "mccba_omni_set_parameters", "mccba_omni_get_parameters", "mccba_omni_solve", "mccba_omni_gram"]
+           "mccba_omni_set_parameters", "mccba_omni_get_parameters", "mccba_omni_solve", "mccba_omni_gram", "mccba_set_precision",
+           "mccba_get_precision"]
 
 _lib = None
 
@@ -80,7 +82,7 @@ def nccl_unique_id():
 class Solver:
     """One handle = one GPU + one stream (include/mccba.h)."""
 
-    def __init__(self, device=0, rank=0, nranks=1, nccl_id=None, use_graph=True):
+    def __init__(self, device=0, rank=0, nranks=1, nccl_id=None, use_graph=True, precision=None):
         L = lib()
         o = Options()
         L.mccba_default_options(C.byref(o))
@@ -98,6 +100,8 @@ class Solver:
             raise MccbaError(rc, msg)
         self.n_cam = self.n_frame = self.n_edge = 0
         self.nranks = nranks
+        if precision is not None:
+            self.set_precision(precision)
 
     def close(self):
         if getattr(self, "_h", None):
@@ -147,6 +151,13 @@ class Solver:
         """rig: dict in the C-ABI layout (tests/rigs.py, synth.make_rig)."""
         self.set_cameras(rig["cam_model"], rig["cam_K5"], rig["cam_dist8"], rig["cam_ndist"], rig["cam_xi"])
         self.set_observations(rig["n_frame"], rig["edge_cam"], rig["edge_pv"], rig["edge_off"], rig["obj"], rig["img"])
+
+    def set_precision(self, policy):
+        """PRECISION_FP64 (0) or PRECISION_MIXED (1, default); discards the current problem when the policy changes."""
+        self._check(lib().mccba_set_precision(self._h, int(policy)))
+
+    def get_precision(self):
+        return int(lib().mccba_get_precision(self._h))
 
     def set_parameters(self, params):
         p = np.ascontiguousarray(params, dtype=np.float64)

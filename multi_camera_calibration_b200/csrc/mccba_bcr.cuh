@@ -20,11 +20,11 @@
 namespace mccba {
 
 __host__ __device__ inline int bcr_blocks(int n, int B) { return (n + B - 1) / B; }
-// shared memory (doubles): Dg[Nb][B][B] | Lo[Nb][B][B] | Tmp[ceil(Nb/2)][B][B] | rhs[Nb * B]
+// shared memory (doubles): Dg[Nb][B][B] | Lo[Nb][B][B] | Tmp[ceil(Nb/2)][B][B] | rhs[Nb * B] | pivot scratch[32 warps][2][B]
 __host__ __device__ inline size_t bcr_smem_bytes(int n, int B)
 {
     const size_t nb = (size_t)bcr_blocks(n, B);
-    return sizeof(double) * ((2 * nb + (nb + 1) / 2) * (size_t)B * B + nb * (size_t)B + 8);
+    return sizeof(double) * ((2 * nb + (nb + 1) / 2) * (size_t)B * B + nb * (size_t)B + 64 * (size_t)B + 8);
 }
 template <int B>
 struct BcrCfg {
@@ -44,29 +44,43 @@ __device__ __forceinline__ double bcr_rcp(double d)
 // phase 1: eliminate super-block i (neighbours a, b; -1 = none).  F_a -> Dg[i], F_b -> Tmp[slot], f -> rhs[i].
 template <int B>
 __device__ __forceinline__ int bcr_eliminate(double* Dg, const double* Lo, double* Tmp, double* rhs, int i, int a, int b,
-                                             int slot, int lane)
+                                             int slot, int lane, double* piv /* this warp's 2 x B scratch */)
 {
+    constexpr bool live = true;
     constexpr int NCOL = 3 * B + 1, CPL = (NCOL + 31) / 32;
     double col[CPL][B];
+    // Branch-free staging: every lane turns its column index into (pointer, stride, valid) once and issues B predicated
+    // loads back to back.  (Branching per element serialised four divergent paths per row: 1700 cycles for 19 columns.)
 #pragma unroll
     for (int c = 0; c < CPL; ++c) {
         const int j = lane + 32 * c;
+        const double* src = Dg + (size_t)i * B * B + j;       // j < B: column j of D_i
+        int stride = B;
+        bool valid = j < B;
+        if (j >= B && j < 2 * B) { src = Lo + (size_t)i * B * B + (j - B); valid = a >= 0; }
+        if (j >= 2 * B && j < 3 * B) { src = Lo + ((size_t)(b >= 0 ? b : 0) * B + (j - 2 * B)) * B; stride = 1; valid = b >= 0; }   // C_b = Lo[b]^T
+        if (j == 3 * B) { src = rhs + (size_t)i * B; stride = 1; valid = true; }
 #pragma unroll
-        for (int r = 0; r < B; ++r) {
-            double v = 0.0;
-            if (j < B) v = Dg[((size_t)i * B + r) * B + j];
-            else if (j < 2 * B) { if (a >= 0) v = Lo[((size_t)i * B + r) * B + (j - B)]; }
-            else if (j < 3 * B) { if (b >= 0) v = Lo[((size_t)b * B + (j - 2 * B)) * B + r]; }   // C_b = Lo[b]^T
-            else if (j == 3 * B) v = rhs[(size_t)i * B + r];
-            col[c][r] = v;
-        }
+        for (int r = 0; r < B; ++r) col[c][r] = valid ? src[r * stride] : 0.0;
     }
     int bad = 0;
+#ifdef MCCBA_BCR_TS
+    if (slot == 777 && lane == 0) g_bcr_ts[40] = clock64();
+#endif
 #pragma unroll
     for (int k = 0; k < B; ++k) {
+        // the pivot column (column k lives in lane k, B < 32) goes to all lanes through the warp's scratch row: B broadcast
+        // loads instead of 2 B shuffles (with 16 warps eliminating at once the shuffle unit was the bottleneck);
+        // double-buffered, so one __syncwarp per pivot is enough
         double pk[B];
+        double* pv = piv + (k & 1) * B;
+        if (lane == k) {
 #pragma unroll
-        for (int r = 0; r < B; ++r) pk[r] = __shfl_sync(0xffffffffu, col[0][r], k);   // column k lives in lane k (B < 32)
+            for (int r = 0; r < B; ++r) pv[r] = col[0][r];
+        }
+        __syncwarp();
+#pragma unroll
+        for (int r = 0; r < B; ++r) pk[r] = pv[r];
         const double d = pk[k];
         if (!(d > 0.0) || !isfinite(d)) bad = 1;
         const double inv = bcr_rcp(d);
@@ -78,16 +92,21 @@ __device__ __forceinline__ int bcr_eliminate(double* Dg, const double* Lo, doubl
                 if (r != k) col[c][r] = fma(-pk[r], t, col[c][r]);
             col[c][k] = t;
         }
+#ifdef MCCBA_BCR_TS
+        if (slot == 777 && lane == 0) g_bcr_ts[41 + k] = clock64();
+#endif
     }
 #pragma unroll
     for (int c = 0; c < CPL; ++c) {
         const int j = lane + 32 * c;
+        double* dst = Dg + (size_t)i * B * B + (j - B);                                      // F_a
+        bool valid = live && j >= B && j < 2 * B;
+        int stride = B;
+        if (j >= 2 * B && j < 3 * B) { dst = Tmp + (size_t)(slot == 777 ? 0 : slot) * B * B + (j - 2 * B); valid = live; }   // F_b (777: timing hook of scripts/ubench/bcr_ts.cu)
+        if (j == 3 * B) { dst = rhs + (size_t)i * B; stride = 1; valid = live; }            // f
 #pragma unroll
-        for (int r = 0; r < B; ++r) {
-            if (j >= B && j < 2 * B) Dg[((size_t)i * B + r) * B + (j - B)] = col[c][r];
-            else if (j >= 2 * B && j < 3 * B) Tmp[((size_t)slot * B + r) * B + (j - 2 * B)] = col[c][r];
-            else if (j == 3 * B) rhs[(size_t)i * B + r] = col[c][r];
-        }
+        for (int r = 0; r < B; ++r)
+            if (valid) dst[r * stride] = col[c][r];
     }
     return bad;
 }
@@ -99,19 +118,21 @@ __device__ __forceinline__ void bcr_update(double* Dg, double* Lo, const double*
                                            int sq, int lane)
 {
     constexpr int NE = (B * B + 31) / 32;
-    double nl[NE];
-    const double* Lj = Lo + (size_t)j * B * B;
-    const double* Lq = Lo + (size_t)(q >= 0 ? q : 0) * B * B;
-    const double* Fbp = Tmp + (size_t)(sp >= 0 ? sp : 0) * B * B;
-    const double* Fap = Dg + (size_t)(p >= 0 ? p : 0) * B * B;
-    const double* Faq = Dg + (size_t)(q >= 0 ? q : 0) * B * B;
+    double nl[NE], nd[NE];
+    const double* __restrict__ Lj = Lo + (size_t)j * B * B;
+    const double* __restrict__ Lq = Lo + (size_t)(q >= 0 ? q : 0) * B * B;
+    const double* __restrict__ Fbp = Tmp + (size_t)(sp >= 0 ? sp : 0) * B * B;
+    const double* __restrict__ Fbq = Tmp + (size_t)(sq >= 0 ? sq : 0) * B * B;
+    const double* __restrict__ Fap = Dg + (size_t)(p >= 0 ? p : 0) * B * B;
+    const double* __restrict__ Faq = Dg + (size_t)(q >= 0 ? q : 0) * B * B;
+    // all loads and sums first (no store in between: the loads of both element slots are in flight together) ...
 #pragma unroll
     for (int e = 0; e < NE; ++e) {
         const int idx = lane + 32 * e;
-        nl[e] = 0.0;
+        nl[e] = 0.0; nd[e] = 0.0;
         if (idx < B * B) {
             const int u = idx / B, v = idx % B;
-            double acc = 0.0, accl = 0.0;
+            double acc = 0.0, acc2 = 0.0, accl = 0.0;
             if (p >= 0) {
 #pragma unroll
                 for (int t = 0; t < B; ++t) {
@@ -122,32 +143,41 @@ __device__ __forceinline__ void bcr_update(double* Dg, double* Lo, const double*
             }
             if (q >= 0) {
 #pragma unroll
-                for (int t = 0; t < B; ++t) acc = fma(Lq[t * B + u], Faq[t * B + v], acc);
+                for (int t = 0; t < B; ++t) acc2 = fma(Lq[t * B + u], Faq[t * B + v], acc2);
             }
-            Dg[(size_t)j * B * B + idx] -= acc;
+            nd[e] = acc + acc2;
             nl[e] = -accl;
         }
     }
+    double racc = 0.0;
     if (lane < B) {
         const int u = lane;
-        double acc = 0.0;
+        double acc = 0.0, acc2 = 0.0;
         if (p >= 0) {
 #pragma unroll
             for (int t = 0; t < B; ++t) acc = fma(Lj[u * B + t], rhs[(size_t)p * B + t], acc);
         }
         if (q >= 0) {
 #pragma unroll
-            for (int t = 0; t < B; ++t) acc = fma(Lq[t * B + u], rhs[(size_t)q * B + t], acc);
+            for (int t = 0; t < B; ++t) acc2 = fma(Lq[t * B + u], rhs[(size_t)q * B + t], acc2);
         }
-        rhs[(size_t)j * B + u] -= acc;
+        racc = acc + acc2;
     }
-    __syncwarp();   // every lane is done with Lo[j] and Lo[q]
+    double fb[NE];
+#pragma unroll
+    for (int e = 0; e < NE; ++e) {
+        const int idx = lane + 32 * e;
+        fb[e] = (q >= 0 && idx < B * B) ? Fbq[idx] : 0.0;
+    }
+    __syncwarp();   // ... every lane is done with Lo[j] and Lo[q]; now the stores
+    if (lane < B) rhs[(size_t)j * B + lane] -= racc;
 #pragma unroll
     for (int e = 0; e < NE; ++e) {
         const int idx = lane + 32 * e;
         if (idx < B * B) {
-            if (p >= 0) Lo[(size_t)j * B * B + idx] = nl[e];                              // coupling to j - 2s
-            if (q >= 0) Lo[(size_t)q * B * B + idx] = Tmp[(size_t)sq * B * B + idx];     // F_b(q), for the back-substitution
+            Dg[(size_t)j * B * B + idx] -= nd[e];
+            if (p >= 0) Lo[(size_t)j * B * B + idx] = nl[e];     // coupling to j - 2s
+            if (q >= 0) Lo[(size_t)q * B * B + idx] = fb[e];     // F_b(q), for the back-substitution
         }
     }
 }
@@ -159,17 +189,25 @@ __device__ inline int bcr_solve_cta(double* Dg, double* Lo, double* Tmp, double*
 {
     __shared__ int s_bad;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    double* piv = rhs + (size_t)Nb * B + (size_t)warp * 2 * B;   // behind rhs (bcr_smem_bytes reserves 32 warps x 2 x B)
     if (threadIdx.x == 0) s_bad = 0;
     __syncthreads();
+#ifdef MCCBA_BCR_TS
+    int ts_i = 3;
+#define BCR_STAMP() do { if (threadIdx.x == 0 && ts_i < 63) g_bcr_ts[ts_i] = clock64(); ++ts_i; } while (0)
+#else
+#define BCR_STAMP() do { } while (0)
+#endif
     int s = 1;
     for (; s < Nb; s <<= 1) {
         const int n_el = (Nb - s + 2 * s - 1) / (2 * s);            // eliminated: s, 3s, 5s, ... < Nb
         for (int e = warp; e < n_el; e += nwarp) {
             const int i = s + 2 * s * e;
             const int b = i + s < Nb ? i + s : -1;
-            if (bcr_eliminate<B>(Dg, Lo, Tmp, rhs, i, i - s, b, e, lane) && lane == 0) s_bad = 1;
+            if (bcr_eliminate<B>(Dg, Lo, Tmp, rhs, i, i - s, b, e, lane, piv) && lane == 0) s_bad = 1;
         }
         __syncthreads();
+        BCR_STAMP();
         const int n_sv = (Nb + 2 * s - 1) / (2 * s);               // surviving: 0, 2s, 4s, ... < Nb
         for (int e = warp; e < n_sv; e += nwarp) {
             const int j = 2 * s * e;
@@ -178,11 +216,13 @@ __device__ inline int bcr_solve_cta(double* Dg, double* Lo, double* Tmp, double*
             bcr_update<B>(Dg, Lo, Tmp, rhs, j, p, q, p >= 0 ? (p - s) / (2 * s) : -1, q >= 0 ? (q - s) / (2 * s) : -1, lane);
         }
         __syncthreads();
+        BCR_STAMP();
     }
     if (warp == 0) {
-        if (bcr_eliminate<B>(Dg, Lo, Tmp, rhs, 0, -1, -1, 0, lane) && lane == 0) s_bad = 1;
+        if (bcr_eliminate<B>(Dg, Lo, Tmp, rhs, 0, -1, -1, 0, lane, piv) && lane == 0) s_bad = 1;
     }
     __syncthreads();
+    BCR_STAMP();
     for (s >>= 1; s >= 1; s >>= 1) {
         const int n_el = (Nb - s + 2 * s - 1) / (2 * s);
         for (int w = threadIdx.x; w < n_el * B; w += blockDim.x) {
@@ -200,6 +240,7 @@ __device__ inline int bcr_solve_cta(double* Dg, double* Lo, double* Tmp, double*
             rhs[(size_t)i * B + u] = acc;
         }
         __syncthreads();
+        BCR_STAMP();
     }
     return s_bad;
 }

@@ -106,6 +106,8 @@ struct mccba_handle_s {
     int ar_len = 0;
     int k2_occ = 2;                   // minimum resident CTAs per SM requested from the Schur kernel (register cap)
     int obs_cap = 0;                  // floats per plane per TMA stage of the residual kernel (0: no staging)
+    int prec = MCCBA_PRECISION_MIXED; // precision policy of the residual / Jacobian pass (mccba_set_precision)
+    int f32_grid = 0, f32_smem = 0;
     int k1_grid = 0, k1_smem = 0, k5_smem = 0, k5_blocked = 0, panel_smem = 0, iter_kernels = 5, dag_grid = 0;
     int band_nw = 0;                  // 6 (block bandwidth + 1) of the reduced system (agreed over the ranks)
     cudaGraphExec_t graph = nullptr;
@@ -210,6 +212,8 @@ int64_t n_param(mccba_handle h) { return 6 * (int64_t)(h->n_cam + h->n_frame - 1
 
 void launch_resid(mccba_handle h, cudaStream_t s, int forced)
 {
+    if (h->P.prec == MCCBA_PRECISION_MIXED) { resid_jac_accum_f32_kernel<true><<<h->f32_grid, kF32Threads, h->f32_smem, s>>>(h->P, forced); return; }
+    if (h->P.prec == MCCBA_PRECISION_FAST32) { resid_jac_accum_f32_kernel<false><<<h->f32_grid, kF32Threads, h->f32_smem, s>>>(h->P, forced); return; }
     if (h->obs_cap > 0) resid_jac_accum_kernel<true><<<h->k1_grid, kK1Threads, h->k1_smem, s>>>(h->P, forced, h->obs_cap);
     else resid_jac_accum_kernel<false><<<h->k1_grid, kK1Threads, h->k1_smem, s>>>(h->P, forced, 0);
 }
@@ -360,6 +364,21 @@ int mccba_default_solve_opts(mccba_solve_opts* o)
     return MCCBA_OK;
 }
 
+int mccba_set_precision(mccba_handle h, int policy)
+{
+    if (!h) return MCCBA_ERR_ARG;
+    if (policy != MCCBA_PRECISION_FP64 && policy != MCCBA_PRECISION_MIXED && policy != MCCBA_PRECISION_FAST32) return fail(h, MCCBA_ERR_ARG, "set_precision: unknown policy %d", policy);
+    if (policy != h->prec && h->have_obs) {   // the observation layout depends on the policy: the problem has to be set again
+        cudaSetDevice(h->opts.device);
+        cudaStreamSynchronize(h->stream);
+        free_problem(h);
+    }
+    h->prec = policy;
+    return MCCBA_OK;
+}
+
+int mccba_get_precision(mccba_handle h) { return h ? h->prec : -1; }
+
 int mccba_nccl_unique_id(unsigned char out[128])
 {
     if (!nccl().ok) return MCCBA_ERR_NCCL;
@@ -395,6 +414,7 @@ int mccba_create(const mccba_options* opts, mccba_handle* out)
     cudaMallocHost((void**)&h->h_small, 64 * sizeof(double));
     cudaMalloc((void**)&h->d_small, 64 * sizeof(double));
     if (const char* occ = getenv("MCCBA_K2_OCC")) h->k2_occ = atoi(occ);
+    if (const char* pr = getenv("MCCBA_PRECISION")) h->prec = (pr[0] == '0' || pr[1] == 'p' || pr[1] == 'P') ? MCCBA_PRECISION_FP64 : (pr[0] == '2' || pr[1] == 'a' || pr[1] == 'A') ? MCCBA_PRECISION_FAST32 : MCCBA_PRECISION_MIXED;
     const char* prof = getenv("MCCBA_PROFILE");
     h->profile = prof && prof[0] == '1';
     if (opts->nranks > 1) {
@@ -879,6 +899,7 @@ int mccba_set_observations(mccba_handle h, int n_frame, int n_edge, const int* e
     if ((rc = dev_alloc(h, &P.dc, (size_t)std::max(P.ns, 1), true))) return rc;
     if ((rc = dev_alloc(h, &P.rinv, (size_t)std::max(P.ns, 1), true))) return rc;
     if ((rc = dev_alloc(h, &P.norm_part, 2 * (size_t)P.n_k4_blocks, true))) return rc;
+    P.prec = h->prec;
     if ((rc = dev_alloc(h, &P.erec, (size_t)P.n_edge_int, true))) return rc;
     {
         std::vector<EdgeMeta> meta((size_t)P.n_edge_int);
@@ -949,6 +970,43 @@ int mccba_set_observations(mccba_handle h, int n_frame, int n_edge, const int* e
     h->k1_grid = std::max(1, std::min(P.n_edge_int / kEdgesPerBlock, h->num_sms * per_sm));
     lap("launch geometry");
     // last: everything above ran while the observation upload was in flight on its own stream
+    if (P.prec) {
+        // packed pair layout of the single-precision pass (Problem::obs2): per tile 4 quarters x kp steps x 5 planes x 32
+        // lanes x 2 floats, kp = ceil(max corners per edge of the tile / 8)
+        const int n_tiles = P.n_edge_int / 32;
+        std::vector<int64_t> tile_off((size_t)n_tiles + 1);
+        std::vector<int> tile_kp((size_t)n_tiles);
+        int64_t tot = 0;
+        for (int t = 0; t < n_tiles; ++t) {
+            int mx = 0;
+            for (int e = 32 * t; e < 32 * t + 32; ++e) mx = std::max(mx, e_off[(size_t)e + 1] - e_off[(size_t)e]);
+            const int kp = (mx + 7) / 8;
+            tile_kp[(size_t)t] = kp;
+            tile_off[(size_t)t] = tot;
+            tot += (int64_t)4 * kp * 5 * 32;
+        }
+        tile_off[(size_t)n_tiles] = tot;
+        if ((rc = dev_upload(h, &P.tile_off, tile_off))) return rc;
+        if ((rc = dev_upload(h, &P.tile_kp, tile_kp))) return rc;
+        float2* obs2 = nullptr;
+        if ((rc = dev_alloc(h, &obs2, (size_t)std::max<int64_t>(tot, 1)))) return rc;
+        P.obs2 = obs2;
+        h->f32_smem = (int)((sizeof(CamF2) + sizeof(CamParams)) * (size_t)nC + 32 * sizeof(PackedPose));
+        int per_sm_f = 1;
+        if (P.prec == MCCBA_PRECISION_MIXED) {
+            if (h->f32_smem > 48 * 1024)
+                CUDA_TRY(h, cudaFuncSetAttribute(resid_jac_accum_f32_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->f32_smem));
+            CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_f, resid_jac_accum_f32_kernel<true>, kF32Threads, h->f32_smem));
+        } else {
+            if (h->f32_smem > 48 * 1024)
+                CUDA_TRY(h, cudaFuncSetAttribute(resid_jac_accum_f32_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->f32_smem));
+            CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_f, resid_jac_accum_f32_kernel<false>, kF32Threads, h->f32_smem));
+        }
+        h->f32_grid = std::max(1, std::min(n_tiles, h->num_sms * std::max(per_sm_f, 1)));
+        CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_copy, 0));
+        gather_obs_packed_kernel<<<std::min(n_tiles, h->num_sms * 16), 256, 0, h->stream>>>(n_tiles, P.tile_off, P.tile_kp, P.e_off, d_esrc,
+                                                                                            d_obj, d_img, obs2);
+    } else {
     // observation planes: one allocation, each plane 256-byte aligned
     const size_t plane = ((size_t)M + 63) / 64 * 64;
     float* planes = nullptr;
@@ -958,6 +1016,7 @@ int mccba_set_observations(mccba_handle h, int n_frame, int n_edge, const int* e
     gather_obs_kernel<<<h->num_sms * 8, 256, 0, h->stream>>>(P.n_edge_int, P.e_off, d_esrc, d_obj, d_img, planes,
                                                             planes + plane, planes + 2 * plane, planes + 3 * plane,
                                                             planes + 4 * plane);
+    }
     CUDA_TRY(h, cudaGetLastError());
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));   // also: the caller's buffers are no longer read
     drain_pool(h);   // whatever the new problem did not reuse
@@ -1204,7 +1263,8 @@ int mccba_reproj_error(mccba_handle h, mccba_error_stats* stats, double* per_edg
     if ((rc = sync_state_cur(h))) return rc;
     Problem& P = h->P;
     vertex_prep_kernel<<<(P.n_vertex + 127) / 128, 128, 0, h->stream>>>(P, -1);
-    reproj_error_kernel<<<h->num_sms * 4, kK1Threads, 0, h->stream>>>(P);
+    if (P.prec) reproj_error_packed_kernel<<<h->num_sms * 8, kF32Threads, 0, h->stream>>>(P);
+    else reproj_error_kernel<<<h->num_sms * 4, kK1Threads, 0, h->stream>>>(P);
     CUDA_TRY(h, cudaGetLastError());
     const size_t E = (size_t)P.n_edge_int;
     std::vector<double> sq(E), nr(E);
@@ -1246,10 +1306,12 @@ int mccba_debug_solve_dense(mccba_handle h, int n, const double* S, const double
     CUDA_TRY(h, cudaMemcpyAsync(dA, S, sizeof(double) * (size_t)n * n, cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(h, cudaMemcpyAsync(dA + (size_t)n * n, g, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, h->stream));
     const size_t pneed = chol_panel_smem_bytes(n);
-    if (blocked && pneed > 227 * 1024) { cudaFree(dA); cudaFree(dx); cudaFree(drinv); cudaFree(dfail); return fail(h, MCCBA_ERR_ARG, "n too large for the tiled solver"); }
+    if ((blocked == 1 || blocked == 2) && pneed > 227 * 1024) { cudaFree(dA); cudaFree(dx); cudaFree(drinv); cudaFree(dfail); return fail(h, MCCBA_ERR_ARG, "n too large for the tiled solver"); }
     const size_t bneed = blocked ? sizeof(double) * ((size_t)n + 2 + (kK5Threads / 32) * kCLD) : sizeof(double) * (size_t)(n + 2);
-    CUDA_TRY(h, cudaFuncSetAttribute(chol_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(pneed, 1024)));
-    CUDA_TRY(h, cudaFuncSetAttribute(dense_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(bneed, 1024)));
+    if (blocked != 3) {
+        CUDA_TRY(h, cudaFuncSetAttribute(chol_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(pneed, 1024)));
+        CUDA_TRY(h, cudaFuncSetAttribute(dense_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(bneed, 1024)));
+    }
     CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));
     double* dflags = nullptr;
     if (blocked == 3) {   // block cyclic reduction: the bandwidth in 6 x 6 blocks is measured on the host copy

@@ -17,6 +17,7 @@
 #include <stdint.h>
 
 #include "mccba_math.cuh"
+#include "mccba_f32x2.cuh"
 #include "mccba_dense.cuh"
 #include "mccba_bcr.cuh"
 
@@ -111,6 +112,13 @@ struct Problem {
     int64_t dag_words;   // chol_dag_words(ns) when the tile DAG is in use, else 0
     double* dag_buf;     // tile-DAG output (chol_dag_words doubles), filled with the all-ones sentinel before every factorisation
     double* norm_part;   // 2 x n_k4_blocks: per-block |step|^2, |trial|^2 of the frames
+    // packed single-precision pass (precision policies 1 and 2, mccba_f32x2.cuh): observations as corner PAIRS in the order
+    // the lanes consume them -- tile (32 edges) -> quarter (8 edges) -> step k -> plane (x y z u v) -> lane -> 2 floats, so
+    // a warp reads five contiguous 256-byte lines per step
+    int prec;                // 0: fp64 per-corner arithmetic (SoA planes); 1: packed f32x2 Jacobian + fp64 residual; 2: all f32x2
+    const float2* obs2;
+    const int64_t* tile_off; // per tile: first float2 of its block
+    const int* tile_kp;      // per tile: steps per quarter = ceil(max corners per edge / 8)
     EdgeRec* erec;       // n_edge_int composed poses of the point the residual kernel evaluates next
     const EdgeMeta* emeta; // n_edge_int camera / corner range of every internal edge
     double* err_sq;      // n_edge_int
@@ -198,7 +206,8 @@ __device__ __forceinline__ void write_edge_records(const Problem& P, int which, 
         } else {
 #pragma unroll
             for (int i = 0; i < 9; ++i) r.R3[i] = 0;
-            r.T3[0] = r.T3[1] = r.T3[2] = 0;
+            r.T3[0] = r.T3[1] = 0;
+            r.T3[2] = 1;      // padding slot: a benign pose (the packed pass evaluates its zero-weight corners)
         }
         P.erec[ebase + v * stride + ls] = r;
     }
@@ -422,6 +431,316 @@ __global__ void __launch_bounds__(kK1Threads, 2) resid_jac_accum_kernel(Problem 
             out[(int64_t)chunk * (kBlk * kEdgesPerBlock) + t] = sh->stage[k][col];   // tile-major: one contiguous 7 KB tile per chunk
         }
         __syncthreads();
+    }
+}
+
+// --------------------------------------------------------------------------------------------------------
+// K1, packed single precision (precision policy 1).  Unit of work = one quarter tile = 8 edges = one warp:
+// lane = 4 * (edge within the quarter) + q, and in step k the lane evaluates corners 8k + 2q and 8k + 2q + 1 of its
+// edge as ONE f32x2 pair (mccba_f32x2.cuh).  The observations are stored in exactly that order (Problem::obs2), so a
+// step is five coalesced 256-byte loads per warp, prefetched kPrefetch steps ahead in registers -- no shared memory, no
+// barrier, no atomics; a warp never waits for another.  At the end of the edge the two halves and the four lanes are
+// summed in float (transposed butterfly, 21 shuffles), promoted to double once, and stored tile-major like the fp64
+// kernel's output (what frame_schur_kernel reads).  kErr: residual-only variant for computeProjectError in double.
+// --------------------------------------------------------------------------------------------------------
+constexpr int kF32Threads = 128;
+constexpr int kPrefetch = 2;
+
+__device__ __forceinline__ float2 ldg_f2(const float2* p)
+{
+    float2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+    return v;
+}
+
+
+// The stream of observation steps a warp consumes, across tile boundaries: the loads of step k + kPrefetch are issued
+// while step k is evaluated, and when the current tile runs out the next tile of this CTA (tile + gridDim.x) takes over
+// without a bubble -- its offset and step count were fetched one tile earlier.  (Without this every quarter tile began with
+// an exposed DRAM round trip: a third of all stall samples in the first profile, profiles/r2_k1_f32_v1.txt.)
+struct ObsStream {
+    const float2* base;     // current tile: first float2 of this lane's column
+    int k, kp, tile;        // next step to load, steps of the current tile, current tile
+    int kp_next;            // prefetched for tile + stride
+    int64_t off_next;
+};
+__device__ __forceinline__ void obs_stream_open(ObsStream& S, const Problem& P, int tile, int stride, int n_tiles, int wq, int lane)
+{
+    S.tile = tile; S.k = 0;
+    S.kp = tile < n_tiles ? P.tile_kp[tile] : 0;
+    S.base = P.obs2 + (tile < n_tiles ? P.tile_off[tile] : 0) + (size_t)wq * S.kp * 5 * 32 + lane;
+    const int nt = tile + stride;
+    S.kp_next = nt < n_tiles ? P.tile_kp[nt] : 0;
+    S.off_next = nt < n_tiles ? P.tile_off[nt] : 0;
+}
+__device__ __forceinline__ void obs_stream_load(ObsStream& S, const Problem& P, int stride, int n_tiles, int wq, int lane, float2 (&dst)[5])
+{
+    if (S.tile >= n_tiles) return;
+#pragma unroll
+    for (int pl = 0; pl < 5; ++pl) dst[pl] = ldg_f2(S.base + ((size_t)S.k * 5 + pl) * 32);
+    if (++S.k == S.kp) {    // on to the next tile of this CTA; fetch the layout of the one after it
+        S.tile += stride; S.k = 0; S.kp = S.kp_next;
+        S.base = P.obs2 + S.off_next + (size_t)wq * S.kp * 5 * 32 + lane;
+        const int nt = S.tile + stride;
+        S.kp_next = nt < n_tiles ? P.tile_kp[nt] : 0;
+        S.off_next = nt < n_tiles ? P.tile_off[nt] : 0;
+    }
+}
+
+// Per-edge pose of the packed pass in shared memory, one record per edge of the warp's quarter tile: the double pose
+// (for the MIXED policy's residual) and the float pose as duplicated pairs (for the f32x2 Jacobian).  26-word stride
+// for the double part: the 8 edges of a warp land in distinct banks.
+struct PackedPose {
+    double Rd[9], Td[3];
+    double pad;
+    f2 Rf[9], Tf[3];
+};
+
+template <int kModel, bool kRational, bool kExactE>
+__device__ __forceinline__ void packed_step(const float2 (&cur)[5], int k, int n, int q, int k_full, const CamF2& cam,
+                                            const CamParams& camd, const PackedPose& pose, f2* acc, double& cost)
+{
+    // pose and intrinsics are re-read from shared memory per step (broadcast loads) instead of living in ~90 registers
+    asm volatile("" ::: "memory");
+    const bool masked = k >= k_full;              // warp-uniform: some lane runs out of corners in this step
+    const int c0 = 8 * k + 2 * q;
+    const float w0 = c0 < n ? 1.0f : 0.0f, w1 = c0 + 1 < n ? 1.0f : 0.0f;
+    f2 e0 = f2_dup(0.0f), e1 = f2_dup(0.0f);
+    if (kExactE) {
+        double ea[2], eb[2];
+        corner_residual<kModel, kRational>(camd, pose.Rd, pose.Td, cur[0].x, cur[1].x, cur[2].x, cur[3].x, cur[4].x, ea);
+        corner_residual<kModel, kRational>(camd, pose.Rd, pose.Td, cur[0].y, cur[1].y, cur[2].y, cur[3].y, cur[4].y, eb);
+        e0 = f2_make((float)ea[0], (float)eb[0]);
+        e1 = f2_make((float)ea[1], (float)eb[1]);
+        // the cost the accept / reject test compares is summed in double from the exact residuals
+        const double ca = fma(ea[0], ea[0], ea[1] * ea[1]), cb = fma(eb[0], eb[0], eb[1] * eb[1]);
+        if (masked) cost += (c0 < n ? ca : 0.0) + (c0 + 1 < n ? cb : 0.0);
+        else cost += ca + cb;
+    }
+    corner_pair_accumulate<kModel, kRational, kExactE>(cam, pose.Rf, pose.Tf, f2_make(cur[0].x, cur[0].y), f2_make(cur[1].x, cur[1].y),
+                                                       f2_make(cur[2].x, cur[2].y), f2_make(cur[3].x, cur[3].y),
+                                                       f2_make(cur[4].x, cur[4].y), f2_make(w0, w1), masked, acc, e0, e1);
+}
+
+template <int kModel, bool kRational, bool kExactE>
+__device__ __forceinline__ void packed_edge_loop(float2 (&buf)[kPrefetch][5], ObsStream& S, const Problem& P, int stride, int n_tiles,
+                                                 int wq, int lane, int kp, int n, int q, int k_full, const CamF2& cam,
+                                                 const CamParams& camd, const PackedPose& pose, f2* acc, double& cost)
+{
+    for (int k0 = 0; k0 < kp; k0 += kPrefetch) {
+#pragma unroll
+        for (int d = 0; d < kPrefetch; ++d) {
+            const int k = k0 + d;
+            if (k < kp) {
+                float2 cur[5];
+#pragma unroll
+                for (int pl = 0; pl < 5; ++pl) cur[pl] = buf[d][pl];
+                obs_stream_load(S, P, stride, n_tiles, wq, lane, buf[d]);      // step k + kPrefetch of the stream
+                packed_step<kModel, kRational, kExactE>(cur, k, n, q, k_full, cam, camd, pose, acc, cost);
+            }
+        }
+    }
+}
+
+// forced: as resid_jac_accum_kernel.  Shared memory: n_cam CamF2 | n_cam CamParams | 32 PackedPose.
+template <bool kExactE>
+__global__ void __launch_bounds__(kF32Threads, 3) resid_jac_accum_f32_kernel(Problem P, int forced)
+{
+    static_assert(kPrefetch == 2, "the ring rotation at the end of a tile is written for two slots");
+    extern __shared__ __align__(16) unsigned char f32_smem[];
+    CamF2* s_cam = reinterpret_cast<CamF2*>(f32_smem);
+    CamParams* s_camd = reinterpret_cast<CamParams*>(s_cam + P.n_cam);
+    PackedPose* s_pose = reinterpret_cast<PackedPose*>(s_camd + P.n_cam);
+    const DevState* st = P.st;
+    int which;
+    if (forced) which = st->cur;
+    else {
+        if (st->done || !st->solved) return;
+        which = 1 - st->cur;
+    }
+    double* __restrict__ out = P.blocks[which];
+    for (int c = threadIdx.x; c < P.n_cam; c += blockDim.x) {
+        const CamParams cp = P.cams[c];
+        s_camd[c] = cp;
+        s_cam[c] = make_cam_f2(cp);
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, q = lane & 3, el = lane >> 2, wq = threadIdx.x >> 5;
+    // one CTA = 4 warps = one tile per pass; the loop runs on the tile index, which is uniform over the CTA, so the warp
+    // collectives below sit in provably convergent control flow (plain SHFL / REDUX, no WARPSYNC wrappers)
+    const int n_tiles = P.n_edge_int >> 5, stride = gridDim.x;
+    if ((int)blockIdx.x >= n_tiles) return;
+    ObsStream S;
+    obs_stream_open(S, P, blockIdx.x, stride, n_tiles, wq, lane);
+    float2 buf[kPrefetch][5];
+#pragma unroll
+    for (int d = 0; d < kPrefetch; ++d) obs_stream_load(S, P, stride, n_tiles, wq, lane, buf[d]);
+    // per-edge record of the first tile: the 4 lanes of an edge share the load (lane q takes doubles q, q + 4, q + 8)
+    EdgeMeta em = P.emeta[(blockIdx.x << 5) + (wq << 3) + el];
+    double rq[3];
+    {
+        const double* r = reinterpret_cast<const double*>(P.erec + ((blockIdx.x << 5) + (wq << 3) + el));
+#pragma unroll
+        for (int i = 0; i < 3; ++i) rq[i] = r[q + 4 * i];
+    }
+    int kp_cur = P.tile_kp[blockIdx.x];
+    for (int tile = blockIdx.x; tile < n_tiles; tile += stride) {
+        const int n = em.end - em.begin, cam_idx = em.cam;
+        const int kp = kp_cur;
+        const int k_full = __reduce_min_sync(kFull, n) >> 3;
+        PackedPose& pose = s_pose[(wq << 3) + el];
+        __syncwarp();                       // the previous tile's reads of this warp's pose records are over
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const int j = q + 4 * i;
+            if (j < 9) { pose.Rd[j] = rq[i]; pose.Rf[j] = f2_dup((float)rq[i]); }
+            else { pose.Td[j - 9] = rq[i]; pose.Tf[j - 9] = f2_dup((float)rq[i]); }
+        }
+        __syncwarp();
+        {   // the next tile's records travel while this one is evaluated
+            const int nt = tile + stride;
+            if (nt < n_tiles) {
+                const int e2 = (nt << 5) + (wq << 3) + el;
+                kp_cur = P.tile_kp[nt];
+                em = P.emeta[e2];
+                const double* r = reinterpret_cast<const double*>(P.erec + e2);
+#pragma unroll
+                for (int i = 0; i < 3; ++i) rq[i] = r[q + 4 * i];
+            }
+        }
+        f2 acc[kBlk];
+#pragma unroll
+        for (int k = 0; k < kBlk; ++k) acc[k] = f2_dup(0.0f);
+        double cost = 0.0;
+        const CamF2& cam = s_cam[cam_idx];      // the 32 edges of a tile are one (group, view) run: one camera per warp
+        const CamParams& camd = s_camd[cam_idx];
+        if (cam.model == kPinhole) {
+            if (cam.rational) packed_edge_loop<kPinhole, true, kExactE>(buf, S, P, stride, n_tiles, wq, lane, kp, n, q, k_full, cam, camd, pose, acc, cost);
+            else packed_edge_loop<kPinhole, false, kExactE>(buf, S, P, stride, n_tiles, wq, lane, kp, n, q, k_full, cam, camd, pose, acc, cost);
+        } else {
+            packed_edge_loop<kOmnidir, false, kExactE>(buf, S, P, stride, n_tiles, wq, lane, kp, n, q, k_full, cam, camd, pose, acc, cost);
+        }
+        if (kp & 1) {   // the ring is one slot out of phase for the next tile: rotate it (10 register moves)
+#pragma unroll
+            for (int pl = 0; pl < 5; ++pl) { const float2 t = buf[0][pl]; buf[0][pl] = buf[1][pl]; buf[1][pl] = t; }
+        }
+        // halves, then the 4 lanes of the edge: 28 -> 14 -> 7 values per lane
+        float v[kBlk];
+#pragma unroll
+        for (int k = 0; k < kBlk; ++k) v[k] = f2_lo(acc[k]) + f2_hi(acc[k]);
+        int kbase = 0;
+        {
+            const bool up = (q & 2) != 0;
+#pragma unroll
+            for (int i = 0; i < 14; ++i) {
+                const float send = up ? v[i] : v[i + 14], keep = up ? v[i + 14] : v[i];
+                v[i] = keep + __shfl_xor_sync(kFull, send, 2);
+            }
+            kbase += up ? 14 : 0;
+        }
+        {
+            const bool up = (q & 1) != 0;
+#pragma unroll
+            for (int i = 0; i < 7; ++i) {
+                const float send = up ? v[i] : v[i + 7], keep = up ? v[i + 7] : v[i];
+                v[i] = keep + __shfl_xor_sync(kFull, send, 1);
+            }
+            kbase += up ? 7 : 0;
+        }
+        double* o = out + ((size_t)tile * kBlk + kbase) * 32 + (wq << 3) + el;
+#pragma unroll
+        for (int i = 0; i < 7; ++i) o[(size_t)i * 32] = (double)v[i];
+        if (kExactE) {   // cost (element 27: the last of lane q == 3) from the double sum
+            cost += __shfl_xor_sync(kFull, cost, 2);
+            cost += __shfl_xor_sync(kFull, cost, 1);
+            if (q == 3) o[(size_t)6 * 32] = cost;
+        }
+    }
+}
+
+// computeProjectError on the packed layout, double arithmetic (src/multicalib.cpp:969-983)
+__global__ void __launch_bounds__(kF32Threads) reproj_error_packed_kernel(Problem P)
+{
+    const int which = P.st->cur;
+    const double* __restrict__ x = P.x[which];
+    const double* __restrict__ vR = P.vR[which];
+    const int lane = threadIdx.x & 31, q = lane & 3, el = lane >> 2;
+    const int n_units = P.n_edge_int >> 3;
+    const int warps_total = (gridDim.x * blockDim.x) >> 5;
+    for (int u = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; u < n_units; u += warps_total) {
+        const int tile = u >> 2, wq = u & 3;
+        const int edge = (u << 3) + el;
+        const int frame = P.e_frame[edge];
+        const EdgeMeta em = P.emeta[edge];
+        const int n = em.end - em.begin;
+        const int kp = P.tile_kp[tile];
+        double sq = 0, nrm = 0;
+        if (frame >= 0) {
+            const int c = em.cam;
+            const int64_t pv = P.n_cam + frame;
+            double Rc[9], tc[3], Rp[9], tp[3], R3[9], T3[3];
+#pragma unroll
+            for (int i = 0; i < 9; ++i) { Rc[i] = vR[9 * c + i]; Rp[i] = vR[9 * pv + i]; }
+#pragma unroll
+            for (int i = 0; i < 3; ++i) { tc[i] = c == 0 ? 0.0 : x[6 * (c - 1) + 3 + i]; tp[i] = x[6 * (pv - 1) + 3 + i]; }
+            compose_pose(Rc, tc, Rp, tp, R3, T3);
+            const CamParams cam = P.cams[c];
+            const float2* base = P.obs2 + P.tile_off[tile] + (size_t)wq * kp * 5 * 32 + lane;
+            for (int k = 0; k < kp; ++k) {
+                const int c0 = 8 * k + 2 * q;
+                if (c0 >= n) break;
+                float2 o[5];
+#pragma unroll
+                for (int pl = 0; pl < 5; ++pl) o[pl] = __ldg(base + ((size_t)k * 5 + pl) * 32);
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    if (c0 + h >= n) break;
+                    const float ox = h ? o[0].y : o[0].x, oy = h ? o[1].y : o[1].x, oz = h ? o[2].y : o[2].x;
+                    const float iu = h ? o[3].y : o[3].x, iv = h ? o[4].y : o[4].x;
+                    if (cam.model == kPinhole) {
+                        if (cam.rational) corner_error<kPinhole, true>(cam, R3, T3, ox, oy, oz, iu, iv, &sq, &nrm);
+                        else corner_error<kPinhole, false>(cam, R3, T3, ox, oy, oz, iu, iv, &sq, &nrm);
+                    } else {
+                        corner_error<kOmnidir, false>(cam, R3, T3, ox, oy, oz, iu, iv, &sq, &nrm);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 2; o > 0; o >>= 1) {
+            sq += __shfl_xor_sync(kFull, sq, o);
+            nrm += __shfl_xor_sync(kFull, nrm, o);
+        }
+        if (q == 0) { P.err_sq[edge] = sq; P.err_nrm[edge] = nrm; }
+    }
+}
+
+// observations: AoS host layout -> packed pair layout of the single-precision pass.  One thread per (step, lane) slot.
+__global__ void gather_obs_packed_kernel(int n_tiles, const int64_t* __restrict__ tile_off, const int* __restrict__ tile_kp,
+                                         const int* __restrict__ e_off, const int64_t* __restrict__ e_src,
+                                         const float* __restrict__ obj, const float* __restrict__ img, float2* __restrict__ obs2)
+{
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int kp = tile_kp[tile];
+        float2* dst = obs2 + tile_off[tile];
+        for (int idx = threadIdx.x; idx < 4 * kp * 32; idx += blockDim.x) {
+            const int lane = idx & 31, wk = idx >> 5, wq = wk / kp, k = wk - wq * kp;
+            const int edge = tile * 32 + wq * 8 + (lane >> 2);
+            const int n = e_off[edge + 1] - e_off[edge];
+            const int64_t src = e_src[edge];
+            const int c0 = 8 * k + 2 * (lane & 3);
+            float a[5] = {0, 0, 0, 0, 0}, b[5] = {0, 0, 0, 0, 0};
+            if (c0 < n) {
+                a[0] = obj[3 * (src + c0)]; a[1] = obj[3 * (src + c0) + 1]; a[2] = obj[3 * (src + c0) + 2];
+                a[3] = img[2 * (src + c0)]; a[4] = img[2 * (src + c0) + 1];
+            }
+            if (c0 + 1 < n) {
+                b[0] = obj[3 * (src + c0 + 1)]; b[1] = obj[3 * (src + c0 + 1) + 1]; b[2] = obj[3 * (src + c0 + 1) + 2];
+                b[3] = img[2 * (src + c0 + 1)]; b[4] = img[2 * (src + c0 + 1) + 1];
+            }
+#pragma unroll
+            for (int pl = 0; pl < 5; ++pl) dst[((size_t)wk * 5 + pl) * 32 + lane] = make_float2(a[pl], b[pl]);
+        }
     }
 }
 
@@ -1262,7 +1581,8 @@ __global__ void __launch_bounds__(kK4Threads) frame_update_kernel(Problem P)
             EdgeRec z;
 #pragma unroll
             for (int i = 0; i < 9; ++i) z.R3[i] = 0;
-            z.T3[0] = z.T3[1] = z.T3[2] = 0;
+            z.T3[0] = z.T3[1] = 0;
+            z.T3[2] = 1;      // padding slot: a benign pose (the packed pass evaluates its zero-weight corners)
             for (int v = 0; v < V; ++v) {
                 if (v < 2) stage[v * 32 + lane] = z;
                 else P.erec[ebase + v * stride + ls] = z;

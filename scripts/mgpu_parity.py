@@ -5,6 +5,8 @@ redundantly.  Rank 0 gathers the parameters and checks them against the CPU orac
 `check(dist, rank, world, local)` is what `bench.py` (N > 1), `__graft_entry__.smoke()` (>= 2 GPUs) and
 `tests/test_multi_gpu.py` run; `python -m torch.distributed.run ... scripts/mgpu_parity.py` prints its result.
 
+The library runs its default precision policy (MIXED: float32 Jacobian products, so the reduced system S agrees with
+the fp64 oracle to float32 accuracy, 5e-6; cost, RMS and parameters to the gate).
 Tolerance: 1e-6 relative (the north star gate).  The exchange changes the summation order of S, and the undamped
 Gauss-Newton system has condition ~1e9, so parameters agree to ~1e-8..1e-7 rather than the 1e-12 of one GPU.  Camera
 parameters must be BIT-identical across ranks (every rank adds the same slots in the same order)."""
@@ -107,7 +109,7 @@ def check(dist, rank, world, local, cases=CASES, verbose=True):
                 crel = abs(rep["cost"] - ref["cost"]) / ref["cost"]
                 # LM with the EPS criterion: the accept/reject sequence must coincide for the counts to coincide
                 iters_ok = rep["iterations"] == ref["iters"]
-                case_ok = (rel < 1e-6 and rs < 1e-9 and same_cams and abs(err["rms"] - eo["rms"]) < 1e-8 * eo["rms"]
+                case_ok = (rel < 1e-6 and rs < 5e-6 and same_cams and abs(err["rms"] - eo["rms"]) < 1e-8 * eo["rms"]
                            and crel < 1e-8 and iters_ok and again_same)
                 line = dict(case=name, world=world, exchange=XNAME[xmode], iters=rep["iterations"], oracle_iters=ref["iters"],
                             rejected=rep["rejected"], param_rel=rel, S_rel=rs, cost_rel=crel, cams_bit_identical=bool(same_cams),

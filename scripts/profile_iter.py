@@ -15,5 +15,7 @@ for it in (5, 3):
     s.restore_parameters()
     rep = s.solve(mode=m.capi.MODE_LM, crit_type=1, max_count=it)
     print("iters", rep["iterations"], "device_ms", rep["device_ms"], "kernels", rep["kernel_launches"], "cost", rep["cost"])
+    if os.environ.get("MCCBA_PROFILE") == "1":      # per-phase CUDA-event times of the plain-stream path (ms per iteration)
+        print("   phases [schur, reduce, exchange, decide+solve+camera, frame_update, resid_jac] ms:", np.round(s.last_kernel_ms(), 4))
 print("k1 ms", s.time_eval(5))
 s.close()

@@ -8,14 +8,16 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "libmath_harness.so")
 _SRC = os.path.join(_HERE, "math_harness.cpp")
-_HDR = os.path.join(os.path.dirname(os.path.dirname(_HERE)), "multi_camera_calibration_b200", "csrc", "mccba_math.cuh")
+_CSRC = os.path.join(os.path.dirname(os.path.dirname(_HERE)), "multi_camera_calibration_b200", "csrc")
+_HDR = os.path.join(_CSRC, "mccba_math.cuh")
+_HDR2 = os.path.join(_CSRC, "mccba_f32x2.cuh")
 _lib = None
 
 
 def lib():
     global _lib
     if _lib is None:
-        newest = max(os.path.getmtime(_SRC), os.path.getmtime(_HDR))
+        newest = max(os.path.getmtime(_SRC), os.path.getmtime(_HDR), os.path.getmtime(_HDR2))
         if not os.path.exists(_SO) or os.path.getmtime(_SO) < newest:
             subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", _SO, _SRC])
         _lib = C.CDLL(_SO)
@@ -26,9 +28,10 @@ def _p(a, t=C.c_double):
     return a.ctypes.data_as(C.POINTER(t))
 
 
-def rig_step(rig, params, lam):
+def rig_step(rig, params, lam, policy=0):
     """Per-edge blocks (E x 28), reduced system (S, gs) and the unscaled additive step, computed on the host with the
-    product's own __host__ __device__ arithmetic (tangent-space formulation)."""
+    product's own __host__ __device__ arithmetic (tangent-space formulation).  policy 1: the per-edge blocks come from
+    the packed single-precision pass (mccba_f32x2.cuh) in the device kernel's lane order."""
     E = rig["edge_cam"].size
     ns = 6 * (rig["n_cam"] - 1)
     p = np.ascontiguousarray(params, dtype=np.float64)
@@ -44,7 +47,7 @@ def rig_step(rig, params, lam):
                             _p(np.ascontiguousarray(rig["cam_dist8"], dtype=np.float64)),
                             _p(np.ascontiguousarray(rig["cam_ndist"], dtype=np.int32), C.c_int),
                             _p(np.ascontiguousarray(rig["cam_xi"], dtype=np.float64)), _p(p), C.c_double(lam), _p(blocks),
-                            _p(S), _p(gs), _p(step))
+                            _p(S), _p(gs), _p(step), int(policy))
     return dict(bad=bad, blocks=blocks, S=S[:ns, :ns], gs=gs[:ns], step=step)
 
 

@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "../../multi_camera_calibration_b200/csrc/mccba_math.cuh"
+#include "../../multi_camera_calibration_b200/csrc/mccba_f32x2.cuh"
 
 using namespace mccba;
 
@@ -36,6 +37,58 @@ static void edge_block(const CamParams& cam, const double* Rc, const double* tc,
     }
 }
 
+// The packed single-precision pass re-enacted in the device kernel's own order: 4 lanes per edge, lane q takes corners
+// 8k + 2q, 8k + 2q + 1 in step k as one f32x2 pair; halves, then lanes (q, q^2), then (q, q^1) are added in float; the
+// 28 sums are promoted to double (resid_jac_accum_f32_kernel).  exact_e: MIXED policy (residual from the double
+// projection); otherwise the all-float32 variant.
+template <bool kExactE>
+static void edge_block_f32(const CamParams& cam, const double* Rc, const double* tc, const double* Rp, const double* tp,
+                           int64_t b, int64_t e, const float* obj, const float* img, double* acc)
+{
+    double R3d[9], T3d[3];
+    compose_pose(Rc, tc, Rp, tp, R3d, T3d);
+    f2 R3[9], T3[3];
+    for (int i = 0; i < 9; ++i) R3[i] = f2_dup((float)R3d[i]);
+    for (int i = 0; i < 3; ++i) T3[i] = f2_dup((float)T3d[i]);
+    const CamF2 c2 = make_cam_f2(cam);
+    const int n = (int)(e - b), kp = (n + 7) / 8;
+    float v[4][kBlk];
+    for (int q = 0; q < 4; ++q) {
+        f2 a[kBlk];
+        for (int k = 0; k < kBlk; ++k) a[k] = f2_dup(0.0f);
+        for (int k = 0; k < kp; ++k) {
+            const int c0 = 8 * k + 2 * q;
+            float o[5][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}, {0, 0}};
+            float ex[2][2] = {{0, 0}, {0, 0}};
+            for (int h = 0; h < 2; ++h)
+                if (c0 + h < n) {
+                    const int64_t i = b + c0 + h;
+                    o[0][h] = obj[3 * i]; o[1][h] = obj[3 * i + 1]; o[2][h] = obj[3 * i + 2]; o[3][h] = img[2 * i]; o[4][h] = img[2 * i + 1];
+                }
+            if (kExactE)
+                for (int h = 0; h < 2; ++h) {
+                    double ed[2];
+                    if (cam.model == kPinhole) {
+                        if (cam.rational) corner_residual<kPinhole, true>(cam, R3d, T3d, o[0][h], o[1][h], o[2][h], o[3][h], o[4][h], ed);
+                        else corner_residual<kPinhole, false>(cam, R3d, T3d, o[0][h], o[1][h], o[2][h], o[3][h], o[4][h], ed);
+                    } else corner_residual<kOmnidir, false>(cam, R3d, T3d, o[0][h], o[1][h], o[2][h], o[3][h], o[4][h], ed);
+                    ex[0][h] = (float)ed[0]; ex[1][h] = (float)ed[1];
+                }
+            const f2 w = f2_make(c0 < n ? 1.0f : 0.0f, c0 + 1 < n ? 1.0f : 0.0f);
+            const bool masked = 8 * k + 8 > n;
+            const f2 X0 = f2_make(o[0][0], o[0][1]), X1 = f2_make(o[1][0], o[1][1]), X2 = f2_make(o[2][0], o[2][1]);
+            const f2 U = f2_make(o[3][0], o[3][1]), V = f2_make(o[4][0], o[4][1]);
+            const f2 e0 = f2_make(ex[0][0], ex[0][1]), e1 = f2_make(ex[1][0], ex[1][1]);
+            if (cam.model == kPinhole) {
+                if (cam.rational) corner_pair_accumulate<kPinhole, true, kExactE>(c2, R3, T3, X0, X1, X2, U, V, w, masked, a, e0, e1);
+                else corner_pair_accumulate<kPinhole, false, kExactE>(c2, R3, T3, X0, X1, X2, U, V, w, masked, a, e0, e1);
+            } else corner_pair_accumulate<kOmnidir, false, kExactE>(c2, R3, T3, X0, X1, X2, U, V, w, masked, a, e0, e1);
+        }
+        for (int k = 0; k < kBlk; ++k) v[q][k] = f2_lo(a[k]) + f2_hi(a[k]);
+    }
+    for (int k = 0; k < kBlk; ++k) acc[k] = (double)((v[0][k] + v[2][k]) + (v[1][k] + v[3][k]));
+}
+
 extern "C" {
 
 // per-edge blocks (E x 28) at params, plus the full normal-equation solve in tangent coordinates:
@@ -43,7 +96,7 @@ extern "C" {
 int hm_rig_step(int n_cam, int n_frame, int n_edge, const int* edge_cam, const int* edge_pv, const int64_t* edge_off,
                 const float* obj, const float* img, const int* cam_model, const double* K5, const double* d8,
                 const int* nd, const double* xi, const double* params, double lambda, double* blocks, double* S,
-                double* gs, double* step)
+                double* gs, double* step, int policy)
 {
     const int nV = n_cam + n_frame, ns = 6 * (n_cam - 1);
     std::vector<CamParams> cams;
@@ -56,9 +109,14 @@ int hm_rig_step(int n_cam, int n_frame, int n_edge, const int* edge_cam, const i
         }
         rodrigues(om, &vR[9 * v]);
     }
-    for (int e = 0; e < n_edge; ++e)
-        edge_block(cams[edge_cam[e]], &vR[9 * edge_cam[e]], &vt[3 * edge_cam[e]], &vR[9 * edge_pv[e]], &vt[3 * edge_pv[e]],
-                   edge_off[e], edge_off[e + 1], obj, img, blocks + (size_t)kBlk * e);
+    for (int e = 0; e < n_edge; ++e) {
+        const CamParams& cm = cams[edge_cam[e]];
+        const double *Rc = &vR[9 * edge_cam[e]], *tc = &vt[3 * edge_cam[e]], *Rp = &vR[9 * edge_pv[e]], *tp = &vt[3 * edge_pv[e]];
+        double* blk = blocks + (size_t)kBlk * e;
+        if (policy == 1) edge_block_f32<true>(cm, Rc, tc, Rp, tp, edge_off[e], edge_off[e + 1], obj, img, blk);        // MIXED
+        else if (policy == 2) edge_block_f32<false>(cm, Rc, tc, Rp, tp, edge_off[e], edge_off[e + 1], obj, img, blk);  // all float32
+        else edge_block(cm, Rc, tc, Rp, tp, edge_off[e], edge_off[e + 1], obj, img, blk);
+    }
     for (int i = 0; i < ns * ns; ++i) S[i] = 0;
     for (int i = 0; i < ns; ++i) gs[i] = 0;
     std::vector<double> U(21 * (size_t)n_frame), Z(6 * (size_t)n_frame), Y(36 * (size_t)n_edge, 0.0);

@@ -1,6 +1,6 @@
-"""Reduced-system solver in isolation (mccba_debug_solve_dense): every size class of the tile DAG -- single tile, ragged
-last block column, g row in its own tile row (n % 32 == 0), the config #5 size -- against numpy, for all three modes
-(0 single-CTA column Cholesky, 1 panel/update kernels, 2 one-launch tile DAG).  Replaces the Eigen CG of
+"""Reduced-system solvers in isolation (mccba_debug_solve_dense): every size class of the tile DAG -- single tile, ragged
+last block column, g row in its own tile row (n % 32 == 0), the config #5 size -- and the block cyclic reduction of banded
+systems (mode 3) against numpy.  Replaces the Eigen CG of
 src/multicalib.cpp:565-592 on the Schur-reduced system."""
 import numpy as np
 import pytest
@@ -70,9 +70,43 @@ def _banded_spd(n, w, seed):
     return S, rng.standard_normal(n)
 
 
-@pytest.mark.parametrize("n,w", [(1, 0), (5, 4), (6, 5), (12, 11), (12, 5), (37, 11), (64, 17), (200, 23), (378, 11), (378, 29), (400, 5)])
+def _block_banded_spd(n_cam, m, seed):
+    """The structure of a reduced camera system: 6 x 6 blocks, block (A, B) non-zero iff |A - B| <= m."""
+    rng = np.random.default_rng(seed)
+    n = 6 * n_cam
+    M = rng.standard_normal((n, n))
+    S = M @ M.T
+    blk = np.arange(n) // 6
+    S[np.abs(blk[:, None] - blk[None, :]) > m] = 0.0
+    S += (np.abs(S).sum(axis=1).max() + 1.0) * np.eye(n)
+    return S, rng.standard_normal(n)
+
+
+@pytest.mark.parametrize("n_cam,m", [(1, 0), (2, 1), (3, 1), (8, 1), (63, 1), (64, 1), (65, 1), (63, 2), (63, 3), (63, 4), (40, 4),
+                                     (127, 1), (200, 1), (21, 3), (5, 4)])
+def test_block_banded_solve_matches_numpy(solver, n_cam, m):
+    """mode 3: block cyclic reduction (mccba_bcr.cuh) on block-banded camera systems -- every super-block size
+    (B = 6, 12, 18, 24), block counts that are / are not powers of two, ragged last super-block."""
+    S, g = _block_banded_spd(n_cam, m, 900 + 10 * n_cam + m)
+    x, _ = solver.debug_solve_dense(S, g, 3)
+    ref = np.linalg.solve(S, g)
+    assert np.abs(x - ref).max() <= 1e-11 * max(np.abs(ref).max(), 1e-300) * S.shape[0]
+
+
+def test_block_banded_solve_ill_conditioned(solver):
+    """cond ~1e9 (undamped Gauss-Newton systems of camera chains): elimination without pivoting must stay backward stable."""
+    n_cam, m = 63, 1
+    S, g = _block_banded_spd(n_cam, m, 5)
+    n = S.shape[0]
+    d = np.logspace(0, 4.5, n)
+    S = (S * d[:, None]) * d[None, :]                    # congruence: SPD, same sparsity, cond ~ 1e9
+    x, _ = solver.debug_solve_dense(S, g, 3)
+    assert np.linalg.norm(S @ x - g) <= 1e-9 * (np.linalg.norm(S, 2) * np.linalg.norm(x) + np.linalg.norm(g))
+
+
+@pytest.mark.parametrize("n,w", [(1, 0), (5, 4), (6, 5), (12, 11), (12, 5), (37, 11), (64, 17), (200, 23), (378, 11), (378, 23), (400, 5)])
 def test_banded_solve_matches_numpy(solver, n, w):
-    """mode 3: banded LDL^T by one warp (block-banded camera graphs), every supported band width."""
+    """mode 3 on generic banded matrices: half bandwidth w <= 23 maps to a block bandwidth <= 4."""
     S, g = _banded_spd(n, w, 300 + n + w)
     x, _ = solver.debug_solve_dense(S, g, 3)
     ref = np.linalg.solve(S, g)

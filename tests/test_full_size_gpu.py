@@ -12,7 +12,7 @@ pytestmark = pytest.mark.gpu
 @pytest.fixture(scope="module")
 def solver():
     import multi_camera_calibration_b200 as m
-    s = m.Solver(device=0)
+    s = m.Solver(device=0, precision=m.capi.PRECISION_FP64)
     yield s
     s.close()
 
@@ -84,6 +84,28 @@ def test_config5_vs_oracle(solver, oracle_lib):
     assert abs(e["rms"] - eo["rms"]) <= 1e-9 * eo["rms"] and e["n_points"] == 10800000
     el = O.error(lit["params"])
     assert abs(e["rms"] - el["rms"]) <= 1e-6 * el["rms"]          # the north star's RMS gate holds against policy 0 too
+
+
+def test_config5_default_policy_gate(oracle_lib):
+    """The headline workload under the DEFAULT precision policy (MIXED), run the way the bench runs it (LM) and under the
+    reference schedule, both to a fixed 25 iterations: every parameter, the cost and the fp64 RMS against the oracle
+    (fp64_direct policy, see test_config5_vs_oracle) within the north star's 1e-6."""
+    import multi_camera_calibration_b200 as m
+    rig = synth.make_config(5)
+    O = rigs.to_oracle_rig(rig)
+    s = m.Solver(device=0)
+    assert s.get_precision() == m.capi.PRECISION_MIXED
+    s.set_rig(rig)
+    for mode, kw in ((1, dict(lambda0=1e-3, lambda_up=10.0, lambda_down=1.0 / 3.0)), (0, {})):
+        s.set_parameters(rig["params_init"])
+        rep = s.solve(mode=mode, crit_type=1, max_count=25, **kw)
+        ref = O.solve(rig["params_init"], mode=mode, crit_type=1, max_count=25, policy=2, **kw)
+        assert rep["iterations"] == 25 == ref["iters"]
+        assert _prel(s.get_parameters(), ref["params"]) < 1e-6
+        assert abs(rep["cost"] - ref["cost"]) <= 1e-8 * ref["cost"]
+        e, eo = s.reproj_error(), O.error(ref["params"], policy=2)
+        assert abs(e["rms"] - eo["rms"]) <= 1e-8 * eo["rms"]
+    s.close()
 
 
 def test_config5_properties(solver):

@@ -65,7 +65,7 @@ RIGS = {
 @pytest.fixture(scope="module")
 def solver():
     import multi_camera_calibration_b200 as m
-    s = m.Solver(device=0)
+    s = m.Solver(device=0, precision=m.capi.PRECISION_FP64)       # parity at rounding level: the fp64 policy (MIXED: tests/test_precision_gpu.py)
     yield s
     s.close()
 
@@ -217,7 +217,7 @@ def test_every_reduced_solver_matches(case, chol, monkeypatch):
     import multi_camera_calibration_b200 as m
     name, rig, O = case
     monkeypatch.setenv("MCCBA_CHOL", chol)
-    s = m.Solver(device=0)
+    s = m.Solver(device=0, precision=m.capi.PRECISION_FP64)
     try:
         s.set_rig(rig)
         s.set_parameters(rig["params_init"])
@@ -233,7 +233,7 @@ def test_every_reduced_solver_matches(case, chol, monkeypatch):
 def test_no_graph_path_matches(case):
     import multi_camera_calibration_b200 as m
     name, rig, O = case
-    s = m.Solver(device=0, use_graph=False)
+    s = m.Solver(device=0, use_graph=False, precision=m.capi.PRECISION_FP64)
     try:
         s.set_rig(rig)
         s.set_parameters(rig["params_init"])

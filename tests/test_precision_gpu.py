@@ -1,0 +1,112 @@
+"""Precision policies of the residual / Jacobian pass (include/mccba.h: MCCBA_PRECISION_*) on the GPU.
+
+FP64     per-corner projection, Jacobian and sums in double: compared with the oracle everywhere else in tests/.
+MIXED    (default) residual in double, Jacobian and per-corner products in packed float32 (f32x2), per-edge sums promoted to
+         double.  The GATE (north star): final parameters and fp64 RMS within 1e-6 relative of the fp64 oracle on every
+         RIGS case and on BASELINE configs #2 and #4 (#5: tests/test_full_size_gpu.py); observed ~1e-8.
+FAST32   everything per corner in packed float32, like the reference's own float32 projection: RMS to 1e-8, parameters to
+         ~2e-6 (the tilt of boards facing a camera squarely) -- looser than the gate, which is why it is opt-in.
+"""
+import numpy as np
+import pytest
+
+from multi_camera_calibration_b200 import synth
+from tests import rigs
+from tests.test_parity_gpu import RIGS, _param_rel
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def solvers():
+    import multi_camera_calibration_b200 as m
+    ss = {p: m.Solver(device=0, precision=p) for p in (m.capi.PRECISION_FP64, m.capi.PRECISION_MIXED, m.capi.PRECISION_FAST32)}
+    yield ss
+    for s in ss.values():
+        s.close()
+
+
+def _converge(s, rig, mode):
+    s.set_rig(rig)
+    s.set_parameters(rig["params_init"])
+    kw = dict(lambda0=1e-3) if mode == 1 else {}
+    rep = s.solve(mode=mode, crit_type=1, max_count=60 if mode == 0 else 40, **kw)
+    return rep, s.get_parameters(), s.reproj_error()
+
+
+@pytest.mark.parametrize("name", sorted(RIGS))
+@pytest.mark.parametrize("mode", [0, 1])
+def test_gate_on_every_rig(solvers, oracle_lib, name, mode):
+    import multi_camera_calibration_b200 as m
+    rig = rigs.make_rig(**RIGS[name])
+    O = rigs.to_oracle_rig(rig)
+    kw = dict(lambda0=1e-3) if mode == 1 else {}
+    ref = O.solve(rig["params_init"], mode=mode, crit_type=1, max_count=60 if mode == 0 else 40, **kw)
+    eo = O.error(ref["params"])
+    rep64, p64, e64 = _converge(solvers[m.capi.PRECISION_FP64], rig, mode)
+    repm, pm, em = _converge(solvers[m.capi.PRECISION_MIXED], rig, mode)
+    repf, pf, ef = _converge(solvers[m.capi.PRECISION_FAST32], rig, mode)
+    assert _param_rel(p64, ref["params"]) < 1e-7
+    # the gate, against the oracle
+    assert _param_rel(pm, ref["params"]) < 1e-6, _param_rel(pm, ref["params"])
+    assert abs(em["rms"] - eo["rms"]) <= 1e-6 * eo["rms"]
+    # observed margin: two orders of magnitude
+    assert _param_rel(pm, p64) < 2e-7
+    assert abs(em["rms"] - e64["rms"]) <= 1e-9 * e64["rms"]
+    # all-float32: RMS still tight, parameters at the reference's own float32 noise level
+    assert abs(ef["rms"] - e64["rms"]) <= 1e-7 * e64["rms"]
+    assert _param_rel(pf, p64) < 2e-5
+
+
+def test_blocks_of_the_packed_pass(solvers, oracle_lib):
+    """Per-edge blocks of the packed pass against the fp64 pass at the same point: H6 to float32 accuracy, g6 / cost of the
+    MIXED policy limited by the float32 rounding of the PRODUCTS only (the residual itself is exact)."""
+    import multi_camera_calibration_b200 as m
+    rig = rigs.make_rig(**RIGS["mixed4_v3_ragged"])
+    outs = {}
+    for p, s in solvers.items():
+        s.set_rig(rig)
+        s.set_parameters(rig["params_init"])
+        outs[p] = s.eval()
+    a, b, c = outs[m.capi.PRECISION_FP64], outs[m.capi.PRECISION_MIXED], outs[m.capi.PRECISION_FAST32]
+    for o in (b, c):
+        assert np.abs(o["H6"] - a["H6"]).max() <= 5e-6 * np.abs(a["H6"]).max()
+        assert np.abs(o["g6"] - a["g6"]).max() <= 5e-6 * np.abs(a["g6"]).max()
+        assert np.abs(o["edge_cost"] - a["edge_cost"]).max() <= 5e-6 * np.abs(a["edge_cost"]).max()
+        assert abs(o["cost"] - a["cost"]) <= 1e-6 * a["cost"]
+
+
+@pytest.mark.parametrize("cfg,mode,iters", [(2, 0, 30), (4, 1, 25)])
+def test_gate_on_baseline_configs(solvers, oracle_lib, cfg, mode, iters):
+    """BASELINE configs #2 (8-camera pinhole, 1k frames) and #4 (16-camera mixed, 10k frames), MIXED against the oracle."""
+    import multi_camera_calibration_b200 as m
+    rig = synth.make_config(cfg)
+    O = rigs.to_oracle_rig(rig)
+    kw = dict(lambda0=1e-3) if mode == 1 else {}
+    ref = O.solve(rig["params_init"], mode=mode, crit_type=1, max_count=iters, policy=2, **kw)
+    s = solvers[m.capi.PRECISION_MIXED]
+    s.set_rig(rig)
+    s.set_parameters(rig["params_init"])
+    rep = s.solve(mode=mode, crit_type=1, max_count=iters, **kw)
+    assert rep["iterations"] == iters
+    assert _param_rel(s.get_parameters(), ref["params"]) < 1e-6
+    e, eo = s.reproj_error(), O.error(ref["params"], policy=2)
+    assert abs(e["rms"] - eo["rms"]) <= 1e-6 * eo["rms"]
+
+
+def test_switching_policy_discards_the_problem(solvers):
+    import multi_camera_calibration_b200 as m
+    rig = rigs.make_rig(**RIGS["pinhole3"])
+    s = m.Solver(device=0)
+    assert s.get_precision() == m.capi.PRECISION_MIXED          # the default
+    s.set_rig(rig)
+    s.set_parameters(rig["params_init"])
+    s.set_precision(m.capi.PRECISION_FP64)
+    with pytest.raises(m.MccbaError):
+        s.solve(mode=0, crit_type=1, max_count=2)               # the problem has to be set again
+    s.set_rig(rig)
+    s.set_parameters(rig["params_init"])
+    assert s.solve(mode=0, crit_type=1, max_count=2)["iterations"] == 2
+    with pytest.raises(m.MccbaError):
+        s.set_precision(7)
+    s.close()
