@@ -61,7 +61,7 @@ public:
                            float patternHeight, int verbose = 0, int showExtration = 0, int nMiniMatches = 20,
                            int flags = 0, TermCriteria criteria = TermCriteria(TermCriteria::COUNT, 20, 1e-7),
                            SolverOptions solver = SolverOptions());
-    ~MultiCameraCalibration();
+    virtual ~MultiCameraCalibration();
     MultiCameraCalibration(const MultiCameraCalibration&) = delete;
     MultiCameraCalibration& operator=(const MultiCameraCalibration&) = delete;
 
@@ -70,7 +70,7 @@ public:
     double optimizeExtrinsics();  // src/multicalib.cpp:462-514, on the GPU
     double run();                 // src/multicalib.cpp:127-133
     void reset();                 // src/multicalib.cpp:134-152
-    void writeParameters(const std::string& filename);   // src/multicalib.cpp:1092-1127, OpenCV XML
+    virtual void writeParameters(const std::string& filename);   // src/multicalib.cpp:1092-1127, OpenCV XML
 
     // outlier loop of the shipped workflow (samples/multi_cameras_calibration.cpp:71-83, src/mymulticalib.cpp:406-423)
     std::set<int> removeOutlier(float threshold = 0.5f);   // returns the indices (load order) of the dropped edges
@@ -84,7 +84,7 @@ public:
     std::vector<double> parameters() const { return _params; }   // 6*(nV-1), [rvec|tvec] per vertex (buildParas layout)
     std::vector<double> initialParameters() const;               // buildParas() of the current vertex poses, widened
 
-private:
+protected:
     struct Impl;
     Impl* _impl;
     int _camType, _nCamera, _nMiniMatches, _flags, _verbose, _showExtraction;
@@ -99,9 +99,42 @@ private:
     std::vector<double> _params;
     std::set<int> _outliers;
 
+    void buildEdges();                                    // src/mymulticalib.cpp:314-403 on the loaded image records
     int getPhotoVertex(int timestamp);                    // src/multicalib.cpp:323-346
     std::vector<float> buildParas() const;                // src/multicalib.cpp:422-440
     void paras2vertex(const std::vector<float>& p);       // src/multicalib.cpp:442-459
+};
+
+// The subclass the reference's sample actually runs (include/opencv2/ccalib/mymulticalib.hpp:95-100,
+// samples/multi_cameras_calibration.cpp:53-83): corners come from <dataFolder>/<serial>/<timestamp>.yaml ("corners",
+// "objects"; files in cv::glob order), intrinsics from <cameraConfigFolder>/<serial>.xml ("Intrinsics", "Distortion"), the
+// initial pattern->camera transform of every image from solvePnP (src/mymulticalib.cpp:118-131, 182-233, 268-301).
+// Only images of the front pattern (frontPatternSize corners) are kept, as in storeReaded (:236-241).
+struct Size {
+    int width = 0, height = 0;
+    Size(int w = 0, int h = 0) : width(w), height(h) {}
+};
+
+class MyMultiCameraCalibration : public MultiCameraCalibration {
+public:
+    MyMultiCameraCalibration(const std::vector<std::string>& cameraSerials, int cameraType, int nCameras,
+                             const std::string& dataFolder, const std::string& cameraConfigFolder,
+                             const std::string doubleSideConfig, Size frontPatternSize, Size backPatternSize, float patternWidth,
+                             float patternHeight, int verbose = 0, int showExtration = 0, int nMiniMatches = 20, int flags = 0,
+                             TermCriteria criteria = TermCriteria(TermCriteria::COUNT + TermCriteria::EPS, 200, 1e-7),
+                             SolverOptions solver = SolverOptions());
+    void loadImages(const std::set<std::string>& outliers = std::set<std::string>());   // src/mymulticalib.cpp:348-405
+    std::set<std::string> removeOutlier();               // files of edges with mean error > 0.5 px (:406-423)
+    void writeParameters(const std::string& filename) override;   // base XML + writeParameters2config (:425-460)
+    void writeParameters2config();
+    double run();                                        // load / initialise / optimise / drop outliers / again (sample :71-80)
+
+private:
+    std::vector<std::string> _serials;
+    std::string _dataFolder, _configFolder, _doubleSideConfig;
+    Size _front, _back;
+    std::set<std::string> _fileOutliers;
+    void readCameraIntrinsics();
 };
 
 }  // namespace mccba
@@ -127,6 +160,17 @@ int mccbah_get_indexing(mccbah h, int* edge_cam, int* edge_pv, int* edge_photo_i
 int mccbah_get_parameters(mccbah h, double* params /* 6*(nV-1) */);
 int mccbah_get_initial_parameters(mccbah h, double* params /* 6*(nV-1), buildParas() of the current poses */);
 int mccbah_get_stats(mccbah h, double* mean_error, double* rms, int* iterations, double* device_ms);
+/* MyMultiCameraCalibration: serials separated by ','; outliers / returned file lists separated by '\n' */
+int mccbah_create_my(const char* serials, int cameraType, int nCameras, const char* dataFolder, const char* cameraConfigFolder,
+                     const char* doubleSideConfig, int frontW, int frontH, int backW, int backH, float patternWidth,
+                     float patternHeight, int verbose, int critType, int critMaxCount, double critEps, int mode, int device,
+                     mccbah* out);
+int mccbah_load_images_my(mccbah h, const char* outliers);
+int mccbah_remove_outlier_my(mccbah h, char* out, int cap, int* n_removed);
+int mccbah_run_my(mccbah h, double* error);
+/* cv::solvePnP (iterative) restated; obj n x 3, img n x 2 (doubles) */
+int mccbah_solve_pnp(int n, const double* obj, const double* img, const double* K5, const double* dist8, int ndist, double* rvec,
+                     double* tvec);
 }
 
 #endif  // MCCBA_HOST_HPP_

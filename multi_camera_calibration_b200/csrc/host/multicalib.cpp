@@ -3,6 +3,7 @@
 // reference, spanning-tree initialisation, parameter (de)serialisation and the OpenCV-format XML output.  All
 // optimisation arithmetic happens in libmccba.so on the GPU.
 #include "mccba_host.hpp"
+#include "host_impl.hpp"
 
 #include <algorithm>
 #include <cmath>
@@ -18,22 +19,6 @@ namespace mccba {
 
 namespace {
 
-struct CameraIntrinsics {
-    int model = 0, ndist = 0;
-    double K5[5] = {0, 0, 0, 0, 0}, dist8[8] = {0, 0, 0, 0, 0, 0, 0, 0}, xi = 0;
-};
-struct ImageRecord {   // one (camera, timestamp) image: what loadOneSerial keeps per file (src/mymulticalib.cpp:268-301)
-    int camera = 0, timestamp = 0, n_points = 0;
-    Mat44f transform{};
-    size_t first = 0;  // offset of its corners in the concatenated point arrays
-};
-
-Mat44f eye4()
-{
-    Mat44f m{};
-    m[0] = m[5] = m[10] = m[15] = 1.f;
-    return m;
-}
 // products / inverses of rigid 4x4 transforms, evaluated in double and stored CV_32F like the reference's poses
 Mat44f mul44(const Mat44f& a, const Mat44f& b)
 {
@@ -71,30 +56,7 @@ void log_so3(const Mat44f& m, double* om)
     const double k = th / (2 * s);
     om[0] = rx * k; om[1] = ry * k; om[2] = rz * k;
 }
-// cv::Rodrigues vector -> matrix (paras2vertex src/multicalib.cpp:449)
-void exp_so3(const double* om, double* R)
-{
-    const double x = om[0], y = om[1], z = om[2], th2 = x * x + y * y + z * z, th = std::sqrt(th2);
-    double a, b;
-    if (th < 1e-8) { a = 1 - th2 / 6; b = 0.5 - th2 / 24; }
-    else { a = std::sin(th) / th; b = (1 - std::cos(th)) / th2; }
-    R[0] = 1 - b * (y * y + z * z); R[1] = b * x * y - a * z; R[2] = b * x * z + a * y;
-    R[3] = b * x * y + a * z; R[4] = 1 - b * (x * x + z * z); R[5] = b * y * z - a * x;
-    R[6] = b * x * z - a * y; R[7] = b * y * z + a * x; R[8] = 1 - b * (x * x + y * y);
-}
-
 }  // namespace
-
-struct MultiCameraCalibration::Impl {
-    mccba_handle h = nullptr;
-    std::vector<CameraIntrinsics> cams;
-    std::vector<ImageRecord> images;                       // load order: cameras outer loop, files in glob order
-    std::vector<std::vector<int>> imagesOfCamera;          // per camera: indices into images (photoIndex order)
-    std::vector<float> obj, img;                           // concatenated CV_32F points of all images
-    std::vector<int> edgeImage;                            // edge -> image record
-    std::unordered_map<int, int> tsToVertex;               // timestamp -> photo vertex (first-seen order)
-    bool loaded = false, initialised = false;
-};
 
 MultiCameraCalibration::MultiCameraCalibration(int cameraType, int nCameras, const std::string& fileName,
                                                float patternWidth, float patternHeight, int verbose, int showExtration,
@@ -196,6 +158,14 @@ void MultiCameraCalibration::loadImages()
         f.read(reinterpret_cast<char*>(I.img.data() + 2 * im.first), sizeof(float) * 2 * (size_t)im.n_points);
     }
     if (!f) throw std::runtime_error("observation file truncated: " + _filename);
+    buildEdges();
+}
+
+// vertices and edges from the loaded image records: the indexing contract of the reference (bit-exact)
+void MultiCameraCalibration::buildEdges()
+{
+    Impl& I = *_impl;
+    const int nC = _nCamera, nImg = (int)I.images.size();
     // photoIndex = index into the camera's own image list (multicalib.hpp:90)
     I.imagesOfCamera.assign(nC, {});
     for (int i = 0; i < nImg; ++i) I.imagesOfCamera[I.images[i].camera].push_back(i);
@@ -467,10 +437,6 @@ void MultiCameraCalibration::writeParameters(const std::string& filename)
 }  // namespace mccba
 
 // ---- plain-C access ------------------------------------------------------------------------------------------
-struct mccbah_s {
-    mccba::MultiCameraCalibration* obj = nullptr;
-    std::string err;
-};
 
 namespace {
 template <typename F>

@@ -991,7 +991,7 @@ int mccba_set_observations(mccba_handle h, int n_frame, int n_edge, const int* e
         float2* obs2 = nullptr;
         if ((rc = dev_alloc(h, &obs2, (size_t)std::max<int64_t>(tot, 1)))) return rc;
         P.obs2 = obs2;
-        h->f32_smem = (int)((sizeof(CamF2) + sizeof(CamParams)) * (size_t)nC + 32 * sizeof(PackedPose));
+        h->f32_smem = (int)f32_smem_bytes(nC);
         int per_sm_f = 1;
         if (P.prec == MCCBA_PRECISION_MIXED) {
             if (h->f32_smem > 48 * 1024)

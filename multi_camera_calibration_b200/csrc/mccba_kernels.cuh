@@ -438,13 +438,12 @@ __global__ void __launch_bounds__(kK1Threads, 2) resid_jac_accum_kernel(Problem 
 // K1, packed single precision (precision policy 1).  Unit of work = one quarter tile = 8 edges = one warp:
 // lane = 4 * (edge within the quarter) + q, and in step k the lane evaluates corners 8k + 2q and 8k + 2q + 1 of its
 // edge as ONE f32x2 pair (mccba_f32x2.cuh).  The observations are stored in exactly that order (Problem::obs2), so a
-// step is five coalesced 256-byte loads per warp, prefetched kPrefetch steps ahead in registers -- no shared memory, no
-// barrier, no atomics; a warp never waits for another.  At the end of the edge the two halves and the four lanes are
+// step is one contiguous 1280-byte block that the TMA engine drops into the warp's private ring several steps ahead --
+// no block-wide barrier, no atomics; a warp never waits for another.  At the end of the edge the two halves and the four lanes are
 // summed in float (transposed butterfly, 21 shuffles), promoted to double once, and stored tile-major like the fp64
 // kernel's output (what frame_schur_kernel reads).  kErr: residual-only variant for computeProjectError in double.
 // --------------------------------------------------------------------------------------------------------
 constexpr int kF32Threads = 128;
-constexpr int kPrefetch = 2;
 
 __device__ __forceinline__ float2 ldg_f2(const float2* p)
 {
@@ -454,33 +453,43 @@ __device__ __forceinline__ float2 ldg_f2(const float2* p)
 }
 
 
-// The stream of observation steps a warp consumes, across tile boundaries: the loads of step k + kPrefetch are issued
-// while step k is evaluated, and when the current tile runs out the next tile of this CTA (tile + gridDim.x) takes over
-// without a bubble -- its offset and step count were fetched one tile earlier.  (Without this every quarter tile began with
-// an exposed DRAM round trip: a third of all stall samples in the first profile, profiles/r2_k1_f32_v1.txt.)
+// The stream of observation steps a warp consumes, across tile boundaries.  A step is one contiguous 1280-byte block
+// (5 planes x 32 lanes x 2 floats), so ONE lane programs the TMA engine (cp.async.bulk + mbarrier) to drop it into the
+// warp's private ring in shared memory kObsStages steps ahead of its use; when the current tile runs out the next tile
+// of this CTA (tile + gridDim.x) takes over without a bubble -- its offset and step count were fetched one tile earlier.
+// (First version: register double buffer filled by LDG.  The compiler rotated the buffer at the END of a step, the
+// prefetch distance collapsed to < 1 step and a third of all stall samples sat on that move waiting for DRAM --
+// profiles/r2_k1_f32_v1.txt.)
+constexpr int kObsStages = 6;
+constexpr int kObsStepBytes = 5 * 32 * 8;
 struct ObsStream {
-    const float2* base;     // current tile: first float2 of this lane's column
+    const float2* base;     // current tile: first float2 of this warp's block
     int k, kp, tile;        // next step to load, steps of the current tile, current tile
     int kp_next;            // prefetched for tile + stride
     int64_t off_next;
+    int issued;             // steps issued so far (stage = issued % kObsStages)
 };
-__device__ __forceinline__ void obs_stream_open(ObsStream& S, const Problem& P, int tile, int stride, int n_tiles, int wq, int lane)
+__device__ __forceinline__ void obs_stream_open(ObsStream& S, const Problem& P, int tile, int stride, int n_tiles, int wq)
 {
-    S.tile = tile; S.k = 0;
+    S.tile = tile; S.k = 0; S.issued = 0;
     S.kp = tile < n_tiles ? P.tile_kp[tile] : 0;
-    S.base = P.obs2 + (tile < n_tiles ? P.tile_off[tile] : 0) + (size_t)wq * S.kp * 5 * 32 + lane;
+    S.base = P.obs2 + (tile < n_tiles ? P.tile_off[tile] : 0) + (size_t)wq * S.kp * 5 * 32;
     const int nt = tile + stride;
     S.kp_next = nt < n_tiles ? P.tile_kp[nt] : 0;
     S.off_next = nt < n_tiles ? P.tile_off[nt] : 0;
 }
-__device__ __forceinline__ void obs_stream_load(ObsStream& S, const Problem& P, int stride, int n_tiles, int wq, int lane, float2 (&dst)[5])
+// called by ONE lane of the warp: issue the copy of the next step of the stream into its ring stage
+__device__ __forceinline__ void obs_stream_issue(ObsStream& S, const Problem& P, int stride, int n_tiles, int wq, float2* ring,
+                                                 unsigned long long* bars)
 {
     if (S.tile >= n_tiles) return;
-#pragma unroll
-    for (int pl = 0; pl < 5; ++pl) dst[pl] = ldg_f2(S.base + ((size_t)S.k * 5 + pl) * 32);
+    const int stg = S.issued % kObsStages;
+    mbar_expect_tx(&bars[stg], kObsStepBytes);
+    tma_load_1d(ring + (size_t)stg * 5 * 32, S.base + (size_t)S.k * 5 * 32, kObsStepBytes, &bars[stg]);
+    ++S.issued;
     if (++S.k == S.kp) {    // on to the next tile of this CTA; fetch the layout of the one after it
         S.tile += stride; S.k = 0; S.kp = S.kp_next;
-        S.base = P.obs2 + S.off_next + (size_t)wq * S.kp * 5 * 32 + lane;
+        S.base = P.obs2 + S.off_next + (size_t)wq * S.kp * 5 * 32;
         const int nt = S.tile + stride;
         S.kp_next = nt < n_tiles ? P.tile_kp[nt] : 0;
         S.off_next = nt < n_tiles ? P.tile_off[nt] : 0;
@@ -495,6 +504,10 @@ struct PackedPose {
     double pad;
     f2 Rf[9], Tf[3];
 };
+__host__ __device__ inline size_t f32_smem_bytes(int n_cam)
+{
+    return (size_t)4 * kObsStages * kObsStepBytes + 4 * kObsStages * 8 + 32 * sizeof(PackedPose) + (sizeof(CamF2) + sizeof(CamParams)) * (size_t)n_cam;
+}
 
 template <int kModel, bool kRational, bool kExactE>
 __device__ __forceinline__ void packed_step(const float2 (&cur)[5], int k, int n, int q, int k_full, const CamF2& cam,
@@ -523,34 +536,33 @@ __device__ __forceinline__ void packed_step(const float2 (&cur)[5], int k, int n
 }
 
 template <int kModel, bool kRational, bool kExactE>
-__device__ __forceinline__ void packed_edge_loop(float2 (&buf)[kPrefetch][5], ObsStream& S, const Problem& P, int stride, int n_tiles,
-                                                 int wq, int lane, int kp, int n, int q, int k_full, const CamF2& cam,
-                                                 const CamParams& camd, const PackedPose& pose, f2* acc, double& cost)
+__device__ __forceinline__ void packed_edge_loop(ObsStream& S, int& consumed, float2* ring, unsigned long long* bars, const Problem& P,
+                                                 int stride, int n_tiles, int wq, int lane, int kp, int n, int q, int k_full,
+                                                 const CamF2& cam, const CamParams& camd, const PackedPose& pose, f2* acc, double& cost)
 {
-    for (int k0 = 0; k0 < kp; k0 += kPrefetch) {
+    for (int k = 0; k < kp; ++k) {
+        const int stg = consumed % kObsStages;
+        mbar_wait(&bars[stg], (unsigned)((consumed / kObsStages) & 1));
+        float2 cur[5];
 #pragma unroll
-        for (int d = 0; d < kPrefetch; ++d) {
-            const int k = k0 + d;
-            if (k < kp) {
-                float2 cur[5];
-#pragma unroll
-                for (int pl = 0; pl < 5; ++pl) cur[pl] = buf[d][pl];
-                obs_stream_load(S, P, stride, n_tiles, wq, lane, buf[d]);      // step k + kPrefetch of the stream
-                packed_step<kModel, kRational, kExactE>(cur, k, n, q, k_full, cam, camd, pose, acc, cost);
-            }
-        }
+        for (int pl = 0; pl < 5; ++pl) cur[pl] = ring[((size_t)stg * 5 + pl) * 32 + lane];
+        ++consumed;
+        __syncwarp();                                   // every lane has taken its pairs out of the stage ...
+        if (lane == 0) obs_stream_issue(S, P, stride, n_tiles, wq, ring, bars);   // ... which is refilled kObsStages steps ahead
+        packed_step<kModel, kRational, kExactE>(cur, k, n, q, k_full, cam, camd, pose, acc, cost);
     }
 }
 
-// forced: as resid_jac_accum_kernel.  Shared memory: n_cam CamF2 | n_cam CamParams | 32 PackedPose.
+// forced: as resid_jac_accum_kernel.  Shared memory: f32_smem_bytes(n_cam).
 template <bool kExactE>
 __global__ void __launch_bounds__(kF32Threads, 3) resid_jac_accum_f32_kernel(Problem P, int forced)
 {
-    static_assert(kPrefetch == 2, "the ring rotation at the end of a tile is written for two slots");
-    extern __shared__ __align__(16) unsigned char f32_smem[];
-    CamF2* s_cam = reinterpret_cast<CamF2*>(f32_smem);
+    extern __shared__ __align__(128) unsigned char f32_smem[];
+    float2* s_ring = reinterpret_cast<float2*>(f32_smem);                                   // [4 warps][kObsStages][5][32]
+    unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(s_ring + 4 * kObsStages * 5 * 32);   // [4][kObsStages]
+    PackedPose* s_pose = reinterpret_cast<PackedPose*>(s_bar + 4 * kObsStages);            // [32]
+    CamF2* s_cam = reinterpret_cast<CamF2*>(s_pose + 32);
     CamParams* s_camd = reinterpret_cast<CamParams*>(s_cam + P.n_cam);
-    PackedPose* s_pose = reinterpret_cast<PackedPose*>(s_camd + P.n_cam);
     const DevState* st = P.st;
     int which;
     if (forced) which = st->cur;
@@ -564,17 +576,25 @@ __global__ void __launch_bounds__(kF32Threads, 3) resid_jac_accum_f32_kernel(Pro
         s_camd[c] = cp;
         s_cam[c] = make_cam_f2(cp);
     }
-    __syncthreads();
     const int lane = threadIdx.x & 31, q = lane & 3, el = lane >> 2, wq = threadIdx.x >> 5;
+    float2* ring = s_ring + (size_t)wq * kObsStages * 5 * 32;
+    unsigned long long* bars = s_bar + wq * kObsStages;
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < kObsStages; ++i) mbar_init(&bars[i], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
     // one CTA = 4 warps = one tile per pass; the loop runs on the tile index, which is uniform over the CTA, so the warp
     // collectives below sit in provably convergent control flow (plain SHFL / REDUX, no WARPSYNC wrappers)
     const int n_tiles = P.n_edge_int >> 5, stride = gridDim.x;
     if ((int)blockIdx.x >= n_tiles) return;
-    ObsStream S;
-    obs_stream_open(S, P, blockIdx.x, stride, n_tiles, wq, lane);
-    float2 buf[kPrefetch][5];
-#pragma unroll
-    for (int d = 0; d < kPrefetch; ++d) obs_stream_load(S, P, stride, n_tiles, wq, lane, buf[d]);
+    ObsStream S;        // producer state: meaningful in lane 0 only
+    obs_stream_open(S, P, blockIdx.x, stride, n_tiles, wq);
+    if (lane == 0) {
+        for (int d = 0; d < kObsStages; ++d) obs_stream_issue(S, P, stride, n_tiles, wq, ring, bars);
+    }
+    int consumed = 0;
     // per-edge record of the first tile: the 4 lanes of an edge share the load (lane q takes doubles q, q + 4, q + 8)
     EdgeMeta em = P.emeta[(blockIdx.x << 5) + (wq << 3) + el];
     double rq[3];
@@ -615,14 +635,10 @@ __global__ void __launch_bounds__(kF32Threads, 3) resid_jac_accum_f32_kernel(Pro
         const CamF2& cam = s_cam[cam_idx];      // the 32 edges of a tile are one (group, view) run: one camera per warp
         const CamParams& camd = s_camd[cam_idx];
         if (cam.model == kPinhole) {
-            if (cam.rational) packed_edge_loop<kPinhole, true, kExactE>(buf, S, P, stride, n_tiles, wq, lane, kp, n, q, k_full, cam, camd, pose, acc, cost);
-            else packed_edge_loop<kPinhole, false, kExactE>(buf, S, P, stride, n_tiles, wq, lane, kp, n, q, k_full, cam, camd, pose, acc, cost);
+            if (cam.rational) packed_edge_loop<kPinhole, true, kExactE>(S, consumed, ring, bars, P, stride, n_tiles, wq, lane, kp, n, q, k_full, cam, camd, pose, acc, cost);
+            else packed_edge_loop<kPinhole, false, kExactE>(S, consumed, ring, bars, P, stride, n_tiles, wq, lane, kp, n, q, k_full, cam, camd, pose, acc, cost);
         } else {
-            packed_edge_loop<kOmnidir, false, kExactE>(buf, S, P, stride, n_tiles, wq, lane, kp, n, q, k_full, cam, camd, pose, acc, cost);
-        }
-        if (kp & 1) {   // the ring is one slot out of phase for the next tile: rotate it (10 register moves)
-#pragma unroll
-            for (int pl = 0; pl < 5; ++pl) { const float2 t = buf[0][pl]; buf[0][pl] = buf[1][pl]; buf[1][pl] = t; }
+            packed_edge_loop<kOmnidir, false, kExactE>(S, consumed, ring, bars, P, stride, n_tiles, wq, lane, kp, n, q, k_full, cam, camd, pose, acc, cost);
         }
         // halves, then the 4 lanes of the edge: 28 -> 14 -> 7 values per lane
         float v[kBlk];

@@ -107,3 +107,47 @@ class MultiCameraCalibration:
         me, rms, it, ms = C.c_double(), C.c_double(), C.c_int(), C.c_double()
         self._check(lib().mccbah_get_stats(self._h, C.byref(me), C.byref(rms), C.byref(it), C.byref(ms)))
         return dict(mean_reproj_error=me.value, rms=rms.value, iterations=it.value, device_ms=ms.value)
+
+
+class MyMultiCameraCalibration(MultiCameraCalibration):
+    """The subclass the reference's sample runs (include/opencv2/ccalib/mymulticalib.hpp:95-100): corner files
+    <dataFolder>/<serial>/<timestamp>.yaml, intrinsics <cameraConfigFolder>/<serial>.xml, solvePnP initial poses."""
+
+    def __init__(self, cameraSerials, cameraType, nCameras, dataFolder, cameraConfigFolder, doubleSideConfig="",
+                 frontPatternSize=(9, 6), backPatternSize=(0, 0), patternWidth=360.0, patternHeight=200.0, verbose=0,
+                 criteria=(3, 200, 1e-7), mode=capi.MODE_REFERENCE_GN, device=0):
+        self._h = C.c_void_p()
+        rc = lib().mccbah_create_my(",".join(cameraSerials).encode(), int(cameraType), int(nCameras), str(dataFolder).encode(),
+                                    str(cameraConfigFolder).encode(), str(doubleSideConfig).encode(), int(frontPatternSize[0]),
+                                    int(frontPatternSize[1]), int(backPatternSize[0]), int(backPatternSize[1]),
+                                    C.c_float(patternWidth), C.c_float(patternHeight), int(verbose), int(criteria[0]),
+                                    int(criteria[1]), C.c_double(criteria[2]), int(mode), int(device), C.byref(self._h))
+        self._check(rc)
+
+    def loadImages(self, outliers=()):
+        self._check(lib().mccbah_load_images_my(self._h, "\n".join(outliers).encode()))
+
+    def removeOutlier(self):
+        """Drops the edges whose mean reprojection error exceeds 0.5 px; returns the set of their corner files."""
+        buf = C.create_string_buffer(1 << 22)
+        n = C.c_int()
+        self._check(lib().mccbah_remove_outlier_my(self._h, buf, len(buf), C.byref(n)))
+        return set(s for s in buf.value.decode().split("\n") if s)
+
+    def run(self):
+        e = C.c_double()
+        self._check(lib().mccbah_run_my(self._h, C.byref(e)))
+        return e.value
+
+
+def solve_pnp(obj, img, K5, dist8, ndist):
+    """cv::solvePnP (SOLVEPNP_ITERATIVE) as restated in csrc/host/pnp.cpp.  Returns (rvec, tvec)."""
+    obj = np.ascontiguousarray(obj, dtype=np.float64).reshape(-1, 3)
+    img = np.ascontiguousarray(img, dtype=np.float64).reshape(-1, 2)
+    K5 = np.ascontiguousarray(K5, dtype=np.float64); d8 = np.zeros(8); d8[:len(dist8)] = dist8
+    r = np.zeros(3); t = np.zeros(3)
+    dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    rc = lib().mccbah_solve_pnp(int(obj.shape[0]), dp(obj), dp(img), dp(K5), dp(d8), int(ndist), dp(r), dp(t))
+    if rc:
+        raise RuntimeError("solve_pnp failed (%d)" % rc)
+    return r, t
