@@ -64,9 +64,11 @@ extern "C" {
 /* precision policy of the residual / Jacobian pass (mccba_set_precision).  Everything summed over many observations
  * (per-edge blocks onwards: Schur complement, reduced solve, update, cost test, the reported RMS) is fp64 in both. */
 #define MCCBA_PRECISION_FP64 0  /* per-corner projection, Jacobian and accumulation in double */
-#define MCCBA_PRECISION_MIXED 1 /* default: residual (projection) in double, Jacobian and the per-corner products in packed
-                                   float32 (two corners per lane), per-edge sums promoted to double.  Final parameters
-                                   agree with FP64 to ~1e-8 relative (tests/test_precision_gpu.py, tests/test_math_host.py) */
+#define MCCBA_PRECISION_MIXED 1 /* default: residual (projection) and cost in double; Jacobian, J^T J and J^T e products in
+                                   packed float32 (two corners per lane), per-edge sums promoted to double.  Final parameters
+                                   agree with FP64 to ~1e-8 relative; the worst of the 600 378 parameters of config #5 -- the
+                                   tilt of a board that faces a camera squarely -- to 1e-6 (tests/test_precision_gpu.py,
+                                   tests/test_full_size_gpu.py) */
 #define MCCBA_PRECISION_FAST32 2 /* everything per corner in packed float32, like the reference, which evaluates the
                                    projection through float32 (src/multicalib.cpp:742-749, 789-792): RMS agrees to 1e-9,
                                    but the tilt of boards that face a camera squarely moves by ~2e-6 -- outside the 1e-6

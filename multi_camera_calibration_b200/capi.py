@@ -8,7 +8,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmccba.so")
+LIB_PATH = os.environ.get("MCCBA_LIB") or os.path.join(_HERE, "libmccba.so")   # MCCBA_LIB: development override (kernel variants)
 
 OK, ERR_ARG, ERR_CUDA, ERR_STATE, ERR_NUMERIC, ERR_NCCL = 0, 1, 2, 3, 4, 5
 PINHOLE, OMNIDIRECTIONAL = 0, 1

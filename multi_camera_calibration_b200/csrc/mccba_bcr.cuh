@@ -28,7 +28,9 @@ __host__ __device__ inline size_t bcr_smem_bytes(int n, int B)
 }
 template <int B>
 struct BcrCfg {
-    static constexpr int kThreads = B <= 12 ? 512 : 256;   // registers: the elimination keeps ceil((3B+1)/32) columns of B rows per lane
+    // one warp per block of the widest level where the registers allow it (the elimination keeps ceil((3B+1)/32) columns of
+    // B rows per lane): B = 6 -> 32 warps, 63 blocks at config #5 are eliminated / updated in one round per level
+    static constexpr int kThreads = B <= 6 ? 1024 : (B <= 12 ? 512 : 256);
 };
 
 __device__ __forceinline__ double bcr_rcp(double d)
@@ -249,15 +251,17 @@ __device__ inline int bcr_solve_cta(double* Dg, double* Lo, double* Tmp, double*
 // (what reduce_records writes and the exchange moves), NW = B + 6;  packed == 0: A = [S (n x n) | g] dense (test hook).
 // Rows beyond n pad the last super-block with the identity.
 template <int B>
-__device__ inline void bcr_stage(const double* __restrict__ A, int n, int packed, double* Dg, double* Lo, double* rhs, int Nb)
+__device__ inline void bcr_stage(const double* __restrict__ A, int n, int packed, double* Dg, double* Lo, double* rhs, int Nb,
+                                 int skip = 0 /* leading threads of the CTA that do not take part */)
 {
+    const int tid = (int)threadIdx.x - skip, nthr = (int)blockDim.x - skip;
     constexpr int NW = B + 6, w = NW - 1;
     auto at = [&](int r, int c) -> double {      // r >= c, both < n
         if (packed) return (r - c <= w) ? A[(size_t)r * NW + (c - r + w)] : 0.0;
         return A[(size_t)r * n + c];
     };
     const int total = Nb * B * B;
-    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+    for (int idx = tid; idx < total; idx += nthr) {
         const int I = idx / (B * B), pq = idx - I * B * B, p = pq / B, q = pq - p * B;
         const int r = I * B + p, c = I * B + q;
         double v;
@@ -269,7 +273,7 @@ __device__ inline void bcr_stage(const double* __restrict__ A, int n, int packed
         Lo[idx] = l;
     }
     const size_t goff = packed ? (size_t)n * NW : (size_t)n * n;
-    for (int idx = threadIdx.x; idx < Nb * B; idx += blockDim.x) rhs[idx] = idx < n ? A[goff + idx] : 0.0;
+    for (int idx = tid; idx < Nb * B; idx += nthr) rhs[idx] = idx < n ? A[goff + idx] : 0.0;
 }
 
 }  // namespace mccba

@@ -92,7 +92,8 @@ struct Problem {
     double* vR[2];       // n_vertex x 9 rotation matrices
     double* blocks[2];   // kBlk x n_edge_int (SoA)
     double* frameL;      // 27 x n_slots (21 packed factor + 6 z)
-    double* edgeY;       // 36 x n_edge_int
+    double* edgeY;       // 36 x n_edge_int: Y = L^-1 W per edge, tile-major; stored as FLOAT when prec != 0 (Y only shapes the step of
+                         // the pattern poses, never the fixed point, and it is the largest record the two per-frame kernels exchange)
     double* records;     // warp records
     double* warp_scal;   // 2 x n_warps: [cost | bad] of every Schur warp, contiguous so that the scalar reduction is coalesced
     double* ar;          // allreduce buffer: S (ns x ns) | g (ns) | cost, step2, param2, bad
@@ -460,7 +461,22 @@ __device__ __forceinline__ float2 ldg_f2(const float2* p)
 // (First version: register double buffer filled by LDG.  The compiler rotated the buffer at the END of a step, the
 // prefetch distance collapsed to < 1 step and a third of all stall samples sat on that move waiting for DRAM --
 // profiles/r2_k1_f32_v1.txt.)
-constexpr int kObsStages = 6;
+#ifndef MCCBA_OBS_STAGES
+#define MCCBA_OBS_STAGES 8
+#endif
+#ifndef MCCBA_F32_MINBLOCKS
+#define MCCBA_F32_MINBLOCKS 3
+#endif
+#ifndef MCCBA_F32_PAIRSTEPS
+#define MCCBA_F32_PAIRSTEPS 0
+#endif
+#ifndef MCCBA_F32_RELOAD
+#define MCCBA_F32_RELOAD 1
+#endif
+#ifndef MCCBA_F32_POSE_REGS
+#define MCCBA_F32_POSE_REGS 0
+#endif
+constexpr int kObsStages = MCCBA_OBS_STAGES;   // power of two: stage and phase are a mask and a shift
 constexpr int kObsStepBytes = 5 * 32 * 8;
 struct ObsStream {
     const float2* base;     // current tile: first float2 of this warp's block
@@ -483,7 +499,7 @@ __device__ __forceinline__ void obs_stream_issue(ObsStream& S, const Problem& P,
                                                  unsigned long long* bars)
 {
     if (S.tile >= n_tiles) return;
-    const int stg = S.issued % kObsStages;
+    const int stg = S.issued & (kObsStages - 1);
     mbar_expect_tx(&bars[stg], kObsStepBytes);
     tma_load_1d(ring + (size_t)stg * 5 * 32, S.base + (size_t)S.k * 5 * 32, kObsStepBytes, &bars[stg]);
     ++S.issued;
@@ -509,17 +525,17 @@ __host__ __device__ inline size_t f32_smem_bytes(int n_cam)
     return (size_t)4 * kObsStages * kObsStepBytes + 4 * kObsStages * 8 + 32 * sizeof(PackedPose) + (sizeof(CamF2) + sizeof(CamParams)) * (size_t)n_cam;
 }
 
-template <int kModel, bool kRational, bool kExactE>
+// One step of one lane: two corners.  kMixed: the residual pair comes from a double projection (corner_residual) and the
+// cost is summed in double (g[6]); Jacobian, J^T J and J^T e in f32x2 (acc[0..26]).  Else everything in f32x2 (acc[0..27]).
+template <int kModel, bool kRational, bool kMixed>
 __device__ __forceinline__ void packed_step(const float2 (&cur)[5], int k, int n, int q, int k_full, const CamF2& cam,
-                                            const CamParams& camd, const PackedPose& pose, f2* acc, double& cost)
+                                            const CamParams& camd, const PackedPose& pose, f2* acc, double* g)
 {
-    // pose and intrinsics are re-read from shared memory per step (broadcast loads) instead of living in ~90 registers
-    asm volatile("" ::: "memory");
     const bool masked = k >= k_full;              // warp-uniform: some lane runs out of corners in this step
     const int c0 = 8 * k + 2 * q;
-    const float w0 = c0 < n ? 1.0f : 0.0f, w1 = c0 + 1 < n ? 1.0f : 0.0f;
+    const f2 w = f2_make(c0 < n ? 1.0f : 0.0f, c0 + 1 < n ? 1.0f : 0.0f);
     f2 e0 = f2_dup(0.0f), e1 = f2_dup(0.0f);
-    if (kExactE) {
+    if (kMixed) {
         double ea[2], eb[2];
         corner_residual<kModel, kRational>(camd, pose.Rd, pose.Td, cur[0].x, cur[1].x, cur[2].x, cur[3].x, cur[4].x, ea);
         corner_residual<kModel, kRational>(camd, pose.Rd, pose.Td, cur[0].y, cur[1].y, cur[2].y, cur[3].y, cur[4].y, eb);
@@ -527,35 +543,63 @@ __device__ __forceinline__ void packed_step(const float2 (&cur)[5], int k, int n
         e1 = f2_make((float)ea[1], (float)eb[1]);
         // the cost the accept / reject test compares is summed in double from the exact residuals
         const double ca = fma(ea[0], ea[0], ea[1] * ea[1]), cb = fma(eb[0], eb[0], eb[1] * eb[1]);
-        if (masked) cost += (c0 < n ? ca : 0.0) + (c0 + 1 < n ? cb : 0.0);
-        else cost += ca + cb;
+        if (masked) g[6] += (c0 < n ? ca : 0.0) + (c0 + 1 < n ? cb : 0.0);
+        else g[6] += ca + cb;
     }
-    corner_pair_accumulate<kModel, kRational, kExactE>(cam, pose.Rf, pose.Tf, f2_make(cur[0].x, cur[0].y), f2_make(cur[1].x, cur[1].y),
-                                                       f2_make(cur[2].x, cur[2].y), f2_make(cur[3].x, cur[3].y),
-                                                       f2_make(cur[4].x, cur[4].y), f2_make(w0, w1), masked, acc, e0, e1);
+    corner_pair_accumulate<kModel, kRational, kMixed>(cam, pose.Rf, pose.Tf, f2_make(cur[0].x, cur[0].y), f2_make(cur[1].x, cur[1].y),
+                                                      f2_make(cur[2].x, cur[2].y), f2_make(cur[3].x, cur[3].y),
+                                                      f2_make(cur[4].x, cur[4].y), w, masked, acc, e0, e1);
 }
 
 template <int kModel, bool kRational, bool kExactE>
 __device__ __forceinline__ void packed_edge_loop(ObsStream& S, int& consumed, float2* ring, unsigned long long* bars, const Problem& P,
                                                  int stride, int n_tiles, int wq, int lane, int kp, int n, int q, int k_full,
-                                                 const CamF2& cam, const CamParams& camd, const PackedPose& pose, f2* acc, double& cost)
+                                                 const CamF2& cam, const CamParams& camd, const PackedPose& pose, f2* acc, double* cost)
 {
-    for (int k = 0; k < kp; ++k) {
-        const int stg = consumed % kObsStages;
+    int k = 0;
+#if MCCBA_F32_PAIRSTEPS
+    // Two steps per trip, evaluated in ONE basic block: their projection chains are independent, so the scheduler can
+    // interleave them -- with 3 warps per scheduler and dependent f32x2 / f64 chains a single step left the issue slots
+    // half empty (profiles/r2_k1_f32_v3.txt: 53 % issue slots busy, "wait" the top stall).
+    for (; k + 1 < kp; k += 2) {
+        const int s0 = consumed & (kObsStages - 1), s1 = (consumed + 1) & (kObsStages - 1);
+        mbar_wait(&bars[s0], (unsigned)((consumed / kObsStages) & 1));
+        mbar_wait(&bars[s1], (unsigned)(((consumed + 1) / kObsStages) & 1));
+        float2 c0[5], c1[5];
+#pragma unroll
+        for (int pl = 0; pl < 5; ++pl) { c0[pl] = ring[((size_t)s0 * 5 + pl) * 32 + lane]; c1[pl] = ring[((size_t)s1 * 5 + pl) * 32 + lane]; }
+        consumed += 2;
+        __syncwarp();                                   // every lane has taken its pairs out of the two stages ...
+        if (lane == 0) {                                // ... which are refilled kObsStages steps ahead
+            obs_stream_issue(S, P, stride, n_tiles, wq, ring, bars);
+            obs_stream_issue(S, P, stride, n_tiles, wq, ring, bars);
+        }
+#if MCCBA_F32_RELOAD
+        asm volatile("" ::: "memory");     // pose and intrinsics are re-read from shared memory per trip, not kept in ~90 registers
+#endif
+        packed_step<kModel, kRational, kExactE>(c0, k, n, q, k_full, cam, camd, pose, acc, cost);
+        packed_step<kModel, kRational, kExactE>(c1, k + 1, n, q, k_full, cam, camd, pose, acc, cost);
+    }
+#endif
+    for (; k < kp; ++k) {
+        const int stg = consumed & (kObsStages - 1);
         mbar_wait(&bars[stg], (unsigned)((consumed / kObsStages) & 1));
         float2 cur[5];
 #pragma unroll
         for (int pl = 0; pl < 5; ++pl) cur[pl] = ring[((size_t)stg * 5 + pl) * 32 + lane];
         ++consumed;
-        __syncwarp();                                   // every lane has taken its pairs out of the stage ...
-        if (lane == 0) obs_stream_issue(S, P, stride, n_tiles, wq, ring, bars);   // ... which is refilled kObsStages steps ahead
+        __syncwarp();
+        if (lane == 0) obs_stream_issue(S, P, stride, n_tiles, wq, ring, bars);
+#if MCCBA_F32_RELOAD
+        asm volatile("" ::: "memory");     // pose and intrinsics are re-read from shared memory per step, not kept in ~90 registers
+#endif
         packed_step<kModel, kRational, kExactE>(cur, k, n, q, k_full, cam, camd, pose, acc, cost);
     }
 }
 
 // forced: as resid_jac_accum_kernel.  Shared memory: f32_smem_bytes(n_cam).
 template <bool kExactE>
-__global__ void __launch_bounds__(kF32Threads, 3) resid_jac_accum_f32_kernel(Problem P, int forced)
+__global__ void __launch_bounds__(kF32Threads, MCCBA_F32_MINBLOCKS) resid_jac_accum_f32_kernel(Problem P, int forced)
 {
     extern __shared__ __align__(128) unsigned char f32_smem[];
     float2* s_ring = reinterpret_cast<float2*>(f32_smem);                                   // [4 warps][kObsStages][5][32]
@@ -631,16 +675,26 @@ __global__ void __launch_bounds__(kF32Threads, 3) resid_jac_accum_f32_kernel(Pro
         f2 acc[kBlk];
 #pragma unroll
         for (int k = 0; k < kBlk; ++k) acc[k] = f2_dup(0.0f);
-        double cost = 0.0;
+        double cost[7] = {0, 0, 0, 0, 0, 0, 0};      // MIXED: [6] = sum |e|^2 in double
+#if MCCBA_F32_POSE_REGS
+        PackedPose pose_r;      // the edge's pose in registers for the whole edge (48 registers, no reloads)
+#pragma unroll
+        for (int i = 0; i < 9; ++i) { pose_r.Rd[i] = pose.Rd[i]; pose_r.Rf[i] = pose.Rf[i]; }
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { pose_r.Td[i] = pose.Td[i]; pose_r.Tf[i] = pose.Tf[i]; }
+#define MCCBA_POSE pose_r
+#else
+#define MCCBA_POSE pose
+#endif
         const CamF2& cam = s_cam[cam_idx];      // the 32 edges of a tile are one (group, view) run: one camera per warp
         const CamParams& camd = s_camd[cam_idx];
         if (cam.model == kPinhole) {
-            if (cam.rational) packed_edge_loop<kPinhole, true, kExactE>(S, consumed, ring, bars, P, stride, n_tiles, wq, lane, kp, n, q, k_full, cam, camd, pose, acc, cost);
-            else packed_edge_loop<kPinhole, false, kExactE>(S, consumed, ring, bars, P, stride, n_tiles, wq, lane, kp, n, q, k_full, cam, camd, pose, acc, cost);
+            if (cam.rational) packed_edge_loop<kPinhole, true, kExactE>(S, consumed, ring, bars, P, stride, n_tiles, wq, lane, kp, n, q, k_full, cam, camd, MCCBA_POSE, acc, cost);
+            else packed_edge_loop<kPinhole, false, kExactE>(S, consumed, ring, bars, P, stride, n_tiles, wq, lane, kp, n, q, k_full, cam, camd, MCCBA_POSE, acc, cost);
         } else {
-            packed_edge_loop<kOmnidir, false, kExactE>(S, consumed, ring, bars, P, stride, n_tiles, wq, lane, kp, n, q, k_full, cam, camd, pose, acc, cost);
+            packed_edge_loop<kOmnidir, false, kExactE>(S, consumed, ring, bars, P, stride, n_tiles, wq, lane, kp, n, q, k_full, cam, camd, MCCBA_POSE, acc, cost);
         }
-        // halves, then the 4 lanes of the edge: 28 -> 14 -> 7 values per lane
+        // halves, then the 4 lanes of the edge: 28 -> 14 -> 7 values per lane (transposed butterfly)
         float v[kBlk];
 #pragma unroll
         for (int k = 0; k < kBlk; ++k) v[k] = f2_lo(acc[k]) + f2_hi(acc[k]);
@@ -667,9 +721,10 @@ __global__ void __launch_bounds__(kF32Threads, 3) resid_jac_accum_f32_kernel(Pro
 #pragma unroll
         for (int i = 0; i < 7; ++i) o[(size_t)i * 32] = (double)v[i];
         if (kExactE) {   // cost (element 27: the last of lane q == 3) from the double sum
-            cost += __shfl_xor_sync(kFull, cost, 2);
-            cost += __shfl_xor_sync(kFull, cost, 1);
-            if (q == 3) o[(size_t)6 * 32] = cost;
+            double c = cost[6];
+            c += __shfl_xor_sync(kFull, c, 2);
+            c += __shfl_xor_sync(kFull, c, 1);
+            if (q == 3) o[(size_t)6 * 32] = c;
         }
     }
 }
@@ -981,7 +1036,10 @@ __global__ void __launch_bounds__(kK2Threads, kMinBlocks) frame_schur_kernel(Pro
 #pragma unroll
             for (int j = 0; j < 6; ++j) chol6_forward(U, Y + j, 6);  // Y = L^-1 W, column by column
 #pragma unroll
-            for (int k = 0; k < 36; ++k) P.edgeY[tile_idx(36, e, k)] = Y[k];
+            for (int k = 0; k < 36; ++k) {
+                if (P.prec) reinterpret_cast<float*>(P.edgeY)[tile_idx(36, e, k)] = (float)Y[k];
+                else P.edgeY[tile_idx(36, e, k)] = Y[k];
+            }
             if (v < 2) {   // keep Y for the off-diagonal pass (own column only: no other lane reads it)
 #pragma unroll
                 for (int k = 0; k < 36; ++k) stage[(v * 36 + k) * 32 + lane] = Y[k];
@@ -1024,7 +1082,10 @@ __global__ void __launch_bounds__(kK2Threads, kMinBlocks) frame_schur_kernel(Pro
                     for (int k = 0; k < 36; ++k) { Ya[k] = stage[k * 32 + lane]; Yb[k] = stage[(36 + k) * 32 + lane]; }
                 } else {
 #pragma unroll
-                    for (int k = 0; k < 36; ++k) { Ya[k] = P.edgeY[tile_idx(36, ea, k)]; Yb[k] = P.edgeY[tile_idx(36, ebx, k)]; }
+                    for (int k = 0; k < 36; ++k) {
+                        if (P.prec) { Ya[k] = reinterpret_cast<const float*>(P.edgeY)[tile_idx(36, ea, k)]; Yb[k] = reinterpret_cast<const float*>(P.edgeY)[tile_idx(36, ebx, k)]; }
+                        else { Ya[k] = P.edgeY[tile_idx(36, ea, k)]; Yb[k] = P.edgeY[tile_idx(36, ebx, k)]; }
+                    }
                 }
 #pragma unroll
                 for (int i = 0; i < 6; ++i)
@@ -1422,18 +1483,17 @@ __global__ void __launch_bounds__(BcrCfg<B>::kThreads) chol_bcr_kernel(const dou
                                                                        const int* go, Problem P, int fused, int packed)
 {
     extern __shared__ __align__(16) unsigned char bcr_smem[];
-    if (fused == 2) {
-        if (threadIdx.x == 0) decide_body(P);
-        __syncthreads();
-    }
-    if (go && !*reinterpret_cast<const volatile int*>(go)) return;
     const int Nb = bcr_blocks(n, B);
     double* Dg = reinterpret_cast<double*>(bcr_smem);
     double* Lo = Dg + (size_t)Nb * B * B;
     double* Tmp = Lo + (size_t)Nb * B * B;
     double* rhs = Tmp + (size_t)((Nb + 1) / 2) * B * B;
-    bcr_stage<B>(A, n, packed, Dg, Lo, rhs, Nb);
+    // the loop control (one thread, a chain of dependent global loads) runs while the other warps stage the system: the
+    // packed buffer is final before this kernel starts whatever the decision will be
+    if (fused == 2 && threadIdx.x == 0) decide_body(P);
+    if (!(fused == 2 && threadIdx.x < 32)) bcr_stage<B>(A, n, packed, Dg, Lo, rhs, Nb, fused == 2 ? 32 : 0);
     __syncthreads();
+    if (go && !*reinterpret_cast<const volatile int*>(go)) return;
     int fail = bcr_solve_cta<B>(Dg, Lo, Tmp, rhs, Nb);
     for (int idx = threadIdx.x; idx < n; idx += blockDim.x) {
         const double v = rhs[idx];
@@ -1503,11 +1563,19 @@ __global__ void __launch_bounds__(kK4Threads) frame_update_kernel(Problem P)
         if (lane == 0) {
             mbar_init(bar, 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-            const unsigned bytes = 27u * 256u + (c0v != 0 ? 36u * 256u : 0u) + (c1v != 0 ? 36u * 256u : 0u);
+            const unsigned ytile = P.prec ? 36u * 128u : 36u * 256u;
+            const unsigned bytes = 27u * 256u + (c0v != 0 ? ytile : 0u) + (c1v != 0 ? ytile : 0u);
             mbar_expect_tx(bar, bytes);
             tma_load_1d(fl, P.frameL + (int64_t)warp * 27 * 32, 27u * 256u, bar);
-            if (c0v != 0) tma_load_1d(ey, P.edgeY + ((ebase + ls) >> 5) * 36 * 32, 36u * 256u, bar);
-            if (c1v != 0) tma_load_1d(ey + 36 * 32, P.edgeY + ((ebase + stride + ls) >> 5) * 36 * 32, 36u * 256u, bar);
+            if (P.prec) {   // float records: half the bytes, same tile geometry
+                const float* yf = reinterpret_cast<const float*>(P.edgeY);
+                float* eyf = reinterpret_cast<float*>(ey);
+                if (c0v != 0) tma_load_1d(eyf, yf + ((ebase + ls) >> 5) * 36 * 32, 36u * 128u, bar);
+                if (c1v != 0) tma_load_1d(eyf + 36 * 32, yf + ((ebase + stride + ls) >> 5) * 36 * 32, 36u * 128u, bar);
+            } else {
+                if (c0v != 0) tma_load_1d(ey, P.edgeY + ((ebase + ls) >> 5) * 36 * 32, 36u * 256u, bar);
+                if (c1v != 0) tma_load_1d(ey + 36 * 32, P.edgeY + ((ebase + stride + ls) >> 5) * 36 * 32, 36u * 256u, bar);
+            }
         }
         __syncwarp();
         // everything else the thread needs is loaded while the tiles are in flight
@@ -1535,7 +1603,8 @@ __global__ void __launch_bounds__(kK4Threads) frame_update_kernel(Problem P)
         for (int v = 0; v < 2; ++v) {
             const int c = v == 0 ? c0v : c1v;
 #pragma unroll
-            for (int k = 0; k < 36; ++k) Y2[v][k] = c != 0 ? ey[(v * 36 + k) * 32 + lane] : 0.0;
+            for (int k = 0; k < 36; ++k)
+                Y2[v][k] = c == 0 ? 0.0 : (P.prec ? (double)reinterpret_cast<const float*>(ey)[(v * 36 + k) * 32 + lane] : ey[(v * 36 + k) * 32 + lane]);
         }
         __syncwarp();   // every lane has taken its columns out of `ey`, which now stages the outgoing edge records
         EdgeRec* stage = reinterpret_cast<EdgeRec*>(ey);
@@ -1558,7 +1627,8 @@ __global__ void __launch_bounds__(kK4Threads) frame_update_kernel(Problem P)
                 for (int i = 0; i < 6; ++i) {
                     double acc = 0;
 #pragma unroll
-                    for (int k = 0; k < 6; ++k) acc += P.edgeY[tile_idx(36, e, i * 6 + k)] * d[k];
+                    for (int k = 0; k < 6; ++k)
+                        acc += (P.prec ? (double)reinterpret_cast<const float*>(P.edgeY)[tile_idx(36, e, i * 6 + k)] : P.edgeY[tile_idx(36, e, i * 6 + k)]) * d[k];
                     r[i] -= acc;
                 }
             }

@@ -412,3 +412,82 @@ def omni_rms(obj_list, img_list, param):
         sq += float((e * e).sum())
         cnt += e.shape[0]
     return float(np.sqrt(sq / cnt))
+
+
+# --------------------------------------------------------------------------------------------
+# omnidir::internal::initializeCalibration (src/omnidir.cpp:551-745) -- closed-form start of omnidir::calibrate,
+# needed to re-enact the per-camera calibration MultiCameraCalibration::initialize runs before the rig loop
+# (src/multicalib.cpp:276-279).  cv2 is used where the reference calls OpenCV (SVD, Rodrigues).
+# --------------------------------------------------------------------------------------------
+def _mean_repro_err(img, proj):
+    d = np.asarray(img, dtype=np.float64).reshape(-1, 2) - np.asarray(proj, dtype=np.float64).reshape(-1, 2)
+    return float(np.mean(np.sqrt((d * d).sum(axis=1))))          # computeMeanReproErr, src/omnidir.cpp:1571-1600
+
+
+def omni_initialize_calibration(obj_list, img_list, size):
+    """Returns (om list, t list, K, xi, idx) for the frames that survive the 100 px filter (:712-721)."""
+    u0, v0 = size[0] // 2, size[1] // 2                             # integer division, :556-557
+    n_img = len(img_list)
+    om_all, t_all, gamma_all = [None] * n_img, [None] * n_img, [0.0] * n_img
+    for ii in range(n_img):
+        obj = np.asarray(obj_list[ii], dtype=np.float64).reshape(-1, 3)
+        img = np.asarray(img_list[ii], dtype=np.float64).reshape(-1, 2)
+        x, y = obj[:, 0], obj[:, 1]
+        u, v = img[:, 0] - u0, img[:, 1] - v0
+        rho2 = u * u + v * v
+        M = np.stack([-v * x, -v * y, u * x, u * y, -v, u], axis=1)
+        _, _, Vt = np.linalg.svd(M, full_matrices=True)
+        V = Vt.T
+        best = 1e5
+        for coef in (1, -1):
+            r11, r12, r21, r22, t1, t2 = (V[:6, 5] * coef)
+            a, b = -(r11 * r12 + r21 * r22) ** 2, r11 * r11 + r21 * r21 - r12 * r12 - r22 * r22
+            roots = np.roots([1.0, b, a])                           # solvePoly(a + b z + z^2)
+            roots = sorted(roots.real, reverse=False)
+            # the reference takes roots[0] if positive, else roots[1] (:613-616); cv::solvePoly's order is not
+            # specified, the positive root is unique here (a <= 0)
+            r31s = np.sqrt(max(roots))
+            for coef2 in (1, -1):
+                r31 = r31s * coef2
+                r32 = -(r11 * r12 + r21 * r22) / r31
+                r1 = np.array([r11, r21, r31]); r2 = np.array([r12, r22, r32]); t = np.array([t1, t2, 0.0])
+                scale = 1.0 / np.linalg.norm(r1)
+                r1, r2, t = r1 * scale, r2 * scale, t * scale
+                n = x.size
+                A = np.zeros((2 * n, 3))
+                A[:n, 0] = (r1[1] * x + r2[1] * y + t[1]) / 2
+                A[n:, 0] = (r1[0] * x + r2[0] * y + t[0]) / 2
+                A[:n, 1] = -A[:n, 0] * rho2
+                A[n:, 1] = -A[n:, 0] * rho2
+                A[:n, 2] = -v
+                A[n:, 2] = -u
+                maxA = np.abs(A).max(axis=0)
+                A = A / maxA
+                B = np.concatenate([v * (r1[2] * x + r2[2] * y), u * (r1[2] * x + r2[2] * y)])
+                res = np.linalg.pinv(A) @ B
+                res = res / maxA
+                with np.errstate(invalid="ignore"):
+                    gamma = np.sqrt(res[0] / res[1])
+                t[2] = res[2]
+                r3 = np.cross(r1, r2)
+                R = np.stack([r1, r2, r3], axis=1)
+                om = cv2.Rodrigues(R)[0].ravel()
+                if not np.isfinite(gamma):
+                    continue
+                Kc = np.array([[gamma, 0, u0], [0, gamma, v0], [0, 0, 1.0]])
+                proj, _ = omnidir_project_points(obj, om, t, Kc, 1.0, np.zeros(4), want_jac=False)
+                err = _mean_repro_err(img, proj)
+                if err < best:
+                    best, om_all[ii], t_all[ii], gamma_all[ii] = err, om, t.copy(), gamma
+    g = sorted(gamma_all)
+    gamma_final = g[len(g) // 2]                                    # nth_element at n/2, :705-707
+    K = np.array([[gamma_final, 0, u0], [0, gamma_final, v0], [0, 0, 1.0]])
+    idx, om_f, t_f = [], [], []
+    for i in range(n_img):
+        if om_all[i] is None:
+            continue
+        proj, _ = omnidir_project_points(np.asarray(obj_list[i], dtype=np.float64).reshape(-1, 3), om_all[i], t_all[i], K, 1.0,
+                                         np.zeros(4), want_jac=False)
+        if _mean_repro_err(img_list[i], proj) < 100:
+            idx.append(i); om_f.append(om_all[i]); t_f.append(t_all[i])
+    return om_f, t_f, K, 1.0, idx

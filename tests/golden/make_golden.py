@@ -135,9 +135,109 @@ def omni_fixture():
     np.savez_compressed(os.path.join(OUT, "omni_fixture.npz"), **d)
 
 
+def stereo_rig_fixture():
+    """BASELINE configs[0] substitute: the only real multi-camera data the reference ships,
+    tutorials/data/omni_stereocalib_data.xml (39 frames x 48 corners, two 704x576 cameras), taken through the reference's
+    own sequence -- per-camera omnidir::calibrate with its closed-form initialisation and criteria (COUNT+EPS, 300, 1e-7)
+    (src/multicalib.cpp:276-279, src/omnidir.cpp:551-745, 1119-1147), spanning-tree pose chaining (:380-420), then the rig
+    loop with the base-class default TermCriteria(COUNT, 20) (:462-514) -- by the literal dense re-enactment
+    (oracle/dense_reenact.py, fp64 policy).  The survey's independent re-enactment reports: cam0 37/39 frames, RMS
+    0.446242, xi 5.7313; cam1 36/39, RMS 0.406593, xi 1.5353; rig 40 vertices, 73 edges, RMS 0.540273 -> 0.456754,
+    camera-1 tvec (-158.800, -19.662, -5.356)."""
+    src = "/root/reference/tutorials/data/omni_stereocalib_data.xml"
+    if not os.path.exists(src):
+        print("reference fixture not available, skipping stereo_rig_fixture")
+        return
+    fs = cv2.FileStorage(src, cv2.FILE_STORAGE_READ)
+    on = fs.getNode("objectPoints")
+    objs = [on.at(i).mat().reshape(-1, 3) for i in range(on.size())]
+    sz = fs.getNode("imageSize1")
+    size = (int(sz.at(0).real()), int(sz.at(1).real()))
+    d = {}
+    cams = []
+    for cam, key in ((0, "imagePoints1"), (1, "imagePoints2")):
+        node = fs.getNode(key)
+        imgs = [node.at(i).mat().reshape(-1, 2) for i in range(node.size())]
+        om, t, K, xi, idx = dr.omni_initialize_calibration(objs, imgs, size)
+        n = len(idx)
+        p0 = np.concatenate([np.concatenate([np.concatenate([om[i], t[i]]) for i in range(n)]),
+                             [K[0, 0], K[1, 1], 0.0, K[0, 2], K[1, 2], xi, 0, 0, 0, 0]])
+        o_k, i_k = [objs[i] for i in idx], [imgs[i] for i in idx]
+        p, it, ch = dr.omni_calibrate_loop(o_k, i_k, p0, 0, 3, 300, 1e-7)
+        rms = dr.omni_rms(o_k, i_k, p)
+        print("stereo fixture cam", cam, "kept", n, "iters", it, "rms", rms, "xi", p[6 * n + 5], "f", p[6 * n], p[6 * n + 1])
+        off = np.concatenate([[0], np.cumsum([o.shape[0] for o in o_k])]).astype(np.int64)
+        d["cam%d_idx" % cam] = np.array(idx, dtype=np.int32); d["cam%d_off" % cam] = off
+        d["cam%d_obj" % cam] = np.concatenate(o_k).astype(np.float32); d["cam%d_img" % cam] = np.concatenate(i_k).astype(np.float32)
+        d["cam%d_p0" % cam] = p0; d["cam%d_params" % cam] = p; d["cam%d_iters" % cam] = it; d["cam%d_rms" % cam] = rms
+        cams.append(dict(idx=idx, p=p, n=n, imgs=imgs))
+    # the rig: vertices 0, 1 = cameras; photo vertices in first-seen order (cameras outer loop, frames in index order);
+    # the base class keeps every frame that survived a camera's own calibration (no multi-camera filter, src/multicalib.cpp:296-321)
+    nC = 2
+    ts2v, vts = {}, [-1, -1]
+    edges, edge_T = [], []
+    for c in range(nC):
+        cc = cams[c]
+        for j, frame in enumerate(cc["idx"]):
+            if frame not in ts2v:
+                ts2v[frame] = len(vts); vts.append(frame)
+            pv = ts2v[frame]
+            om, tt = cc["p"][6 * j:6 * j + 3], cc["p"][6 * j + 3:6 * j + 6]
+            T = np.eye(4, dtype=np.float32)
+            T[:3, :3] = cv2.Rodrigues(om.astype(np.float32))[0]; T[:3, 3] = tt.astype(np.float32)   # CV_32F transform, :300-318
+            edges.append((c, pv, objs[frame].astype(np.float32), cc["imgs"][frame].astype(np.float32)))
+            edge_T.append(T)
+    nV = len(vts)
+    # initialize(): BFS from vertex 0 over the camera-photo graph, neighbours in index order, last edge wins (:380-420)
+    pose = [np.eye(4, dtype=np.float32) for _ in range(nV)]
+    adj = [dict() for _ in range(nV)]
+    for e, (c, pv, _, _) in enumerate(edges):
+        adj[c][pv] = e; adj[pv][c] = e
+    seen, order, pre, pre_e = {0}, [0], {}, {}
+    q = [0]
+    while q:
+        v = q.pop(0)
+        for w in sorted(adj[v]):
+            if w not in seen:
+                seen.add(w); pre[w] = v; pre_e[w] = adj[v][w]; q.append(w); order.append(w)
+    for v in order[1:]:
+        T = edge_T[pre_e[v]].astype(np.float64); P = pose[pre[v]].astype(np.float64)
+        pose[v] = ((T @ np.linalg.inv(P)) if v < nC else (np.linalg.inv(P) @ T)).astype(np.float32)
+    p_init = np.zeros(6 * (nV - 1), dtype=np.float32)
+    for v in range(1, nV):
+        p_init[6 * (v - 1):6 * (v - 1) + 3] = cv2.Rodrigues(pose[v][:3, :3].astype(np.float64))[0].ravel()
+        p_init[6 * (v - 1) + 3:6 * v] = pose[v][:3, 3]
+    K = np.zeros((nC, 3, 3)); xi = np.zeros(nC); dist = []
+    for c in range(nC):
+        pc, n = cams[c]["p"], cams[c]["n"]
+        # intrinsics are kept CV_32F by the rig class (src/multicalib.cpp:281-283)
+        f32 = lambda a: np.asarray(a, dtype=np.float32).astype(np.float64)
+        K[c] = f32([[pc[6 * n], pc[6 * n + 2], pc[6 * n + 3]], [0, pc[6 * n + 1], pc[6 * n + 4]], [0, 0, 1]])
+        xi[c] = f32(pc[6 * n + 5]); dist.append(f32(pc[6 * n + 6:6 * n + 10]))
+    prob = dr.RigProblem([dr.OMNIDIRECTIONAL] * nC, K, dist, xi, edges, nV)
+    rec = []
+    p_fin, it, ch = dr.optimize_extrinsics(prob, p_init.astype(np.float64), 1, 20, 1e-7, policy="fp64", record=rec)
+    err = dr.compute_project_error(prob, p_fin, policy="fp64")
+    rms_seq = []
+    for r in rec[:6]:
+        rms_seq.append(dr.compute_project_error(prob, r["params"], policy="fp64")["rms"])
+    rms0 = dr.compute_project_error(prob, p_init.astype(np.float64), policy="fp64")["rms"]
+    print("stereo rig: vertices", nV, "edges", len(edges), "params", p_init.size, "corners", sum(e[2].shape[0] for e in edges))
+    print("  rms init", rms0, "then", rms_seq, "final", err["rms"], "mean|e|", err["mean_reproj_error"] * 1.0)
+    print("  camera 1 rvec", p_fin[0:3], "tvec", p_fin[3:6])
+    d.update(rig_edge_cam=np.array([e[0] for e in edges], dtype=np.int32), rig_edge_pv=np.array([e[1] for e in edges], dtype=np.int32),
+             rig_edge_off=np.concatenate([[0], np.cumsum([e[2].shape[0] for e in edges])]).astype(np.int64),
+             rig_obj=np.concatenate([e[2] for e in edges]), rig_img=np.concatenate([e[3] for e in edges]),
+             rig_vertex_timestamp=np.array(vts, dtype=np.int32), rig_K=K, rig_xi=xi, rig_dist=np.array(dist),
+             rig_p_init=p_init.astype(np.float64), rig_p_final=p_fin, rig_iters=it, rig_rms_init=rms0, rig_rms_seq=np.array(rms_seq),
+             rig_rms=err["rms"], rig_mean_error=err["mean_reproj_error"], rig_iter3=rec[2]["params"])
+    np.savez_compressed(os.path.join(OUT, "stereo_rig_fixture.npz"), **d)
+
+
 if __name__ == "__main__":
     primitives()
     omni()
     rig_dense()
     omni_fixture()
+    stereo_rig_fixture()
     print("golden fixtures written to", OUT)
