@@ -216,6 +216,21 @@ int mccba_debug_solve_dense(mccba_handle h, int n, const double *S, const double
  * the handle's stream; returns average ms per launch (benchmark helper, no other side effects) */
 int mccba_time_eval(mccba_handle h, int reps, double *avg_ms);
 
+/* ---- omnidir stereo bundle adjustment --------------------------------------------------
+ * The optimisation loop of cv::omnidir::stereoCalibrate (src/omnidir.cpp:1268-1296 with computeJacobianStereo :937-1020,
+ * flags2idxStereo :2078-2136) and estimateUncertaintiesStereo (:1804-1889), without the closed-form initialisation.
+ * Parameter vector (encodeParametersStereo :1570-1620): [om, T of camera 2 relative to camera 1 | om_i, T_i of the n
+ * frames in camera 1 | fx fy s cx cy xi k1 k2 p1 p2 of camera 1 | the same of camera 2] = 6 (n + 1) + 20 doubles.
+ * Every frame is seen by both cameras with the same object points (frame_off[n_frame + 1] corner offsets). */
+int mccba_stereo_set_observations(mccba_handle h, int n_frame, const int64_t *frame_off, const float *obj_xyz,
+                                  const float *img1_uv, const float *img2_uv);
+int mccba_stereo_set_parameters(mccba_handle h, int64_t n, const double *params);
+int mccba_stereo_get_parameters(mccba_handle h, int64_t n, double *params);
+/* flags: cv::omnidir::CALIB_FIX_* bits (applied to both cameras); criteria decoded as at :1271-1274 */
+int mccba_stereo_solve(mccba_handle h, int flags, int crit_type, int max_count, double epsilon, mccba_report *rep);
+/* errors[6 (n + 1) + 20] = 3 s sqrt(diag((J^T J)^-1)) (0 at fixed parameters), std_error = (sigma_x, sigma_y), rms */
+int mccba_stereo_uncertainties(mccba_handle h, int flags, double *errors, double std_error[2], double *rms);
+
 #ifdef __cplusplus
 }
 #endif

@@ -43,7 +43,8 @@ EXPORTS = ["mccba_exchange_mode", "mccba_default_options", "mccba_default_solve_
            "mccba_get_parameters", "mccba_save_parameters", "mccba_restore_parameters", "mccba_eval", "mccba_reduced_system", "mccba_solve", "mccba_reproj_error",
            "mccba_allreduce_sum", "mccba_last_kernel_ms", "mccba_time_eval", "mccba_debug_solve_dense", "mccba_omni_set_observations",
            "mccba_omni_set_parameters", "mccba_omni_get_parameters", "mccba_omni_solve", "mccba_omni_gram", "mccba_set_precision",
-           "mccba_get_precision"]
+           "mccba_get_precision", "mccba_stereo_set_observations", "mccba_stereo_set_parameters", "mccba_stereo_get_parameters",
+           "mccba_stereo_solve", "mccba_stereo_uncertainties"]
 
 _lib = None
 
@@ -263,6 +264,38 @@ class Solver:
         g = np.zeros((self._omni_n, 17, 17)); cost = C.c_double()
         self._check(lib().mccba_omni_gram(self._h, _ptr(g, C.c_double), C.byref(cost)))
         return g, cost.value
+
+    # ---- omnidir stereo bundle adjustment (cv::omnidir::stereoCalibrate's loop + estimateUncertaintiesStereo) ----------
+    def stereo_set_observations(self, frame_off, obj_xyz, img1_uv, img2_uv):
+        off = np.ascontiguousarray(frame_off, dtype=np.int64)
+        obj = np.ascontiguousarray(obj_xyz, dtype=np.float32)
+        i1 = np.ascontiguousarray(img1_uv, dtype=np.float32); i2 = np.ascontiguousarray(img2_uv, dtype=np.float32)
+        self._st_n = off.size - 1
+        self._st_pts = int(off[-1])
+        self._check(lib().mccba_stereo_set_observations(self._h, int(self._st_n), _ptr(off, C.c_int64), _ptr(obj, C.c_float),
+                                                        _ptr(i1, C.c_float), _ptr(i2, C.c_float)))
+
+    def stereo_set_parameters(self, params):
+        p = np.ascontiguousarray(params, dtype=np.float64)
+        self._check(lib().mccba_stereo_set_parameters(self._h, C.c_int64(p.size), _ptr(p, C.c_double)))
+
+    def stereo_get_parameters(self):
+        p = np.zeros(6 * (self._st_n + 1) + 20)
+        self._check(lib().mccba_stereo_get_parameters(self._h, C.c_int64(p.size), _ptr(p, C.c_double)))
+        return p
+
+    def stereo_solve(self, flags=0, crit_type=3, max_count=200, eps=1e-6, check=True):
+        r = Report()
+        rc = lib().mccba_stereo_solve(self._h, int(flags), int(crit_type), int(max_count), C.c_double(eps), C.byref(r))
+        if rc and check:
+            self._check(rc)
+        return dict(rc=rc, iterations=r.iterations, status=r.status, change=r.change, cost=r.cost,
+                    rms=float(np.sqrt(r.cost / (2 * self._st_pts))), device_ms=r.device_ms, kernel_launches=r.kernel_launches)
+
+    def stereo_uncertainties(self, flags=0):
+        e = np.zeros(6 * (self._st_n + 1) + 20); sd = np.zeros(2); rms = C.c_double()
+        self._check(lib().mccba_stereo_uncertainties(self._h, int(flags), _ptr(e, C.c_double), _ptr(sd, C.c_double), C.byref(rms)))
+        return dict(errors=e, std_error=sd, rms=rms.value)
 
     def time_eval(self, reps=10):
         ms = C.c_double()

@@ -16,6 +16,7 @@
 #include "../../include/mccba.h"
 #include "mccba_kernels.cuh"
 #include "mccba_omni.cuh"
+#include "mccba_stereo.cuh"
 
 using namespace mccba;
 
@@ -124,6 +125,11 @@ struct mccba_handle_s {
     bool omni_have = false, omni_have_params = false;
     cudaGraphExec_t omni_graph = nullptr;
     bool have_saved = false;
+    // omnidir stereo bundle adjustment (mccba_stereo_*)
+    StereoProblem S;
+    std::vector<void*> stereo_allocs;
+    bool stereo_have = false, stereo_have_params = false;
+    cudaGraphExec_t stereo_graph = nullptr;
 };
 
 namespace {
@@ -400,6 +406,7 @@ int mccba_create(const mccba_options* opts, mccba_handle* out)
     h->opts = *opts;
     memset(&h->P, 0, sizeof(h->P));
     memset(&h->O, 0, sizeof(h->O));
+    memset(&h->S, 0, sizeof(h->S));
     if (cudaSetDevice(opts->device) != cudaSuccess) { delete h; return MCCBA_ERR_CUDA; }
     cudaDeviceProp prop;
     cudaGetDeviceProperties(&prop, opts->device);
@@ -438,6 +445,8 @@ int mccba_destroy(mccba_handle h)
     drain_pool(h);
     if (h->omni_graph) cudaGraphExecDestroy(h->omni_graph);
     for (void* q : h->omni_allocs) cudaFree(q);
+    if (h->stereo_graph) cudaGraphExecDestroy(h->stereo_graph);
+    for (void* q : h->stereo_allocs) cudaFree(q);
     if (h->d_cams) cudaFree(h->d_cams);
     p2p_teardown(h);
     if (h->comm) nccl().CommDestroy(h->comm);
@@ -1619,6 +1628,220 @@ int mccba_omni_gram(mccba_handle h, double* gram /* n_frame x 17 x 17 */, double
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     CUDA_TRY(h, cudaGetLastError());
     if (d) cudaFree(d);
+    return MCCBA_OK;
+}
+
+}  // extern "C"
+
+// ---- omnidir stereo bundle adjustment (cv::omnidir::stereoCalibrate's loop + estimateUncertaintiesStereo) ------------
+namespace {
+template <typename T>
+int stereo_alloc(mccba_handle h, T** p, size_t count)
+{
+    void* q = nullptr;
+    const size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+    CUDA_TRY(h, cudaMalloc(&q, bytes));
+    CUDA_TRY(h, cudaMemsetAsync(q, 0, bytes, h->stream));
+    h->stereo_allocs.push_back(q);
+    *p = (T*)q;
+    return MCCBA_OK;
+}
+int stereo_enqueue_iteration(mccba_handle h)
+{
+    StereoProblem& S = h->S;
+    cudaStream_t s = h->stream;
+    stereo_frame_kernel<<<S.n_frame, kStThreads, 0, s>>>(S, 0);
+    stereo_reduce_kernel<<<kStRec, 256, 0, s>>>(S, 0);
+    stereo_solve_kernel<<<1, 32, 0, s>>>(S);
+    stereo_update_kernel<<<S.n_blocks_upd, 128, 0, s>>>(S);
+    stereo_decide_kernel<<<1, 256, 0, s>>>(S);
+    CUDA_TRY(h, cudaGetLastError());
+    return MCCBA_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int mccba_stereo_set_observations(mccba_handle h, int n_frame, const int64_t* frame_off, const float* obj_xyz, const float* img1_uv,
+                                  const float* img2_uv)
+{
+    if (!h) return MCCBA_ERR_ARG;
+    if (n_frame < 1 || !frame_off || !obj_xyz || !img1_uv || !img2_uv || frame_off[0] != 0) return fail(h, MCCBA_ERR_ARG, "stereo_set_observations: bad input");
+    CUDA_TRY(h, cudaSetDevice(h->opts.device));
+    const int64_t M = frame_off[n_frame];
+    if (M <= 0 || M >= (int64_t)1000000000) return fail(h, MCCBA_ERR_ARG, "stereo_set_observations: corner count out of range");
+    for (int f = 0; f < n_frame; ++f)
+        if (frame_off[f + 1] <= frame_off[f]) return fail(h, MCCBA_ERR_ARG, "frame %d has no observation", f);
+    if (h->stereo_graph) { cudaGraphExecDestroy(h->stereo_graph); h->stereo_graph = nullptr; }
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    for (void* q : h->stereo_allocs) cudaFree(q);
+    h->stereo_allocs.clear();
+    StereoProblem& S = h->S;
+    memset(&S, 0, sizeof(S));
+    S.n_frame = n_frame; S.n_pts = M; S.n_blocks_upd = (n_frame + 127) / 128;
+    std::vector<int> off((size_t)n_frame + 1);
+    for (int f = 0; f <= n_frame; ++f) off[f] = (int)frame_off[f];
+    // SoA planes (x y z | u1 v1 | u2 v2), split on the host: the problem sizes of this path are small
+    std::vector<float> planes(7 * (size_t)M);
+    for (int64_t i = 0; i < M; ++i) {
+        planes[i] = obj_xyz[3 * i]; planes[M + i] = obj_xyz[3 * i + 1]; planes[2 * M + i] = obj_xyz[3 * i + 2];
+        planes[3 * M + i] = img1_uv[2 * i]; planes[4 * M + i] = img1_uv[2 * i + 1];
+        planes[5 * M + i] = img2_uv[2 * i]; planes[6 * M + i] = img2_uv[2 * i + 1];
+    }
+    int* d_off = nullptr; float* d_pl = nullptr;
+    int rc;
+    if ((rc = stereo_alloc(h, &d_off, off.size()))) return rc;
+    if ((rc = stereo_alloc(h, &d_pl, planes.size()))) return rc;
+    CUDA_TRY(h, cudaMemcpyAsync(d_off, off.data(), off.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(d_pl, planes.data(), planes.size() * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    S.f_off = d_off;
+    S.ox = d_pl; S.oy = d_pl + M; S.oz = d_pl + 2 * M; S.u1 = d_pl + 3 * M; S.v1 = d_pl + 4 * M; S.u2 = d_pl + 5 * M; S.v2 = d_pl + 6 * M;
+    const size_t np = 6 * ((size_t)n_frame + 1) + 20;
+    if ((rc = stereo_alloc(h, &S.param, np))) return rc;
+    if ((rc = stereo_alloc(h, &S.rec, (size_t)kStRec * n_frame))) return rc;
+    if ((rc = stereo_alloc(h, &S.save, (size_t)kStSave * n_frame))) return rc;
+    if ((rc = stereo_alloc(h, &S.tot, kStRec))) return rc;
+    if ((rc = stereo_alloc(h, &S.norm_part, 2 * (size_t)S.n_blocks_upd))) return rc;
+    if ((rc = stereo_alloc(h, &S.sinv, kStNS * kStNS))) return rc;
+    if ((rc = stereo_alloc(h, &S.diag, np))) return rc;
+    if ((rc = stereo_alloc(h, &S.st, 1))) return rc;
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    h->stereo_have = true;
+    h->stereo_have_params = false;
+    return MCCBA_OK;
+}
+
+int mccba_stereo_set_parameters(mccba_handle h, int64_t n, const double* params)
+{
+    if (!h) return MCCBA_ERR_ARG;
+    if (!h->stereo_have) return fail(h, MCCBA_ERR_STATE, "stereo_set_parameters before stereo_set_observations");
+    const int64_t np = 6 * ((int64_t)h->S.n_frame + 1) + 20;
+    if (!params || n != np) return fail(h, MCCBA_ERR_ARG, "stereo_set_parameters: expected %lld doubles", (long long)np);
+    CUDA_TRY(h, cudaSetDevice(h->opts.device));
+    CUDA_TRY(h, cudaMemcpyAsync(h->S.param, params, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    h->stereo_have_params = true;
+    return MCCBA_OK;
+}
+
+int mccba_stereo_get_parameters(mccba_handle h, int64_t n, double* params)
+{
+    if (!h) return MCCBA_ERR_ARG;
+    if (!h->stereo_have_params) return fail(h, MCCBA_ERR_STATE, "stereo_get_parameters before stereo_set_parameters");
+    const int64_t np = 6 * ((int64_t)h->S.n_frame + 1) + 20;
+    if (!params || n != np) return fail(h, MCCBA_ERR_ARG, "stereo_get_parameters: wrong size");
+    CUDA_TRY(h, cudaSetDevice(h->opts.device));
+    CUDA_TRY(h, cudaMemcpyAsync(params, h->S.param, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return MCCBA_OK;
+}
+
+int mccba_stereo_solve(mccba_handle h, int flags, int crit_type, int max_count, double epsilon, mccba_report* rep)
+{
+    if (!h) return MCCBA_ERR_ARG;
+    if (!h->stereo_have_params) return fail(h, MCCBA_ERR_STATE, "stereo_solve before stereo_set_parameters");
+    if (crit_type < 1 || crit_type > 3 || max_count < 0) return fail(h, MCCBA_ERR_ARG, "stereo_solve: bad criteria");
+    CUDA_TRY(h, cudaSetDevice(h->opts.device));
+    StereoProblem& S = h->S;
+    cudaStream_t s = h->stream;
+    int rc;
+    CUDA_TRY(h, cudaEventRecord(h->ev0, s));
+    stereo_init_state_kernel<<<1, 1, 0, s>>>(S.st, flags, crit_type, max_count, epsilon);
+    if (h->opts.use_graph && !h->stereo_graph) {
+        cudaGraph_t g = nullptr;
+        CUDA_TRY(h, cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed));
+        rc = stereo_enqueue_iteration(h);
+        cudaError_t ce = cudaStreamEndCapture(s, &g);
+        if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+        if (ce != cudaSuccess) return fail(h, MCCBA_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(ce));
+        ce = cudaGraphInstantiate(&h->stereo_graph, g, 0);
+        cudaGraphDestroy(g);
+        if (ce != cudaSuccess) return fail(h, MCCBA_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(ce));
+    }
+    const bool exact = crit_type == 1;
+    const int64_t max_launches = (crit_type & 1) ? max_count : 200000;
+    int64_t launched = 0;
+    int slot = 0;
+    cudaEvent_t evs[2];
+    cudaEventCreateWithFlags(&evs[0], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&evs[1], cudaEventDisableTiming);
+    bool pending[2] = {false, false}, stop = false;
+    while (launched < max_launches && !stop) {
+        const int nl = (int)std::min<int64_t>(exact ? max_launches : 8, max_launches - launched);
+        for (int i = 0; i < nl; ++i) {
+            if (h->opts.use_graph) CUDA_TRY(h, cudaGraphLaunch(h->stereo_graph, s));
+            else if ((rc = stereo_enqueue_iteration(h))) return rc;
+        }
+        launched += nl;
+        if (exact) break;
+        CUDA_TRY(h, cudaMemcpyAsync(h->h_done + slot, &S.st->done, sizeof(int), cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(h, cudaEventRecord(evs[slot], s));
+        pending[slot] = true;
+        const int prev = slot ^ 1;
+        if (pending[prev]) {
+            CUDA_TRY(h, cudaEventSynchronize(evs[prev]));
+            if (h->h_done[prev]) stop = true;
+            pending[prev] = false;
+        }
+        slot ^= 1;
+    }
+    cudaEventDestroy(evs[0]);
+    cudaEventDestroy(evs[1]);
+    // final cost at the returned parameters (estimateUncertaintiesStereo's rms, :1879-1888)
+    stereo_frame_kernel<<<S.n_frame, kStThreads, 0, s>>>(S, 1);
+    stereo_reduce_kernel<<<kStRec, 256, 0, s>>>(S, 1);
+    StereoState hs;
+    double cost = 0;
+    CUDA_TRY(h, cudaMemcpyAsync(&hs, S.st, sizeof(StereoState), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(h, cudaMemcpyAsync(&cost, S.tot + kStSTri + 2 * kStNS + 2, sizeof(double), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(h, cudaEventRecord(h->ev1, s));
+    CUDA_TRY(h, cudaStreamSynchronize(s));
+    CUDA_TRY(h, cudaGetLastError());
+    float ms = 0;
+    cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+    if (rep) {
+        memset(rep, 0, sizeof(*rep));
+        rep->iterations = hs.iter; rep->accepted = hs.iter; rep->status = hs.status;
+        rep->graph_launches = (int)launched; rep->kernel_launches = (int)launched * 5 + 3;
+        rep->change = hs.change; rep->cost = cost; rep->lambda = hs.epsilon; rep->device_ms = ms;
+    }
+    if (hs.status) return fail(h, MCCBA_ERR_NUMERIC, "stereo_solve: numeric failure at iteration %d", hs.iter);
+    if (!hs.done) return fail(h, MCCBA_ERR_NUMERIC, "stereo_solve: launch budget exhausted (iter %d)", hs.iter);
+    return MCCBA_OK;
+}
+
+int mccba_stereo_uncertainties(mccba_handle h, int flags, double* errors, double std_error[2], double* rms)
+{
+    if (!h) return MCCBA_ERR_ARG;
+    if (!h->stereo_have_params) return fail(h, MCCBA_ERR_STATE, "stereo_uncertainties before stereo_set_parameters");
+    CUDA_TRY(h, cudaSetDevice(h->opts.device));
+    StereoProblem& S = h->S;
+    cudaStream_t s = h->stream;
+    const size_t np = 6 * ((size_t)S.n_frame + 1) + 20;
+    CUDA_TRY(h, cudaMemsetAsync(&S.st->status, 0, sizeof(int), s));
+    stereo_frame_kernel<<<S.n_frame, kStThreads, 0, s>>>(S, 1);
+    stereo_reduce_kernel<<<kStRec, 256, 0, s>>>(S, 1);
+    stereo_cov_shared_kernel<<<1, 32, 0, s>>>(S, flags);
+    stereo_cov_frame_kernel<<<(S.n_frame + 127) / 128, 128, 0, s>>>(S);
+    CUDA_TRY(h, cudaGetLastError());
+    std::vector<double> diag(np);
+    double mom[7];
+    int status = 0;
+    CUDA_TRY(h, cudaMemcpyAsync(diag.data(), S.diag, sizeof(double) * np, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(h, cudaMemcpyAsync(mom, S.tot + kStSTri + 2 * kStNS, sizeof(double) * 7, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(h, cudaMemcpyAsync(&status, &S.st->status, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(h, cudaStreamSynchronize(s));
+    if (status) return fail(h, MCCBA_ERR_NUMERIC, "stereo_uncertainties: the normal matrix is singular");
+    // moments: mom[2] = sum |e|^2, mom[3..6] = sum ex, ey, ex^2, ey^2 over the N = 2 * corners residual points
+    const double N = 2.0 * (double)S.n_pts;
+    const double mx = mom[3] / N, my = mom[4] / N;
+    const double vx = mom[5] / N - mx * mx, vy = mom[6] / N - my * my;
+    if (std_error) { std_error[0] = sqrt(vx) * sqrt(N / (N - 1.0)); std_error[1] = sqrt(vy) * sqrt(N / (N - 1.0)); }   // :1862-1863
+    const double mall = (mom[3] + mom[4]) / (2 * N), vall = (mom[5] + mom[6]) / (2 * N) - mall * mall;
+    const double sdev = sqrt(vall) * sqrt(2.0 * N / (2.0 * N - 1.0));                                                    // :1865-1868
+    if (errors)
+        for (size_t i = 0; i < np; ++i) errors[i] = 3.0 * sdev * sqrt(diag[i]);                                          // :1875
+    if (rms) *rms = sqrt(mom[2] / N);
     return MCCBA_OK;
 }
 

@@ -491,3 +491,131 @@ def omni_initialize_calibration(obj_list, img_list, size):
         if _mean_repro_err(img_list[i], proj) < 100:
             idx.append(i); om_f.append(om_all[i]); t_f.append(t_all[i])
     return om_f, t_f, K, 1.0, idx
+
+
+# --------------------------------------------------------------------------------------------
+# omnidir::stereoCalibrate: computeJacobianStereo src/omnidir.cpp:937-1020, the loop :1268-1296,
+# flags2idxStereo :2078-2136, fillFixedStereo :2155-2170, initializeStereoCalibration :750-830, findMedian(3) :2172-2189,
+# estimateUncertaintiesStereo :1804-1889.  Parameter vector (encodeParametersStereo :1570-1620):
+#   [om, T (pose of camera 2 relative to camera 1) | om_i, T_i of the n frames in camera 1 | fx fy s cx cy xi k1 k2 p1 p2 of camera 1 | same of camera 2]
+# --------------------------------------------------------------------------------------------
+def flags2idx_stereo(flags, n):
+    idx = np.ones(6 * (n + 1) + 20, dtype=np.int64)
+    f = int(flags)
+    o1, o2 = 6 * (n + 1), 6 * (n + 1) + 10
+    for bit, cols in ((CALIB_FIX_CENTER, (3, 4)), (CALIB_FIX_GAMMA, (0, 1)), (CALIB_FIX_XI, (5,)), (CALIB_FIX_P2, (9,)),
+                      (CALIB_FIX_P1, (8,)), (CALIB_FIX_K2, (7,)), (CALIB_FIX_K1, (6,))):
+        if f >= bit:
+            for c in cols:
+                idx[o1 + c] = 0; idx[o2 + c] = 0
+            f -= bit
+    if f >= CALIB_FIX_SKEW:
+        idx[o1 + 2] = 0; idx[o2 + 2] = 0
+    return idx
+
+
+def _stereo_unpack(param, n):
+    o1, o2 = 6 * (n + 1), 6 * (n + 1) + 10
+    K1 = np.array([[param[o1], param[o1 + 2], param[o1 + 3]], [0, param[o1 + 1], param[o1 + 4]], [0, 0, 1.0]])
+    K2 = np.array([[param[o2], param[o2 + 2], param[o2 + 3]], [0, param[o2 + 1], param[o2 + 4]], [0, 0, 1.0]])
+    return K1, param[o1 + 5], param[o1 + 6:o1 + 10], K2, param[o2 + 5], param[o2 + 6:o2 + 10]
+
+
+def omni_stereo_jacobian(obj_list, img1_list, img2_list, param, flags, epsilon):
+    """Dense J (rows: per frame the left image's 2N rows, then the right image's 2N rows) exactly as :937-1020."""
+    n = len(obj_list)
+    P = 6 * (n + 1) + 20
+    K1, xi1, D1, K2, xi2, D2 = _stereo_unpack(param, n)
+    om, T = param[0:3], param[3:6]
+    rows, errs = [], []
+    for i in range(n):
+        obj = np.asarray(obj_list[i], dtype=np.float64).reshape(-1, 3)
+        npt = obj.shape[0]
+        om1, T1 = param[6 + 6 * i:9 + 6 * i], param[9 + 6 * i:12 + 6 * i]
+        p1, j1 = omnidir_project_points(obj, om1, T1, K1, xi1, D1)
+        J = np.zeros((4 * npt, P))
+        J[:2 * npt, 6 * (n + 1):6 * (n + 1) + 10] = j1[:, 6:16]
+        J[:2 * npt, 6 + 6 * i:12 + 6 * i] = j1[:, 0:6]
+        e1 = (np.asarray(img1_list[i], dtype=np.float64).reshape(-1, 2) - p1).reshape(-1)
+        (om2, T2, dom2dom1, dom2dT1, dom2dom, dom2dT, dT2dom1, dT2dT1, dT2dom, dT2dT) = compose_motion(om1, T1, om, T)
+        p2, j2 = omnidir_project_points(obj, om2, T2, K2, xi2, D2)
+        e2 = (np.asarray(img2_list[i], dtype=np.float64).reshape(-1, 2) - p2).reshape(-1)
+        J[2 * npt:, 0:3] = j2[:, 0:3] @ dom2dom + j2[:, 3:6] @ dT2dom
+        J[2 * npt:, 3:6] = j2[:, 0:3] @ dom2dT + j2[:, 3:6] @ dT2dT
+        J[2 * npt:, 6 + 6 * i:9 + 6 * i] = j2[:, 0:3] @ dom2dom1 + j2[:, 3:6] @ dT2dom1
+        J[2 * npt:, 9 + 6 * i:12 + 6 * i] = j2[:, 0:3] @ dom2dT1 + j2[:, 3:6] @ dT2dT1
+        J[2 * npt:, 6 * (n + 1) + 10:6 * (n + 1) + 20] = j2[:, 6:16]
+        rows.append(J); errs.append(np.concatenate([e1, e2]))
+    J = np.vstack(rows); E = np.concatenate(errs)
+    idx = flags2idx_stereo(flags, n).astype(bool)
+    JTJ = (J.T @ J)[np.ix_(idx, idx)]
+    JTE = (J.T @ E)[idx]
+    return np.linalg.inv(JTJ + epsilon), JTE, idx, float(E @ E), E
+
+
+def omni_stereo_calibrate_loop(obj_list, img1_list, img2_list, param0, flags, crit_type, max_count, eps, record=None):
+    """src/omnidir.cpp:1268-1296 (same alpha / epsilon schedule as the single-camera loop)."""
+    cur = np.asarray(param0, dtype=np.float64).copy()
+    change, it = 1.0, 0
+    while True:
+        if ((crit_type == 1 and it >= max_count) or (crit_type == 2 and change <= eps) or
+                (crit_type == 3 and (change <= eps or it >= max_count))):
+            break
+        alpha = 1 - (1 - 0.01) ** (it + 1.0)
+        epsilon = 0.01 * 0.9 ** (it / 10.0)
+        JTJ_inv, JTE, idx, cost, _ = omni_stereo_jacobian(obj_list, img1_list, img2_list, cur, flags, epsilon)
+        G = np.zeros_like(cur)
+        G[idx] = alpha * (JTJ_inv @ JTE)
+        change = float(np.linalg.norm(G) / np.linalg.norm(cur))
+        cur = cur + G
+        if record is not None:
+            record.append(dict(iter=it, cost_before=cost, change=change, params=cur.copy()))
+        it += 1
+    return cur, it, change
+
+
+def omni_stereo_uncertainties(obj_list, img1_list, img2_list, param, flags):
+    """estimateUncertaintiesStereo :1804-1889 -> (errors = 3 s sqrt(diag((J^T J)^-1)) over the free parameters, std_error (x, y), rms).
+    The reference projects the right image through Rodrigues(R R1) (a log / exp round trip); the residuals are the same."""
+    JTJ_inv, _, idx, _, E = omni_stereo_jacobian(obj_list, img1_list, img2_list, param, flags, 0.0)
+    e = E.reshape(-1, 2)
+    N = e.shape[0]
+    std_error = e.std(axis=0) * np.sqrt(N / (N - 1.0))
+    s = E.std() * np.sqrt(2.0 * N / (2.0 * N - 1.0))
+    errors = 3 * s * np.sqrt(np.diag(JTJ_inv))
+    rms = float(np.sqrt((e * e).sum() / N))
+    return errors, std_error, rms, idx
+
+
+def _find_median(v):
+    """findMedian :2172-2181, with its even / odd quirk kept."""
+    t = np.sort(np.asarray(v, dtype=np.float64))
+    m = t.size
+    return t[m // 2] if m % 2 == 0 else 0.5 * (t[m // 2] + t[m // 2 - 1])
+
+
+def omni_initialize_stereo(obj_list, img1_list, img2_list, size1, size2, flags=0):
+    """initializeStereoCalibration :750-830 -> (param0, idx of the frames both cameras kept)."""
+    res = []
+    for imgs, size in ((img1_list, size1), (img2_list, size2)):
+        om, t, K, xi, idx = omni_initialize_calibration(obj_list, imgs, size)
+        n = len(idx)
+        p0 = np.concatenate([np.concatenate([np.concatenate([om[i], t[i]]) for i in range(n)]), [K[0, 0], K[1, 1], 0.0, K[0, 2], K[1, 2], xi, 0, 0, 0, 0]])
+        p, _, _ = omni_calibrate_loop([obj_list[i] for i in idx], [imgs[i] for i in idx], p0, flags, 3, 100, 1e-6)
+        res.append((idx, p, n))
+    (idx1, p1, n1), (idx2, p2, n2) = res
+    inter = [i for i in idx1 if i in idx2]
+    om_est, t_est, omL, tL = [], [], [], []
+    for fr in inter:
+        a, b = idx1.index(fr), idx2.index(fr)
+        R1 = cv2.Rodrigues(p1[6 * a:6 * a + 3])[0]; R2 = cv2.Rodrigues(p2[6 * b:6 * b + 3])[0]
+        T1, T2 = p1[6 * a + 3:6 * a + 6], p2[6 * b + 3:6 * b + 6]
+        RLR = R2 @ R1.T
+        om_est.append(cv2.Rodrigues(RLR)[0].ravel()); t_est.append(T2 - RLR @ T1)
+        omL.append(p1[6 * a:6 * a + 3]); tL.append(T1)
+    om_est, t_est = np.array(om_est), np.array(t_est)
+    om0 = np.array([_find_median(om_est[:, k]) for k in range(3)])
+    t0 = np.array([_find_median(t_est[:, k]) for k in range(3)])
+    n = len(inter)
+    param0 = np.concatenate([om0, t0, np.concatenate([np.concatenate([omL[i], tL[i]]) for i in range(n)]), p1[6 * n1:6 * n1 + 10], p2[6 * n2:6 * n2 + 10]])
+    return param0, inter

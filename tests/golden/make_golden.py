@@ -234,10 +234,47 @@ def stereo_rig_fixture():
     np.savez_compressed(os.path.join(OUT, "stereo_rig_fixture.npz"), **d)
 
 
+def stereo_ba_fixture():
+    """cv::omnidir::stereoCalibrate on tutorials/data/omni_stereocalib_data.xml by the literal dense re-enactment
+    (oracle/dense_reenact.py): initializeStereoCalibration (two omnidir::calibrate runs with criteria (3, 100, 1e-6), frame
+    intersection, median relative pose), the loop with the tutorial's criteria (COUNT+EPS, 200, 1e-6), and
+    estimateUncertaintiesStereo.  Golden vectors for SURVEY.md 8(f) row 3."""
+    src = "/root/reference/tutorials/data/omni_stereocalib_data.xml"
+    if not os.path.exists(src):
+        print("reference fixture not available, skipping stereo_ba_fixture")
+        return
+    fs = cv2.FileStorage(src, cv2.FILE_STORAGE_READ)
+    on, n1, n2 = fs.getNode("objectPoints"), fs.getNode("imagePoints1"), fs.getNode("imagePoints2")
+    objs = [on.at(i).mat().reshape(-1, 3) for i in range(on.size())]
+    im1 = [n1.at(i).mat().reshape(-1, 2) for i in range(n1.size())]
+    im2 = [n2.at(i).mat().reshape(-1, 2) for i in range(n2.size())]
+    s1 = fs.getNode("imageSize1"); s2 = fs.getNode("imageSize2")
+    size1 = (int(s1.at(0).real()), int(s1.at(1).real())); size2 = (int(s2.at(0).real()), int(s2.at(1).real()))
+    p0, inter = dr.omni_initialize_stereo(objs, im1, im2, size1, size2, 0)
+    # the GPU path stores the points as float32 (20 B per corner): the golden run uses the same rounded data
+    f32 = lambda a: np.asarray(a, dtype=np.float32).astype(np.float64)
+    o_k, a_k, b_k = [f32(objs[i]) for i in inter], [f32(im1[i]) for i in inter], [f32(im2[i]) for i in inter]
+    d = dict(idx=np.array(inter, dtype=np.int32), off=np.concatenate([[0], np.cumsum([o.shape[0] for o in o_k])]).astype(np.int64),
+             obj=np.concatenate(o_k).astype(np.float32), img1=np.concatenate(a_k).astype(np.float32),
+             img2=np.concatenate(b_k).astype(np.float32), p0=p0)
+    for flags, crit in ((0, (3, 200, 1e-6)), (2 + 64, (1, 30, 0.0))):
+        rec = []
+        p, it, ch = dr.omni_stereo_calibrate_loop(o_k, a_k, b_k, p0, flags, crit[0], crit[1], crit[2], rec)
+        err, sd, rms, idx = dr.omni_stereo_uncertainties(o_k, a_k, b_k, p, flags)
+        key = "f%d" % flags
+        full = np.zeros(p.size); full[idx] = err
+        d[key + "_params"] = p; d[key + "_iters"] = it; d[key + "_change"] = ch; d[key + "_iter3"] = rec[2]["params"]
+        d[key + "_errors"] = full; d[key + "_std"] = sd; d[key + "_rms"] = rms
+        n = len(inter)
+        print("stereo BA flags", flags, "frames", n, "iters", it, "rms", rms, "om", p[:3], "T", p[3:6], "xi", p[6 * (n + 1) + 5], p[6 * (n + 1) + 15])
+    np.savez_compressed(os.path.join(OUT, "stereo_ba_fixture.npz"), **d)
+
+
 if __name__ == "__main__":
     primitives()
     omni()
     rig_dense()
     omni_fixture()
     stereo_rig_fixture()
+    stereo_ba_fixture()
     print("golden fixtures written to", OUT)
