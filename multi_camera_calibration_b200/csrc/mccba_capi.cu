@@ -7,6 +7,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <cmath>
 #include <chrono>
 #include <map>
 #include <unordered_map>
@@ -109,7 +110,7 @@ struct mccba_handle_s {
     int obs_cap = 0;                  // floats per plane per TMA stage of the residual kernel (0: no staging)
     int prec = MCCBA_PRECISION_MIXED; // precision policy of the residual / Jacobian pass (mccba_set_precision)
     int f32_grid = 0, f32_smem = 0;
-    int k1_grid = 0, k1_smem = 0, k5_smem = 0, k5_blocked = 0, panel_smem = 0, iter_kernels = 5, dag_grid = 0;
+    int k1_grid = 0, k1_smem = 0, k5_blocked = 2, iter_kernels = 5, dag_grid = 0;   // k5_blocked: 2 tile DAG, 3 block cyclic reduction
     int band_nw = 0;                  // 6 (block bandwidth + 1) of the reduced system (agreed over the ranks)
     cudaGraphExec_t graph = nullptr;
     int* h_done = nullptr;            // pinned
@@ -269,9 +270,7 @@ int enqueue_iteration(mccba_handle h, bool timed)
         for (auto& e : ev) cudaEventCreate(&e);
     if (timed) cudaEventRecord(ev[0], s);
     // reduce_records rewrites every block that has a source and nothing else writes into its buffer (the collective
-    // is out of place, the tile DAG does not factor in place), so blocks without sources stay zero from allocation;
-    // only the in-place factorisations (MCCBA_CHOL=0/1) on a single rank need the buffer cleared again
-    if (h->opts.nranks == 1 && h->k5_blocked < 2) CUDA_TRY(h, cudaMemsetAsync(P.ar, 0, sizeof(double) * (size_t)h->ar_len, s));
+    // is out of place, neither solver factors in place), so blocks without sources stay zero from allocation
     launch_schur(h, s, -1, 0.0);
     if (timed) cudaEventRecord(ev[1], s);
     reduce_records_kernel<<<P.n_dest, kK3Threads, 0, s>>>(P, 0);
@@ -302,15 +301,9 @@ int enqueue_iteration(mccba_handle h, bool timed)
         attr[0].val.cooperative = 1;
         cfg.attrs = attr; cfg.numAttrs = 1;
         CUDA_TRY(h, cudaLaunchKernelEx(&cfg, chol_dag_kernel, D, P, P.ns <= 512 ? 1 : 0));
-    } else if (h->k5_blocked == 1 && P.ns > 0) {
-        const int ntc = chol_col_tiles(P.ns), ntr = chol_row_tiles(P.ns);
-        for (int k = 0; k < ntc; ++k) {
-            chol_panel_kernel<<<1, kPanelThreads, h->panel_smem, s>>>(P.ar, P.ns, k, &P.st->go, &P.st->chol_fail, P.rinv);
-            if (k + 1 < ntc) chol_update_kernel<<<dim3(ntc - k - 1, ntr - k - 1), kUpdThreads, 0, s>>>(P.ar, P.ns, k, &P.st->go);
-        }
     }
     if (!((h->k5_blocked == 3 && P.ns > 0) || (h->k5_blocked == 2 && P.ns > 0 && P.ns <= 512)))   // otherwise fused into the solve
-        camera_update_kernel<<<1, kK5Threads, h->k5_smem, s>>>(P, h->k5_blocked);
+        camera_update_kernel<<<1, kK5Threads, 0, s>>>(P);
     if (timed) cudaEventRecord(ev[4], s);
     frame_update_kernel<<<P.n_k4_blocks, kK4Threads, kK4SmemBytes, s>>>(P);
     if (timed) cudaEventRecord(ev[5], s);
@@ -848,12 +841,11 @@ int mccba_set_observations(mccba_handle h, int n_frame, int n_edge, const int* e
     h->edge_cam_h.assign(edge_cam, edge_cam + n_edge);
     h->edge_n_h.resize((size_t)n_edge);
     for (int e = 0; e < n_edge; ++e) h->edge_n_h[e] = edge_off[e + 1] - edge_off[e];
-    {   // reduced-system solver: 3 = banded LDL^T by one warp when the camera graph is banded (block bandwidth <= 4),
-        // 2 = one-launch tile DAG, 1 = panel/update kernels per block column, 0 = plain single-CTA column Cholesky
+    {   // reduced-system solver: 3 = block cyclic reduction when the camera graph is block-banded (bandwidth <= 4 and the
+        // super-blocks fit one CTA's shared memory), 2 = one-launch tile DAG otherwise; MCCBA_CHOL=2 forces the latter
         const char* sel = getenv("MCCBA_CHOL");
         int mode = band_fits(h->band_nw, P.ns) ? 3 : 2;
-        if (sel && sel[0] >= '0' && sel[0] <= '3') mode = sel[0] - '0';
-        if (mode == 3 && !band_fits(h->band_nw, P.ns)) mode = 2;
+        if (sel && sel[0] == '2') mode = 2;
         h->k5_blocked = mode;
     }
     P.band_nw = (h->k5_blocked == 3 && P.ns > 0) ? h->band_nw : 0;
@@ -906,7 +898,6 @@ int mccba_set_observations(mccba_handle h, int n_frame, int n_edge, const int* e
     if (h->opts.nranks > 1 && (rc = dev_alloc(h, &P.ar_part, (size_t)h->ar_len, true))) return rc;
     if ((rc = dev_alloc(h, &h->x_saved, (size_t)P.n_param, true))) return rc;
     if ((rc = dev_alloc(h, &P.dc, (size_t)std::max(P.ns, 1), true))) return rc;
-    if ((rc = dev_alloc(h, &P.rinv, (size_t)std::max(P.ns, 1), true))) return rc;
     if ((rc = dev_alloc(h, &P.norm_part, 2 * (size_t)P.n_k4_blocks, true))) return rc;
     P.prec = h->prec;
     if ((rc = dev_alloc(h, &P.erec, (size_t)P.n_edge_int, true))) return rc;
@@ -940,30 +931,20 @@ int mccba_set_observations(mccba_handle h, int n_frame, int n_edge, const int* e
         h->obs_cap = cap;
         h->k1_smem = (int)(fixed + (size_t)cap * 40);
     }
-    {   // reduced-system solver: 2 = one-launch tile DAG (default), 1 = panel/update kernels per block column,
-        // 0 = plain single-CTA column Cholesky (also the fallback when a block column does not fit in shared memory)
-        const size_t need = chol_panel_smem_bytes(P.ns);
-        int mode = h->k5_blocked;   // chosen above, before the packed buffer was sized
-        if (need > 227 * 1024 && mode == 1) mode = 0;
+    {   // the tile DAG spins on hand-overs between its CTAs: every one of them has to be resident at once
         const int ntc = chol_col_tiles(P.ns), ntr = chol_row_tiles(P.ns);
         int grid = 0;
         for (int j = 0; j < ntc; ++j) grid += ntr - j;
-        if (mode == 2) {   // every CTA of the DAG stays resident until the backward sweep has passed it
+        if (h->k5_blocked == 2 && P.ns > 0) {
             int per_sm_dag = 0;
             CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_dag, chol_dag_kernel, 256, 0));
-            if (per_sm_dag * h->num_sms < grid) mode = need <= 227 * 1024 ? 1 : 0;
+            if (per_sm_dag * h->num_sms < grid)
+                return fail(h, MCCBA_ERR_ARG, "reduced camera system of %d unknowns needs %d co-resident CTAs, the device holds %d (dense camera graphs: up to ~250 cameras)", P.ns, grid, per_sm_dag * h->num_sms);
         }
-        h->k5_blocked = mode;
         h->dag_grid = grid;
-        h->panel_smem = (int)need;
-        h->k5_smem = mode == 0 ? (int)(sizeof(double) * (size_t)(P.ns + 2)) : (int)(sizeof(double) * ((size_t)P.ns + 2 + (kK5Threads / 32) * kCLD));
-        if (mode == 1 && h->panel_smem > 48 * 1024)
-            CUDA_TRY(h, cudaFuncSetAttribute(chol_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->panel_smem));
-        if (h->k5_smem > 48 * 1024)
-            CUDA_TRY(h, cudaFuncSetAttribute(camera_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->k5_smem));
-        h->iter_kernels = 6 + (P.ns > 0 ? (mode == 3 ? -1 : mode == 2 ? (P.ns <= 512 ? 0 : 1) : (mode == 1 ? 2 * ntc - 1 : 0)) : 0);
+        h->iter_kernels = 6 + (P.ns > 0 ? (h->k5_blocked == 3 ? -1 : (P.ns <= 512 ? 0 : 1)) : 0);
         if ((rc = dev_alloc(h, &P.dag_buf, chol_dag_words(P.ns) + 8))) return rc;
-        P.dag_words = (mode == 2 && P.ns > 0) ? (int64_t)chol_dag_words(P.ns) : 0;
+        P.dag_words = (h->k5_blocked == 2 && P.ns > 0) ? (int64_t)chol_dag_words(P.ns) : 0;
     }
     int per_sm = 1;
     if (h->obs_cap > 0) {
@@ -1304,82 +1285,45 @@ int mccba_reproj_error(mccba_handle h, mccba_error_stats* stats, double* per_edg
 int mccba_debug_solve_dense(mccba_handle h, int n, const double* S, const double* g, double* x, int blocked)
 {
     if (!h || n < 1 || !S || !g || !x) return MCCBA_ERR_ARG;
+    if (blocked != 2 && blocked != 3) return fail(h, MCCBA_ERR_ARG, "debug_solve_dense: solver %d (2 = tile DAG, 3 = block cyclic reduction)", blocked);
     CUDA_TRY(h, cudaSetDevice(h->opts.device));
-    double *dA = nullptr, *dx = nullptr, *drinv = nullptr;
+    double *dA = nullptr, *dx = nullptr;
     int* dfail = nullptr;
     CUDA_TRY(h, cudaMalloc((void**)&dA, sizeof(double) * (size_t)(n + 1) * n));
     CUDA_TRY(h, cudaMalloc((void**)&dx, sizeof(double) * (size_t)n));
-    CUDA_TRY(h, cudaMalloc((void**)&drinv, sizeof(double) * (size_t)n));
     CUDA_TRY(h, cudaMalloc((void**)&dfail, sizeof(int)));
     CUDA_TRY(h, cudaMemsetAsync(dfail, 0, sizeof(int), h->stream));
     CUDA_TRY(h, cudaMemcpyAsync(dA, S, sizeof(double) * (size_t)n * n, cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(h, cudaMemcpyAsync(dA + (size_t)n * n, g, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, h->stream));
-    const size_t pneed = chol_panel_smem_bytes(n);
-    if ((blocked == 1 || blocked == 2) && pneed > 227 * 1024) { cudaFree(dA); cudaFree(dx); cudaFree(drinv); cudaFree(dfail); return fail(h, MCCBA_ERR_ARG, "n too large for the tiled solver"); }
-    const size_t bneed = blocked ? sizeof(double) * ((size_t)n + 2 + (kK5Threads / 32) * kCLD) : sizeof(double) * (size_t)(n + 2);
-    if (blocked != 3) {
-        CUDA_TRY(h, cudaFuncSetAttribute(chol_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(pneed, 1024)));
-        CUDA_TRY(h, cudaFuncSetAttribute(dense_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(bneed, 1024)));
-    }
-    CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));
+    auto release = [&]() { cudaFree(dA); cudaFree(dx); cudaFree(dfail); };
     double* dflags = nullptr;
+    Problem none;
+    memset(&none, 0, sizeof(none));
     if (blocked == 3) {   // block cyclic reduction: the bandwidth in 6 x 6 blocks is measured on the host copy
         int m = 1;
         for (int i = 0; i < n; ++i)
             for (int j = 0; j < i; ++j)
                 if (S[(size_t)i * n + j] != 0.0) m = std::max(m, i / 6 - j / 6);
         const int nw = 6 * (m + 1);
-        if (!band_fits(nw, n)) { cudaFree(dA); cudaFree(dx); cudaFree(drinv); cudaFree(dfail); return fail(h, MCCBA_ERR_ARG, "block bandwidth %d is too wide for the banded solver", m); }
-        Problem none;
-        memset(&none, 0, sizeof(none));
+        if (!band_fits(nw, n)) { release(); return fail(h, MCCBA_ERR_ARG, "block bandwidth %d is too wide for the banded solver", m); }
         CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));
         CUDA_TRY(h, launch_band(nw, dA, n, dx, dfail, nullptr, none, 0, 0, h->stream));
-    } else if (blocked == 2) {
+    } else {
         const int ntc = chol_col_tiles(n), ntr = chol_row_tiles(n);
         int grid = 0;
         for (int j = 0; j < ntc; ++j) grid += ntr - j;
-        {   // every CTA of the DAG must be resident at once (see chol_dag_tile)
-            int per_sm_dag = 0;
-            CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_dag, chol_dag_kernel, 256, 0));
-            if (per_sm_dag * h->num_sms < grid) {
-                cudaFree(dA); cudaFree(dx); cudaFree(drinv); cudaFree(dfail);
-                return fail(h, MCCBA_ERR_ARG, "n = %d needs %d co-resident CTAs for the tile DAG, the device holds %d", n, grid, per_sm_dag * h->num_sms);
-            }
+        int per_sm_dag = 0;   // every CTA of the DAG must be resident at once (see chol_dag_tile)
+        CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_dag, chol_dag_kernel, 256, 0));
+        if (per_sm_dag * h->num_sms < grid) {
+            release();
+            return fail(h, MCCBA_ERR_ARG, "n = %d needs %d co-resident CTAs for the tile DAG, the device holds %d", n, grid, per_sm_dag * h->num_sms);
         }
         CUDA_TRY(h, cudaMalloc((void**)&dflags, sizeof(double) * chol_dag_words(n)));
         CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));
         CUDA_TRY(h, cudaMemsetAsync(dflags, 0xFF, sizeof(double) * chol_dag_words(n), h->stream));
-        unsigned long long* dtrace = nullptr;
-        if (getenv("MCCBA_DAG_TRACE")) {
-            CUDA_TRY(h, cudaMalloc((void**)&dtrace, sizeof(unsigned long long) * 8 * (size_t)grid));
-            CUDA_TRY(h, cudaMemsetAsync(dtrace, 0, sizeof(unsigned long long) * 8 * (size_t)grid, h->stream));
-        }
-        CholDag D{dA, dflags, n, dx, nullptr, dfail, dtrace};
-        chol_dag_kernel<<<grid, 256, 0, h->stream>>>(D, h->P, 0);
-        if (dtrace) {   // diagnostics: per-tile timeline in ns relative to the first stamp
-            std::vector<unsigned long long> tr(8 * (size_t)grid);
-            CUDA_TRY(h, cudaMemcpyAsync(tr.data(), dtrace, sizeof(unsigned long long) * tr.size(), cudaMemcpyDeviceToHost, h->stream));
-            CUDA_TRY(h, cudaStreamSynchronize(h->stream));
-            unsigned long long t0 = ~0ull;
-            for (size_t b = 0; b < (size_t)grid; ++b) if (tr[8 * b]) t0 = std::min(t0, tr[8 * b]);
-            int bi = 0;
-            for (int j = 0; j < ntc; ++j)
-                for (int i = j; i < ntr; ++i, ++bi) {
-                    if (i > j + 1 && i != ntr - 1) continue;   // diagonal, first sub-diagonal and the g-row tile
-                    fprintf(stderr, "tile(%2d,%2d):", i, j);
-                    for (int k = 0; k < 7; ++k) fprintf(stderr, " %8lld", tr[8 * bi + k] ? (long long)(tr[8 * bi + k] - t0) : -1LL);
-                    fprintf(stderr, "\n");
-                }
-            cudaFree(dtrace);
-        }
-    } else if (blocked) {
-        const int ntc = chol_col_tiles(n), ntr = chol_row_tiles(n);
-        for (int k = 0; k < ntc; ++k) {
-            chol_panel_kernel<<<1, kPanelThreads, pneed, h->stream>>>(dA, n, k, nullptr, dfail, drinv);
-            if (k + 1 < ntc) chol_update_kernel<<<dim3(ntc - k - 1, ntr - k - 1), kUpdThreads, 0, h->stream>>>(dA, n, k, nullptr);
-        }
+        CholDag D{dA, dflags, n, dx, nullptr, dfail, nullptr};
+        chol_dag_kernel<<<grid, 256, 0, h->stream>>>(D, none, 0);
     }
-    if (blocked != 3) dense_backward_kernel<<<1, kK5Threads, bneed, h->stream>>>(dA, n, drinv, dx, dfail, blocked);
     CUDA_TRY(h, cudaEventRecord(h->ev1, h->stream));
     int f = 0;
     CUDA_TRY(h, cudaMemcpyAsync(x, dx, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
@@ -1389,8 +1333,11 @@ int mccba_debug_solve_dense(mccba_handle h, int n, const double* S, const double
     float ms = 0;
     cudaEventElapsedTime(&ms, h->ev0, h->ev1);
     h->prof_ms[0] = ms;
-    cudaFree(dA); cudaFree(dx); cudaFree(drinv); cudaFree(dfail);
+    release();
     if (dflags) cudaFree(dflags);
+    if (!f)
+        for (int i = 0; i < n; ++i)
+            if (!std::isfinite(x[i])) f = 1;     // the tile DAG reports a bad pivot as non-finite entries of the solution
     return f ? fail(h, MCCBA_ERR_NUMERIC, "matrix is not positive definite") : MCCBA_OK;
 }
 

@@ -9,8 +9,9 @@
 //   frame_schur_kernel       (new math) eliminates the per-frame pattern-pose blocks; replaces the P x P solve
 //   reduce_records_kernel    deterministic, atomic-free sum of the warp records into the reduced camera system
 //   decide_kernel            optimizeExtrinsics' loop control (src/multicalib.cpp:473-507) + accept/reject (LM)
-//   chol_panel/update_kernel tiled Cholesky of the reduced system (replaces Eigen CG, :565-592)
-//   camera_update_kernel     backward substitution + camera part of the update (:491-504)
+//   chol_bcr_kernel          block cyclic reduction of the block-banded reduced system (replaces Eigen CG, :565-592)
+//   chol_dag_kernel          one-launch tiled Cholesky of a dense reduced system (same)
+//   camera_update_body       camera part of the update (:491-504), fused into the tail of the two solvers
 //   frame_update_kernel      back-substitution + parameter update (:491-504)
 #pragma once
 #include <cuda_runtime.h>
@@ -98,7 +99,6 @@ struct Problem {
     double* warp_scal;   // 2 x n_warps: [cost | bad] of every Schur warp, contiguous so that the scalar reduction is coalesced
     double* ar;          // allreduce buffer: S (ns x ns) | g (ns) | cost, step2, param2, bad
     double* dc;          // ns: camera step in tangent coordinates
-    double* rinv;        // ns: reciprocal diagonal of the Cholesky factor
     // peer-memory exchange of the packed reduced system (N > 1, see p2p_exchange_kernel): every rank's window is
     // [header | parity 0: n ranks x p2p_stride doubles | parity 1: ...] (a slot holds 2 words per element, LL protocol),
     // mapped into every process by CUDA IPC
@@ -1204,57 +1204,6 @@ __global__ void __launch_bounds__(kK3Threads) reduce_records_kernel(Problem P, i
     }
 }
 
-// --------------------------------------------------------------------------------------------------------
-// K5: loop control + Cholesky solve of the reduced camera system.  Single CTA.
-// Augmented matrix A = [S; g^T] ((ns+1) x ns, exactly the allreduce buffer layout): the right-looking
-// factorisation also produces y = L^-1 g in the extra row; a backward sweep gives dc.
-// --------------------------------------------------------------------------------------------------------
-__device__ int chol_solve_cta(double* A, int n, double* xout, double* s_col, double* s_bcast)
-{
-    const int tid = threadIdx.x, nt = blockDim.x;
-    __shared__ int s_fail;
-    if (tid == 0) s_fail = 0;
-    __syncthreads();
-    for (int j = 0; j < n; ++j) {
-        if (tid == 0) {
-            const double d = A[(int64_t)j * n + j];
-            if (!(d > 0.0) || !isfinite(d)) s_fail = 1;
-            const double inv = 1.0 / sqrt(d > 0.0 ? d : 1.0);
-            s_bcast[0] = inv;
-            A[(int64_t)j * n + j] = d * inv;
-        }
-        __syncthreads();
-        const double inv = s_bcast[0];
-        for (int i = j + 1 + tid; i <= n; i += nt) {
-            const double v = A[(int64_t)i * n + j] * inv;
-            A[(int64_t)i * n + j] = v;
-            s_col[i] = v;
-        }
-        __syncthreads();
-        const int w = n - 1 - j;  // trailing columns j+1 .. n-1
-        if (w > 0) {
-            const int rows = n - j;  // rows j+1 .. n
-            for (int idx = tid; idx < rows * w; idx += nt) {
-                const int i = j + 1 + idx / w, k = j + 1 + idx % w;
-                if (k <= i) A[(int64_t)i * n + k] -= s_col[i] * s_col[k];
-            }
-        }
-        __syncthreads();
-    }
-    // backward: L^T x = y, y = row n of A
-    for (int i = tid; i < n; i += nt) s_col[i] = A[(int64_t)n * n + i];
-    __syncthreads();
-    for (int j = n - 1; j >= 0; --j) {
-        if (tid == 0) s_bcast[0] = s_col[j] / A[(int64_t)j * n + j];
-        __syncthreads();
-        const double xj = s_bcast[0];
-        for (int i = tid; i < j; i += nt) s_col[i] -= A[(int64_t)j * n + i] * xj;
-        if (tid == 0) xout[j] = xj;
-        __syncthreads();
-    }
-    return s_fail;
-}
-
 // loop control (single warp): accept/reject of the trial point, damping, termination; sets st->go
 // --------------------------------------------------------------------------------------------------------
 // C1 (N > 1): the per-iteration exchange of the packed buffer [S | g | scalars] over NVLink peer memory.
@@ -1380,21 +1329,6 @@ __global__ void decide_kernel(Problem P)
     if (threadIdx.x == 0) decide_body(P);
 }
 
-// Cholesky of the reduced system, one block column per launch pair (mccba_dense.cuh).  go == nullptr: always run.
-__global__ void __launch_bounds__(kPanelThreads) chol_panel_kernel(double* A, int n, int k, const int* go, int* fail, double* rinv)
-{
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    if (go && !*go) return;
-    chol_panel(A, n, k, fail, rinv, reinterpret_cast<double*>(smem_raw));
-}
-__global__ void __launch_bounds__(kUpdThreads) chol_update_kernel(double* A, int n, int k, const int* go)
-{
-    if (go && !*go) return;
-    const int ti = k + 1 + blockIdx.y, tj = k + 1 + blockIdx.x;
-    if (tj > ti) return;
-    chol_update_tile(A, n, k, ti, tj);
-}
-
 // the whole factorisation + both substitutions in one launch (mccba_dense.cuh, tile DAG)
 __device__ __forceinline__ void camera_update_body(const Problem& P, const double* dc, int fail);
 
@@ -1505,28 +1439,13 @@ __global__ void __launch_bounds__(BcrCfg<B>::kThreads) chol_bcr_kernel(const dou
     else if (threadIdx.x == 0 && fail) *fail_out = 1;
 }
 
-// backward substitution + camera update (replicated on every rank) + end-of-iteration state.  Single CTA.
-__global__ void __launch_bounds__(kK5Threads) camera_update_kernel(Problem P, int tiled)
+// camera update for the cases where it is not fused into the solve (tile DAG with n_s > 512, or no camera unknowns at
+// all): the solution is already in P.dc.  Single CTA.
+__global__ void __launch_bounds__(kK5Threads) camera_update_kernel(Problem P)
 {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    double* s_dyn = reinterpret_cast<double*>(smem_raw);
-    __shared__ double s_bcast[2];
     DevState* st = P.st;
     if (!st->go) return;
-    const int ns = P.ns;
-    int fail = 0;
-    if (ns > 0) {
-        if (tiled == 2) {
-            fail = st->chol_fail;                      // chol_dag_kernel already left the solution in P.dc
-        } else if (tiled == 1) {
-            chol_backward(P.ar, ns, P.rinv, P.dc, s_dyn);
-            fail = st->chol_fail;
-        } else {
-            fail = chol_solve_cta(P.ar, ns, P.dc, s_dyn, s_bcast);
-        }
-    }
-    __syncthreads();
-    camera_update_body(P, P.dc, fail);
+    camera_update_body(P, P.dc, P.ns > 0 ? st->chol_fail : 0);
 }
 
 // --------------------------------------------------------------------------------------------------------
@@ -1692,20 +1611,6 @@ __global__ void __launch_bounds__(kK4Threads) frame_update_kernel(Problem P)
         for (int w = 0; w < kK4Threads / 32; ++w) { a += s_red[0][w]; b += s_red[1][w]; }
         P.norm_part[blockIdx.x] = a;
         P.norm_part[P.n_k4_blocks + blockIdx.x] = b;
-    }
-}
-
-// test hook: backward substitution of the tiled solver / the plain single-CTA solver on a standalone matrix
-__global__ void __launch_bounds__(kK5Threads) dense_backward_kernel(double* A, int n, const double* rinv, double* x, int* fail, int tiled)
-{
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    double* s_dyn = reinterpret_cast<double*>(smem_raw);
-    __shared__ double s_bcast[2];
-    if (tiled == 2) return;
-    if (tiled) chol_backward(A, n, rinv, x, s_dyn);
-    else {
-        const int f = chol_solve_cta(A, n, x, s_dyn, s_bcast);
-        if (threadIdx.x == 0 && f) *fail = 1;
     }
 }
 

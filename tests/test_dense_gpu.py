@@ -1,6 +1,6 @@
 """Reduced-system solvers in isolation (mccba_debug_solve_dense): every size class of the tile DAG -- single tile, ragged
 last block column, g row in its own tile row (n % 32 == 0), the config #5 size -- and the block cyclic reduction of banded
-systems (mode 3) against numpy.  Replaces the Eigen CG of
+systems (mode 3) against numpy.  (The per-column and panel / update solvers of round 1 are gone: two solvers ship.)  Replaces the Eigen CG of
 src/multicalib.cpp:565-592 on the Schur-reduced system."""
 import numpy as np
 import pytest
@@ -24,7 +24,7 @@ def _spd(n, seed):
     return M @ M.T + n * np.eye(n), rng.standard_normal(n)
 
 
-@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("mode", [2])
 @pytest.mark.parametrize("n", SIZES)
 def test_dense_solve_matches_numpy(solver, n, mode):
     S, g = _spd(n, 100 + n)
@@ -33,7 +33,7 @@ def test_dense_solve_matches_numpy(solver, n, mode):
     assert np.abs(x - ref).max() <= 1e-11 * max(np.abs(ref).max(), 1e-300) * n      # fp64, cond ~ 10
 
 
-@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("mode", [2])
 def test_dense_solve_ill_conditioned(solver, mode):
     """Reduced camera systems of real rigs have condition numbers ~1e9: the factorisation must stay backward stable."""
     n = 190
@@ -46,7 +46,7 @@ def test_dense_solve_ill_conditioned(solver, mode):
     assert np.linalg.norm(S @ x - g) <= 1e-9 * (np.linalg.norm(S, 2) * np.linalg.norm(x) + np.linalg.norm(g))
 
 
-@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("mode", [2])
 @pytest.mark.parametrize("n", [7, 40, 100])
 def test_dense_solve_rejects_indefinite(solver, n, mode):
     import multi_camera_calibration_b200 as m
