@@ -40,6 +40,25 @@ def _peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def _pipe_block(M, k1_ms, clocks):
+    """Arithmetic-pipe view of the dominant kernel: instruction counts per corner from the ncu source page of the committed
+    capture (profiles/r2_summary.md), pipe rates measured on the box with scripts/ubench (profiles/r2_pipe_peaks.txt)."""
+    p = os.path.join(ROOT, "profiles", "k1_pipes.json")
+    try:
+        d = json.load(open(p))
+    except Exception:
+        return None
+    mhz = (clocks or {}).get("sm_mhz") or d.get("sm_mhz", 1965.0)
+    sm = d.get("sms", 148)
+    out = dict(d)
+    # lane-instructions per clock per SM measured for realistic operand patterns (3 distinct registers)
+    fp64_us = d["fp64_instr_per_corner"] * M / (d["dfma_lane_instr_per_clk_sm"] * sm * mhz * 1e6) * 1e6
+    fma_us = d["f32x2_instr_per_corner"] * M / (d["ffma2_lane_instr_per_clk_sm"] * sm * mhz * 1e6) * 1e6
+    out.update(fp64_pipe_floor_us=fp64_us, fma_pipe_floor_us=fma_us, kernel_us=k1_ms * 1e3,
+               frac_of_binding_pipe=max(fp64_us, fma_us) / (k1_ms * 1e3))
+    return out
+
+
 def _k1_traffic():
     p = os.path.join(ROOT, "profiles", "k1_traffic.json")
     if os.path.exists(p):
@@ -243,6 +262,67 @@ def _extra_legs(args, m, s, rig, pin, kw, world, rank, local, barrier):
     out["config4"] = {"workload": "BASELINE configs[3]: 16-camera mixed pinhole/omnidir rig, %d frames in total over %d GPU(s)" % (fr4 * world, world),
                       "us_per_lm_iteration": ms * 1e3 / it, "lm_iters_per_sec": it / (ms * 1e-3),
                       "corner_obs_per_s": world * r4["n_points"] * it / (ms * 1e-3), "rms_px": err["rms"]}
+    # (e) the other precision policies on the headline rig (rank-local timing; the default policy is the headline itself)
+    if world == 1:
+        pol = {}
+        for name, prec in (("fp64", m.capi.PRECISION_FP64), ("mixed", m.capi.PRECISION_MIXED), ("fast32", m.capi.PRECISION_FAST32)):
+            sp = m.Solver(device=local, precision=prec)
+            sp.set_cameras(rig["cam_model"], rig["cam_K5"], rig["cam_dist8"], rig["cam_ndist"], rig["cam_xi"])
+            sp.set_observations(rig["n_frame"], rig["edge_cam"], rig["edge_pv"], rig["edge_off"], pin["obj"], pin["img"])
+            sp.set_parameters(pin["params_init"])
+            sp.save_parameters()
+            ms, rep = _time_solves(sp, kw, 5, 3, 1, barrier)
+            k1 = min(sp.time_eval(reps=10) for _ in range(2))
+            e = sp.reproj_error()
+            pol[name] = {"resjac_kernel_us": k1 * 1e3, "resjac_gbs": 20.0 * M / (k1 * 1e-3) / 1e9,
+                         "us_per_lm_iteration": ms * 1e3 / max(rep["iterations"], 1), "final_cost": rep["cost"], "rms_px": e["rms"],
+                         "accepted": rep["accepted"], "rejected": rep["rejected"]}
+            sp.close()
+        pol["default"] = "mixed"
+        pol["parity"] = ("fp64: oracle to 1e-8; mixed: cameras 1e-8, worst pattern-pose parameter of config #5 1.0e-6 "
+                         "(tests/test_full_size_gpu.py); fast32: ~2e-6, outside the gate, opt-in")
+        out["precision_policies"] = pol
+    # (f) BASELINE configs[2]: single-camera Mei calibration (omnidir::calibrate loop), 5k frames, intrinsics + distortion
+    if world == 1:
+        r3 = synth.make_config(3)
+        n3 = r3["n_frame"]
+        pt = r3["params_true"].reshape(-1, 6)
+        K5, D, xi = r3["cam_K5"][0], r3["cam_dist8"][0][:4], r3["cam_xi"][0]
+        poses = np.array([pt[r3["edge_pv"][e] - 1] for e in range(n3)])
+        p3 = np.concatenate([poses.ravel(), [K5[0] * 1.03, K5[1] * 1.03, K5[4], K5[2], K5[3], xi + 0.1], np.zeros(4)])
+        so = m.Solver(device=local)
+        so.omni_set_observations(r3["edge_off"], r3["obj"], r3["img"])
+        its = 50
+        t3 = []
+        for _ in range(4):
+            so.omni_set_parameters(p3)
+            t3.append(so.omni_solve(0, 1, its, 0.0)["device_ms"])
+        ms3 = float(np.median(t3[1:]))
+        out["config3"] = {"workload": "BASELINE configs[2]: single Mei camera, %d frames, %d corners, 6n+10 = %d parameters; %d iterations of the omnidir::calibrate schedule" % (n3, r3["n_points"], 6 * n3 + 10, its),
+                          "us_per_iteration": ms3 * 1e3 / its, "iters_per_sec": its / (ms3 * 1e-3),
+                          "resjac_evals_per_sec": r3["n_points"] * its / (ms3 * 1e-3)}
+        so.close()
+    # (g) second end-to-end figure: the drop-in CLASS (file ingest, indexing, initialisation, optimisation, XML output) on
+    # BASELINE configs[3] (16 cameras, 10k frames): MultiCameraCalibration(...).run(); writeParameters(...)
+    if world == 1:
+        import tempfile
+        from multi_camera_calibration_b200 import multicalib, obsfile
+        r4f = synth.make_config(4)
+        with tempfile.TemporaryDirectory() as td:
+            path = os.path.join(td, "rig.mccb")
+            obsfile.write_rig(path, r4f)
+            tt = []
+            for _ in range(3):
+                t0 = time.perf_counter()
+                mc = multicalib.MultiCameraCalibration(0, 16, path, 360.0, 200.0, criteria=(1, 20, 1e-7), mode=m.capi.MODE_LM, device=local)
+                mc.run()
+                mc.writeParameters(os.path.join(td, "out.xml"))
+                tt.append(time.perf_counter() - t0)
+                st4 = mc.stats()
+                mc.close()
+            out["e2e_host_class"] = {"workload": "MultiCameraCalibration(16 cameras, 10k frames).run() + writeParameters(): observation file -> XML, 20 LM iterations",
+                                     "seconds": float(np.median(tt[1:])), "file_mb": os.path.getsize(path) / 1e6, "rms_px": st4["rms"],
+                                     "device_ms_of_the_solve": st4["device_ms"]}
     # (d) parity of the sharded path (both exchanges) against the oracle on the whole rig
     if world > 1:
         from scripts import mgpu_parity
@@ -253,6 +333,33 @@ def _extra_legs(args, m, s, rig, pin, kw, world, rank, local, barrier):
                              "cases": [c["case"] + ":" + c["exchange"] for c in res["cases"]],
                              "checker": "oracle/ on the whole rig (rank 0), tolerance 1e-6"}
     return out
+
+
+def _literal_reference_toy():
+    """BASELINE configs[0] substitute, part (c): the reference's LITERAL algorithm -- dense 2M x P Jacobian, dense J^T J, full
+    P x P solve per iteration (src/multicalib.cpp:593-703) -- timed where it still fits: a 3-camera x 60-frame rig (the
+    author's own use case: 3 serials, samples/multi_cameras_calibration.cpp:53), through the numpy re-enactment
+    (oracle/dense_reenact.py, cv2 where the reference calls OpenCV).  CPU baseline leg only."""
+    from multi_camera_calibration_b200 import synth
+    from oracle import dense_reenact as dr
+    rig = synth.make_rig(n_cam=3, n_frame=60, seed=1001)
+    nC = rig["n_cam"]
+    K = np.zeros((nC, 3, 3))
+    for c in range(nC):
+        fx, fy, cx, cy, sk = rig["cam_K5"][c]
+        K[c] = [[fx, sk, cx], [0, fy, cy], [0, 0, 1]]
+    dist = [rig["cam_dist8"][c][:rig["cam_ndist"][c]] for c in range(nC)]
+    edges = []
+    for e in range(rig["edge_cam"].size):
+        a, b = rig["edge_off"][e], rig["edge_off"][e + 1]
+        edges.append((int(rig["edge_cam"][e]), int(rig["edge_pv"][e]), rig["obj"][a:b], rig["img"][a:b]))
+    prob = dr.RigProblem(rig["cam_model"], K, dist, rig["cam_xi"], edges, nC + rig["n_frame"])
+    t0 = time.perf_counter()
+    p, it, ch = dr.optimize_extrinsics(prob, rig["params_init"], 1, 5, 1e-7, policy="fp64")
+    dt = (time.perf_counter() - t0) / 5
+    return {"workload": "3 cameras x 60 frames, %d corners, P = %d parameters: dense J (%d x %d), dense J^T J, full solve" %
+                        (rig["n_points"], rig["params_init"].size, 2 * rig["n_points"], rig["params_init"].size),
+            "seconds_per_iteration": dt, "corner_obs_per_s": rig["n_points"] / dt, "kind": "literal re-enactment (numpy + cv2)"}
 
 
 def run_ours(args):
@@ -376,6 +483,11 @@ def run_ours(args):
         cpu = {"value": M * ci * reps / cdt, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": "full rig (%d corners), %d solves of %d LM iterations (%.1f s of CPU work)" % (M, reps, ci, cdt),
                "lm_iters_per_sec": ci * reps / cdt}
+    if cpu is not None:
+        try:
+            cpu["literal_reference_toy"] = _literal_reference_toy()
+        except Exception as e:                     # cv2 missing on the box: the toy leg is informative only
+            cpu["literal_reference_toy"] = {"unavailable": str(e)[:200]}
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
@@ -386,10 +498,14 @@ def run_ours(args):
                        "final_cost": rep["cost"], "rms_px": err["rms"]},
                 "roofline": {"bound": "hbm", "achieved": k1_gbs, "peak": peak, "unit": "GB/s", "frac": k1_gbs / peak,
                              "traffic": (traffic or {}).get("dram_bytes_per_launch"), "peak_source": peak_src,
-                             "kernel": "resid_jac_accum_kernel", "kernel_ms": k1_ms,
+                             "kernel": {0: "resid_jac_accum_kernel (FP64)", 1: "resid_jac_accum_f32_kernel<true> (MIXED)",
+                                        2: "resid_jac_accum_f32_kernel<false> (FAST32)"}[s.get_precision()], "kernel_ms": k1_ms,
                              "algorithmic_bytes_per_launch": 20.0 * M,
                              "whole_iteration_gbs": iter_gbs, "whole_iteration_frac": iter_gbs / peak,
-                             "note": "fp64 arithmetic: the kernel is FP64-pipe-bound, see DESIGN.md"},
+                             "traffic_source": "static: ncu --set full capture of this kernel (profiles/k1_traffic.json)",
+                             "pipes": _pipe_block(M, k1_ms, clocks),
+                             "note": "MIXED policy: residual in double, Jacobian products in packed float32; the kernel is bound by "
+                                     "the FMA / FP64 pipes, not by HBM (DESIGN.md section 4)"},
                 "exchange": {0: "none", 1: "ncclAllReduce", 2: "nvlink-peer-memory"}[s.exchange_mode()],
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                         "ms_per_step": e2e_ms, "steps": e2e_steps},
