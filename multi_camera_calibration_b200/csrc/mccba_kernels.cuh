@@ -24,6 +24,9 @@
 
 namespace mccba {
 
+// Y = L^-1 W records as float for the non-fp64 policies: measured slower (frame_update 30 -> 38 us: the conversions cost more
+// than the halved tile traffic saves, the tiles come out of L2 anyway), so off.
+constexpr bool kYFloat = false;
 constexpr int kLanesPerEdge = 8;
 constexpr int kK1Threads = 256;
 constexpr int kEdgesPerBlock = kK1Threads / kLanesPerEdge;  // 32
@@ -1037,7 +1040,7 @@ __global__ void __launch_bounds__(kK2Threads, kMinBlocks) frame_schur_kernel(Pro
             for (int j = 0; j < 6; ++j) chol6_forward(U, Y + j, 6);  // Y = L^-1 W, column by column
 #pragma unroll
             for (int k = 0; k < 36; ++k) {
-                if (P.prec) reinterpret_cast<float*>(P.edgeY)[tile_idx(36, e, k)] = (float)Y[k];
+                if (kYFloat && P.prec) reinterpret_cast<float*>(P.edgeY)[tile_idx(36, e, k)] = (float)Y[k];
                 else P.edgeY[tile_idx(36, e, k)] = Y[k];
             }
             if (v < 2) {   // keep Y for the off-diagonal pass (own column only: no other lane reads it)
@@ -1083,7 +1086,7 @@ __global__ void __launch_bounds__(kK2Threads, kMinBlocks) frame_schur_kernel(Pro
                 } else {
 #pragma unroll
                     for (int k = 0; k < 36; ++k) {
-                        if (P.prec) { Ya[k] = reinterpret_cast<const float*>(P.edgeY)[tile_idx(36, ea, k)]; Yb[k] = reinterpret_cast<const float*>(P.edgeY)[tile_idx(36, ebx, k)]; }
+                        if (kYFloat && P.prec) { Ya[k] = reinterpret_cast<const float*>(P.edgeY)[tile_idx(36, ea, k)]; Yb[k] = reinterpret_cast<const float*>(P.edgeY)[tile_idx(36, ebx, k)]; }
                         else { Ya[k] = P.edgeY[tile_idx(36, ea, k)]; Yb[k] = P.edgeY[tile_idx(36, ebx, k)]; }
                     }
                 }
@@ -1482,11 +1485,11 @@ __global__ void __launch_bounds__(kK4Threads) frame_update_kernel(Problem P)
         if (lane == 0) {
             mbar_init(bar, 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-            const unsigned ytile = P.prec ? 36u * 128u : 36u * 256u;
+            const unsigned ytile = (kYFloat && P.prec) ? 36u * 128u : 36u * 256u;
             const unsigned bytes = 27u * 256u + (c0v != 0 ? ytile : 0u) + (c1v != 0 ? ytile : 0u);
             mbar_expect_tx(bar, bytes);
             tma_load_1d(fl, P.frameL + (int64_t)warp * 27 * 32, 27u * 256u, bar);
-            if (P.prec) {   // float records: half the bytes, same tile geometry
+            if (kYFloat && P.prec) {   // float records: half the bytes, same tile geometry
                 const float* yf = reinterpret_cast<const float*>(P.edgeY);
                 float* eyf = reinterpret_cast<float*>(ey);
                 if (c0v != 0) tma_load_1d(eyf, yf + ((ebase + ls) >> 5) * 36 * 32, 36u * 128u, bar);
@@ -1523,7 +1526,7 @@ __global__ void __launch_bounds__(kK4Threads) frame_update_kernel(Problem P)
             const int c = v == 0 ? c0v : c1v;
 #pragma unroll
             for (int k = 0; k < 36; ++k)
-                Y2[v][k] = c == 0 ? 0.0 : (P.prec ? (double)reinterpret_cast<const float*>(ey)[(v * 36 + k) * 32 + lane] : ey[(v * 36 + k) * 32 + lane]);
+                Y2[v][k] = c == 0 ? 0.0 : ((kYFloat && P.prec) ? (double)reinterpret_cast<const float*>(ey)[(v * 36 + k) * 32 + lane] : ey[(v * 36 + k) * 32 + lane]);
         }
         __syncwarp();   // every lane has taken its columns out of `ey`, which now stages the outgoing edge records
         EdgeRec* stage = reinterpret_cast<EdgeRec*>(ey);
@@ -1547,7 +1550,7 @@ __global__ void __launch_bounds__(kK4Threads) frame_update_kernel(Problem P)
                     double acc = 0;
 #pragma unroll
                     for (int k = 0; k < 6; ++k)
-                        acc += (P.prec ? (double)reinterpret_cast<const float*>(P.edgeY)[tile_idx(36, e, i * 6 + k)] : P.edgeY[tile_idx(36, e, i * 6 + k)]) * d[k];
+                        acc += ((kYFloat && P.prec) ? (double)reinterpret_cast<const float*>(P.edgeY)[tile_idx(36, e, i * 6 + k)] : P.edgeY[tile_idx(36, e, i * 6 + k)]) * d[k];
                     r[i] -= acc;
                 }
             }
