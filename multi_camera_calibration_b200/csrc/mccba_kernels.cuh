@@ -1455,12 +1455,19 @@ __global__ void __launch_bounds__(kK5Threads) camera_update_kernel(Problem P)
 // K4: back-substitution of the pattern-pose steps + trial parameters + rotations of the trial point.
 // One thread per frame slot.  d_p = L^-T (z - sum_v Y_v dc_v).
 // --------------------------------------------------------------------------------------------------------
-// Shared memory per warp: the frame-factor tile (27 x 32 doubles) and the Y tiles of the first two views (36 x 32
-// doubles each), fetched by the TMA engine (tile-major records: each is one contiguous block) while the lanes load the
-// camera steps and poses; 4 mbarriers behind the tiles.
-constexpr int kK4WarpDoubles = (27 + 2 * 36) * 32;
-constexpr int kK4SmemBytes = (kK4Threads / 32) * kK4WarpDoubles * 8 + (kK4Threads / 32) * 8;
-__global__ void __launch_bounds__(kK4Threads) frame_update_kernel(Problem P)
+// Every record the thread reads is tile-major, so lane-indexed loads of one value are one contiguous 256-byte row per
+// warp: the factor (27 values) and the Y blocks (36 per view) are read straight from global memory, ~100 independent
+// coalesced loads per thread in flight, and Y is consumed as it arrives (6 accumulators instead of 72 registers).  Shared
+// memory only stages the outgoing composed edge poses (two 3 KB bulk stores per warp), which leaves the register file
+// as the only limit on residency: kK4MinBlocks CTAs per SM instead of the 2 the 25 KB-per-warp TMA staging allowed
+// (measured on config #5: 33.4 us with the staged tiles, 30.9 / 29.2 / 33.0 us at 4 / 3 / 5 CTAs per SM = 128 / 168 / 96 registers).
+#ifndef MCCBA_K4_MINBLOCKS
+#define MCCBA_K4_MINBLOCKS 3
+#endif
+constexpr int kK4MinBlocks = MCCBA_K4_MINBLOCKS;
+constexpr int kK4WarpBytes = 2 * 32 * (int)sizeof(EdgeRec);
+constexpr int kK4SmemBytes = (kK4Threads / 32) * kK4WarpBytes;
+__global__ void __launch_bounds__(kK4Threads, kK4MinBlocks) frame_update_kernel(Problem P)
 {
     extern __shared__ __align__(128) unsigned char k4_smem[];
     const DevState* st = P.st;
@@ -1469,9 +1476,7 @@ __global__ void __launch_bounds__(kK4Threads) frame_update_kernel(Problem P)
     const double alpha = st->alpha;
     const int slot = blockIdx.x * blockDim.x + threadIdx.x;
     const int wic = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    double* fl = reinterpret_cast<double*>(k4_smem) + wic * kK4WarpDoubles;
-    double* ey = fl + 27 * 32;
-    unsigned long long* bar = reinterpret_cast<unsigned long long*>(k4_smem + (kK4Threads / 32) * kK4WarpDoubles * 8) + wic;
+    EdgeRec* stage = reinterpret_cast<EdgeRec*>(k4_smem + wic * kK4WarpBytes);
     double step2 = 0, par2 = 0;
     if (slot < P.n_slots) {   // n_slots is a multiple of 32: whole warps
         const int frame = P.slot_frame[slot];
@@ -1481,76 +1486,29 @@ __global__ void __launch_bounds__(kK4Threads) frame_update_kernel(Problem P)
         const int* gc = P.group_cams + m0.y;
         const int ls = m1.x + lane;
         const int64_t ebase = m0.z, stride = m0.w;
-        const int c0v = gc[0], c1v = V > 1 ? gc[1] : 0;
-        if (lane == 0) {
-            mbar_init(bar, 1);
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-            const unsigned ytile = (kYFloat && P.prec) ? 36u * 128u : 36u * 256u;
-            const unsigned bytes = 27u * 256u + (c0v != 0 ? ytile : 0u) + (c1v != 0 ? ytile : 0u);
-            mbar_expect_tx(bar, bytes);
-            tma_load_1d(fl, P.frameL + (int64_t)warp * 27 * 32, 27u * 256u, bar);
-            if (kYFloat && P.prec) {   // float records: half the bytes, same tile geometry
-                const float* yf = reinterpret_cast<const float*>(P.edgeY);
-                float* eyf = reinterpret_cast<float*>(ey);
-                if (c0v != 0) tma_load_1d(eyf, yf + ((ebase + ls) >> 5) * 36 * 32, 36u * 128u, bar);
-                if (c1v != 0) tma_load_1d(eyf + 36 * 32, yf + ((ebase + stride + ls) >> 5) * 36 * 32, 36u * 128u, bar);
-            } else {
-                if (c0v != 0) tma_load_1d(ey, P.edgeY + ((ebase + ls) >> 5) * 36 * 32, 36u * 256u, bar);
-                if (c1v != 0) tma_load_1d(ey + 36 * 32, P.edgeY + ((ebase + stride + ls) >> 5) * 36 * 32, 36u * 256u, bar);
-            }
-        }
-        __syncwarp();
-        // everything else the thread needs is loaded while the tiles are in flight
-        const int64_t pv = P.n_cam + (frame >= 0 ? frame : 0);
-        double pold[6], d2[2][6], Rc2[2][9], tc2[2][3];
-#pragma unroll
-        for (int k = 0; k < 6; ++k) pold[k] = frame >= 0 ? P.x[cur][6 * (pv - 1) + k] : 0.0;
-#pragma unroll
-        for (int v = 0; v < 2; ++v) {
-            const int c = v == 0 ? c0v : c1v;
-#pragma unroll
-            for (int k = 0; k < 6; ++k) d2[v][k] = c != 0 ? P.dc[6 * (c - 1) + k] : 0.0;
-#pragma unroll
-            for (int k = 0; k < 9; ++k) Rc2[v][k] = c != 0 ? P.vR[tr][9 * c + k] : ((k == 0 || k == 4 || k == 8) ? 1.0 : 0.0);
-#pragma unroll
-            for (int k = 0; k < 3; ++k) tc2[v][k] = c != 0 ? P.x[tr][6 * (c - 1) + 3 + k] : 0.0;
-        }
-        mbar_wait(bar, 0);
-        double U[21], r[6], Y2[2][36];
-#pragma unroll
-        for (int k = 0; k < 21; ++k) U[k] = fl[k * 32 + lane];
-#pragma unroll
-        for (int k = 0; k < 6; ++k) r[k] = fl[(21 + k) * 32 + lane];
-#pragma unroll
-        for (int v = 0; v < 2; ++v) {
-            const int c = v == 0 ? c0v : c1v;
-#pragma unroll
-            for (int k = 0; k < 36; ++k)
-                Y2[v][k] = c == 0 ? 0.0 : ((kYFloat && P.prec) ? (double)reinterpret_cast<const float*>(ey)[(v * 36 + k) * 32 + lane] : ey[(v * 36 + k) * 32 + lane]);
-        }
-        __syncwarp();   // every lane has taken its columns out of `ey`, which now stages the outgoing edge records
-        EdgeRec* stage = reinterpret_cast<EdgeRec*>(ey);
+        const double* __restrict__ fl = P.frameL + (int64_t)warp * 27 * 32 + lane;
+        const double* __restrict__ dc = P.dc;
         if (frame >= 0) {
+            const int64_t pv = P.n_cam + frame;
+            double U[21], r[6], pold[6];
 #pragma unroll
-            for (int v = 0; v < 2; ++v)
+            for (int k = 0; k < 21; ++k) U[k] = fl[k * 32];
 #pragma unroll
-                for (int i = 0; i < 6; ++i) {
-                    double acc = 0;
+            for (int k = 0; k < 6; ++k) r[k] = fl[(21 + k) * 32];
 #pragma unroll
-                    for (int k = 0; k < 6; ++k) acc += Y2[v][i * 6 + k] * d2[v][k];
-                    r[i] -= acc;
-                }
-            for (int v = 2; v < V; ++v) {   // frames seen by more than two cameras
+            for (int k = 0; k < 6; ++k) pold[k] = P.x[cur][6 * (pv - 1) + k];
+            for (int v = 0; v < V; ++v) {
                 const int c = gc[v];
                 if (c == 0) continue;
-                const int64_t e = ebase + v * stride + ls;
-                const double* d = P.dc + 6 * (c - 1);
+                const double* __restrict__ y = P.edgeY + ((ebase + v * stride + ls) >> 5) * 36 * 32 + lane;   // ls & 31 == lane
+                double d[6];
+#pragma unroll
+                for (int k = 0; k < 6; ++k) d[k] = dc[6 * (c - 1) + k];
 #pragma unroll
                 for (int i = 0; i < 6; ++i) {
                     double acc = 0;
 #pragma unroll
-                    for (int k = 0; k < 6; ++k)
-                        acc += ((kYFloat && P.prec) ? (double)reinterpret_cast<const float*>(P.edgeY)[tile_idx(36, e, i * 6 + k)] : P.edgeY[tile_idx(36, e, i * 6 + k)]) * d[k];
+                    for (int k = 0; k < 6; ++k) acc += y[(i * 6 + k) * 32] * d[k];
                     r[i] -= acc;
                 }
             }
@@ -1571,19 +1529,19 @@ __global__ void __launch_bounds__(kK4Threads) frame_update_kernel(Problem P)
             for (int i = 0; i < 9; ++i) P.vR[tr][9 * pv + i] = R[i];
             // composed poses the residual kernel evaluates next: the first two views go out through shared memory as
             // one 3 KB bulk store per view (32 consecutive edge records), the rest straight from registers
-#pragma unroll
-            for (int v = 0; v < 2; ++v)
-                if (v < V) compose_pose(Rc2[v], tc2[v], R, q + 3, stage[v * 32 + lane].R3, stage[v * 32 + lane].T3);
-            for (int v = 2; v < V; ++v) {
+            for (int v = 0; v < V; ++v) {
                 const int c = gc[v];
                 double Rc[9], tc[3];
 #pragma unroll
                 for (int k = 0; k < 9; ++k) Rc[k] = c != 0 ? P.vR[tr][9 * c + k] : ((k == 0 || k == 4 || k == 8) ? 1.0 : 0.0);
 #pragma unroll
                 for (int k = 0; k < 3; ++k) tc[k] = c != 0 ? P.x[tr][6 * (c - 1) + 3 + k] : 0.0;
-                EdgeRec er;
-                compose_pose(Rc, tc, R, q + 3, er.R3, er.T3);
-                P.erec[ebase + v * stride + ls] = er;
+                if (v < 2) compose_pose(Rc, tc, R, q + 3, stage[v * 32 + lane].R3, stage[v * 32 + lane].T3);
+                else {
+                    EdgeRec er;
+                    compose_pose(Rc, tc, R, q + 3, er.R3, er.T3);
+                    P.erec[ebase + v * stride + ls] = er;
+                }
             }
         } else {
             EdgeRec z;
@@ -1599,8 +1557,8 @@ __global__ void __launch_bounds__(kK4Threads) frame_update_kernel(Problem P)
         tma_store_fence();
         __syncwarp();
         if (lane == 0) {
-            tma_store_1d(P.erec + ebase + ls, ey, 32u * (unsigned)sizeof(EdgeRec));
-            if (V > 1) tma_store_1d(P.erec + ebase + stride + ls, reinterpret_cast<EdgeRec*>(ey) + 32, 32u * (unsigned)sizeof(EdgeRec));
+            tma_store_1d(P.erec + ebase + ls, stage, 32u * (unsigned)sizeof(EdgeRec));
+            if (V > 1) tma_store_1d(P.erec + ebase + stride + ls, stage + 32, 32u * (unsigned)sizeof(EdgeRec));
             tma_store_commit_wait();
         }
     }
