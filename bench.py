@@ -491,7 +491,10 @@ def run_ours(args):
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_dict(args, world),
+                "vs_baseline": None,
+                "dtype": {0: "f64", 1: "f64 residual/cost/Schur/solve + packed f32 Jacobian products (MIXED policy, parity gate 1e-6)",
+                          2: "f32 (FAST32 policy)"}[s.get_precision()],
+                "data": "synthetic", "config": config_dict(args, world),
                 "lm_iters_per_sec": iters_done / (ms_step * 1e-3), "us_per_lm_iteration": ms_step * 1e3 / max(iters_done, 1),
                 "resjac_evals_per_sec": world * M / (k1_ms * 1e-3), "wall_ms_per_step": wall_step,
                 "lm": {"iterations": iters_done, "accepted": rep["accepted"], "rejected": rep["rejected"],

@@ -1393,7 +1393,7 @@ int omni_enqueue_iteration(mccba_handle h)
 {
     OmniProblem& O = h->O;
     cudaStream_t s = h->stream;
-    omni_frame_kernel<<<O.n_frame, kOmniThreads, 0, s>>>(O, 0);
+    omni_frame_kernel<<<(O.n_frame + kOmniWarps - 1) / kOmniWarps, kOmniThreads, 0, s>>>(O, 0);
     omni_reduce_kernel<<<kOmniRec, 256, 0, s>>>(O, 0);
     omni_solve_kernel<<<1, 32, 0, s>>>(O);
     omni_update_kernel<<<O.n_blocks_upd, 128, 0, s>>>(O);
@@ -1537,7 +1537,7 @@ int mccba_omni_solve(mccba_handle h, int flags, int crit_type, int max_count, do
     cudaEventDestroy(evs[0]);
     cudaEventDestroy(evs[1]);
     // final cost at the returned parameters (estimateUncertainties' rms, src/omnidir.cpp:1794-1802)
-    omni_frame_kernel<<<O.n_frame, kOmniThreads, 0, s>>>(O, 1);
+    omni_frame_kernel<<<(O.n_frame + kOmniWarps - 1) / kOmniWarps, kOmniThreads, 0, s>>>(O, 1);
     omni_reduce_kernel<<<kOmniRec, 256, 0, s>>>(O, 1);
     OmniState hs;
     double cost = 0;
@@ -1568,7 +1568,7 @@ int mccba_omni_gram(mccba_handle h, double* gram /* n_frame x 17 x 17 */, double
     double* d = nullptr;
     const size_t cnt = (size_t)O.n_frame * 289;
     if (gram) { CUDA_TRY(h, cudaMalloc((void**)&d, sizeof(double) * cnt)); O.dump = d; }
-    omni_frame_kernel<<<O.n_frame, kOmniThreads, 0, h->stream>>>(O, 1);
+    omni_frame_kernel<<<(O.n_frame + kOmniWarps - 1) / kOmniWarps, kOmniThreads, 0, h->stream>>>(O, 1);
     omni_reduce_kernel<<<kOmniRec, 256, 0, h->stream>>>(O, 1);
     if (gram) CUDA_TRY(h, cudaMemcpyAsync(gram, d, sizeof(double) * cnt, cudaMemcpyDeviceToHost, h->stream));
     if (cost) CUDA_TRY(h, cudaMemcpyAsync(cost, O.tot + 77, sizeof(double), cudaMemcpyDeviceToHost, h->stream));

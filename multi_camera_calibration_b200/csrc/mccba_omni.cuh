@@ -6,11 +6,11 @@
 // the iterates are the reference's to rounding (this path works in the reference's additive Rodrigues coordinates,
 // because the eps 11^T term is not invariant under a change of coordinates).
 //
-//   omni_frame_kernel    CTA per frame: rows a = [J(16) | e] of every corner -> shared memory; 153 threads accumulate
-//                        the 17x17 Gram matrix sum a^T a (= all arrow blocks + gradient + cost of the frame); then the
-//                        frame's 6x6 Cholesky, Y = L^-1 H_pI, z_g, z_u and its Schur record
+//   omni_frame_kernel    warp per frame: rows a = [J(16) | e] of every corner -> shared memory; the 17x17 Gram matrix
+//                        sum a^T a (= all arrow blocks + gradient + cost of the frame) on the FP64 tensor cores; then
+//                        the frame's 6x6 Cholesky, Y = L^-1 H_pI, z_g, z_u and its Schur record
 //   omni_reduce_kernel   fixed-order sums of the 78 record entries over the frames (no atomics)
-//   omni_solve_kernel    bordered (m+1) x (m+1) system, Gaussian elimination with partial pivoting (m <= 10)
+//   omni_solve_kernel    bordered (m+1) x (m+1) system, Gaussian elimination with partial pivoting (m <= 10), one warp
 //   omni_update_kernel   back-substitution per frame, G = alpha * x, parameter update, norm partials
 //   omni_decide_kernel   change = |G| / |param_old| (:1141), iteration count, termination (:1125-1127)
 #pragma once
@@ -21,8 +21,13 @@
 
 namespace mccba {
 
-constexpr int kOmniThreads = 160;   // >= 153 Gram entries
-constexpr int kOmniChunk = 64;      // corners staged per pass (128 rows x 17 doubles = 17 KB)
+#ifndef MCCBA_OMNI_MINBLOCKS
+#define MCCBA_OMNI_MINBLOCKS 3
+#endif
+constexpr int kOmniWarps = 4;        // frames per CTA: one warp per frame
+constexpr int kOmniThreads = 32 * kOmniWarps;
+constexpr int kOmniChunk = 32;      // corners staged per pass: one per lane (64 rows)
+constexpr int kOmniLd = 20;         // row stride (doubles) of the staged rows: the 8 x 4 MMA fragment loads take 2 wavefronts, the minimum
 constexpr int kOmniRec = 78;        // 55 (S upper) + 10 (rg) + 10 (ru) + d, c, cost
 constexpr int kOmniSave = 93;       // 21 (U) + 6 (z_g) + 6 (z_u) + 60 (Y)
 
@@ -48,21 +53,23 @@ struct OmniProblem {
     OmniState* st;
 };
 
-__device__ __forceinline__ void omni_tri17(int t, int& i, int& j)   // t in [0,153) -> (i <= j) of a 17x17 upper triangle
+// One WARP per frame.  Per pass of 32 corners every lane evaluates one corner (projection + the two 17-wide rows
+// a = [J(16) | e]) into the warp's shared-memory stage; the 17 x 17 Gram matrix sum a^T a is then accumulated by the
+// FP64 tensor cores: with R the staged 64 x 17 row block, the six upper 8 x 8 tiles of R^T R are 16 k-steps of
+// mma.m8n8k4 each, and the A and B fragments of a tile pair are the same three 8-column slices of R (3 loads per
+// k-step per lane for 6 MMAs).  The per-frame algebra (6 x 6 Cholesky, 12 forward solves, Schur record) follows in the
+// same warp.  (Round 1: one 160-thread CTA per frame, 153 threads x 108 scalar FMAs, ~200 registers for every thread of
+// which 54 projected: 91 us per pass over 5000 frames.)
+__global__ void __launch_bounds__(kOmniThreads, MCCBA_OMNI_MINBLOCKS) omni_frame_kernel(OmniProblem P, int forced)
 {
-    int r = 0, rem = t;
-    while (rem >= 17 - r) { rem -= 17 - r; ++r; }
-    i = r; j = r + rem;
-}
-
-__global__ void __launch_bounds__(kOmniThreads) omni_frame_kernel(OmniProblem P, int forced)
-{
-    __shared__ double rows[2 * kOmniChunk][17];
-    __shared__ double M[17][17];
-    __shared__ double sU[21], szg[6], szu[6], sY[6][10];
+    __shared__ __align__(16) double s_rows[kOmniWarps][2 * kOmniChunk * kOmniLd];
+    __shared__ double s_fac[kOmniWarps][96];    // U 21 | z_g 6 | z_u 6 | Y 6 x 10
     const OmniState* st = P.st;
     if (!forced && st->done) return;
-    const int f = blockIdx.x, tid = threadIdx.x, n = P.n_frame;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, n = P.n_frame;
+    const int f = blockIdx.x * kOmniWarps + w;
+    if (f >= n) return;                          // whole warps leave; nothing below synchronises across warps
+    double* rows = s_rows[w];
     const double* par = P.param;
     CamParams cam;
     cam.model = kOmnidir; cam.rational = 0;
@@ -74,14 +81,18 @@ __global__ void __launch_bounds__(kOmniThreads) omni_frame_kernel(OmniProblem P,
     double R[9], Jl[9];
     rodrigues(om, R);
     left_jacobian(om, Jl);
-    int gi = 0, gj = 0;
-    if (tid < 153) omni_tri17(tid, gi, gj);
-    double acc = 0.0;
+    const int g = lane >> 2, t = lane & 3;
+    double acc[6][2];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) acc[i][0] = acc[i][1] = 0.0;
     const int b = P.f_off[f], e = P.f_off[f + 1];
     for (int c0 = b; c0 < e; c0 += kOmniChunk) {
         const int nc = min(kOmniChunk, e - c0);
-        if (tid < nc) {
-            const int i = c0 + tid;
+        __syncwarp();                            // the previous pass has been consumed
+        double* row0 = rows + (2 * lane) * kOmniLd;
+        double* row1 = row0 + kOmniLd;
+        if (lane < nc) {
+            const int i = c0 + lane;
             const double X[3] = {(double)P.ox[i], (double)P.oy[i], (double)P.oz[i]};
             double Q[3], Xc[3], uv[2], A[6], Jin[20];
             mat3_vec(R, X, Q);
@@ -92,7 +103,7 @@ __global__ void __launch_bounds__(kOmniThreads) omni_frame_kernel(OmniProblem P,
             for (int r = 0; r < 2; ++r) {
                 double jphi[3];
                 cross3(Q, A + 3 * r, jphi);
-                double* row = rows[2 * tid + r];
+                double* row = r == 0 ? row0 : row1;
 #pragma unroll
                 for (int k = 0; k < 3; ++k) row[k] = jphi[0] * Jl[k] + jphi[1] * Jl[3 + k] + jphi[2] * Jl[6 + k];   // d/d om
 #pragma unroll
@@ -101,85 +112,104 @@ __global__ void __launch_bounds__(kOmniThreads) omni_frame_kernel(OmniProblem P,
                 for (int k = 0; k < 10; ++k) row[6 + k] = Jin[10 * r + k];
                 row[16] = err[r];
             }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 17; ++k) { row0[k] = 0.0; row1[k] = 0.0; }     // rows past the last corner add zeros
         }
-        __syncthreads();
-        if (tid < 153)
-            for (int r = 0; r < 2 * nc; ++r) acc = fma(rows[r][gi], rows[r][gj], acc);
-        __syncthreads();
+        __syncwarp();
+        const int ksteps = (2 * nc + 3) >> 2;
+        for (int ks = 0; ks < ksteps; ++ks) {
+            const double* r = rows + (4 * ks + t) * kOmniLd + g;
+            const double f0 = r[0], f1 = r[8], f2 = g == 0 ? r[16] : 0.0;
+            dmma(acc[0][0], acc[0][1], f0, f0);
+            dmma(acc[1][0], acc[1][1], f0, f1);
+            dmma(acc[2][0], acc[2][1], f0, f2);
+            dmma(acc[3][0], acc[3][1], f1, f1);
+            dmma(acc[4][0], acc[4][1], f1, f2);
+            dmma(acc[5][0], acc[5][1], f2, f2);
+        }
     }
-    if (tid < 153) { M[gi][gj] = acc; M[gj][gi] = acc; }
-    __syncthreads();
+    __syncwarp();
+    double (*M)[17] = reinterpret_cast<double (*)[17]>(rows);   // the Gram matrix takes the place of the staged rows
+    {
+        const int mt[6] = {0, 0, 0, 1, 1, 2}, nt[6] = {0, 1, 2, 1, 2, 2};
+#pragma unroll
+        for (int i = 0; i < 6; ++i)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int r = 8 * mt[i] + g, c = 8 * nt[i] + 2 * t + h;
+                if (r < 17 && c < 17 && r <= c) { M[r][c] = acc[i][h]; M[c][r] = acc[i][h]; }
+            }
+    }
+    __syncwarp();
     if (P.dump)
-        for (int t = tid; t < 289; t += blockDim.x) P.dump[(int64_t)f * 289 + t] = M[t / 17][t % 17];
-    // per-frame algebra: Cholesky of H_pp, z_g, z_u (thread 0), Y columns (threads 0..9), Schur record
+        for (int k = lane; k < 289; k += 32) P.dump[(int64_t)f * 289 + k] = M[k / 17][k % 17];
+    // per-frame algebra: Cholesky of H_pp (lane 0), then z_g, z_u and the 10 columns of Y (lanes 0..11), Schur record
+    double* sU = s_fac[w];
+    double* szg = sU + 21;
+    double* szu = sU + 27;
+    double (*sY)[10] = reinterpret_cast<double (*)[10]>(sU + 33);
     int bad = 0;
-    if (tid == 0) {
-        double U[21], zg[6], zu[6];
+    if (lane == 0) {
+        double U[21];
 #pragma unroll
         for (int i = 0; i < 6; ++i)
 #pragma unroll
             for (int j = i; j < 6; ++j) U[tri6(i, j)] = M[i][j];
         if (!chol6_packed(U)) bad = 1;
 #pragma unroll
-        for (int i = 0; i < 6; ++i) { zg[i] = M[i][16]; zu[i] = 1.0; }
-        chol6_forward(U, zg, 1);
-        chol6_forward(U, zu, 1);
-#pragma unroll
         for (int i = 0; i < 21; ++i) sU[i] = U[i];
-#pragma unroll
-        for (int i = 0; i < 6; ++i) { szg[i] = zg[i]; szu[i] = zu[i]; }
     }
-    __syncthreads();
-    if (tid < 10) {
+    __syncwarp();
+    if (lane < 12) {
         double U[21], col[6];
 #pragma unroll
         for (int i = 0; i < 21; ++i) U[i] = sU[i];
 #pragma unroll
-        for (int i = 0; i < 6; ++i) col[i] = M[i][6 + tid];
+        for (int i = 0; i < 6; ++i) col[i] = lane < 10 ? M[i][6 + lane] : (lane == 10 ? M[i][16] : 1.0);
         chol6_forward(U, col, 1);
 #pragma unroll
-        for (int i = 0; i < 6; ++i) sY[i][tid] = col[i];
+        for (int i = 0; i < 6; ++i) {
+            if (lane < 10) sY[i][lane] = col[i];
+            else if (lane == 10) szg[i] = col[i];
+            else szu[i] = col[i];
+        }
     }
-    __syncthreads();
+    __syncwarp();
     const int64_t nf = n;
-    if (tid < 55) {   // S record: upper triangle of H_II - Y^T Y
-        int a = 0, rem = tid;
-        while (rem >= 10 - a) { rem -= 10 - a; ++a; }
-        const int c = a + rem;
-        double s = M[6 + a][6 + c];
+    for (int tid = lane; tid < 76; tid += 32) {
+        if (tid < 55) {   // S record: upper triangle of H_II - Y^T Y
+            int a = 0, rem = tid;
+            while (rem >= 10 - a) { rem -= 10 - a; ++a; }
+            const int c = a + rem;
+            double s = M[6 + a][6 + c];
 #pragma unroll
-        for (int k = 0; k < 6; ++k) s -= sY[k][a] * sY[k][c];
-        P.rec[(int64_t)tid * nf + f] = s;
-    } else if (tid < 65) {
-        const int a = tid - 55;
-        double s = M[6 + a][16];
+            for (int k = 0; k < 6; ++k) s -= sY[k][a] * sY[k][c];
+            P.rec[(int64_t)tid * nf + f] = s;
+        } else if (tid < 65) {
+            const int a = tid - 55;
+            double s = M[6 + a][16];
 #pragma unroll
-        for (int k = 0; k < 6; ++k) s -= sY[k][a] * szg[k];
-        P.rec[(int64_t)tid * nf + f] = s;
-    } else if (tid < 75) {
-        const int a = tid - 65;
-        double s = 0.0;
+            for (int k = 0; k < 6; ++k) s -= sY[k][a] * szg[k];
+            P.rec[(int64_t)tid * nf + f] = s;
+        } else if (tid < 75) {
+            const int a = tid - 65;
+            double s = 0.0;
 #pragma unroll
-        for (int k = 0; k < 6; ++k) s -= sY[k][a] * szu[k];
-        P.rec[(int64_t)tid * nf + f] = s;
-    } else if (tid == 75) {
-        double d = 0, c = 0;
+            for (int k = 0; k < 6; ++k) s -= sY[k][a] * szu[k];
+            P.rec[(int64_t)tid * nf + f] = s;
+        } else {
+            double d = 0, c = 0;
 #pragma unroll
-        for (int k = 0; k < 6; ++k) { d += szu[k] * szu[k]; c += szu[k] * szg[k]; }
-        P.rec[(int64_t)75 * nf + f] = d;
-        P.rec[(int64_t)76 * nf + f] = c;
-        P.rec[(int64_t)77 * nf + f] = M[16][16];
+            for (int k = 0; k < 6; ++k) { d += szu[k] * szu[k]; c += szu[k] * szg[k]; }
+            P.rec[(int64_t)75 * nf + f] = d;
+            P.rec[(int64_t)76 * nf + f] = c;
+            P.rec[(int64_t)77 * nf + f] = M[16][16];
+        }
     }
     // saved factors for the back-substitution
-    for (int t = tid; t < kOmniSave; t += blockDim.x) {
-        double v;
-        if (t < 21) v = sU[t];
-        else if (t < 27) v = szg[t - 21];
-        else if (t < 33) v = szu[t - 27];
-        else v = sY[(t - 33) / 10][(t - 33) % 10];
-        P.save[(int64_t)t * nf + f] = v;
-    }
-    if (tid == 0 && bad) P.st->status = 4;   // benign race: every writer stores the same value
+    for (int k = lane; k < kOmniSave; k += 32) P.save[(int64_t)k * nf + f] = sU[k];    // U | z_g | z_u | Y are contiguous
+    if (lane == 0 && bad) P.st->status = 4;   // benign race: every writer stores the same value
 }
 
 // one block per record entry: fixed-order sum over the frames
@@ -217,63 +247,115 @@ __device__ __forceinline__ void omni_flags2free(int flags, int* fr)
     if (f >= 2) { fr[2] = 0; }
 }
 
-__global__ void omni_solve_kernel(OmniProblem P)
+// One warp: lane i holds row i of the bordered system [B | rhs] (at most 11 x 11); the elimination order, the pivot
+// rule (first row of maximal modulus) and the order of every sum are those of a serial Gaussian elimination with partial
+// pivoting, the rows just live in different lanes (round 1 ran it on one thread out of local memory: 37 us).
+__global__ void __launch_bounds__(32) omni_solve_kernel(OmniProblem P)
 {
-    if (threadIdx.x != 0) return;
     OmniState* st = P.st;
     if (st->done) return;
+    const int lane = threadIdx.x;
+    const int status = st->status;
     // schedule of this iteration (src/omnidir.cpp:1129-1131)
-    st->alpha = 1.0 - pow(1.0 - 0.01, (double)st->iter + 1.0);
-    st->epsilon = 0.01 * pow(0.9, (double)st->iter / 10.0);
-    if (st->status) { st->done = 1; return; }
+    const double alpha = 1.0 - pow(1.0 - 0.01, (double)st->iter + 1.0);
+    const double epsilon = 0.01 * pow(0.9, (double)st->iter / 10.0);
     int fr[10], map[10], m = 0;
     omni_flags2free(st->flags, fr);
+    __syncwarp();                                // every lane has read the state before lane 0 writes it
+    if (lane == 0) {
+        st->alpha = alpha; st->epsilon = epsilon;
+        if (status) st->done = 1;
+    }
+    if (status) return;
     for (int a = 0; a < 10; ++a)
         if (fr[a]) map[m++] = a;
     const double* tot = P.tot;
-    const double se = sqrt(st->epsilon);
+    const double se = sqrt(epsilon);
     const int Q = m + 1;
-    double B[121], rhs[11];
     auto Sfull = [&](int a, int c) {   // upper-triangle record index of (a, c)
         if (a > c) { const int t = a; a = c; c = t; }
         int idx = 0;
         for (int r = 0; r < a; ++r) idx += 10 - r;
         return tot[idx + (c - a)];
     };
-    for (int a = 0; a < m; ++a) {
-        for (int c = 0; c < m; ++c) B[a * Q + c] = Sfull(map[a], map[c]);
-        const double ru = 1.0 + tot[65 + map[a]];
-        B[a * Q + m] = se * ru;
-        B[m * Q + a] = se * ru;
-        rhs[a] = tot[55 + map[a]];
+    double B[11], rhs = 0.0;
+#pragma unroll
+    for (int c = 0; c < 11; ++c) {
+        double v = 0.0;
+        if (lane < m) {
+            if (c < m) v = Sfull(map[lane], map[c]);
+            else if (c == m) v = se * (1.0 + tot[65 + map[lane]]);
+        } else if (lane == m) {
+            if (c < m) v = se * (1.0 + tot[65 + map[c]]);
+            else if (c == m) v = -(1.0 + epsilon * tot[75]);
+        }
+        B[c] = v;
     }
-    B[m * Q + m] = -(1.0 + st->epsilon * tot[75]);
-    rhs[m] = -se * tot[76];
+    if (lane < m) rhs = tot[55 + map[lane]];
+    else if (lane == m) rhs = -se * tot[76];
     int fail = 0;
-    for (int k = 0; k < Q && !fail; ++k) {
-        int piv = k;
-        for (int i = k + 1; i < Q; ++i)
-            if (fabs(B[i * Q + k]) > fabs(B[piv * Q + k])) piv = i;
-        if (B[piv * Q + k] == 0.0 || !isfinite(B[piv * Q + k])) { fail = 1; break; }
-        if (piv != k) {
-            for (int j = 0; j < Q; ++j) { const double t = B[k * Q + j]; B[k * Q + j] = B[piv * Q + j]; B[piv * Q + j] = t; }
-            const double t = rhs[k]; rhs[k] = rhs[piv]; rhs[piv] = t;
-        }
-        for (int i = k + 1; i < Q; ++i) {
-            const double fct = B[i * Q + k] / B[k * Q + k];
-            for (int j = k; j < Q; ++j) B[i * Q + j] -= fct * B[k * Q + j];
-            rhs[i] -= fct * rhs[k];
+#pragma unroll
+    for (int k = 0; k < 11; ++k) {
+        if (k < Q && !fail) {                    // warp-uniform
+            const bool live = lane >= k && lane < Q;
+            const bool nonfinite = __any_sync(0xffffffffu, live && !isfinite(B[k]));
+            double v = live ? fabs(B[k]) : -1.0;
+            int idx = lane;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const double ov = __shfl_xor_sync(0xffffffffu, v, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+                if (ov > v || (ov == v && oi < idx)) { v = ov; idx = oi; }
+            }
+            const int piv = idx;
+            if (nonfinite || !(v > 0.0)) fail = 1;
+            else {
+                if (piv != k) {
+                    const int partner = lane == k ? piv : (lane == piv ? k : lane);
+#pragma unroll
+                    for (int j = 0; j < 11; ++j) B[j] = __shfl_sync(0xffffffffu, B[j], partner);
+                    rhs = __shfl_sync(0xffffffffu, rhs, partner);
+                }
+                const double fct = B[k] / __shfl_sync(0xffffffffu, B[k], k);
+                const double prhs = __shfl_sync(0xffffffffu, rhs, k);
+                const bool below = lane > k && lane < Q;
+#pragma unroll
+                for (int j = k; j < 11; ++j) {
+                    const double pj = __shfl_sync(0xffffffffu, B[j], k);
+                    if (below) B[j] -= fct * pj;
+                }
+                if (below) rhs -= fct * prhs;
+            }
         }
     }
-    if (fail) { st->status = 4; st->done = 1; return; }
-    for (int i = Q - 1; i >= 0; --i) {
-        double s = rhs[i];
-        for (int j = i + 1; j < Q; ++j) s -= B[i * Q + j] * rhs[j];
-        rhs[i] = s / B[i * Q + i];
+    if (fail) {
+        if (lane == 0) { st->status = 4; st->done = 1; }
+        return;
     }
-    for (int a = 0; a < 10; ++a) st->x_intr[a] = 0.0;
-    for (int a = 0; a < m; ++a) st->x_intr[map[a]] = rhs[a];
-    st->t = rhs[m];
+    double x[11];
+#pragma unroll
+    for (int i = 10; i >= 0; --i) {
+        x[i] = 0.0;
+        if (i < Q) {                             // warp-uniform
+            double s = rhs;
+#pragma unroll
+            for (int j = i + 1; j < 11; ++j)
+                if (j < Q) s -= B[j] * x[j];
+            s = s / B[i];
+            x[i] = __shfl_sync(0xffffffffu, s, i);
+        }
+    }
+    if (lane == 0) {
+        for (int a = 0; a < 10; ++a) st->x_intr[a] = 0.0;
+#pragma unroll
+        for (int a = 0; a < 10; ++a)
+            if (a < m) st->x_intr[map[a]] = x[a];
+        double tv = 0.0;
+#pragma unroll
+        for (int a = 0; a < 11; ++a)
+            if (a == m) tv = x[a];
+        st->t = tv;
+    }
 }
 
 __global__ void __launch_bounds__(128) omni_update_kernel(OmniProblem P)
