@@ -407,6 +407,8 @@ def run_ours(args):
         s.restore_parameters()
         rep = s.solve(**kw)
     barrier()
+    if world > 1:
+        s.exchange_stats()                       # reset the exchange counters: the timed region only
     sampler = ClockSampler(local) if rank == 0 else None
     ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
     launches = 0
@@ -420,6 +422,17 @@ def run_ours(args):
     barrier()
     wall_ms = (time.perf_counter() - t0) * 1e3
     clocks = sampler.stop() if sampler else None
+    xstats = None
+    if world > 1:
+        # per-launch %globaltimer stamps of the peer-memory exchange: posting the stores vs waiting for the last peer's words
+        xs = s.exchange_stats()
+        tx = torch.tensor([xs["store_us"], xs["wait_us"], xs["max_wait_us"]], dtype=torch.float64, device="cuda")
+        tmax = tx.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tmin = tx.clone(); dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
+        xstats = {"launches_per_rank": xs["launches"], "store_us_mean_max_over_ranks": float(tmax[0]),
+                  "wait_us_mean_min_over_ranks": float(tmin[1]), "wait_us_mean_max_over_ranks": float(tmax[1]),
+                  "wait_us_worst_launch": float(tmax[2]),
+                  "note": "wait = arrival skew of the ranks + one NVLink trip; the rank that arrives last sees only the trip (min over ranks)"}
     t = torch.tensor([dev_ms / args.steps, wall_ms / args.steps], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -510,6 +523,7 @@ def run_ours(args):
                              "note": "MIXED policy: residual in double, Jacobian products in packed float32; the kernel is bound by "
                                      "the FMA / FP64 pipes, not by HBM (DESIGN.md section 4)"},
                 "exchange": {0: "none", 1: "ncclAllReduce", 2: "nvlink-peer-memory"}[s.exchange_mode()],
+                "exchange_stats": xstats,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                         "ms_per_step": e2e_ms, "steps": e2e_steps},
                 "gpu_launches": int(launches), "clocks": clocks}

@@ -204,6 +204,11 @@ int mccba_last_kernel_ms(mccba_handle h, double out[6]);
  * when all ranks can map all windows (<= 8 ranks on one NVLink domain); MCCBA_P2P=0 in the environment of every rank
  * forces mode 1. */
 int mccba_exchange_mode(mccba_handle h);
+/* Timing of the peer-memory exchange since the last call (device %globaltimer stamps of one thread per launch):
+ * out[0] mean microseconds to post the stores into the peers' windows, out[1] mean microseconds from there until the
+ * last peer's words have arrived (arrival skew of the ranks + one NVLink trip), out[2] launches counted, out[3] the
+ * largest wait in microseconds.  Zeros in exchange modes 0 and 1.  Resets the counters. */
+int mccba_exchange_stats(mccba_handle h, double out[4]);
 
 /* Test hook: solve the SPD system S x = g (n x n row-major, lower triangle read) on the device with the loop's own
  * solvers (blocked: 3 = banded LDL^T by one warp -- the half bandwidth is measured from S and must be <= 29; this is

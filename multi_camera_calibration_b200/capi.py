@@ -226,6 +226,12 @@ class Solver:
         """0 single rank, 1 ncclAllReduce, 2 NVLink peer-memory windows (include/mccba.h: mccba_exchange_mode)."""
         return int(lib().mccba_exchange_mode(self._h))
 
+    def exchange_stats(self):
+        """Mean store / wait microseconds of the peer-memory exchange since the last call (mccba_exchange_stats)."""
+        out = (C.c_double * 4)()
+        self._check(lib().mccba_exchange_stats(self._h, out))
+        return dict(store_us=out[0], wait_us=out[1], launches=int(out[2]), max_wait_us=out[3])
+
     def debug_solve_dense(self, S, g, blocked=True):
         S = np.ascontiguousarray(S, dtype=np.float64); g = np.ascontiguousarray(g, dtype=np.float64)
         n = g.size

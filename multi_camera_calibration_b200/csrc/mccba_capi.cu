@@ -1229,6 +1229,22 @@ int mccba_solve(mccba_handle h, const mccba_solve_opts* o, mccba_report* rep)
     return MCCBA_OK;
 }
 
+int mccba_exchange_stats(mccba_handle h, double out[4])
+{
+    if (!h || !out) return MCCBA_ERR_ARG;
+    out[0] = out[1] = out[2] = out[3] = 0.0;
+    if (!h->p2p_ok || !h->p2p_epoch) return MCCBA_OK;
+    CUDA_TRY(h, cudaSetDevice(h->opts.device));
+    unsigned long long w[4] = {0, 0, 0, 0};
+    CUDA_TRY(h, cudaMemcpyAsync(w, h->p2p_epoch + kP2pStatsWord, sizeof(w), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaMemsetAsync(h->p2p_epoch + kP2pStatsWord, 0, sizeof(w), h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    if (w[2]) { out[0] = 1e-3 * (double)w[0] / (double)w[2]; out[1] = 1e-3 * (double)w[1] / (double)w[2]; }
+    out[2] = (double)w[2];
+    out[3] = 1e-3 * (double)w[3];
+    return MCCBA_OK;
+}
+
 int mccba_allreduce_sum(mccba_handle h, double* buf, int n)
 {
     if (!h || !buf || n < 0 || n > 64) return MCCBA_ERR_ARG;

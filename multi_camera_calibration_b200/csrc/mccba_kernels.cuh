@@ -1217,6 +1217,7 @@ __global__ void __launch_bounds__(kK3Threads) reduce_records_kernel(Problem P, i
 // --------------------------------------------------------------------------------------------------------
 constexpr int kP2pFlagWords = 32;   // header of a window (unused by the LL protocol, keeps the slots 256-byte aligned)
 constexpr int kP2pThreads = 256;
+constexpr int kP2pStatsWord = 8;    // p2p_epoch[8..12): sum of store ns, sum of wait ns, launches, max wait ns
 // Low-latency protocol (the one NCCL calls LL): every double travels as two 8-byte words {32 data bits | 32-bit epoch},
 // so the data carry their own arrival flag -- no fence, no separate flag, no grid-wide step.  A thread stores its
 // elements into slot[rank] of every window, then spins on the n slots of its own window until both words of an
@@ -1259,11 +1260,17 @@ __global__ void __launch_bounds__(kP2pThreads) p2p_exchange_kernel(Problem P, in
     const int n = P.p2p_n, me = P.p2p_rank;
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, step = (int64_t)gridDim.x * blockDim.x;
     const int64_t par = (int64_t)((e & 1) * n) * P.p2p_stride;          // slots of this parity (in doubles)
+    // %globaltimer stamps of one thread (mccba_exchange_stats): time to post the stores, then time until the last peer's
+    // words have arrived = arrival skew of the ranks + one NVLink trip
+    const bool stamp = blockIdx.x == 0 && threadIdx.x == 0;
+    unsigned long long t_in = 0, t_sent = 0;
+    if (stamp) t_in = p2p_now_ns();
     for (int r = 0; r < n; ++r) {
         const int peer = (me + r) % n;      // spread the traffic: own window first, then the next rank ...
         unsigned long long* dst = reinterpret_cast<unsigned long long*>(P.p2p_peer[peer] + kP2pFlagWords + par + (int64_t)me * P.p2p_stride);
         for (int64_t i = tid; i < len; i += step) p2p_ll_store(dst + 2 * i, P.ar_part[i], flag);
     }
+    if (stamp) t_sent = p2p_now_ns();
     const unsigned long long* win = reinterpret_cast<const unsigned long long*>(P.p2p_peer[me] + kP2pFlagWords + par);
     int timed_out = 0;
     for (int64_t i = tid; i < len; i += step) {
@@ -1271,6 +1278,14 @@ __global__ void __launch_bounds__(kP2pThreads) p2p_exchange_kernel(Problem P, in
         for (int r = 1; r < n && !timed_out; ++r) acc += p2p_ll_load(win + (int64_t)r * P.p2p_stride + 2 * i, flag, budget_ns, &timed_out);
         P.ar[i] = timed_out ? 0.0 : acc;
         if (timed_out) break;
+    }
+    if (stamp) {
+        const unsigned long long t_done = p2p_now_ns();
+        unsigned long long* stats = P.p2p_epoch + kP2pStatsWord;
+        stats[0] += t_sent - t_in;
+        stats[1] += t_done - t_sent;
+        stats[2] += 1;
+        if (t_done - t_sent > stats[3]) stats[3] = t_done - t_sent;
     }
     if (timed_out) {   // sticky: the loop control of this launch (decide_body) sees done and does nothing else
         P.st->status = 5;

@@ -253,20 +253,15 @@ __device__ __forceinline__ void omni_flags2free(int flags, int* fr)
 __global__ void __launch_bounds__(32) omni_solve_kernel(OmniProblem P)
 {
     OmniState* st = P.st;
-    if (st->done) return;
+    // no early exit on the loaded state: everything is computed unconditionally and only the stores at the end are guarded,
+    // so the warp provably stays converged
+    const int done = st->done, status = st->status;
     const int lane = threadIdx.x;
-    const int status = st->status;
     // schedule of this iteration (src/omnidir.cpp:1129-1131)
     const double alpha = 1.0 - pow(1.0 - 0.01, (double)st->iter + 1.0);
     const double epsilon = 0.01 * pow(0.9, (double)st->iter / 10.0);
     int fr[10], map[10], m = 0;
     omni_flags2free(st->flags, fr);
-    __syncwarp();                                // every lane has read the state before lane 0 writes it
-    if (lane == 0) {
-        st->alpha = alpha; st->epsilon = epsilon;
-        if (status) st->done = 1;
-    }
-    if (status) return;
     for (int a = 0; a < 10; ++a)
         if (fr[a]) map[m++] = a;
     const double* tot = P.tot;
@@ -278,6 +273,8 @@ __global__ void __launch_bounds__(32) omni_solve_kernel(OmniProblem P)
         for (int r = 0; r < a; ++r) idx += 10 - r;
         return tot[idx + (c - a)];
     };
+    // rows and columns Q..10 are padded with the identity, so all 11 elimination steps run unconditionally: every shuffle
+    // below sits in straight-line code (no WARPSYNC wrappers), and the padding never wins a pivot search
     double B[11], rhs = 0.0;
 #pragma unroll
     for (int c = 0; c < 11; ++c) {
@@ -288,73 +285,66 @@ __global__ void __launch_bounds__(32) omni_solve_kernel(OmniProblem P)
         } else if (lane == m) {
             if (c < m) v = se * (1.0 + tot[65 + map[c]]);
             else if (c == m) v = -(1.0 + epsilon * tot[75]);
-        }
+        } else if (lane == c) v = 1.0;
         B[c] = v;
     }
     if (lane < m) rhs = tot[55 + map[lane]];
     else if (lane == m) rhs = -se * tot[76];
-    int fail = 0;
+    bool fail = false;
 #pragma unroll
     for (int k = 0; k < 11; ++k) {
-        if (k < Q && !fail) {                    // warp-uniform
-            const bool live = lane >= k && lane < Q;
-            const bool nonfinite = __any_sync(0xffffffffu, live && !isfinite(B[k]));
-            double v = live ? fabs(B[k]) : -1.0;
-            int idx = lane;
+        const bool live = lane >= k && lane < 11;
+        fail = fail || !isfinite(B[k]);          // reduced over the warp at the end
+        double v = live ? fabs(B[k]) : -1.0;
+        if (!(v == v)) v = -1.0;
+        int idx = lane;
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const double ov = __shfl_xor_sync(0xffffffffu, v, o);
-                const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
-                if (ov > v || (ov == v && oi < idx)) { v = ov; idx = oi; }
-            }
-            const int piv = idx;
-            if (nonfinite || !(v > 0.0)) fail = 1;
-            else {
-                if (piv != k) {
-                    const int partner = lane == k ? piv : (lane == piv ? k : lane);
-#pragma unroll
-                    for (int j = 0; j < 11; ++j) B[j] = __shfl_sync(0xffffffffu, B[j], partner);
-                    rhs = __shfl_sync(0xffffffffu, rhs, partner);
-                }
-                const double fct = B[k] / __shfl_sync(0xffffffffu, B[k], k);
-                const double prhs = __shfl_sync(0xffffffffu, rhs, k);
-                const bool below = lane > k && lane < Q;
-#pragma unroll
-                for (int j = k; j < 11; ++j) {
-                    const double pj = __shfl_sync(0xffffffffu, B[j], k);
-                    if (below) B[j] -= fct * pj;
-                }
-                if (below) rhs -= fct * prhs;
-            }
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ov = __shfl_xor_sync(0xffffffffu, v, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+            if (ov > v || (ov == v && oi < idx)) { v = ov; idx = oi; }
         }
+        fail = fail || !(v > 0.0);
+        const int piv = idx;
+        const int partner = lane == k ? piv : (lane == piv ? k : lane);     // piv == k: everybody reads itself
+#pragma unroll
+        for (int j = 0; j < 11; ++j) B[j] = __shfl_sync(0xffffffffu, B[j], partner);
+        rhs = __shfl_sync(0xffffffffu, rhs, partner);
+        const double fct = B[k] / __shfl_sync(0xffffffffu, B[k], k);
+        const double prhs = __shfl_sync(0xffffffffu, rhs, k);
+        const bool below = lane > k && lane < 11;
+#pragma unroll
+        for (int j = k; j < 11; ++j) {
+            const double pj = __shfl_sync(0xffffffffu, B[j], k);
+            if (below) B[j] -= fct * pj;
+        }
+        if (below) rhs -= fct * prhs;
     }
-    if (fail) {
-        if (lane == 0) { st->status = 4; st->done = 1; }
-        return;
-    }
+    const bool failed = __any_sync(0xffffffffu, fail && lane < Q);
     double x[11];
 #pragma unroll
     for (int i = 10; i >= 0; --i) {
-        x[i] = 0.0;
-        if (i < Q) {                             // warp-uniform
-            double s = rhs;
+        double s = rhs;
 #pragma unroll
-            for (int j = i + 1; j < 11; ++j)
-                if (j < Q) s -= B[j] * x[j];
-            s = s / B[i];
-            x[i] = __shfl_sync(0xffffffffu, s, i);
-        }
+        for (int j = i + 1; j < 11; ++j) s -= B[j] * x[j];
+        s = s / B[i];
+        x[i] = __shfl_sync(0xffffffffu, s, i);
     }
-    if (lane == 0) {
-        for (int a = 0; a < 10; ++a) st->x_intr[a] = 0.0;
+    if (lane == 0 && !done) {
+        st->alpha = alpha; st->epsilon = epsilon;
+        if (status) st->done = 1;
+        else if (failed) { st->status = 4; st->done = 1; }
+        else {
+            for (int a = 0; a < 10; ++a) st->x_intr[a] = 0.0;
 #pragma unroll
-        for (int a = 0; a < 10; ++a)
-            if (a < m) st->x_intr[map[a]] = x[a];
-        double tv = 0.0;
+            for (int a = 0; a < 10; ++a)
+                if (a < m) st->x_intr[map[a]] = x[a];
+            double tv = 0.0;
 #pragma unroll
-        for (int a = 0; a < 11; ++a)
-            if (a == m) tv = x[a];
-        st->t = tv;
+            for (int a = 0; a < 11; ++a)
+                if (a == m) tv = x[a];
+            st->t = tv;
+        }
     }
 }
 
