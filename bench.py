@@ -327,10 +327,12 @@ def _extra_legs(args, m, s, rig, pin, kw, world, rank, local, barrier):
     if world > 1:
         from scripts import mgpu_parity
         res = mgpu_parity.check(dist, rank, world, local, verbose=False)
+        omni = mgpu_parity.check_omni(dist, rank, world, local, verbose=False)     # frame-sharded omnidir::calibrate path
         if rank == 0:
-            out["parity"] = {"ok": res["ok"], "param_rel": res["param_rel"], "S_rel": res["S_rel"], "cost_rel": res["cost_rel"],
+            out["parity"] = {"ok": bool(res["ok"] and omni["ok"]), "param_rel": res["param_rel"], "S_rel": res["S_rel"], "cost_rel": res["cost_rel"],
                              "cams_bit_identical": res["cams_bit_identical"], "exchange": res["exchange"],
                              "cases": [c["case"] + ":" + c["exchange"] for c in res["cases"]],
+                             "omni_calibrate": {k: omni[k] for k in ("case", "iters", "oracle_iters", "param_rel", "intrinsics_bit_identical", "ok")},
                              "checker": "oracle/ on the whole rig (rank 0), tolerance 1e-6"}
     return out
 

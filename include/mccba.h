@@ -178,7 +178,11 @@ int mccba_reproj_error(mccba_handle h, mccba_error_stats *stats, double *per_edg
  * [om_i, T_i] * n, fx, fy, s, cx, cy, xi, k1, k2, p1, p2 (encodeParameters, :1541-1568), step
  * G = (1 - 0.99^(iter+1)) (JTJ_sub + eps 11^T)^-1 JTE_sub with eps = 0.01 * 0.9^(iter/10), fixed parameters selected
  * by the omnidir::CALIB_FIX_* bits of `flags`.  The closed-form initialisation (initializeCalibration) is out of
- * scope: the caller supplies the starting parameters.  Single GPU. */
+ * scope: the caller supplies the starting parameters.
+ * Several ranks (mccba_options.nranks > 1): the frames shard over the ranks -- every rank passes ITS frames and the
+ * parameter vector [its poses | the 10 intrinsics]; the 78 sums of the reduced intrinsic system and the two norms of
+ * the `change` criterion are summed with ncclAllReduce inside the iteration graph, every rank solves the 10-wide block
+ * redundantly (bit-identical intrinsics), report->cost is the whole job's. */
 int mccba_omni_set_observations(mccba_handle h, int n_frame, const int64_t *frame_off, const float *obj_xyz,
                                 const float *img_uv);
 int mccba_omni_set_parameters(mccba_handle h, int64_t n, const double *params);   /* n = 6 n_frame + 10 */

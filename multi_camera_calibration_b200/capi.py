@@ -248,6 +248,8 @@ class Solver:
         self._omni_pts = int(off[-1])
         self._check(lib().mccba_omni_set_observations(self._h, int(self._omni_n), _ptr(off, C.c_int64), _ptr(obj, C.c_float),
                                                       _ptr(img, C.c_float)))
+        if self.nranks > 1:      # frames shard over the ranks: the cost of a report is the whole job's, so is the corner count
+            self._omni_pts = int(round(self.allreduce_sum([float(self._omni_pts)])[0]))
 
     def omni_set_parameters(self, params):
         p = np.ascontiguousarray(params, dtype=np.float64)

@@ -1405,15 +1405,31 @@ int omni_alloc(mccba_handle h, T** p, size_t count)
     *p = (T*)q;
     return MCCBA_OK;
 }
+// sum over the ranks in place (no-op for a single rank); inside the captured iteration graph as well
+int omni_allreduce(mccba_handle h, double* buf, int n)
+{
+    if (h->opts.nranks <= 1) return MCCBA_OK;
+    ncclResult_t r = nccl().AllReduce(buf, buf, (size_t)n, kNcclFloat64, kNcclSum, h->comm, h->stream);
+    if (r != 0) return fail(h, MCCBA_ERR_NCCL, "ncclAllReduce failed: %s", nccl().GetErrorString ? nccl().GetErrorString(r) : "?");
+    return MCCBA_OK;
+}
 int omni_enqueue_iteration(mccba_handle h)
 {
     OmniProblem& O = h->O;
     cudaStream_t s = h->stream;
     omni_frame_kernel<<<(O.n_frame + kOmniWarps - 1) / kOmniWarps, kOmniThreads, 0, s>>>(O, 0);
     omni_reduce_kernel<<<kOmniRec, 256, 0, s>>>(O, 0);
-    omni_solve_kernel<<<1, 32, 0, s>>>(O);
+    int rc;
+    if ((rc = omni_allreduce(h, O.tot, kOmniRec))) return rc;     // frames shard over the ranks: 78 doubles
+    omni_solve_kernel<<<1, 32, 0, s>>>(O);                         // identical on every rank
     omni_update_kernel<<<O.n_blocks_upd, 128, 0, s>>>(O);
-    omni_decide_kernel<<<1, 256, 0, s>>>(O);
+    if (h->opts.nranks > 1) {
+        omni_decide_kernel<<<1, 256, 0, s>>>(O, 1);
+        if ((rc = omni_allreduce(h, O.norm_tot, 2))) return rc;
+        omni_decide_kernel<<<1, 256, 0, s>>>(O, 2);
+    } else {
+        omni_decide_kernel<<<1, 256, 0, s>>>(O, 0);
+    }
     CUDA_TRY(h, cudaGetLastError());
     return MCCBA_OK;
 }
@@ -1469,6 +1485,8 @@ int mccba_omni_set_observations(mccba_handle h, int n_frame, const int64_t* fram
     if ((rc = omni_alloc(h, &O.save, (size_t)kOmniSave * n_frame))) return rc;
     if ((rc = omni_alloc(h, &O.tot, kOmniRec))) return rc;
     if ((rc = omni_alloc(h, &O.norm_part, 2 * (size_t)O.n_blocks_upd))) return rc;
+    if ((rc = omni_alloc(h, &O.norm_tot, 2))) return rc;
+    O.count_intr = h->opts.rank == 0 ? 1 : 0;
     if ((rc = omni_alloc(h, &O.st, 1))) return rc;
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     cudaFree(d_obj);
@@ -1555,6 +1573,7 @@ int mccba_omni_solve(mccba_handle h, int flags, int crit_type, int max_count, do
     // final cost at the returned parameters (estimateUncertainties' rms, src/omnidir.cpp:1794-1802)
     omni_frame_kernel<<<(O.n_frame + kOmniWarps - 1) / kOmniWarps, kOmniThreads, 0, s>>>(O, 1);
     omni_reduce_kernel<<<kOmniRec, 256, 0, s>>>(O, 1);
+    if ((rc = omni_allreduce(h, O.tot, kOmniRec))) return rc;
     OmniState hs;
     double cost = 0;
     CUDA_TRY(h, cudaMemcpyAsync(&hs, O.st, sizeof(OmniState), cudaMemcpyDeviceToHost, s));
@@ -1567,7 +1586,7 @@ int mccba_omni_solve(mccba_handle h, int flags, int crit_type, int max_count, do
     if (rep) {
         memset(rep, 0, sizeof(*rep));
         rep->iterations = hs.iter; rep->accepted = hs.iter; rep->status = hs.status;
-        rep->graph_launches = (int)launched; rep->kernel_launches = (int)launched * 5 + 3;
+        rep->graph_launches = (int)launched; rep->kernel_launches = (int)launched * (h->opts.nranks > 1 ? 6 : 5) + 3;
         rep->change = hs.change; rep->cost = cost; rep->lambda = hs.epsilon; rep->device_ms = ms;
     }
     if (hs.status) return fail(h, MCCBA_ERR_NUMERIC, "omni_solve: numeric failure at iteration %d", hs.iter);
@@ -1586,6 +1605,10 @@ int mccba_omni_gram(mccba_handle h, double* gram /* n_frame x 17 x 17 */, double
     if (gram) { CUDA_TRY(h, cudaMalloc((void**)&d, sizeof(double) * cnt)); O.dump = d; }
     omni_frame_kernel<<<(O.n_frame + kOmniWarps - 1) / kOmniWarps, kOmniThreads, 0, h->stream>>>(O, 1);
     omni_reduce_kernel<<<kOmniRec, 256, 0, h->stream>>>(O, 1);
+    {
+        int rc2 = omni_allreduce(h, O.tot, kOmniRec);      // cost: the whole job's
+        if (rc2) { if (d) cudaFree(d); return rc2; }
+    }
     if (gram) CUDA_TRY(h, cudaMemcpyAsync(gram, d, sizeof(double) * cnt, cudaMemcpyDeviceToHost, h->stream));
     if (cost) CUDA_TRY(h, cudaMemcpyAsync(cost, O.tot + 77, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
@@ -1765,7 +1788,7 @@ int mccba_stereo_solve(mccba_handle h, int flags, int crit_type, int max_count, 
     if (rep) {
         memset(rep, 0, sizeof(*rep));
         rep->iterations = hs.iter; rep->accepted = hs.iter; rep->status = hs.status;
-        rep->graph_launches = (int)launched; rep->kernel_launches = (int)launched * 5 + 3;
+        rep->graph_launches = (int)launched; rep->kernel_launches = (int)launched * (h->opts.nranks > 1 ? 6 : 5) + 3;
         rep->change = hs.change; rep->cost = cost; rep->lambda = hs.epsilon; rep->device_ms = ms;
     }
     if (hs.status) return fail(h, MCCBA_ERR_NUMERIC, "stereo_solve: numeric failure at iteration %d", hs.iter);

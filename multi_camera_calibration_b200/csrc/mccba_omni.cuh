@@ -49,8 +49,10 @@ struct OmniProblem {
     double* save;         // kOmniSave x n_frame (SoA)
     double* tot;          // kOmniRec
     double* norm_part;    // 2 x n_blocks_upd
+    double* norm_tot;     // 2: |G|^2, |param_old|^2 (frame-sharded runs: summed over the ranks before the decision)
     double* dump;         // optional: n_frame x 289 Gram matrices (tests)
     OmniState* st;
+    int count_intr;       // 1 on the rank that adds the 10 intrinsics to the norms (rank 0); every rank updates them
 };
 
 // One WARP per frame.  Per pass of 32 corners every lane evaluates one corner (projection + the two 17-wide rows
@@ -379,7 +381,7 @@ __global__ void __launch_bounds__(128) omni_update_kernel(OmniProblem P)
     if (blockIdx.x == 0 && threadIdx.x < 10) {   // intrinsic block (fixed parameters get G = 0, fillFixed)
         const int a = threadIdx.x;
         const double old = P.param[6 * (int64_t)n + a], G = alpha * st->x_intr[a];
-        g2 += G * G; p2 += old * old;
+        if (P.count_intr) { g2 += G * G; p2 += old * old; }
         P.param[6 * (int64_t)n + a] = old + G;
     }
     __shared__ double sr[2][4];
@@ -393,13 +395,16 @@ __global__ void __launch_bounds__(128) omni_update_kernel(OmniProblem P)
     }
 }
 
-__global__ void __launch_bounds__(256) omni_decide_kernel(OmniProblem P)
+// phase 0: sum the norm partials and decide (single rank).  Frame-sharded runs split it around the collective:
+// phase 1 writes the rank's two sums to norm_tot, phase 2 decides from the all-reduced norm_tot.
+__global__ void __launch_bounds__(256) omni_decide_kernel(OmniProblem P, int phase)
 {
     OmniState* st = P.st;
     if (st->done) return;
     __shared__ double sm[2][8];
     double a = 0.0, b = 0.0;
-    for (int k = threadIdx.x; k < P.n_blocks_upd; k += blockDim.x) { a += P.norm_part[k]; b += P.norm_part[P.n_blocks_upd + k]; }
+    if (phase != 2)
+        for (int k = threadIdx.x; k < P.n_blocks_upd; k += blockDim.x) { a += P.norm_part[k]; b += P.norm_part[P.n_blocks_upd + k]; }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
     if ((threadIdx.x & 31) == 0) { sm[0][threadIdx.x >> 5] = a; sm[1][threadIdx.x >> 5] = b; }
@@ -407,6 +412,8 @@ __global__ void __launch_bounds__(256) omni_decide_kernel(OmniProblem P)
     if (threadIdx.x == 0) {
         double g2 = 0, p2 = 0;
         for (int w = 0; w < 8; ++w) { g2 += sm[0][w]; p2 += sm[1][w]; }
+        if (phase == 1) { P.norm_tot[0] = g2; P.norm_tot[1] = p2; return; }
+        if (phase == 2) { g2 = P.norm_tot[0]; p2 = P.norm_tot[1]; }
         st->change = sqrt(g2) / sqrt(p2);   // src/omnidir.cpp:1141: the norm of the parameters BEFORE the update
         st->iter += 1;
         const int t = st->crit_type;

@@ -47,3 +47,6 @@ def test_rank_parity(nproc, port):
     # the two exchanges sum in different orders: agreement to rounding, not bitwise
     for a, b in zip(first, second):
         assert abs(a["rms"] - b["rms"]) <= 1e-9 * b["rms"]
+    # the omnidir::calibrate path, frames sharded over the same ranks (10-wide shared block)
+    omni = [json.loads(l.split(" ", 1)[1]) for l in text.splitlines() if l.startswith("mgpu_parity_omni {")]
+    assert len(omni) == 1 and omni[0]["ok"] and omni[0]["intrinsics_bit_identical"] and omni[0]["param_rel"] < 1e-6, omni
