@@ -240,6 +240,26 @@ int mccba_stereo_solve(mccba_handle h, int flags, int crit_type, int max_count, 
 /* errors[6 (n + 1) + 20] = 3 s sqrt(diag((J^T J)^-1)) (0 at fixed parameters), std_error = (sigma_x, sigma_y), rms */
 int mccba_stereo_uncertainties(mccba_handle h, int flags, double *errors, double std_error[2], double *rms);
 
+/* ---- double-sided board calibration --------------------------------------------------------
+ * The optimisation of cv::multicalib::DoubleSideCalibration (src/doubleSide.cpp): the cameras are FIXED at known poses;
+ * unknown are the front<->back transform D of the board and one pose per frame.  An edge that sees the back pattern is
+ * composed with D innermost, X_cam = R_c (R_p (R_D X + t_D) + t_p) + t_c (computePhotoCameraJacobian, :288-429;
+ * the same chain as the back-pattern branch of src/mymulticalib.cpp:468-614); parameter vector
+ * [D | frame 0 | frame 1 | ...], 6 values [rvec | tvec] each (buildParas, :233-261); step schedule and termination as
+ * optimizeExtrinsics (src/multicalib.cpp:462-514).  The problem sits on top of mccba_set_cameras +
+ * mccba_set_observations (edges, corners, intrinsics; the camera parameters of the rig path are not used).
+ *   edge_back[e] (reference edge order): 1 if edge e sees the back pattern (edge::patternSide == BACK_PATTERN)
+ *   cam_pose: n_cam x 6 [rvec | tvec], world -> camera (DoubleSideCalibration::camerasPose, loadCameraPose :276-287)
+ * MCCBA_ERR_ARG if no edge sees the back pattern (D would not be observable).  Single rank. */
+int mccba_ds_set_problem(mccba_handle h, const unsigned char *edge_back, const double *cam_pose);
+int mccba_ds_set_parameters(mccba_handle h, int64_t n, const double *params);   /* n = 6 + 6 n_frame */
+int mccba_ds_get_parameters(mccba_handle h, int64_t n, double *params);
+/* report->cost = sum of squared residuals at the returned parameters */
+int mccba_ds_solve(mccba_handle h, int crit_type, int max_count, double epsilon, mccba_report *report);
+/* test hook: the 6 x 6 system of D after elimination of the frame poses (tangent coordinates) and the cost, at the
+ * current parameters */
+int mccba_ds_normal(mccba_handle h, double *S36, double *g6, double *cost);
+
 #ifdef __cplusplus
 }
 #endif

@@ -226,6 +226,35 @@ class Solver:
         """0 single rank, 1 ncclAllReduce, 2 NVLink peer-memory windows (include/mccba.h: mccba_exchange_mode)."""
         return int(lib().mccba_exchange_mode(self._h))
 
+    # ---- double-sided board calibration (include/mccba.h: mccba_ds_*) ----
+    def ds_set_problem(self, edge_back, cam_pose):
+        b = np.ascontiguousarray(edge_back, dtype=np.uint8)
+        cp = np.ascontiguousarray(cam_pose, dtype=np.float64)
+        self._check(lib().mccba_ds_set_problem(self._h, _ptr(b, C.c_ubyte), _ptr(cp, C.c_double)))
+
+    def ds_set_parameters(self, params):
+        p = np.ascontiguousarray(params, dtype=np.float64)
+        self._ds_n = p.size
+        self._check(lib().mccba_ds_set_parameters(self._h, C.c_int64(p.size), _ptr(p, C.c_double)))
+
+    def ds_get_parameters(self):
+        p = np.zeros(self._ds_n)
+        self._check(lib().mccba_ds_get_parameters(self._h, C.c_int64(p.size), _ptr(p, C.c_double)))
+        return p
+
+    def ds_solve(self, crit_type=3, max_count=200, eps=1e-7, check=True):
+        r = Report()
+        rc = lib().mccba_ds_solve(self._h, int(crit_type), int(max_count), C.c_double(eps), C.byref(r))
+        if rc and check:
+            self._check(rc)
+        return dict(rc=rc, iterations=r.iterations, status=r.status, change=r.change, cost=r.cost, device_ms=r.device_ms,
+                    kernel_launches=r.kernel_launches)
+
+    def ds_normal(self):
+        S = np.zeros((6, 6)); g = np.zeros(6); c = C.c_double(0.0)
+        self._check(lib().mccba_ds_normal(self._h, _ptr(S, C.c_double), _ptr(g, C.c_double), C.byref(c)))
+        return S, g, float(c.value)
+
     def exchange_stats(self):
         """Mean store / wait microseconds of the peer-memory exchange since the last call (mccba_exchange_stats)."""
         out = (C.c_double * 4)()

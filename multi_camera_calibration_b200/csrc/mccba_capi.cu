@@ -18,6 +18,7 @@
 #include "mccba_kernels.cuh"
 #include "mccba_omni.cuh"
 #include "mccba_stereo.cuh"
+#include "mccba_ds.cuh"
 
 using namespace mccba;
 
@@ -131,6 +132,10 @@ struct mccba_handle_s {
     std::vector<void*> stereo_allocs;
     bool stereo_have = false, stereo_have_params = false;
     cudaGraphExec_t stereo_graph = nullptr;
+    // double-sided board calibration (mccba_ds_*): lives on top of the rig problem (cameras + observations)
+    DsProblem D;
+    std::vector<void*> ds_allocs;
+    bool ds_have = false, ds_have_params = false;
 };
 
 namespace {
@@ -440,6 +445,7 @@ int mccba_destroy(mccba_handle h)
     for (void* q : h->omni_allocs) cudaFree(q);
     if (h->stereo_graph) cudaGraphExecDestroy(h->stereo_graph);
     for (void* q : h->stereo_allocs) cudaFree(q);
+    for (void* q : h->ds_allocs) cudaFree(q);
     if (h->d_cams) cudaFree(h->d_cams);
     p2p_teardown(h);
     if (h->comm) nccl().CommDestroy(h->comm);
@@ -606,6 +612,7 @@ int mccba_set_observations(mccba_handle h, int n_frame, int n_edge, const int* e
     if (n_frame < 1 || n_edge < 1 || !edge_cam || !edge_pv || !edge_off || !obj_xyz || !img_uv)
         return fail(h, MCCBA_ERR_ARG, "set_observations: null or empty input");
     CUDA_TRY(h, cudaSetDevice(h->opts.device));
+    h->ds_have = h->ds_have_params = false;     // a double-sided problem is tied to the edge order of the observations it was set on
     const char* timing_env = getenv("MCCBA_TIMING");
     const bool timing = timing_env != nullptr, timing_sync = timing && timing_env[0] != '2';   // "2": host laps only, no stream sync
     auto t_start = std::chrono::steady_clock::now();
@@ -1828,6 +1835,187 @@ int mccba_stereo_uncertainties(mccba_handle h, int flags, double* errors, double
     if (errors)
         for (size_t i = 0; i < np; ++i) errors[i] = 3.0 * sdev * sqrt(diag[i]);                                          // :1875
     if (rms) *rms = sqrt(mom[2] / N);
+    return MCCBA_OK;
+}
+
+}  // extern "C"
+
+// ---- double-sided board calibration (cv::multicalib::DoubleSideCalibration's optimisation, src/doubleSide.cpp) ---------
+namespace {
+template <typename T>
+int ds_alloc(mccba_handle h, T** p, size_t count)
+{
+    void* q = nullptr;
+    const size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+    CUDA_TRY(h, cudaMalloc(&q, bytes));
+    CUDA_TRY(h, cudaMemsetAsync(q, 0, bytes, h->stream));
+    h->ds_allocs.push_back(q);
+    *p = (T*)q;
+    return MCCBA_OK;
+}
+void ds_free(mccba_handle h)
+{
+    for (void* q : h->ds_allocs) cudaFree(q);
+    h->ds_allocs.clear();
+    h->ds_have = h->ds_have_params = false;
+}
+// one pass at the current parameters: composed poses, per-edge blocks (the rig path's residual / Jacobian kernel), Schur records
+int ds_enqueue_eval(mccba_handle h, int forced)
+{
+    Problem& P = h->P;
+    DsProblem& D = h->D;
+    cudaStream_t s = h->stream;
+    const int nb = (P.n_slots + 127) / 128;
+    ds_pose_kernel<<<nb, 128, 0, s>>>(P, D, forced);
+    launch_resid(h, s, 1);                       // evaluates Problem::erec, writes blocks[st->cur]
+    ds_schur_kernel<<<nb, 128, 0, s>>>(P, D, forced);
+    ds_reduce_kernel<<<kDsRec, 256, 0, s>>>(P, D, forced);
+    CUDA_TRY(h, cudaGetLastError());
+    return MCCBA_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int mccba_ds_set_problem(mccba_handle h, const unsigned char* edge_back, const double* cam_pose)
+{
+    if (!h) return MCCBA_ERR_ARG;
+    if (!h->have_obs) return fail(h, MCCBA_ERR_STATE, "ds_set_problem before set_observations");
+    if (!edge_back || !cam_pose) return fail(h, MCCBA_ERR_ARG, "ds_set_problem: null argument");
+    if (h->opts.nranks > 1) return fail(h, MCCBA_ERR_ARG, "ds_set_problem: the double-sided path runs on one rank");
+    CUDA_TRY(h, cudaSetDevice(h->opts.device));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    ds_free(h);
+    Problem& P = h->P;
+    DsProblem& D = h->D;
+    memset(&D, 0, sizeof(D));
+    std::vector<unsigned char> back((size_t)P.n_edge_int, 0);
+    int n_back = 0;
+    for (int e = 0; e < h->n_edge; ++e) {
+        if (edge_back[e] > 1) return fail(h, MCCBA_ERR_ARG, "ds_set_problem: edge_back[%d] = %d (0 = front, 1 = back)", e, (int)edge_back[e]);
+        back[(size_t)h->int_of_edge[e]] = edge_back[e];
+        n_back += edge_back[e];
+    }
+    if (n_back == 0) return fail(h, MCCBA_ERR_ARG, "ds_set_problem: no edge sees the back pattern (the front<->back transform is not observable)");
+    std::vector<double> R((size_t)9 * h->n_cam), t((size_t)3 * h->n_cam);
+    for (int c = 0; c < h->n_cam; ++c) {
+        for (int i = 0; i < 6; ++i)
+            if (!std::isfinite(cam_pose[6 * c + i])) return fail(h, MCCBA_ERR_ARG, "ds_set_problem: camera %d pose is not finite", c);
+        rodrigues(cam_pose + 6 * c, R.data() + 9 * c);
+        for (int i = 0; i < 3; ++i) t[(size_t)3 * c + i] = cam_pose[6 * c + 3 + i];
+    }
+    unsigned char* d_back = nullptr; double *d_R = nullptr, *d_t = nullptr;
+    int rc;
+    if ((rc = ds_alloc(h, &d_back, back.size()))) return rc;
+    if ((rc = ds_alloc(h, &d_R, R.size()))) return rc;
+    if ((rc = ds_alloc(h, &d_t, t.size()))) return rc;
+    CUDA_TRY(h, cudaMemcpyAsync(d_back, back.data(), back.size(), cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(d_R, R.data(), R.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(d_t, t.data(), t.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    D.back = d_back; D.cam_R = d_R; D.cam_t = d_t;
+    D.n_blocks = (P.n_slots + 127) / 128;
+    if ((rc = ds_alloc(h, &D.par, 6 + 6 * (size_t)h->n_frame))) return rc;
+    if ((rc = ds_alloc(h, &D.rec, (size_t)kDsRec * (size_t)P.n_slots))) return rc;
+    if ((rc = ds_alloc(h, &D.save, (size_t)kDsSave * (size_t)P.n_slots))) return rc;
+    if ((rc = ds_alloc(h, &D.tot, kDsRec))) return rc;
+    if ((rc = ds_alloc(h, &D.norm_part, 2 * (size_t)D.n_blocks))) return rc;
+    if ((rc = ds_alloc(h, &D.st, 1))) return rc;
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    h->ds_have = true;
+    return MCCBA_OK;
+}
+
+int mccba_ds_set_parameters(mccba_handle h, int64_t n, const double* params)
+{
+    if (!h) return MCCBA_ERR_ARG;
+    if (!h->ds_have) return fail(h, MCCBA_ERR_STATE, "ds_set_parameters before ds_set_problem");
+    if (!params || n != 6 + 6 * (int64_t)h->n_frame) return fail(h, MCCBA_ERR_ARG, "ds_set_parameters: expected %lld values", (long long)(6 + 6 * (int64_t)h->n_frame));
+    for (int64_t i = 0; i < n; ++i)
+        if (!std::isfinite(params[i])) return fail(h, MCCBA_ERR_ARG, "ds_set_parameters: parameter %lld is not finite", (long long)i);
+    CUDA_TRY(h, cudaSetDevice(h->opts.device));
+    CUDA_TRY(h, cudaMemcpyAsync(h->D.par, params, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    h->ds_have_params = true;
+    return MCCBA_OK;
+}
+
+int mccba_ds_get_parameters(mccba_handle h, int64_t n, double* params)
+{
+    if (!h) return MCCBA_ERR_ARG;
+    if (!h->ds_have_params) return fail(h, MCCBA_ERR_STATE, "ds_get_parameters before ds_set_parameters");
+    if (!params || n != 6 + 6 * (int64_t)h->n_frame) return fail(h, MCCBA_ERR_ARG, "ds_get_parameters: expected %lld values", (long long)(6 + 6 * (int64_t)h->n_frame));
+    CUDA_TRY(h, cudaSetDevice(h->opts.device));
+    CUDA_TRY(h, cudaMemcpyAsync(params, h->D.par, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return MCCBA_OK;
+}
+
+int mccba_ds_normal(mccba_handle h, double* S36, double* g6, double* cost)
+{
+    if (!h) return MCCBA_ERR_ARG;
+    if (!h->ds_have_params) return fail(h, MCCBA_ERR_STATE, "ds_normal before ds_set_parameters");
+    CUDA_TRY(h, cudaSetDevice(h->opts.device));
+    int rc;
+    if ((rc = sync_state_cur(h))) return rc;
+    if ((rc = ds_enqueue_eval(h, 1))) return rc;
+    double tot[kDsRec];
+    CUDA_TRY(h, cudaMemcpyAsync(tot, h->D.tot, sizeof(tot), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    if (S36) memcpy(S36, tot, 36 * sizeof(double));
+    if (g6) memcpy(g6, tot + 36, 6 * sizeof(double));
+    if (cost) *cost = tot[42];
+    if (tot[43] != 0.0) return fail(h, MCCBA_ERR_NUMERIC, "ds_normal: a frame block is not positive definite");
+    return MCCBA_OK;
+}
+
+int mccba_ds_solve(mccba_handle h, int crit_type, int max_count, double epsilon, mccba_report* rep)
+{
+    if (!h) return MCCBA_ERR_ARG;
+    if (!h->ds_have_params) return fail(h, MCCBA_ERR_STATE, "ds_solve before ds_set_parameters");
+    if (crit_type < 1 || crit_type > 3 || max_count < 0) return fail(h, MCCBA_ERR_ARG, "ds_solve: bad criteria");
+    CUDA_TRY(h, cudaSetDevice(h->opts.device));
+    Problem& P = h->P;
+    DsProblem& D = h->D;
+    cudaStream_t s = h->stream;
+    int rc;
+    CUDA_TRY(h, cudaEventRecord(h->ev0, s));
+    if ((rc = sync_state_cur(h))) return rc;
+    ds_init_state_kernel<<<1, 1, 0, s>>>(D.st, crit_type, max_count, epsilon);
+    const int64_t max_launches = (crit_type & 1) ? max_count : 200000;
+    int64_t launched = 0;
+    bool stop = false;
+    while (launched < max_launches && !stop) {
+        const int nl = (int)std::min<int64_t>(8, max_launches - launched);
+        for (int i = 0; i < nl; ++i) {
+            if ((rc = ds_enqueue_eval(h, 0))) return rc;
+            ds_solve_kernel<<<1, 32, 0, s>>>(P, D);
+            ds_update_kernel<<<D.n_blocks, 128, 0, s>>>(P, D);
+            ds_decide_kernel<<<1, 256, 0, s>>>(D);
+        }
+        launched += nl;
+        CUDA_TRY(h, cudaMemcpyAsync(h->h_done, &D.st->done, sizeof(int), cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(h, cudaStreamSynchronize(s));
+        if (h->h_done[0]) stop = true;
+    }
+    // cost at the returned parameters
+    if ((rc = ds_enqueue_eval(h, 1))) return rc;
+    DsState hs;
+    double cost = 0;
+    CUDA_TRY(h, cudaMemcpyAsync(&hs, D.st, sizeof(DsState), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(h, cudaMemcpyAsync(&cost, D.tot + 42, sizeof(double), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(h, cudaEventRecord(h->ev1, s));
+    CUDA_TRY(h, cudaStreamSynchronize(s));
+    CUDA_TRY(h, cudaGetLastError());
+    float ms = 0;
+    cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+    if (rep) {
+        memset(rep, 0, sizeof(*rep));
+        rep->iterations = hs.iter; rep->accepted = hs.iter; rep->status = hs.status;
+        rep->graph_launches = 0; rep->kernel_launches = (int)launched * 7 + 6;
+        rep->change = hs.change; rep->cost = cost; rep->device_ms = ms;
+    }
+    if (hs.status) return fail(h, MCCBA_ERR_NUMERIC, "ds_solve: numeric failure at iteration %d (non-finite cost or a block that is not positive definite)", hs.iter);
+    if (!hs.done) return fail(h, MCCBA_ERR_NUMERIC, "ds_solve: launch budget exhausted (iter %d)", hs.iter);
     return MCCBA_OK;
 }
 

@@ -225,6 +225,79 @@ CONFIGS = {
 }
 
 
+def make_double_side_rig(n_frame=60, seed=4001, theta=2.0, noise_px=0.3, init_rot=0.02, init_trans=10.0, third_every=3):
+    """Synthetic problem of the double-sided board calibration (src/doubleSide.cpp): three FIXED pinhole cameras --
+    camera 0 at the origin looks at the front pattern, camera 1 sits `theta` rad around the board and looks at the back
+    pattern, camera 2 (0.35 rad off camera 0) sees the front pattern of every `third_every`-th frame -- and a board whose
+    back pattern is related to the front pattern by D (X_front = R_D X_back + t_D).  theta stays well away from pi so
+    that the reference's Rodrigues round trips (compose_motion) are accurate in the oracle.
+    Returns the rig in the C-ABI layout plus edge_back, cam_pose (nC x 6), ds_params_true / ds_params_init
+    ([D | frame poses] in photo-vertex order)."""
+    cams = make_cameras(3, seed, [0, 0, 0], 5)
+    B = board(); nB = B.shape[0]; Bc = B.mean(axis=0)
+    rng = _rng(seed, 50)
+    centre_w = np.array([0.0, 0.0, 1500.0])
+
+    def cam_at(angle):     # world -> camera for a camera on the circle around the board centre, looking at it
+        R = rodrigues_batch(np.array([[0.0, angle, 0.0]]))[0]
+        c = centre_w + 1500.0 * np.array([np.sin(angle), 0.0, -np.cos(angle)])
+        return R, -R @ c
+    poses = [cam_at(0.0), cam_at(theta), cam_at(-0.35)]
+    cR = np.stack([p[0] for p in poses]); ct = np.stack([p[1] for p in poses])
+    cam_pose = np.concatenate([log_so3_batch(cR), ct], axis=1)
+    # D: the back pattern faces camera 1 the way the front pattern faces camera 0
+    t0 = centre_w - Bc
+    Rd = cR[1].T
+    td = cR[1].T @ (t0 - ct[1]) - t0
+    D_true = np.concatenate([log_so3_batch(Rd[None])[0], td])
+    frame_R = np.zeros((n_frame, 3, 3)); frame_t = np.zeros((n_frame, 3))
+    for f in range(n_frame):
+        for _ in range(200):
+            ax = rng.standard_normal(3); ax /= np.linalg.norm(ax)
+            Rp = rodrigues_batch((ax * rng.uniform(0, 0.25))[None])[0]
+            tp = t0 + rng.uniform(-60, 60, 3) + (Bc - Rp @ Bc)
+            ok = True
+            for c, back in ((0, False), (1, True), (2, False)):
+                X = B @ Rd.T + td if back else B
+                Xc = (X @ Rp.T + tp) @ cR[c].T + ct[c]
+                uv = project(cams["cam_model"][c], cams["cam_K5"][c], cams["cam_dist8"][c], cams["cam_xi"][c], Xc)
+                ok &= bool(Xc[:, 2].min() > 300 and uv[:, 0].min() > MARGIN and uv[:, 0].max() < IMG_W - MARGIN and
+                           uv[:, 1].min() > MARGIN and uv[:, 1].max() < IMG_H - MARGIN)
+            if ok:
+                break
+        else:
+            raise RuntimeError("could not place frame %d" % f)
+        frame_R[f] = Rp; frame_t[f] = tp
+    # edges sorted by (camera, frame) as the reference loads them; photo vertices in first-seen order = frame order
+    ev = [(0, f, 0) for f in range(n_frame)] + [(1, f, 1) for f in range(n_frame)] + \
+         [(2, f, 0) for f in range(n_frame) if f % third_every == 0]
+    edge_cam = np.array([e[0] for e in ev], dtype=np.int32)
+    edge_f = np.array([e[1] for e in ev])
+    edge_back = np.array([e[2] for e in ev], dtype=np.uint8)
+    edge_pv = (3 + edge_f).astype(np.int32)
+    E = edge_cam.size
+    edge_off = np.arange(E + 1, dtype=np.int64) * nB
+    obj = np.tile(B.astype(np.float32), (E, 1))
+    img = np.empty((E * nB, 2), dtype=np.float32)
+    nrng = _rng(seed, 51)
+    for e in range(E):
+        c, f = edge_cam[e], edge_f[e]
+        X = B @ Rd.T + td if edge_back[e] else B
+        Xc = (X @ frame_R[f].T + frame_t[f]) @ cR[c].T + ct[c]
+        uv = project(cams["cam_model"][c], cams["cam_K5"][c], cams["cam_dist8"][c], cams["cam_xi"][c], Xc)
+        img[e * nB:(e + 1) * nB] = (uv + noise_px * nrng.standard_normal(uv.shape)).astype(np.float32)
+    p_true = np.concatenate([D_true[None], np.concatenate([log_so3_batch(frame_R), frame_t], axis=1)], axis=0)
+    pert = _rng(seed, 52).standard_normal(p_true.shape)
+    p_init = p_true.copy()
+    p_init[:, :3] += init_rot * pert[:, :3]
+    p_init[:, 3:] += init_trans * pert[:, 3:]
+    p_init = p_init.astype(np.float32).astype(np.float64)
+    return dict(n_cam=3, n_frame=n_frame, edge_cam=edge_cam, edge_pv=edge_pv, edge_off=edge_off, obj=obj, img=img,
+                cam_model=cams["cam_model"], cam_K5=cams["cam_K5"], cam_dist8=cams["cam_dist8"], cam_ndist=cams["cam_ndist"],
+                cam_xi=cams["cam_xi"], n_points=int(E * nB), edge_back=edge_back, cam_pose=cam_pose,
+                ds_params_true=p_true.ravel(), ds_params_init=p_init.ravel())
+
+
 def make_config(idx, n_frame=None, frame_stream=0):
     cfg = dict(CONFIGS[idx])
     models = cfg.pop("models", None)

@@ -270,6 +270,96 @@ def optimize_extrinsics(prob, params0, crit_type, max_count, eps, policy='fp64',
     return params.astype(np.float64), it, change
 
 
+# --------------------------------------------------------------------------------------------
+# Double-sided board calibration: src/doubleSide.cpp (cameras fixed, unknown = front<->back transform D + frame poses)
+# --------------------------------------------------------------------------------------------
+def ds_photo_doubleside_jacobian(prob, e, back, rvecP, tvecP, rvecC, tvecC, rvecD, tvecD):
+    """src/doubleSide.cpp:288-429 (fp64 policy).  Returns (jacobianPhoto (2N,6), jacobianDoubleside (2N,6), E (2N,))."""
+    cam, _, obj32, img32 = prob.edges[e]
+    # front pose = camera o photo (:312-314): om1 = photo, om2 = camera
+    (omF, TF, dRF_drP, dRF_dtP, _, _, dTF_drP, dTF_dtP, _, _) = compose_motion(rvecP, tvecP, rvecC, tvecC)
+    if back:
+        # back pose = front o doubleside (:318-321): om1 = doubleside, om2 = front
+        (omT, TT, dRT_drD, dRT_dtD, dRT_drF, dRT_dtF, dTT_drD, dTT_dtD, dTT_drF, dTT_dtF) = compose_motion(rvecD, tvecD, omF, TF)
+        dRT_drP = dRT_drF @ dRF_drP                  # :324-327
+        dRT_dtP = dRT_dtF @ dTF_dtP
+        dTT_drP = dTT_drF @ dRF_drP
+        dTT_dtP = dTT_dtF @ dTF_dtP
+    else:
+        omT, TT = omF, TF                            # :328-338
+        dRT_drP, dRT_dtP, dTT_drP, dTT_dtP = dRF_drP, dRF_dtP, dTF_drP, dTF_dtP
+        dRT_drD = dRT_dtD = dTT_drD = dTT_dtD = np.zeros((3, 3))
+    obj = obj32.astype(np.float64)
+    proj, jac = _project_with_jac(prob, cam, obj, omT, TT)
+    E = (img32.astype(np.float64) - proj).reshape(-1)
+    dx_drD = jac[:, 0:3] @ dRT_drD + jac[:, 3:6] @ dTT_drD      # :393-394
+    dx_dtD = jac[:, 0:3] @ dRT_dtD + jac[:, 3:6] @ dTT_dtD
+    dx_drP = jac[:, 0:3] @ dRT_drP + jac[:, 3:6] @ dTT_drP      # :409-410
+    dx_dtP = jac[:, 0:3] @ dRT_dtP + jac[:, 3:6] @ dTT_dtP
+    return np.hstack([dx_drP, dx_dtP]), np.hstack([dx_drD, dx_dtD]), E
+
+
+def ds_compute_jacobian(prob, back, cam_pose, params, dense_out=False):
+    """src/doubleSide.cpp:434-581.  params = [D | photo vertices in vertex order] (buildParas :233-261); the column block
+    of photo vertex pv is pv - nCamera + 1 (getPhotoVertexParameters :431-433).  cam_pose: (nC, 6) fixed [rvec | tvec]."""
+    nE = len(prob.edges)
+    nC = prob.n_camera
+    loc = np.zeros(nE + 1, dtype=np.int64)
+    for e in range(nE):
+        loc[e + 1] = loc[e] + 2 * prob.edges[e][2].shape[0]
+    P = params.size
+    J = np.zeros((loc[nE], P))
+    E = np.zeros(loc[nE])
+    rvecD, tvecD = params[0:3], params[3:6]
+    for e in range(nE):
+        cam, pv = prob.edges[e][0], prob.edges[e][1]
+        row = pv - nC + 1
+        rvecP, tvecP = params[row * 6:row * 6 + 3], params[row * 6 + 3:row * 6 + 6]
+        Jp, Jd, err = ds_photo_doubleside_jacobian(prob, e, bool(back[e]), rvecP, tvecP, cam_pose[cam, 0:3], cam_pose[cam, 3:6], rvecD, tvecD)
+        J[loc[e]:loc[e + 1], 0:6] = Jd                                  # :544-545
+        J[loc[e]:loc[e + 1], row * 6:(row + 1) * 6] = Jp                # :547-548
+        E[loc[e]:loc[e + 1]] = err
+    JTJ = J.T @ J
+    JTE = J.T @ E
+    x = np.linalg.solve(JTJ, JTE)          # conjungate(JTJ, JTE): CG on an SPD system -> its exact solution
+    if dense_out:
+        return x, J, E, JTJ, JTE
+    return x, float(E @ E)
+
+
+def ds_optimize(prob, back, cam_pose, params0, crit_type, max_count, eps, record=None):
+    """The loop DoubleSideCalibration inherits (src/multicalib.cpp:462-514) on its own parameter vector."""
+    params = np.asarray(params0, dtype=np.float64).copy()
+    cam_pose = np.asarray(cam_pose, dtype=np.float64).reshape(-1, 6)
+    change, it = 1.0, 0
+    while True:
+        if ((crit_type == 1 and it >= max_count) or (crit_type == 2 and change <= eps) or
+                (crit_type == 3 and (change <= eps or it >= max_count))):
+            break
+        alpha = 0.95 ** (it + 1.0)
+        x, cost = ds_compute_jacobian(prob, back, cam_pose, params)
+        G = alpha * x
+        params = params + G
+        change = float(np.linalg.norm(G) / np.linalg.norm(params))
+        if record is not None:
+            record.append(dict(iter=it, cost_before=cost, change=change, params=params.copy()))
+        it += 1
+    return params, it, change
+
+
+def ds_cost(prob, back, cam_pose, params):
+    cam_pose = np.asarray(cam_pose, dtype=np.float64).reshape(-1, 6)
+    nC = prob.n_camera
+    c = 0.0
+    for e in range(len(prob.edges)):
+        cam, pv = prob.edges[e][0], prob.edges[e][1]
+        row = pv - nC + 1
+        _, _, err = ds_photo_doubleside_jacobian(prob, e, bool(back[e]), params[row * 6:row * 6 + 3], params[row * 6 + 3:row * 6 + 6],
+                                                 cam_pose[cam, 0:3], cam_pose[cam, 3:6], params[0:3], params[3:6])
+        c += float(err @ err)
+    return c
+
+
 def compute_project_error(prob, params, policy='fp64'):
     """src/multicalib.cpp:895-1006.  Returns dict with the reference's (quirky) mean error, the per-edge
     means, and the fp64 RMS of src/omnidir.cpp:1794-1802 (the north star's 'fp64 final RMS')."""
