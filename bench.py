@@ -262,6 +262,19 @@ def _extra_legs(args, m, s, rig, pin, kw, world, rank, local, barrier):
     out["config4"] = {"workload": "BASELINE configs[3]: 16-camera mixed pinhole/omnidir rig, %d frames in total over %d GPU(s)" % (fr4 * world, world),
                       "us_per_lm_iteration": ms * 1e3 / it, "lm_iters_per_sec": it / (ms * 1e-3),
                       "corner_obs_per_s": world * r4["n_points"] * it / (ms * 1e-3), "rms_px": err["rms"]}
+    # (c2) the layouts off the tuned path: frames seen by three cameras (views beyond the second are not
+    # TMA-staged in the Schur kernel) and a board of 130 corners per view (longer edges, fewer of them per tile of work)
+    if world == 1:
+        cl = {}
+        for name, rk in (("views3_16cam_10k_frames", dict(n_cam=16, n_frame=10000, seed=1014, views_per_frame=3)),
+                         ("board13x10_16cam_4k_frames", dict(n_cam=16, n_frame=4000, seed=1015, board_shape=(13, 10, 25.0)))):
+            rc_ = synth.make_rig(**rk)
+            msc, repc, errc = _sharded_leg(m, dist, rc_, kw, world, rank, local, barrier)
+            itc = max(repc["iterations"], 1)
+            cl[name] = {"corners": rc_["n_points"], "us_per_lm_iteration": msc * 1e3 / itc,
+                        "corner_obs_per_s": rc_["n_points"] * itc / (msc * 1e-3), "rms_px": errc["rms"]}
+        cl["note"] = "compare corner_obs_per_s with config4 (2 views per frame, 54 corners per view, same camera count)"
+        out["other_layouts"] = cl
     # (e) the other precision policies on the headline rig (rank-local timing; the default policy is the headline itself)
     if world == 1:
         pol = {}

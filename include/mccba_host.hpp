@@ -45,11 +45,13 @@ struct SolverOptions {             // extensions that have no counterpart in the
 class MultiCameraCalibration {
 public:
     enum aa1 { PINHOLE, OMNIDIRECTIONAL };      // multicalib.hpp:76-80
+    enum PatternSide { FRONT_PATTERN, BACK_PATTERN };   // multicalib.hpp:81-84
 
     struct edge {                               // multicalib.hpp:86-103
         int cameraVertex, photoVertex, photoIndex;
         Mat44f transform;                       // pattern -> camera
         float reprojecterror = 0.f;
+        int patternSide = FRONT_PATTERN;        // multicalib.hpp:91
     };
     struct vertex {                             // multicalib.hpp:105-122
         Mat44f pose;                            // relative pose to the first camera
@@ -129,12 +131,41 @@ public:
     void writeParameters2config();
     double run();                                        // load / initialise / optimise / drop outliers / again (sample :71-80)
 
-private:
+protected:
     std::vector<std::string> _serials;
     std::string _dataFolder, _configFolder, _doubleSideConfig;
     Size _front, _back;
     std::set<std::string> _fileOutliers;
+    bool _keepBackPattern = false;                       // DoubleSideCalibration::storeReaded keeps both sides (src/doubleSide.cpp:114-118)
     void readCameraIntrinsics();
+};
+
+// Double-sided board calibration (include/opencv2/ccalib/doubleSide.hpp:82-178, src/doubleSide.cpp): the cameras are
+// FIXED at the poses their config files hold ("CameraMatrix", what writeParameters2config wrote), a board carries a
+// front pattern (frontPatternSize corners) and a back pattern (backPatternSize corners, a different count); unknown
+// are the front<->back transform and one board pose per timestamp.  loadImages keeps the images of both sides;
+// initialize() takes the transform from the first timestamp that one camera sees from the front and another from the
+// back (findTransformOfTwoEdge, :119-148) and the board poses from the first edge of each timestamp; the optimisation
+// runs on the GPU (mccba_ds_*).  writeParameters writes doublesideTransform.yaml (key "transform", 4 x 4: back-pattern
+// coordinates -> front-pattern coordinates), the file MyMultiCameraCalibration::readDoubleSide reads (:98-104).
+class DoubleSideCalibration : public MyMultiCameraCalibration {
+public:
+    DoubleSideCalibration(const std::vector<std::string>& cameraSerials, int cameraType, int nCameras, const std::string& dataFolder,
+                          const std::string& cameraConfigFolder, Size frontPatternSize, Size backPatternSize, float patternWidth,
+                          float patternHeight, int verbose = 0, int showExtration = 0, int nMiniMatches = 20, int flags = 0,
+                          TermCriteria criteria = TermCriteria(TermCriteria::COUNT + TermCriteria::EPS, 200, 1e-8),
+                          SolverOptions solver = SolverOptions());
+    void initialize();                                   // src/doubleSide.cpp:150-231
+    double optimizeExtrinsics();                         // the inherited loop on [transform | board poses], on the GPU; returns the RMS
+    double run();                                        // loadImages(); initialize(); optimizeExtrinsics()
+    void writeParameters(const std::string& filename) override;   // :582-590; filename = the yaml to write
+    const std::array<double, 16>& doubleSideTransform() const { return _dst; }
+    const std::vector<std::array<double, 16>>& camerasPose() const { return _camPose; }
+
+private:
+    std::array<double, 16> _dst{};                       // row-major 4 x 4
+    std::vector<std::array<double, 16>> _camPose;        // world -> camera, per camera
+    void loadCameraPose();                               // :276-287
 };
 
 }  // namespace mccba
@@ -168,6 +199,13 @@ int mccbah_create_my(const char* serials, int cameraType, int nCameras, const ch
 int mccbah_load_images_my(mccbah h, const char* outliers);
 int mccbah_remove_outlier_my(mccbah h, char* out, int cap, int* n_removed);
 int mccbah_run_my(mccbah h, double* error);
+/* DoubleSideCalibration */
+int mccbah_create_ds(const char* serials, int cameraType, int nCameras, const char* dataFolder, const char* cameraConfigFolder,
+                     int frontW, int frontH, int backW, int backH, float patternWidth, float patternHeight, int verbose,
+                     int critType, int critMaxCount, double critEps, int device, mccbah* out);
+int mccbah_initialize_ds(mccbah h);
+int mccbah_optimize_ds(mccbah h, double* rms);
+int mccbah_get_double_side_transform(mccbah h, double* T16);
 /* cv::solvePnP (iterative) restated; obj n x 3, img n x 2 (doubles) */
 int mccbah_solve_pnp(int n, const double* obj, const double* img, const double* K5, const double* dist8, int ndist, double* rvec,
                      double* tvec);

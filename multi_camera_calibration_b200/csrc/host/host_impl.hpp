@@ -18,6 +18,7 @@ struct ImageRecord {   // one (camera, timestamp) image: what loadOneSerial keep
     Mat44f transform{};
     size_t first = 0;  // offset of its corners in the concatenated point arrays
     std::string path;  // source file (directory ingest only)
+    int side = 0;      // 0 front pattern, 1 back pattern (double-sided boards)
 };
 
 struct MultiCameraCalibration::Impl {

@@ -193,6 +193,7 @@ void MultiCameraCalibration::buildEdges()
             e.photoVertex = getPhotoVertex(im.timestamp);
             e.photoIndex = pi;
             e.transform = im.transform;
+            e.patternSide = im.side;
             _edgeList.push_back(e);
             I.edgeImage.push_back(ii);
         }

@@ -89,8 +89,13 @@ void MyMultiCameraCalibration::loadImages(const std::set<std::string>& outliers)
             const double r = std::sqrt((double)tf[0] * tf[0] + (double)tf[1] * tf[1] + (double)tf[2] * tf[2]);
             if (!(r < 3000 && r > 300))                                                   // isValidPose, src/multicalib.cpp:107-113
                 throw std::runtime_error(file + ": pattern pose outside (300, 3000) units (the reference asserts here, src/mymulticalib.cpp:294-298)");
-            if (n != _front.width * _front.height) continue;                             // storeReaded, :236-241: front pattern only
+            int side = 0;
+            if (n != _front.width * _front.height) {                                     // storeReaded, :236-241: front pattern only ...
+                if (!(_keepBackPattern && n == _back.width * _back.height)) continue;    // ... unless the subclass keeps both sides
+                side = 1;
+            }
             ImageRecord im;
+            im.side = side;
             im.camera = c; im.timestamp = timestamp; im.n_points = n; im.first = total; im.path = file;
             const double omf[3] = {(double)(float)rvec[0], (double)(float)rvec[1], (double)(float)rvec[2]};   // :387-390 CV_32F
             double R[9];

@@ -284,7 +284,7 @@ int enqueue_iteration(mccba_handle h, bool timed)
     if (h->opts.nranks > 1 && no_exchange) {
         CUDA_TRY(h, cudaMemcpyAsync(P.ar, P.ar_part, sizeof(double) * (size_t)h->ar_len, cudaMemcpyDeviceToDevice, s));
     } else if (h->opts.nranks > 1 && h->p2p_ok) {
-        const int grid = std::max(1, std::min(h->num_sms, (h->ar_len + 4 * kP2pThreads - 1) / (4 * kP2pThreads)));
+        const int grid = std::max(1, std::min(h->num_sms, (h->ar_len + kP2pThreads - 1) / kP2pThreads));   // one element per thread
         p2p_exchange_kernel<<<grid, kP2pThreads, 0, s>>>(P, (int64_t)h->ar_len, h->p2p_budget_ns);
     } else if (h->opts.nranks > 1) {
         ncclResult_t r = nccl().AllReduce(P.ar_part, P.ar, (size_t)h->ar_len, kNcclFloat64, kNcclSum, h->comm, s);

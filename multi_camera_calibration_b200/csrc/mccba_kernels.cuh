@@ -1238,20 +1238,37 @@ __device__ __forceinline__ unsigned long long p2p_now_ns()
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
-__device__ __forceinline__ double p2p_ll_load(const unsigned long long* src, unsigned flag, unsigned long long budget_ns, int* timed_out)
+// Sum of element i over the n rank slots of the own window, in rank order.  All slots that have not arrived yet are
+// polled in ONE batch of independent loads per round (a round costs one memory round trip, not n of them: at 8 ranks the
+// slot-after-slot version spent 11-15 us per exchange just on serialised polling, profiles/r2_bench_n8.json).
+__device__ __forceinline__ double p2p_ll_sum(const unsigned long long* win, int64_t stride, int n, int64_t i, unsigned flag,
+                                             unsigned long long budget_ns, int* timed_out)
 {
-    unsigned long long w0, w1, t0 = 0;
-    unsigned polls = 0;
+    unsigned long long w0[8], w1[8], t0 = 0;
+    unsigned pending = (1u << n) - 1u, polls = 0;
     for (;;) {
-        asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(src) : "memory");
-        if ((unsigned)(w0 >> 32) == flag && (unsigned)(w1 >> 32) == flag) break;
-        if ((++polls & 1023u) == 0) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+            if ((pending >> r) & 1u)
+                asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0[r]), "=l"(w1[r]) : "l"(win + (int64_t)r * stride + 2 * i) : "memory");
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+            if (((pending >> r) & 1u) && (unsigned)(w0[r] >> 32) == flag && (unsigned)(w1[r] >> 32) == flag) pending &= ~(1u << r);
+        if (!pending) break;
+        if ((++polls & 255u) == 0) {
             const unsigned long long now = p2p_now_ns();
             if (t0 == 0) t0 = now;
             else if (now - t0 > budget_ns) { *timed_out = 1; return 0.0; }
         }
     }
-    return __longlong_as_double((long long)((w0 & 0xffffffffull) | (w1 << 32)));
+    double acc = 0.0;
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+        if (r < n) {
+            const double v = __longlong_as_double((long long)((w0[r] & 0xffffffffull) | (w1[r] << 32)));
+            acc = r == 0 ? v : acc + v;
+        }
+    return acc;
 }
 __global__ void __launch_bounds__(kP2pThreads) p2p_exchange_kernel(Problem P, int64_t len, unsigned long long budget_ns)
 {
@@ -1274,8 +1291,7 @@ __global__ void __launch_bounds__(kP2pThreads) p2p_exchange_kernel(Problem P, in
     const unsigned long long* win = reinterpret_cast<const unsigned long long*>(P.p2p_peer[me] + kP2pFlagWords + par);
     int timed_out = 0;
     for (int64_t i = tid; i < len; i += step) {
-        double acc = p2p_ll_load(win + 2 * i, flag, budget_ns, &timed_out);
-        for (int r = 1; r < n && !timed_out; ++r) acc += p2p_ll_load(win + (int64_t)r * P.p2p_stride + 2 * i, flag, budget_ns, &timed_out);
+        const double acc = p2p_ll_sum(win, P.p2p_stride, n, i, flag, budget_ns, &timed_out);
         P.ar[i] = timed_out ? 0.0 : acc;
         if (timed_out) break;
     }

@@ -151,3 +151,39 @@ def solve_pnp(obj, img, K5, dist8, ndist):
     if rc:
         raise RuntimeError("solve_pnp failed (%d)" % rc)
     return r, t
+
+
+class DoubleSideCalibration(MyMultiCameraCalibration):
+    """Double-sided board in front of fixed cameras (include/opencv2/ccalib/doubleSide.hpp:82-178): camera poses from the
+    "CameraMatrix" of <cameraConfigFolder>/<serial>.xml, images of both pattern sides, unknown front<->back transform +
+    one board pose per timestamp, optimised on the GPU (include/mccba.h: mccba_ds_*)."""
+
+    def __init__(self, cameraSerials, cameraType, nCameras, dataFolder, cameraConfigFolder, frontPatternSize=(9, 6),
+                 backPatternSize=(8, 5), patternWidth=360.0, patternHeight=200.0, verbose=0, criteria=(3, 200, 1e-8), device=0):
+        self._h = C.c_void_p()
+        rc = lib().mccbah_create_ds(",".join(cameraSerials).encode(), int(cameraType), int(nCameras), str(dataFolder).encode(),
+                                    str(cameraConfigFolder).encode(), int(frontPatternSize[0]), int(frontPatternSize[1]),
+                                    int(backPatternSize[0]), int(backPatternSize[1]), C.c_float(patternWidth),
+                                    C.c_float(patternHeight), int(verbose), int(criteria[0]), int(criteria[1]),
+                                    C.c_double(criteria[2]), int(device), C.byref(self._h))
+        self._check(rc)
+
+    def initialize(self):
+        self._check(lib().mccbah_initialize_ds(self._h))
+
+    def optimizeExtrinsics(self):
+        """Returns the RMS reprojection error (pixels) at the optimum."""
+        r = C.c_double()
+        self._check(lib().mccbah_optimize_ds(self._h, C.byref(r)))
+        return r.value
+
+    def run(self):
+        self.loadImages()
+        self.initialize()
+        return self.optimizeExtrinsics()
+
+    def doubleSideTransform(self):
+        """4 x 4: back-pattern coordinates -> front-pattern coordinates."""
+        T = np.zeros((4, 4))
+        self._check(lib().mccbah_get_double_side_transform(self._h, T.ctypes.data_as(C.POINTER(C.c_double))))
+        return T

@@ -112,13 +112,13 @@ def make_cameras(n_cam, seed, models=None, ndist=5):
 
 def make_rig(n_cam=8, n_frame=1000, seed=1002, models=None, views_per_frame=2, noise_px=0.3, init_rot=0.02,
              init_trans=10.0, ndist=5, frame_stream=0, cameras=None, perturb_cameras=True, board_distance=(1200.0, 2000.0),
-             tilt_max_deg=30.0, lateral=120.0, min_depth=300.0):
+             tilt_max_deg=30.0, lateral=120.0, min_depth=300.0, board_shape=(9, 6, 40.0)):
     """Full rig in the C-ABI layout.  frame_stream selects an independent set of frames for the same cameras (used to
     give every rank its own shard in the weak-scaling benchmark)."""
     cams = cameras if cameras is not None else make_cameras(n_cam, seed, models, ndist)
     n_cam = cams["n_cam"]
     rng = _rng(seed, 1000 + frame_stream)
-    B = board()
+    B = board(*board_shape)
     nB = B.shape[0]
     Bc = B.mean(axis=0)
     V = min(views_per_frame, n_cam)
@@ -225,16 +225,19 @@ CONFIGS = {
 }
 
 
-def make_double_side_rig(n_frame=60, seed=4001, theta=2.0, noise_px=0.3, init_rot=0.02, init_trans=10.0, third_every=3):
+def make_double_side_rig(n_frame=60, seed=4001, theta=2.0, noise_px=0.3, init_rot=0.02, init_trans=10.0, third_every=3,
+                         back_shape=(9, 6, 40.0)):
     """Synthetic problem of the double-sided board calibration (src/doubleSide.cpp): three FIXED pinhole cameras --
     camera 0 at the origin looks at the front pattern, camera 1 sits `theta` rad around the board and looks at the back
     pattern, camera 2 (0.35 rad off camera 0) sees the front pattern of every `third_every`-th frame -- and a board whose
     back pattern is related to the front pattern by D (X_front = R_D X_back + t_D).  theta stays well away from pi so
     that the reference's Rodrigues round trips (compose_motion) are accurate in the oracle.
     Returns the rig in the C-ABI layout plus edge_back, cam_pose (nC x 6), ds_params_true / ds_params_init
-    ([D | frame poses] in photo-vertex order)."""
+    ([D | frame poses] in photo-vertex order).  back_shape: the back pattern's own corner grid (the reference tells the
+    sides apart by their corner count)."""
     cams = make_cameras(3, seed, [0, 0, 0], 5)
-    B = board(); nB = B.shape[0]; Bc = B.mean(axis=0)
+    B = board(); Bc = B.mean(axis=0)
+    Bb = board(*back_shape)
     rng = _rng(seed, 50)
     centre_w = np.array([0.0, 0.0, 1500.0])
 
@@ -258,7 +261,7 @@ def make_double_side_rig(n_frame=60, seed=4001, theta=2.0, noise_px=0.3, init_ro
             tp = t0 + rng.uniform(-60, 60, 3) + (Bc - Rp @ Bc)
             ok = True
             for c, back in ((0, False), (1, True), (2, False)):
-                X = B @ Rd.T + td if back else B
+                X = Bb @ Rd.T + td if back else B
                 Xc = (X @ Rp.T + tp) @ cR[c].T + ct[c]
                 uv = project(cams["cam_model"][c], cams["cam_K5"][c], cams["cam_dist8"][c], cams["cam_xi"][c], Xc)
                 ok &= bool(Xc[:, 2].min() > 300 and uv[:, 0].min() > MARGIN and uv[:, 0].max() < IMG_W - MARGIN and
@@ -276,16 +279,16 @@ def make_double_side_rig(n_frame=60, seed=4001, theta=2.0, noise_px=0.3, init_ro
     edge_back = np.array([e[2] for e in ev], dtype=np.uint8)
     edge_pv = (3 + edge_f).astype(np.int32)
     E = edge_cam.size
-    edge_off = np.arange(E + 1, dtype=np.int64) * nB
-    obj = np.tile(B.astype(np.float32), (E, 1))
-    img = np.empty((E * nB, 2), dtype=np.float32)
+    edge_off = np.concatenate([[0], np.cumsum([Bb.shape[0] if b else B.shape[0] for b in edge_back])]).astype(np.int64)
+    obj = np.concatenate([(Bb if b else B).astype(np.float32) for b in edge_back], axis=0)
+    img = np.empty((int(edge_off[-1]), 2), dtype=np.float32)
     nrng = _rng(seed, 51)
     for e in range(E):
         c, f = edge_cam[e], edge_f[e]
-        X = B @ Rd.T + td if edge_back[e] else B
+        X = Bb @ Rd.T + td if edge_back[e] else B
         Xc = (X @ frame_R[f].T + frame_t[f]) @ cR[c].T + ct[c]
         uv = project(cams["cam_model"][c], cams["cam_K5"][c], cams["cam_dist8"][c], cams["cam_xi"][c], Xc)
-        img[e * nB:(e + 1) * nB] = (uv + noise_px * nrng.standard_normal(uv.shape)).astype(np.float32)
+        img[edge_off[e]:edge_off[e + 1]] = (uv + noise_px * nrng.standard_normal(uv.shape)).astype(np.float32)
     p_true = np.concatenate([D_true[None], np.concatenate([log_so3_batch(frame_R), frame_t], axis=1)], axis=0)
     pert = _rng(seed, 52).standard_normal(p_true.shape)
     p_init = p_true.copy()
@@ -294,7 +297,7 @@ def make_double_side_rig(n_frame=60, seed=4001, theta=2.0, noise_px=0.3, init_ro
     p_init = p_init.astype(np.float32).astype(np.float64)
     return dict(n_cam=3, n_frame=n_frame, edge_cam=edge_cam, edge_pv=edge_pv, edge_off=edge_off, obj=obj, img=img,
                 cam_model=cams["cam_model"], cam_K5=cams["cam_K5"], cam_dist8=cams["cam_dist8"], cam_ndist=cams["cam_ndist"],
-                cam_xi=cams["cam_xi"], n_points=int(E * nB), edge_back=edge_back, cam_pose=cam_pose,
+                cam_xi=cams["cam_xi"], n_points=int(edge_off[-1]), edge_back=edge_back, cam_pose=cam_pose, cam_R=cR, cam_t=ct,
                 ds_params_true=p_true.ravel(), ds_params_init=p_init.ravel())
 
 

@@ -146,3 +146,74 @@ def test_gpu_rejects_unobservable_transform(gpu_case):
     with pytest.raises(m.MccbaError):
         s.ds_solve(1, 1, 0.0)                                                # no problem set
     s.close()
+
+
+# ---- the host class: reference directory layout -> DoubleSideCalibration -> doublesideTransform.yaml ---------------------
+SERIALS = ["839112060578", "839512061262", "f0220380"]
+
+
+def _write_ds_dataset(tmp, r):
+    import os
+    cv2 = pytest.importorskip("cv2")
+    data = os.path.join(tmp, "color"); cfg = os.path.join(tmp, "configs")
+    os.makedirs(cfg)
+    for c in range(r["n_cam"]):
+        os.makedirs(os.path.join(data, SERIALS[c]))
+        fs = cv2.FileStorage(os.path.join(cfg, SERIALS[c] + ".xml"), cv2.FILE_STORAGE_WRITE)
+        fx, fy, cx, cy, _ = r["cam_K5"][c]
+        pose = np.eye(4); pose[:3, :3] = r["cam_R"][c]; pose[:3, 3] = r["cam_t"][c]
+        fs.write("CameraMatrix", pose)                     # what writeParameters2config wrote (src/mymulticalib.cpp:425-454)
+        fs.write("Intrinsics", np.array([[fx, 0, cx], [0, fy, cy], [0, 0, 1]], dtype=np.float64))
+        fs.write("Distortion", r["cam_dist8"][c][:5].reshape(1, 5).astype(np.float64))
+        fs.release()
+    off = r["edge_off"]
+    for e in range(r["edge_cam"].size):
+        c = int(r["edge_cam"][e]); ts = int(r["edge_pv"][e]) - r["n_cam"] + 100      # three digits: cv::glob (string) order = numeric order
+        fs = cv2.FileStorage(os.path.join(data, SERIALS[c], "%d.yaml" % ts), cv2.FILE_STORAGE_WRITE)
+        fs.write("corners", r["img"][off[e]:off[e + 1]].astype(np.float64))
+        fs.write("objects", r["obj"][off[e]:off[e + 1]].astype(np.float64))
+        fs.release()
+    return data, cfg
+
+
+def _host_case(tmp_path):
+    cv2 = pytest.importorskip("cv2")
+    from multi_camera_calibration_b200 import multicalib
+    r, prob = _problem(24, back_shape=(8, 5, 40.0))
+    data, cfg = _write_ds_dataset(str(tmp_path), r)
+    calib = multicalib.DoubleSideCalibration(SERIALS, multicalib.PINHOLE, 3, data, cfg, (9, 6), (8, 5), criteria=(3, 200, 1e-8))
+    calib.loadImages()
+    calib.initialize()
+    return cv2, r, prob, calib
+
+
+def test_host_class_loads_both_sides_and_initialises(tmp_path):
+    cv2, r, prob, calib = _host_case(tmp_path)
+    idx = calib.indexing()
+    # both pattern sides are kept (src/doubleSide.cpp:114-118); MyMultiCameraCalibration would drop the 8 x 5 images
+    assert idx["vertex_timestamp"].size == 3 + r["n_frame"] and idx["edge_cam"].size == r["edge_cam"].size
+    assert np.array_equal(idx["edge_cam"], r["edge_cam"]) and np.array_equal(idx["edge_pv"], r["edge_pv"])
+    T0 = calib.doubleSideTransform()
+    Rd = cv2.Rodrigues(r["ds_params_true"][:3].reshape(3, 1))[0]
+    assert np.abs(T0[:3, :3] - Rd).max() < 2e-2 and np.abs(T0[:3, 3] - r["ds_params_true"][3:6]).max() < 15.0   # PnP accuracy
+    calib.close()
+
+
+@pytest.mark.gpu
+def test_host_class_from_the_reference_directory_layout(tmp_path):
+    import os
+    cv2, r, prob, calib = _host_case(tmp_path)
+    rms = calib.optimizeExtrinsics()
+    T = calib.doubleSideTransform()
+    # the same minimum as the oracle reaches from its own (different) starting point
+    ref, it, _ = dr.ds_optimize(prob, r["edge_back"], r["cam_pose"], r["ds_params_init"], 3, 200, 1e-9)
+    Rref = cv2.Rodrigues(ref[:3].reshape(3, 1))[0]
+    assert np.abs(T[:3, :3] - Rref).max() < 2e-6 and np.abs(T[:3, 3] - ref[3:6]).max() < 2e-3
+    assert abs(rms - np.sqrt(dr.ds_cost(prob, r["edge_back"], r["cam_pose"], ref) / r["n_points"])) < 1e-5
+    out = os.path.join(str(tmp_path), "doublesideTransform.yaml")
+    calib.writeParameters(out)
+    fs = cv2.FileStorage(out, cv2.FILE_STORAGE_READ)                    # MyMultiCameraCalibration::readDoubleSide (:98-104)
+    Tr = fs.getNode("transform").mat()
+    fs.release()
+    assert Tr.shape == (4, 4) and np.abs(Tr - T).max() < 1e-12
+    calib.close()
