@@ -1272,6 +1272,10 @@ __device__ __forceinline__ double p2p_ll_sum(const unsigned long long* win, int6
 }
 __global__ void __launch_bounds__(kP2pThreads) p2p_exchange_kernel(Problem P, int64_t len, unsigned long long budget_ns)
 {
+    // A finished loop exchanges nothing (every rank takes the same decisions from the same sums, so all of them stop at the
+    // same launch; decide_body still advances the epoch with every launch).  After a time-out (status 5) this also keeps the
+    // remaining launches of the chunk from spinning through their budgets again.
+    if (P.st->done) return;
     const unsigned long long e = *P.p2p_epoch + 1;
     const unsigned flag = (unsigned)e;
     const int n = P.p2p_n, me = P.p2p_rank;

@@ -50,3 +50,17 @@ def test_rank_parity(nproc, port):
     # the omnidir::calibrate path, frames sharded over the same ranks (10-wide shared block)
     omni = [json.loads(l.split(" ", 1)[1]) for l in text.splitlines() if l.startswith("mgpu_parity_omni {")]
     assert len(omni) == 1 and omni[0]["ok"] and omni[0]["intrinsics_bit_identical"] and omni[0]["param_rel"] < 1e-6, omni
+
+
+@pytest.mark.gpu
+def test_exchange_timeout_is_an_error_not_a_hang():
+    """a peer that stops launching must not hang the GPU.  scripts/mgpu_timeout.py gives the two ranks different
+    iteration counts: the bounded spin of the peer-memory exchange ends the longer solve with MCCBA_ERR_NCCL within its
+    budget, and the next solve (epoch re-agreed) is bit-identical to a clean one."""
+    import torch
+    if torch.cuda.device_count() < 2 or not _peer_ok(2):
+        pytest.skip("needs 2 GPUs with peer access")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29537", os.path.join(ROOT, "scripts", "mgpu_timeout.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert "MGPU_TIMEOUT_OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
