@@ -4,10 +4,14 @@
 //   gather_obs_kernel        layout change only: AoS CV_32F points -> SoA planes in processing order
 //   vertex_prep_kernel       cv::Rodrigues per vertex (src/multicalib.cpp:1023-1024 inside compose_motion)
 //   resid_jac_accum_kernel   computePhotoCameraJacobian + scatter + J^T J / J^T E, per edge
-//                            (src/multicalib.cpp:611-678, 688-689, 717-824; src/omnidir.cpp:141-244)
+//                            (src/multicalib.cpp:611-678, 688-689, 717-824; src/omnidir.cpp:141-244), FP64 policy
+//   resid_jac_accum_f32_kernel   the same pass on the packed observation layout: two corners per lane in f32x2 registers,
+//                            fp64 residual under the default MIXED policy (mccba_f32x2.cuh)
+//   gather_obs_packed_kernel, reproj_error_packed_kernel   layout change / computeProjectError for that layout
 //   reproj_error_kernel      computeProjectError (src/multicalib.cpp:912-984)
 //   frame_schur_kernel       (new math) eliminates the per-frame pattern-pose blocks; replaces the P x P solve
 //   reduce_records_kernel    deterministic, atomic-free sum of the warp records into the reduced camera system
+//   p2p_exchange_kernel      (no counterpart) sum of the packed reduced system over the ranks through NVLink peer memory
 //   decide_kernel            optimizeExtrinsics' loop control (src/multicalib.cpp:473-507) + accept/reject (LM)
 //   chol_bcr_kernel          block cyclic reduction of the block-banded reduced system (replaces Eigen CG, :565-592)
 //   chol_dag_kernel          one-launch tiled Cholesky of a dense reduced system (same)
