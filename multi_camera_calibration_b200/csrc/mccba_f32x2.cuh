@@ -70,7 +70,7 @@ MC_HD f2 f2_rsqrt(f2 a) { return f2_make(1.0f / sqrtf(a.x), 1.0f / sqrtf(a.y)); 
 MC_HD f2 f2_dup(float a) { return f2_make(a, a); }
 
 // Intrinsics of one camera as duplicated float pairs, with the constant factors the Jacobian needs folded in once.
-struct CamF2 {
+struct alignas(16) CamF2 {
     f2 fx, fy, skew, xi;
     f2 cx, cy;
     f2 k1, k2, k3, k4, k5, k6, p1, p2;

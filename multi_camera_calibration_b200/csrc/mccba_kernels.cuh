@@ -522,10 +522,10 @@ __device__ __forceinline__ void obs_stream_issue(ObsStream& S, const Problem& P,
 // Per-edge pose of the packed pass in shared memory, one record per edge of the warp's quarter tile: the double pose
 // (for the MIXED policy's residual) and the float pose as duplicated pairs (for the f32x2 Jacobian).  26-word stride
 // for the double part: the 8 edges of a warp land in distinct banks.
-struct PackedPose {
+struct alignas(16) PackedPose {
     double Rd[9], Td[3];
-    double pad;
     f2 Rf[9], Tf[3];
+    double pad[2];
 };
 __host__ __device__ inline size_t f32_smem_bytes(int n_cam)
 {

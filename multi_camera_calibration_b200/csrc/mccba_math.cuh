@@ -58,7 +58,7 @@ constexpr int kOmnidir = 1;
 constexpr int kBlk = 28;  // per-edge block record: 21 (upper triangle of H6) + 6 (g6) + 1 (sum sq residual)
 
 // Intrinsics of one camera, widened to double.  Mirrors _cameraMatrix/_distortCoeffs/_xi (multicalib.hpp:211-213).
-struct CamParams {
+struct alignas(16) CamParams {
     double fx, fy, cx, cy, skew, xi;
     double k1, k2, p1, p2, k3, k4, k5, k6;
     int model;     // kPinhole / kOmnidir
