@@ -27,8 +27,9 @@
  *
  * Multi-GPU: frames shard across ranks.  Each rank creates its own handle (rank, nranks, shared ncclUniqueId),
  * passes ALL cameras and only ITS frames/edges (photo vertices renumbered nC..nC+F_local-1), and calls
- * mccba_solve collectively.  One ncclAllReduce per iteration sums the reduced camera system; every rank solves it
- * redundantly.  Camera parameters are replicated, frame parameters stay on their rank.
+ * mccba_solve collectively.  One exchange per iteration sums the reduced camera system (a kernel over NVLink peer
+ * memory when every rank can map every other rank's window, else ncclAllReduce: mccba_exchange_mode); every rank solves
+ * it redundantly.  Camera parameters are replicated, frame parameters stay on their rank.
  */
 #ifndef MCCBA_H_
 #define MCCBA_H_
@@ -215,10 +216,11 @@ int mccba_exchange_mode(mccba_handle h);
 int mccba_exchange_stats(mccba_handle h, double out[4]);
 
 /* Test hook: solve the SPD system S x = g (n x n row-major, lower triangle read) on the device with the loop's own
- * solvers (blocked: 3 = banded LDL^T by one warp -- the half bandwidth is measured from S and must be <= 29; this is
- * what the loop uses when the camera graph is banded -- 2 = one-launch tile DAG (the loop's choice for dense camera
- * graphs), 1 = panel/update kernels, 0 = plain single-CTA column version).  Replaces the Eigen conjugate-gradient
- * solve of src/multicalib.cpp:565-592 on the Schur-reduced system.
+ * solvers.  blocked = 3: block cyclic reduction of a block-banded system (mccba_bcr.cuh) -- the bandwidth is measured
+ * from S in 6 x 6 blocks and must be <= 4 blocks (half bandwidth <= 29); this is what the loop uses when the camera
+ * graph is banded.  blocked = 2: one-launch tile-DAG Cholesky (the loop's choice for dense camera graphs).  Other values
+ * are rejected with MCCBA_ERR_ARG.  Replaces the Eigen conjugate-gradient solve of src/multicalib.cpp:565-592 on the
+ * Schur-reduced system.
  * The kernel time in ms is left in mccba_last_kernel_ms()[0]. */
 int mccba_debug_solve_dense(mccba_handle h, int n, const double *S, const double *g, double *x, int blocked);
 /* time `reps` back-to-back launches of the residual+Jacobian kernel at the current parameters with CUDA events on
