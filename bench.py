@@ -315,6 +315,50 @@ def _extra_legs(args, m, s, rig, pin, kw, world, rank, local, barrier):
                           "us_per_iteration": ms3 * 1e3 / its, "iters_per_sec": its / (ms3 * 1e-3),
                           "resjac_evals_per_sec": r3["n_points"] * its / (ms3 * 1e-3)}
         so.close()
+    # (f2) the two small "next" paths of SURVEY 8(f): omnidir stereo bundle adjustment (+ uncertainties) and the double-sided
+    # board calibration; per-iteration times on synthetic problems (parity: tests/test_stereo_ba.py, tests/test_double_side.py)
+    if world == 1:
+        try:
+            rng = np.random.default_rng(9)
+            cams2 = synth.make_cameras(2, 77, models=[1, 1])
+            rs = synth.make_rig(n_cam=2, n_frame=400, seed=77, cameras=cams2, board_distance=(300.0, 700.0), tilt_max_deg=45.0,
+                                lateral=200.0, min_depth=150.0)
+            nF = rs["n_frame"]; offs = rs["edge_off"]
+            E0 = np.nonzero(rs["edge_cam"] == 0)[0]; E1 = np.nonzero(rs["edge_cam"] == 1)[0]
+            sl = lambda e: slice(offs[e], offs[e + 1])
+            objs = np.concatenate([rs["obj"][sl(e)] for e in E0]); i1 = np.concatenate([rs["img"][sl(e)] for e in E0])
+            i2 = np.concatenate([rs["img"][sl(e)] for e in E1])
+            foff = np.concatenate([[0], np.cumsum([offs[e + 1] - offs[e] for e in E0])]).astype(np.int64)
+            pts = rs["params_true"].reshape(-1, 6)
+            intr = lambda c: np.concatenate([[rs["cam_K5"][c][0], rs["cam_K5"][c][1], rs["cam_K5"][c][4], rs["cam_K5"][c][2],
+                                              rs["cam_K5"][c][3], rs["cam_xi"][c]], rs["cam_dist8"][c][:4]])
+            p0s = np.concatenate([pts[0], pts[rs["edge_pv"][E0] - 1].ravel(), intr(0), intr(1)])
+            p0s[:6] += np.array([0.01] * 3 + [4.0] * 3) * rng.standard_normal(6)
+            ss = m.Solver(device=local)
+            ss.stereo_set_observations(foff, objs, i1, i2)
+            its = 100
+            tt = []
+            for _ in range(3):
+                ss.stereo_set_parameters(p0s)
+                tt.append(ss.stereo_solve(0, 1, its, 0.0)["device_ms"])
+            t0 = time.perf_counter(); ss.stereo_uncertainties(0); tu = (time.perf_counter() - t0) * 1e3
+            ss.close()
+            out["stereo_ba"] = {"workload": "omnidir stereo pair, %d frames, %d corners per view, 6 + 6n + 20 = %d parameters; %d iterations" % (nF, int(foff[-1]), 6 + 6 * nF + 20, its),
+                                "us_per_iteration": float(np.median(tt[1:])) * 1e3 / its, "uncertainties_ms": tu}
+            rd = synth.make_double_side_rig(2000, seed=4002)
+            sd = m.Solver(device=local)
+            sd.set_rig(rd)
+            sd.ds_set_problem(rd["edge_back"], rd["cam_pose"])
+            itd = 20
+            td = []
+            for _ in range(3):
+                sd.ds_set_parameters(rd["ds_params_init"])
+                td.append(sd.ds_solve(1, itd, 0.0)["device_ms"])
+            sd.close()
+            out["double_side"] = {"workload": "3 fixed cameras, double-sided board, %d frames, %d corners, 6 + 6n = %d parameters; %d iterations" % (rd["n_frame"], rd["n_points"], 6 + 6 * rd["n_frame"], itd),
+                                  "us_per_iteration": float(np.median(td[1:])) * 1e3 / itd}
+        except Exception as e:                      # informative legs only
+            out["stereo_ba"] = out.get("stereo_ba") or {"unavailable": str(e)[:200]}
     # (g) second end-to-end figure: the drop-in CLASS (file ingest, indexing, initialisation, optimisation, XML output) on
     # BASELINE configs[3] (16 cameras, 10k frames): MultiCameraCalibration(...).run(); writeParameters(...)
     if world == 1:
