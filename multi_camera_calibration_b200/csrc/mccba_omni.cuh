@@ -18,6 +18,7 @@
 #include <stdint.h>
 
 #include "mccba_math.cuh"
+#include "mccba_warp_solve.cuh"
 
 namespace mccba {
 
@@ -292,46 +293,9 @@ __global__ void __launch_bounds__(32) omni_solve_kernel(OmniProblem P)
     }
     if (lane < m) rhs = tot[55 + map[lane]];
     else if (lane == m) rhs = -se * tot[76];
-    bool fail = false;
-#pragma unroll
-    for (int k = 0; k < 11; ++k) {
-        const bool live = lane >= k && lane < 11;
-        fail = fail || !isfinite(B[k]);          // reduced over the warp at the end
-        double v = live ? fabs(B[k]) : -1.0;
-        if (!(v == v)) v = -1.0;
-        int idx = lane;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const double ov = __shfl_xor_sync(0xffffffffu, v, o);
-            const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
-            if (ov > v || (ov == v && oi < idx)) { v = ov; idx = oi; }
-        }
-        fail = fail || !(v > 0.0);
-        const int piv = idx;
-        const int partner = lane == k ? piv : (lane == piv ? k : lane);     // piv == k: everybody reads itself
-#pragma unroll
-        for (int j = 0; j < 11; ++j) B[j] = __shfl_sync(0xffffffffu, B[j], partner);
-        rhs = __shfl_sync(0xffffffffu, rhs, partner);
-        const double fct = B[k] / __shfl_sync(0xffffffffu, B[k], k);
-        const double prhs = __shfl_sync(0xffffffffu, rhs, k);
-        const bool below = lane > k && lane < 11;
-#pragma unroll
-        for (int j = k; j < 11; ++j) {
-            const double pj = __shfl_sync(0xffffffffu, B[j], k);
-            if (below) B[j] -= fct * pj;
-        }
-        if (below) rhs -= fct * prhs;
-    }
-    const bool failed = __any_sync(0xffffffffu, fail && lane < Q);
+    __shared__ double s_rows[2 * 12];
     double x[11];
-#pragma unroll
-    for (int i = 10; i >= 0; --i) {
-        double s = rhs;
-#pragma unroll
-        for (int j = i + 1; j < 11; ++j) s -= B[j] * x[j];
-        s = s / B[i];
-        x[i] = __shfl_sync(0xffffffffu, s, i);
-    }
+    const bool failed = warp_gauss_solve<11>(B, rhs, lane, Q, s_rows, x);
     if (lane == 0 && !done) {
         st->alpha = alpha; st->epsilon = epsilon;
         if (status) st->done = 1;

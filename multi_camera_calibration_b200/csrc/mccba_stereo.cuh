@@ -21,6 +21,7 @@
 #include <stdint.h>
 
 #include "mccba_math.cuh"
+#include "mccba_warp_solve.cuh"
 
 namespace mccba {
 
@@ -292,56 +293,63 @@ __device__ __forceinline__ void stereo_flags2free(int flags, int* fr)
     if (f >= 2) { fix(2); }
 }
 
-__global__ void stereo_solve_kernel(StereoProblem P)
+// One warp, lane = row of the bordered (m + 1) x (m + 1) system (mccba_warp_solve.cuh); round 2 first ran this on one
+// thread out of local memory, which was most of the iteration (368 us per iteration at 400 frames).
+__global__ void __launch_bounds__(32) stereo_solve_kernel(StereoProblem P)
 {
-    if (threadIdx.x != 0) return;
+    constexpr int N = kStNS + 1;
+    __shared__ double s_rows[2 * (N + 1)];
+    __shared__ int s_map[kStNS];
     StereoState* st = P.st;
-    if (st->done) return;
-    st->alpha = 1.0 - pow(1.0 - 0.01, (double)st->iter + 1.0);       // :1276
-    st->epsilon = 0.01 * pow(0.9, (double)st->iter / 10.0);           // :1278
-    if (st->status) { st->done = 1; return; }
-    int fr[kStNS], map[kStNS], m = 0;
-    stereo_flags2free(st->flags, fr);
-    for (int a = 0; a < kStNS; ++a)
-        if (fr[a]) map[m++] = a;
+    // no early exit on the loaded state (the warp must provably stay converged): only the stores at the end are guarded
+    const int done = st->done, status = st->status;
+    const int lane = threadIdx.x;
+    const double alpha = 1.0 - pow(1.0 - 0.01, (double)st->iter + 1.0);       // :1276
+    const double epsilon = 0.01 * pow(0.9, (double)st->iter / 10.0);           // :1278
+    int m = 0;
+    {
+        int fr[kStNS];
+        stereo_flags2free(st->flags, fr);
+        for (int a = 0; a < kStNS; ++a)
+            if (fr[a]) { if (lane == 0) s_map[m] = a; ++m; }
+    }
+    __syncwarp();
     const double* tot = P.tot;
-    const double se = sqrt(st->epsilon);
+    const double se = sqrt(epsilon);
     const int Q = m + 1;
-    double B[(kStNS + 1) * (kStNS + 1)], rhs[kStNS + 1];
-    for (int a = 0; a < m; ++a) {
-        for (int c = 0; c < m; ++c) B[a * Q + c] = tot[stereo_sidx(map[a], map[c])];
-        const double ru = 1.0 + tot[kStSTri + kStNS + map[a]];
-        B[a * Q + m] = se * ru;
-        B[m * Q + a] = se * ru;
-        rhs[a] = tot[kStSTri + map[a]];
+    const int mine = lane < m ? s_map[lane] : 0;
+    double B[N], rhs = 0.0;
+#pragma unroll
+    for (int c = 0; c < N; ++c) {
+        double v = 0.0;
+        if (lane < m) {
+            if (c < m) v = tot[stereo_sidx(mine, s_map[c])];
+            else if (c == m) v = se * (1.0 + tot[kStSTri + kStNS + mine]);
+        } else if (lane == m) {
+            if (c < m) v = se * (1.0 + tot[kStSTri + kStNS + s_map[c]]);
+            else if (c == m) v = -(1.0 + epsilon * tot[kStSTri + 2 * kStNS]);
+        } else if (lane == c) v = 1.0;          // identity padding of the rows and columns past the system
+        B[c] = v;
     }
-    B[m * Q + m] = -(1.0 + st->epsilon * tot[kStSTri + 2 * kStNS]);
-    rhs[m] = -se * tot[kStSTri + 2 * kStNS + 1];
-    int fail = 0;
-    for (int k = 0; k < Q && !fail; ++k) {
-        int piv = k;
-        for (int i = k + 1; i < Q; ++i)
-            if (fabs(B[i * Q + k]) > fabs(B[piv * Q + k])) piv = i;
-        if (B[piv * Q + k] == 0.0 || !isfinite(B[piv * Q + k])) { fail = 1; break; }
-        if (piv != k) {
-            for (int j = 0; j < Q; ++j) { const double t = B[k * Q + j]; B[k * Q + j] = B[piv * Q + j]; B[piv * Q + j] = t; }
-            const double t = rhs[k]; rhs[k] = rhs[piv]; rhs[piv] = t;
+    if (lane < m) rhs = tot[kStSTri + mine];
+    else if (lane == m) rhs = -se * tot[kStSTri + 2 * kStNS + 1];
+    double x[N];
+    const bool failed = warp_gauss_solve<N>(B, rhs, lane, Q, s_rows, x);
+    if (lane == 0 && !done) {
+        st->alpha = alpha; st->epsilon = epsilon;
+        if (status) st->done = 1;
+        else if (failed) { st->status = 4; st->done = 1; }
+        else {
+            for (int a = 0; a < kStNS; ++a) st->x_sh[a] = 0.0;
+            double tv = 0.0;
+#pragma unroll
+            for (int a = 0; a < N; ++a) {
+                if (a < m) st->x_sh[s_map[a]] = x[a];
+                if (a == m) tv = x[a];
+            }
+            st->t = tv;
         }
-        for (int i = k + 1; i < Q; ++i) {
-            const double fct = B[i * Q + k] / B[k * Q + k];
-            for (int j = k; j < Q; ++j) B[i * Q + j] -= fct * B[k * Q + j];
-            rhs[i] -= fct * rhs[k];
-        }
     }
-    if (fail) { st->status = 4; st->done = 1; return; }
-    for (int i = Q - 1; i >= 0; --i) {
-        double s = rhs[i];
-        for (int j = i + 1; j < Q; ++j) s -= B[i * Q + j] * rhs[j];
-        rhs[i] = s / B[i * Q + i];
-    }
-    for (int a = 0; a < kStNS; ++a) st->x_sh[a] = 0.0;
-    for (int a = 0; a < m; ++a) st->x_sh[map[a]] = rhs[a];
-    st->t = rhs[m];
 }
 
 // shared index a -> position in the parameter vector
