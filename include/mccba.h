@@ -69,7 +69,9 @@ extern "C" {
                                    packed float32 (two corners per lane), per-edge sums promoted to double.  Final parameters
                                    agree with FP64 to ~1e-8 relative; the worst of the 600 378 parameters of config #5 -- the
                                    tilt of a board that faces a camera squarely -- to 1e-6 (tests/test_precision_gpu.py,
-                                   tests/test_full_size_gpu.py) */
+                                   tests/test_full_size_gpu.py).  The error grows with the conditioning of the rig: boards
+                                   that subtend less than ~8 degrees (extent / distance < 0.15) exceed 1e-6 -- select
+                                   MCCBA_PRECISION_FP64 for those (profiles/r2_precision_vs_board.txt) */
 #define MCCBA_PRECISION_FAST32 2 /* everything per corner in packed float32, like the reference, which evaluates the
                                    projection through float32 (src/multicalib.cpp:742-749, 789-792): RMS agrees to 1e-9,
                                    but the tilt of boards that face a camera squarely moves by ~2e-6 -- outside the 1e-6

@@ -1,0 +1,55 @@
+"""Randomised parity sweep (development aid): random small rigs -- camera count, frame count, views per frame, camera models,
+distortion length, board size, ragged corner counts -- solved on the GPU under every precision policy and compared with the
+CPU oracle (checker only).  python scripts/random_parity.py [n_cases] [seed]"""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np
+import multi_camera_calibration_b200 as m
+from tests import rigs
+
+n_cases = int(sys.argv[1]) if len(sys.argv) > 1 else 30
+rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 1)
+worst = {}
+bad = 0
+for i in range(n_cases):
+    n_cam = int(rng.integers(2, 9))
+    kw = dict(n_cam=n_cam, n_frame=int(rng.integers(n_cam + 2, 150)) if i % 4 else int(rng.integers(300, 1500)),
+              cam_models=[int(x) for x in rng.integers(0, 2, n_cam)],
+              views_per_frame=int(rng.integers(1, min(n_cam, 4) + 1)), seed=int(rng.integers(1, 10**6)),
+              ndist=int(rng.choice([4, 5, 8])), ragged=bool(rng.integers(0, 2)))
+    nx, ny = [(9, 6), (7, 5), (13, 10), (4, 3)][int(rng.integers(0, 4))]
+    kw.update(nx=nx, ny=ny)
+    if kw["views_per_frame"] == 1 and n_cam > 1:
+        kw["views_per_frame"] = 2            # a rig needs frames shared between cameras
+    try:
+        rig = rigs.make_rig(**kw)
+    except Exception as e:
+        print("case %d: generator refused %s (%s)" % (i, kw, str(e)[:60]))
+        continue
+    O = rigs.to_oracle_rig(rig)
+    # COUNT criteria: at the rounding floor the iteration at which `change` crosses an EPS threshold is not a parity property
+    for mode, skw in ((0, dict(mode=0, crit_type=1, max_count=5)), (1, dict(mode=1, crit_type=1, max_count=15, lambda0=1e-3))):
+        ref = O.solve(rig["params_init"], **skw)
+        for prec, tol in ((m.capi.PRECISION_FP64, 1e-8), (m.capi.PRECISION_MIXED, 1e-6)):
+            s = m.Solver(device=0, precision=prec)
+            s.set_rig(rig)
+            s.set_parameters(rig["params_init"])
+            rep = s.solve(**skw)
+            p = s.get_parameters()
+            err = s.reproj_error()
+            s.close()
+            scale = np.maximum(np.abs(ref["params"]), 1.0)
+            rel = float(np.max(np.abs(p - ref["params"]) / scale))
+            ok = rel < tol and rep["iterations"] == ref["iters"] and abs(rep["cost"] - ref["cost"]) <= 1e-8 * ref["cost"]
+            key = (mode, prec)
+            worst[key] = max(worst.get(key, 0.0), rel)
+            if os.environ.get("VERBOSE") and prec == m.capi.PRECISION_MIXED:
+                print("case %d corners %d frames %d cams %d board %dx%d views %d mode %d: mixed rel %.2e" %
+                      (i, int(rig["edge_off"][-1]), rig["n_frame"], n_cam, nx, ny, kw["views_per_frame"], mode, rel), flush=True)
+            if not ok:
+                bad += 1
+                print("MISMATCH case %d %s mode %d prec %d: rel %.3e iters %d/%d cost %.12e/%.12e" %
+                      (i, kw, mode, prec, rel, rep["iterations"], ref["iters"], rep["cost"], ref["cost"]), flush=True)
+print("worst relative parameter difference per (mode, policy):", {str(k): "%.2e" % v for k, v in worst.items()})
+print("RANDOM_PARITY_OK" if bad == 0 else "RANDOM_PARITY_FAIL (%d)" % bad)
