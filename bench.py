@@ -564,8 +564,8 @@ def run_ours(args):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None,
-                "dtype": {0: "f64", 1: "f64 residual/cost/Schur/solve + packed f32 Jacobian products (MIXED policy, parity gate 1e-6)",
-                          2: "f32 (FAST32 policy)"}[s.get_precision()],
+                "dtype": {0: "f64", 1: "f64 residual/cost/Schur/solve + packed f32 Jacobian products (MIXED policy, chosen by the default AUTO policy for this rig; parity gate 1e-6)",
+                          2: "f32 (FAST32 policy)"}[s.effective_precision()],
                 "data": "synthetic", "config": config_dict(args, world),
                 "lm_iters_per_sec": iters_done / (ms_step * 1e-3), "us_per_lm_iteration": ms_step * 1e3 / max(iters_done, 1),
                 "resjac_evals_per_sec": world * M / (k1_ms * 1e-3), "wall_ms_per_step": wall_step,
@@ -574,7 +574,7 @@ def run_ours(args):
                 "roofline": {"bound": "hbm", "achieved": k1_gbs, "peak": peak, "unit": "GB/s", "frac": k1_gbs / peak,
                              "traffic": (traffic or {}).get("dram_bytes_per_launch"), "peak_source": peak_src,
                              "kernel": {0: "resid_jac_accum_kernel (FP64)", 1: "resid_jac_accum_f32_kernel<true> (MIXED)",
-                                        2: "resid_jac_accum_f32_kernel<false> (FAST32)"}[s.get_precision()], "kernel_ms": k1_ms,
+                                        2: "resid_jac_accum_f32_kernel<false> (FAST32)"}[s.effective_precision()], "kernel_ms": k1_ms,
                              "algorithmic_bytes_per_launch": 20.0 * M,
                              "whole_iteration_gbs": iter_gbs, "whole_iteration_frac": iter_gbs / peak,
                              "traffic_source": "static: ncu --set full capture of this kernel (profiles/k1_traffic.json)",

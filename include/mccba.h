@@ -65,7 +65,7 @@ extern "C" {
 /* precision policy of the residual / Jacobian pass (mccba_set_precision).  Everything summed over many observations
  * (per-edge blocks onwards: Schur complement, reduced solve, update, cost test, the reported RMS) is fp64 in both. */
 #define MCCBA_PRECISION_FP64 0  /* per-corner projection, Jacobian and accumulation in double */
-#define MCCBA_PRECISION_MIXED 1 /* default: residual (projection) and cost in double; Jacobian, J^T J and J^T e products in
+#define MCCBA_PRECISION_MIXED 1 /* residual (projection) and cost in double; Jacobian, J^T J and J^T e products in
                                    packed float32 (two corners per lane), per-edge sums promoted to double.  Final parameters
                                    agree with FP64 to ~1e-8 relative; the worst of the 600 378 parameters of config #5 -- the
                                    tilt of a board that faces a camera squarely -- to 1e-6 (tests/test_precision_gpu.py,
@@ -76,6 +76,12 @@ extern "C" {
                                    projection through float32 (src/multicalib.cpp:742-749, 789-792): RMS agrees to 1e-9,
                                    but the tilt of boards that face a camera squarely moves by ~2e-6 -- outside the 1e-6
                                    parity gate, hence opt-in */
+#define MCCBA_PRECISION_AUTO 3   /* default: MIXED where it is safe, FP64 otherwise, decided for every solve / evaluation from the
+                                   geometry at the current parameters: MIXED iff every image sees its board under an angular
+                                   extent (diameter of the object points / distance to the camera) of at least 0.15; below that
+                                   one view no longer pins the tilt of the board and the float32 Jacobian products of MIXED would
+                                   show above 1e-6 (profiles/r2_precision_vs_board.txt).  Both observation layouts are kept on
+                                   the device; mccba_effective_precision tells what ran last. */
 
 typedef struct mccba_handle_s *mccba_handle;
 
@@ -127,12 +133,15 @@ int mccba_nccl_unique_id(unsigned char out[128]);
 int mccba_create(const mccba_options *opts, mccba_handle *out);
 int mccba_destroy(mccba_handle h);
 const char *mccba_last_error(mccba_handle h);
-/* Precision policy of the residual / Jacobian pass (MCCBA_PRECISION_*; default MIXED, or the environment variable
- * MCCBA_PRECISION=fp64|mixed|fast32 read at mccba_create).  The observation layout on the device depends on it: changing the
+/* Precision policy of the residual / Jacobian pass (MCCBA_PRECISION_*; default AUTO, or the environment variable
+ * MCCBA_PRECISION=auto|fp64|mixed|fast32 read at mccba_create).  The observation layout on the device depends on it: changing the
  * policy discards the current problem (set_observations / set_parameters have to be called again).
  * Replaces the float32 conversions of src/multicalib.cpp:742-749. */
 int mccba_set_precision(mccba_handle h, int policy);
 int mccba_get_precision(mccba_handle h);
+/* the policy the last solve / evaluation actually ran (MCCBA_PRECISION_FP64, _MIXED or _FAST32): differs from
+ * mccba_get_precision only under MCCBA_PRECISION_AUTO */
+int mccba_effective_precision(mccba_handle h);
 
 /* ---- problem ----------------------------------------------------------------------------------------------- */
 /* Replaces _cameraMatrix / _distortCoeffs / _xi (multicalib.hpp:211-213).  K5 = fx fy cx cy skew per camera

@@ -14,7 +14,7 @@ OK, ERR_ARG, ERR_CUDA, ERR_STATE, ERR_NUMERIC, ERR_NCCL = 0, 1, 2, 3, 4, 5
 PINHOLE, OMNIDIRECTIONAL = 0, 1
 CRIT_COUNT, CRIT_EPS = 1, 2
 MODE_REFERENCE_GN, MODE_LM = 0, 1
-PRECISION_FP64, PRECISION_MIXED, PRECISION_FAST32 = 0, 1, 2
+PRECISION_FP64, PRECISION_MIXED, PRECISION_FAST32, PRECISION_AUTO = 0, 1, 2, 3
 
 
 class Options(C.Structure):
@@ -43,7 +43,7 @@ EXPORTS = ["mccba_exchange_mode", "mccba_default_options", "mccba_default_solve_
            "mccba_get_parameters", "mccba_save_parameters", "mccba_restore_parameters", "mccba_eval", "mccba_reduced_system", "mccba_solve", "mccba_reproj_error",
            "mccba_allreduce_sum", "mccba_last_kernel_ms", "mccba_time_eval", "mccba_debug_solve_dense", "mccba_omni_set_observations",
            "mccba_omni_set_parameters", "mccba_omni_get_parameters", "mccba_omni_solve", "mccba_omni_gram", "mccba_set_precision",
-           "mccba_get_precision", "mccba_stereo_set_observations", "mccba_stereo_set_parameters", "mccba_stereo_get_parameters",
+           "mccba_get_precision", "mccba_effective_precision", "mccba_stereo_set_observations", "mccba_stereo_set_parameters", "mccba_stereo_get_parameters",
            "mccba_stereo_solve", "mccba_stereo_uncertainties"]
 
 _lib = None
@@ -154,11 +154,16 @@ class Solver:
         self.set_observations(rig["n_frame"], rig["edge_cam"], rig["edge_pv"], rig["edge_off"], rig["obj"], rig["img"])
 
     def set_precision(self, policy):
-        """PRECISION_FP64 (0) or PRECISION_MIXED (1, default); discards the current problem when the policy changes."""
+        """PRECISION_AUTO (3, default), PRECISION_FP64 (0), PRECISION_MIXED (1) or PRECISION_FAST32 (2); discards the current
+        problem when the policy changes."""
         self._check(lib().mccba_set_precision(self._h, int(policy)))
 
     def get_precision(self):
         return int(lib().mccba_get_precision(self._h))
+
+    def effective_precision(self):
+        """What the last solve / evaluation ran: differs from get_precision() only under PRECISION_AUTO."""
+        return int(lib().mccba_effective_precision(self._h))
 
     def set_parameters(self, params):
         p = np.ascontiguousarray(params, dtype=np.float64)

@@ -109,7 +109,9 @@ struct mccba_handle_s {
     int ar_len = 0;
     int k2_occ = 2;                   // minimum resident CTAs per SM requested from the Schur kernel (register cap)
     int obs_cap = 0;                  // floats per plane per TMA stage of the residual kernel (0: no staging)
-    int prec = MCCBA_PRECISION_MIXED; // precision policy of the residual / Jacobian pass (mccba_set_precision)
+    int prec = MCCBA_PRECISION_AUTO;  // requested precision policy of the residual / Jacobian pass (mccba_set_precision)
+    int graph_prec = -1;              // effective policy the iteration graph was captured with
+    double* d_ext_part = nullptr;     // AUTO: 64 partial minima of the angular extent
     int f32_grid = 0, f32_smem = 0;
     int k1_grid = 0, k1_smem = 0, k5_blocked = 2, iter_kernels = 5, dag_grid = 0;   // k5_blocked: 2 tile DAG, 3 block cyclic reduction
     int band_nw = 0;                  // 6 (block bandwidth + 1) of the reduced system (agreed over the ranks)
@@ -327,11 +329,31 @@ int enqueue_iteration(mccba_handle h, bool timed)
     return MCCBA_OK;
 }
 
+// AUTO precision policy: MIXED iff every live edge sees its board under an angular extent >= kAutoMinExtent at the composed
+// poses just written to Problem::erec (profiles/r2_precision_vs_board.txt); else FP64.  One small kernel + an 0.5 KB readback.
+constexpr double kAutoMinExtent = 0.15;
+int resolve_precision(mccba_handle h)
+{
+    if (h->prec != MCCBA_PRECISION_AUTO) return MCCBA_OK;
+    Problem& P = h->P;
+    double part[64];
+    min_angular_extent_kernel<<<64, 256, 0, h->stream>>>(P, h->d_ext_part);
+    CUDA_TRY(h, cudaMemcpyAsync(part, h->d_ext_part, sizeof(part), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    double mn = 1e300;
+    for (double v : part) mn = std::min(mn, v);
+    P.prec = (mn >= kAutoMinExtent) ? MCCBA_PRECISION_MIXED : MCCBA_PRECISION_FP64;   // NaN poses: FP64
+    if (h->graph && h->graph_prec != P.prec) { cudaGraphExecDestroy(h->graph); h->graph = nullptr; }
+    return MCCBA_OK;
+}
+
 int launch_forced_eval(mccba_handle h)
 {
     Problem& P = h->P;
     vertex_prep_kernel<<<(P.n_vertex + 127) / 128, 128, 0, h->stream>>>(P, -1);
     edge_pose_kernel<<<(P.n_slots + 127) / 128, 128, 0, h->stream>>>(P, -1);
+    int rcp = resolve_precision(h);
+    if (rcp) return rcp;
     launch_resid(h, h->stream, 1);
     CUDA_TRY(h, cudaGetLastError());
     return MCCBA_OK;
@@ -371,7 +393,7 @@ int mccba_default_solve_opts(mccba_solve_opts* o)
 int mccba_set_precision(mccba_handle h, int policy)
 {
     if (!h) return MCCBA_ERR_ARG;
-    if (policy != MCCBA_PRECISION_FP64 && policy != MCCBA_PRECISION_MIXED && policy != MCCBA_PRECISION_FAST32) return fail(h, MCCBA_ERR_ARG, "set_precision: unknown policy %d", policy);
+    if (policy < MCCBA_PRECISION_FP64 || policy > MCCBA_PRECISION_AUTO) return fail(h, MCCBA_ERR_ARG, "set_precision: unknown policy %d", policy);
     if (policy != h->prec && h->have_obs) {   // the observation layout depends on the policy: the problem has to be set again
         cudaSetDevice(h->opts.device);
         cudaStreamSynchronize(h->stream);
@@ -382,6 +404,12 @@ int mccba_set_precision(mccba_handle h, int policy)
 }
 
 int mccba_get_precision(mccba_handle h) { return h ? h->prec : -1; }
+int mccba_effective_precision(mccba_handle h)
+{
+    if (!h) return -1;
+    if (h->prec != MCCBA_PRECISION_AUTO) return h->prec;
+    return h->have_obs ? h->P.prec : MCCBA_PRECISION_MIXED;
+}
 
 int mccba_nccl_unique_id(unsigned char out[128])
 {
@@ -419,7 +447,12 @@ int mccba_create(const mccba_options* opts, mccba_handle* out)
     cudaMallocHost((void**)&h->h_small, 64 * sizeof(double));
     cudaMalloc((void**)&h->d_small, 64 * sizeof(double));
     if (const char* occ = getenv("MCCBA_K2_OCC")) h->k2_occ = atoi(occ);
-    if (const char* pr = getenv("MCCBA_PRECISION")) h->prec = (pr[0] == '0' || pr[1] == 'p' || pr[1] == 'P') ? MCCBA_PRECISION_FP64 : (pr[0] == '2' || pr[1] == 'a' || pr[1] == 'A') ? MCCBA_PRECISION_FAST32 : MCCBA_PRECISION_MIXED;
+    if (const char* pr = getenv("MCCBA_PRECISION")) {   // auto | fp64 | mixed | fast32 (or 3 | 0 | 1 | 2)
+        const char c0 = pr[0], c1 = pr[0] ? pr[1] : 0;
+        h->prec = (c0 == '0' || c1 == 'p' || c1 == 'P') ? MCCBA_PRECISION_FP64
+                  : (c0 == '2' || ((c0 == 'f' || c0 == 'F') && (c1 == 'a' || c1 == 'A'))) ? MCCBA_PRECISION_FAST32
+                  : (c0 == '1' || c0 == 'm' || c0 == 'M') ? MCCBA_PRECISION_MIXED : MCCBA_PRECISION_AUTO;
+    }
     const char* prof = getenv("MCCBA_PROFILE");
     h->profile = prof && prof[0] == '1';
     if (opts->nranks > 1) {
@@ -906,7 +939,9 @@ int mccba_set_observations(mccba_handle h, int n_frame, int n_edge, const int* e
     if ((rc = dev_alloc(h, &h->x_saved, (size_t)P.n_param, true))) return rc;
     if ((rc = dev_alloc(h, &P.dc, (size_t)std::max(P.ns, 1), true))) return rc;
     if ((rc = dev_alloc(h, &P.norm_part, 2 * (size_t)P.n_k4_blocks, true))) return rc;
-    P.prec = h->prec;
+    const bool autop = h->prec == MCCBA_PRECISION_AUTO;
+    P.prec = autop ? MCCBA_PRECISION_MIXED : h->prec;    // AUTO: resolved per evaluation (resolve_precision), both layouts are built
+    P.edge_extent = nullptr;
     if ((rc = dev_alloc(h, &P.erec, (size_t)P.n_edge_int, true))) return rc;
     {
         std::vector<EdgeMeta> meta((size_t)P.n_edge_int);
@@ -967,6 +1002,12 @@ int mccba_set_observations(mccba_handle h, int n_frame, int n_edge, const int* e
     h->k1_grid = std::max(1, std::min(P.n_edge_int / kEdgesPerBlock, h->num_sms * per_sm));
     lap("launch geometry");
     // last: everything above ran while the observation upload was in flight on its own stream
+    if (autop) {
+        float* ext = nullptr;
+        if ((rc = dev_alloc(h, &ext, (size_t)P.n_edge_int))) return rc;
+        if ((rc = dev_alloc(h, &h->d_ext_part, 64, true))) return rc;
+        P.edge_extent = ext;
+    }
     if (P.prec) {
         // packed pair layout of the single-precision pass (Problem::obs2): per tile 4 quarters x kp steps x 5 planes x 32
         // lanes x 2 floats, kp = ceil(max corners per edge of the tile / 8)
@@ -1003,7 +1044,9 @@ int mccba_set_observations(mccba_handle h, int n_frame, int n_edge, const int* e
         CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_copy, 0));
         gather_obs_packed_kernel<<<std::min(n_tiles, h->num_sms * 16), 256, 0, h->stream>>>(n_tiles, P.tile_off, P.tile_kp, P.e_off, d_esrc,
                                                                                             d_obj, d_img, obs2);
-    } else {
+        if (autop) edge_extent_kernel<<<h->num_sms * 8, 256, 0, h->stream>>>(P.n_edge_int, P.e_off, d_esrc, d_obj, const_cast<float*>(P.edge_extent));
+    }
+    if (!P.prec || autop) {
     // observation planes: one allocation, each plane 256-byte aligned
     const size_t plane = ((size_t)M + 63) / 64 * 64;
     float* planes = nullptr;
@@ -1176,6 +1219,7 @@ int mccba_solve(mccba_handle h, const mccba_solve_opts* o, mccba_report* rep)
         ce = cudaGraphInstantiate(&h->graph, g, 0);
         cudaGraphDestroy(g);
         if (ce != cudaSuccess) return fail(h, MCCBA_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(ce));
+        h->graph_prec = P.prec;
     }
     for (double& v : h->prof_ms) v = 0;
     const bool has_count = (o->crit_type & MCCBA_CRIT_COUNT) != 0;

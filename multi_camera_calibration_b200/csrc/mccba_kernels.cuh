@@ -103,6 +103,7 @@ struct Problem {
     double* edgeY;       // 36 x n_edge_int: Y = L^-1 W per edge, tile-major; stored as FLOAT when prec != 0 (Y only shapes the step of
                          // the pattern poses, never the fixed point, and it is the largest record the two per-frame kernels exchange)
     double* records;     // warp records
+    const float* edge_extent;   // n_edge_int: diameter of the object points of every edge (AUTO precision policy), else null
     double* warp_scal;   // 2 x n_warps: [cost | bad] of every Schur warp, contiguous so that the scalar reduction is coalesced
     double* ar;          // allreduce buffer: S (ns x ns) | g (ns) | cost, step2, param2, bad
     double* dc;          // ns: camera step in tangent coordinates
@@ -164,6 +165,56 @@ __global__ void gather_obs_kernel(int n_edge_int, const int* __restrict__ e_off,
             iu[b + i] = img[2 * (s + i)];
             iv[b + i] = img[2 * (s + i) + 1];
         }
+    }
+}
+
+// AUTO precision policy: diameter of the object points of every edge (twice the largest distance from their centroid) ...
+__global__ void edge_extent_kernel(int n_edge_int, const int* __restrict__ e_off, const int64_t* __restrict__ e_src,
+                                   const float* __restrict__ obj, float* __restrict__ extent)
+{
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const int nw = (gridDim.x * blockDim.x) >> 5;
+    for (int e = warp; e < n_edge_int; e += nw) {
+        const int n = e_off[e + 1] - e_off[e];
+        const int64_t s = e_src[e];
+        float cx = 0, cy = 0, cz = 0;
+        for (int i = lane; i < n; i += 32) { cx += obj[3 * (s + i)]; cy += obj[3 * (s + i) + 1]; cz += obj[3 * (s + i) + 2]; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            cx += __shfl_xor_sync(kFull, cx, o); cy += __shfl_xor_sync(kFull, cy, o); cz += __shfl_xor_sync(kFull, cz, o);
+        }
+        const float inv = n > 0 ? 1.0f / (float)n : 0.0f;
+        cx *= inv; cy *= inv; cz *= inv;
+        float d2 = 0;
+        for (int i = lane; i < n; i += 32) {
+            const float dx = obj[3 * (s + i)] - cx, dy = obj[3 * (s + i) + 1] - cy, dz = obj[3 * (s + i) + 2] - cz;
+            d2 = fmaxf(d2, dx * dx + dy * dy + dz * dz);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) d2 = fmaxf(d2, __shfl_xor_sync(kFull, d2, o));
+        if (lane == 0) extent[e] = 2.0f * sqrtf(d2);
+    }
+}
+// ... and the smallest angular extent  diameter / distance  over the live edges at the composed poses in Problem::erec
+// (one partial minimum per block; the host takes the minimum of the partials)
+__global__ void __launch_bounds__(256) min_angular_extent_kernel(Problem P, double* __restrict__ part)
+{
+    __shared__ double sm[8];
+    double v = 1e300;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < P.n_edge_int; e += gridDim.x * blockDim.x) {
+        const EdgeMeta em = P.emeta[e];
+        if (em.end > em.begin) {
+            const double* T = P.erec[e].T3;
+            v = fmin(v, (double)P.edge_extent[e] / sqrt(T[0] * T[0] + T[1] * T[1] + T[2] * T[2]));
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(kFull, v, o));
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) v = fmin(v, sm[w]);
+        part[blockIdx.x] = fmin(v, sm[0]);
     }
 }
 

@@ -87,7 +87,7 @@ def test_config5_vs_oracle(solver, oracle_lib):
 
 
 def test_config5_default_policy_gate(oracle_lib):
-    """The headline workload under the DEFAULT precision policy (MIXED), run the way the bench runs it (LM) and under the
+    """The headline workload under the DEFAULT precision policy (AUTO, which resolves to MIXED for this rig), run the way the bench runs it (LM) and under the
     reference schedule, both to a fixed 25 iterations, against the oracle (fp64_direct policy, see test_config5_vs_oracle).
     Cost and fp64 RMS: 1e-8.  Camera poses -- the calibration result -- 1e-7 (observed ~1e-9).  Of the 600 000 pattern-pose
     parameters all but a handful agree to 1e-7; the worst -- the tilt of a board that faces its camera squarely, which the
@@ -98,13 +98,14 @@ def test_config5_default_policy_gate(oracle_lib):
     O = rigs.to_oracle_rig(rig)
     nC = rig["n_cam"]
     s = m.Solver(device=0)
-    assert s.get_precision() == m.capi.PRECISION_MIXED
+    assert s.get_precision() == m.capi.PRECISION_AUTO
     s.set_rig(rig)
     for mode, kw in ((1, dict(lambda0=1e-3, lambda_up=10.0, lambda_down=1.0 / 3.0)), (0, {})):
         s.set_parameters(rig["params_init"])
         rep = s.solve(mode=mode, crit_type=1, max_count=25, **kw)
         ref = O.solve(rig["params_init"], mode=mode, crit_type=1, max_count=25, policy=2, **kw)
         assert rep["iterations"] == 25 == ref["iters"]
+        assert s.effective_precision() == m.capi.PRECISION_MIXED      # 9 x 6 board at 1.2-2 m: the AUTO policy runs MIXED
         p = s.get_parameters()
         rel = np.abs(p - ref["params"]) / np.maximum(np.abs(ref["params"]), 1.0)
         print("config #5, MIXED, mode %d: cameras %.2e, pattern poses max %.2e, beyond 1e-7: %d of %d" %

@@ -98,7 +98,7 @@ def test_switching_policy_discards_the_problem(solvers):
     import multi_camera_calibration_b200 as m
     rig = rigs.make_rig(**RIGS["pinhole3"])
     s = m.Solver(device=0)
-    assert s.get_precision() == m.capi.PRECISION_MIXED          # the default
+    assert s.get_precision() == m.capi.PRECISION_AUTO           # the default
     s.set_rig(rig)
     s.set_parameters(rig["params_init"])
     s.set_precision(m.capi.PRECISION_FP64)
@@ -110,3 +110,33 @@ def test_switching_policy_discards_the_problem(solvers):
     with pytest.raises(m.MccbaError):
         s.set_precision(7)
     s.close()
+
+
+def test_auto_policy_follows_the_board_geometry(oracle_lib):
+    """The default policy (AUTO) runs MIXED when every image sees its board under an angular extent >= 0.15 and FP64
+    otherwise (profiles/r2_precision_vs_board.txt: below that the float32 Jacobian products of MIXED show above the 1e-6
+    gate).  A 9 x 6 board at 40 mm pitch, 1.2-2 m away: MIXED, parameters within the gate.  The same rig with a 4 x 3
+    board (120 x 80 mm): FP64, parameters at rounding level -- where MIXED is off by up to 2e-3 (asserted, so that the
+    test notices if the study behind the threshold stops being true)."""
+    import multi_camera_calibration_b200 as m
+    kw = dict(mode=0, crit_type=1, max_count=8)
+    for nx, ny, want, tol in ((9, 6, m.capi.PRECISION_MIXED, 1e-6), (4, 3, m.capi.PRECISION_FP64, 1e-8)):
+        rig = rigs.make_rig(n_cam=4, n_frame=120, cam_models=[0, 0, 1, 0], seed=5, nx=nx, ny=ny)
+        ref = rigs.to_oracle_rig(rig).solve(rig["params_init"], **kw)
+        s = m.Solver(device=0)
+        assert s.get_precision() == m.capi.PRECISION_AUTO
+        s.set_rig(rig)
+        s.set_parameters(rig["params_init"])
+        rep = s.solve(**kw)
+        assert s.effective_precision() == want, (nx, ny, s.effective_precision())
+        assert rep["iterations"] == ref["iters"]
+        assert _param_rel(s.get_parameters(), ref["params"]) < tol
+        e = s.reproj_error()                                  # both observation layouts are resident: the error pass follows the policy
+        assert abs(e["rms"] - rigs.to_oracle_rig(rig).error(ref["params"])["rms"]) <= 1e-7 * e["rms"]
+        s.close()
+        if want == m.capi.PRECISION_FP64:
+            sm = m.Solver(device=0, precision=m.capi.PRECISION_MIXED)
+            sm.set_rig(rig); sm.set_parameters(rig["params_init"])
+            sm.solve(**kw)
+            assert _param_rel(sm.get_parameters(), ref["params"]) > 1e-6      # what AUTO avoided
+            sm.close()
