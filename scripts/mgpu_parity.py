@@ -5,7 +5,7 @@ redundantly.  Rank 0 gathers the parameters and checks them against the CPU orac
 `check(dist, rank, world, local)` is what `bench.py` (N > 1), `__graft_entry__.smoke()` (>= 2 GPUs) and
 `tests/test_multi_gpu.py` run; `python -m torch.distributed.run ... scripts/mgpu_parity.py` prints its result.
 
-The library runs its default precision policy (MIXED: float32 Jacobian products, so the reduced system S agrees with
+The library runs its default precision policy (AUTO, which runs MIXED on these rigs: float32 Jacobian products, so the reduced system S agrees with
 the fp64 oracle to float32 accuracy, 5e-6; cost, RMS and parameters to the gate).
 Tolerance: 1e-6 relative (the north star gate).  The exchange changes the summation order of S, and the undamped
 Gauss-Newton system has condition ~1e9, so parameters agree to ~1e-8..1e-7 rather than the 1e-12 of one GPU.  Camera
