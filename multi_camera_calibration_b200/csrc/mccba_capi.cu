@@ -1903,6 +1903,13 @@ void ds_free(mccba_handle h)
     h->ds_allocs.clear();
     h->ds_have = h->ds_have_params = false;
 }
+// AUTO precision policy (resolve_precision) at the composed poses of the double-sided problem
+int ds_resolve_precision(mccba_handle h)
+{
+    if (h->prec != MCCBA_PRECISION_AUTO) return MCCBA_OK;
+    ds_pose_kernel<<<(h->P.n_slots + 127) / 128, 128, 0, h->stream>>>(h->P, h->D, 1);
+    return resolve_precision(h);
+}
 // one pass at the current parameters: composed poses, per-edge blocks (the rig path's residual / Jacobian kernel), Schur records
 int ds_enqueue_eval(mccba_handle h, int forced)
 {
@@ -2001,6 +2008,7 @@ int mccba_ds_normal(mccba_handle h, double* S36, double* g6, double* cost)
     CUDA_TRY(h, cudaSetDevice(h->opts.device));
     int rc;
     if ((rc = sync_state_cur(h))) return rc;
+    if ((rc = ds_resolve_precision(h))) return rc;
     if ((rc = ds_enqueue_eval(h, 1))) return rc;
     double tot[kDsRec];
     CUDA_TRY(h, cudaMemcpyAsync(tot, h->D.tot, sizeof(tot), cudaMemcpyDeviceToHost, h->stream));
@@ -2024,6 +2032,7 @@ int mccba_ds_solve(mccba_handle h, int crit_type, int max_count, double epsilon,
     int rc;
     CUDA_TRY(h, cudaEventRecord(h->ev0, s));
     if ((rc = sync_state_cur(h))) return rc;
+    if ((rc = ds_resolve_precision(h))) return rc;
     ds_init_state_kernel<<<1, 1, 0, s>>>(D.st, crit_type, max_count, epsilon);
     const int64_t max_launches = (crit_type & 1) ? max_count : 200000;
     int64_t launched = 0;
