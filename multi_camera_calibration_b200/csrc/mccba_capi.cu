@@ -1687,7 +1687,7 @@ int stereo_enqueue_iteration(mccba_handle h)
 {
     StereoProblem& S = h->S;
     cudaStream_t s = h->stream;
-    stereo_frame_kernel<<<S.n_frame, kStThreads, 0, s>>>(S, 0);
+    stereo_frame_kernel<<<(S.n_frame + kStWarps - 1) / kStWarps, kStThreads, kStFrameSmem, s>>>(S, 0);
     stereo_reduce_kernel<<<kStRec, 256, 0, s>>>(S, 0);
     stereo_solve_kernel<<<1, 32, 0, s>>>(S);
     stereo_update_kernel<<<S.n_blocks_upd, 128, 0, s>>>(S);
@@ -1710,6 +1710,7 @@ int mccba_stereo_set_observations(mccba_handle h, int n_frame, const int64_t* fr
     for (int f = 0; f < n_frame; ++f)
         if (frame_off[f + 1] <= frame_off[f]) return fail(h, MCCBA_ERR_ARG, "frame %d has no observation", f);
     if (h->stereo_graph) { cudaGraphExecDestroy(h->stereo_graph); h->stereo_graph = nullptr; }
+    CUDA_TRY(h, cudaFuncSetAttribute(stereo_frame_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStFrameSmem));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     for (void* q : h->stereo_allocs) cudaFree(q);
     h->stereo_allocs.clear();
@@ -1825,7 +1826,7 @@ int mccba_stereo_solve(mccba_handle h, int flags, int crit_type, int max_count, 
     cudaEventDestroy(evs[0]);
     cudaEventDestroy(evs[1]);
     // final cost at the returned parameters (estimateUncertaintiesStereo's rms, :1879-1888)
-    stereo_frame_kernel<<<S.n_frame, kStThreads, 0, s>>>(S, 1);
+    stereo_frame_kernel<<<(S.n_frame + kStWarps - 1) / kStWarps, kStThreads, kStFrameSmem, s>>>(S, 1);
     stereo_reduce_kernel<<<kStRec, 256, 0, s>>>(S, 1);
     StereoState hs;
     double cost = 0;
@@ -1856,7 +1857,7 @@ int mccba_stereo_uncertainties(mccba_handle h, int flags, double* errors, double
     cudaStream_t s = h->stream;
     const size_t np = 6 * ((size_t)S.n_frame + 1) + 20;
     CUDA_TRY(h, cudaMemsetAsync(&S.st->status, 0, sizeof(int), s));
-    stereo_frame_kernel<<<S.n_frame, kStThreads, 0, s>>>(S, 1);
+    stereo_frame_kernel<<<(S.n_frame + kStWarps - 1) / kStWarps, kStThreads, kStFrameSmem, s>>>(S, 1);
     stereo_reduce_kernel<<<kStRec, 256, 0, s>>>(S, 1);
     stereo_cov_shared_kernel<<<1, 32, 0, s>>>(S, flags);
     stereo_cov_frame_kernel<<<(S.n_frame + 127) / 128, 128, 0, s>>>(S);

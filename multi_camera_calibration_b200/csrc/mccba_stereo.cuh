@@ -8,7 +8,7 @@
 // so -- exactly as in the single-camera loop (mccba_omni.cuh) -- the per-frame 6 x 6 blocks are eliminated, the reduced
 // system is 26 x 26, and the reference's "+ eps on EVERY element" (a rank-one eps 11^T) is carried as one bordered
 // unknown.  Additive Rodrigues coordinates, because that term is not invariant under a change of coordinates.
-//   stereo_frame_kernel   CTA per frame: rows [d/d(om_i,T_i) (6) | d/d(om,T) (6) | intrinsics 1 (10) | intrinsics 2 (10) | e] of
+//   stereo_frame_kernel   warp per frame: rows [d/d(om_i,T_i) (6) | d/d(om,T) (6) | intrinsics 1 (10) | intrinsics 2 (10) | e] of
 //                         the left and right image of every corner -> 33 x 33 Gram matrix; 6 x 6 Cholesky, Y = L^-1 H_pS,
 //                         Schur record (406 numbers), residual moments for the uncertainties
 //   stereo_reduce_kernel  fixed-order sums of the record entries over the frames (no atomics)
@@ -28,8 +28,7 @@ namespace mccba {
 constexpr int kStNS = 26;                  // shared parameters: 6 (relative pose) + 10 + 10
 constexpr int kStW = 6 + kStNS + 1;        // row width: frame pose | shared | residual
 constexpr int kStTri = kStW * (kStW + 1) / 2;   // 561
-constexpr int kStThreads = 192;
-constexpr int kStChunk = 32;               // corners staged per pass: 128 rows x 33 doubles
+constexpr int kStThreads = 128;                // 4 warps = 4 frames per CTA
 constexpr int kStSTri = kStNS * (kStNS + 1) / 2;   // 351
 constexpr int kStRec = kStSTri + 2 * kStNS + 3 + 4;   // S | rg | ru | d, c, cost | sum ex, ey, ex^2, ey^2  = 410
 constexpr int kStSave = 21 + 6 + 6 + 6 * kStNS;       // U | z_g | z_u | Y = 189
@@ -77,19 +76,34 @@ __device__ __forceinline__ void stereo_cam(const double* p, CamParams& cam)
     cam.k3 = cam.k4 = cam.k5 = cam.k6 = 0.0;
 }
 
+// One WARP per frame (the layout of omni_frame_kernel): per pass of 16 corners lanes 0..15 evaluate the left image and
+// lanes 16..31 the right image of the same corners, two 33-wide rows each, into the warp's shared-memory stage (64 rows);
+// the 33 x 33 Gram matrix sum a^T a is accumulated by the FP64 tensor cores: 15 upper 8 x 8 tile pairs of the five
+// 8-column slices, 16 k-steps of mma.m8n8k4 per pass (5 fragment loads for 15 MMAs).  The per-frame algebra (6 x 6
+// Cholesky, 28 forward solves, the 410-entry Schur record) follows in the same warp.
+constexpr int kStWarps = 4;                 // frames per CTA
+constexpr int kStLd = 36;                   // row stride (doubles): 8 x 4 fragment loads in the minimal 2 wavefronts
+constexpr int kStRows = 64;                 // rows staged per pass = 16 corners x (2 left + 2 right)
 __global__ void __launch_bounds__(kStThreads) stereo_frame_kernel(StereoProblem P, int forced)
 {
-    __shared__ double rows[4 * kStChunk][kStW];
-    __shared__ double M[kStW][kStW];
-    __shared__ double sU[21], szg[6], szu[6], sY[6][kStNS], smom[4][kStThreads / 32];
+    extern __shared__ __align__(16) unsigned char st_smem[];
+    double* s_rows_all = reinterpret_cast<double*>(st_smem);                        // [kStWarps][kStRows * kStLd]
+    double* s_fac_all = s_rows_all + kStWarps * kStRows * kStLd;                    // [kStWarps][192]: U 21 | z_g 6 | z_u 6 | Y 6 x 26
     const StereoState* st = P.st;
     if (!forced && st->done) return;
-    const int f = blockIdx.x, tid = threadIdx.x, n = P.n_frame;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, n = P.n_frame;
+    const int f = blockIdx.x * kStWarps + w;
+    if (f >= n) return;                          // whole warps leave; nothing below synchronises across warps
+    double* rows = s_rows_all + w * kStRows * kStLd;
+    double* sU = s_fac_all + w * 192;
+    double* szg = sU + 21;
+    double* szu = sU + 27;
+    double (*sY)[kStNS] = reinterpret_cast<double (*)[kStNS]>(sU + 33);
     const double* par = P.param;
     const int o1 = 6 * (n + 1), o2 = o1 + 10;
-    CamParams cam1, cam2;
-    stereo_cam(par + o1, cam1);
-    stereo_cam(par + o2, cam2);
+    const bool right = lane >= 16;
+    CamParams cam;
+    stereo_cam(par + (right ? o2 : o1), cam);
     const double om[3] = {par[0], par[1], par[2]}, T[3] = {par[3], par[4], par[5]};
     const double om1[3] = {par[6 + 6 * f], par[7 + 6 * f], par[8 + 6 * f]}, T1[3] = {par[9 + 6 * f], par[10 + 6 * f], par[11 + 6 * f]};
     double R[9], R1[9], R2[9], Jl[9], Jl1[9], s[3], T2[3];
@@ -100,62 +114,55 @@ __global__ void __launch_bounds__(kStThreads) stereo_frame_kernel(StereoProblem 
     mat3_mul(R, R1, R2);                     // compose_motion(om1, T1, om, T): R2 = R R1, T2 = R T1 + T (:989)
     mat3_vec(R, T1, s);
     T2[0] = s[0] + T[0]; T2[1] = s[1] + T[1]; T2[2] = s[2] + T[2];
-    int gi[3], gj[3];
+    const int g = lane >> 2, t = lane & 3;
+    double acc[15][2];
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        gi[k] = gj[k] = 0;
-        if (tid + k * kStThreads < kStTri) stereo_tri(tid + k * kStThreads, gi[k], gj[k]);
-    }
-    double acc[3] = {0, 0, 0};
+    for (int i = 0; i < 15; ++i) acc[i][0] = acc[i][1] = 0.0;
     double mom[4] = {0, 0, 0, 0};
     const int b = P.f_off[f], e = P.f_off[f + 1];
-    for (int c0 = b; c0 < e; c0 += kStChunk) {
-        const int nc = min(kStChunk, e - c0);
-        if (tid < nc) {
-            const int i = c0 + tid;
+    for (int c0 = b; c0 < e; c0 += 16) {
+        const int nc = min(16, e - c0);
+        const int cl = lane & 15;                // corner of the pass this lane evaluates
+        __syncwarp();                            // the previous pass has been consumed
+        double* row0 = rows + (4 * cl + (right ? 2 : 0)) * kStLd;
+        double* row1 = row0 + kStLd;
+        if (cl < nc) {
+            const int i = c0 + cl;
             const double X[3] = {(double)P.ox[i], (double)P.oy[i], (double)P.oz[i]};
             double Q[3], Xc[3], uv[2], A[6], Jin[20];
-            // left image: camera 1 at the frame's pose
-            mat3_vec(R1, X, Q);
-            Xc[0] = Q[0] + T1[0]; Xc[1] = Q[1] + T1[1]; Xc[2] = Q[2] + T1[2];
-            omnidir_point_full(cam1, Xc, uv, A, Jin);
-            {
-                const double err[2] = {(double)P.u1[i] - uv[0], (double)P.v1[i] - uv[1]};
-                mom[0] += err[0]; mom[1] += err[1]; mom[2] += err[0] * err[0]; mom[3] += err[1] * err[1];
+            if (!right) {                        // left image: camera 1 at the frame's pose
+                mat3_vec(R1, X, Q);
+                Xc[0] = Q[0] + T1[0]; Xc[1] = Q[1] + T1[1]; Xc[2] = Q[2] + T1[2];
+            } else {                             // right image: camera 2 at the composed pose
+                mat3_vec(R2, X, Q);
+                Xc[0] = Q[0] + T2[0]; Xc[1] = Q[1] + T2[1]; Xc[2] = Q[2] + T2[2];
+            }
+            omnidir_point_full(cam, Xc, uv, A, Jin);
+            const double err[2] = {(double)(right ? P.u2[i] : P.u1[i]) - uv[0], (double)(right ? P.v2[i] : P.v1[i]) - uv[1]};
+            mom[0] += err[0]; mom[1] += err[1]; mom[2] += err[0] * err[0]; mom[3] += err[1] * err[1];
 #pragma unroll
-                for (int r = 0; r < 2; ++r) {
-                    double jphi[3];
-                    cross3(Q, A + 3 * r, jphi);
-                    double* row = rows[4 * tid + r];
+            for (int r = 0; r < 2; ++r) {
+                double* row = r == 0 ? row0 : row1;
+                const double* a = A + 3 * r;
+                double jphi[3];
+                cross3(Q, a, jphi);
+                if (!right) {
 #pragma unroll
                     for (int k = 0; k < 3; ++k) row[k] = jphi[0] * Jl1[k] + jphi[1] * Jl1[3 + k] + jphi[2] * Jl1[6 + k];
 #pragma unroll
-                    for (int k = 0; k < 3; ++k) row[3 + k] = A[3 * r + k];
+                    for (int k = 0; k < 3; ++k) row[3 + k] = a[k];
 #pragma unroll
                     for (int k = 0; k < 6; ++k) row[6 + k] = 0.0;
 #pragma unroll
                     for (int k = 0; k < 10; ++k) { row[12 + k] = Jin[10 * r + k]; row[22 + k] = 0.0; }
-                    row[32] = err[r];
-                }
-            }
-            // right image: camera 2 at the composed pose.  Left perturbations: frame psi_1 -> phi_2 = R psi_1, tau_2 = R dT_1;
-            // relative pose psi -> phi_2 = psi, tau_2 = psi x (R T_1) + dT
-            mat3_vec(R2, X, Q);
-            Xc[0] = Q[0] + T2[0]; Xc[1] = Q[1] + T2[1]; Xc[2] = Q[2] + T2[2];
-            omnidir_point_full(cam2, Xc, uv, A, Jin);
-            {
-                const double err[2] = {(double)P.u2[i] - uv[0], (double)P.v2[i] - uv[1]};
-                mom[0] += err[0]; mom[1] += err[1]; mom[2] += err[0] * err[0]; mom[3] += err[1] * err[1];
-#pragma unroll
-                for (int r = 0; r < 2; ++r) {
-                    const double* a = A + 3 * r;
-                    double jphi[3], jf[3], jt[3], sc[3], jr[3];
-                    cross3(Q, a, jphi);                       // d/d phi_2
+                } else {
+                    // left perturbations: frame psi_1 -> phi_2 = R psi_1, tau_2 = R dT_1; relative pose psi -> phi_2 = psi,
+                    // tau_2 = psi x (R T_1) + dT
+                    double jf[3], jt[3], sc[3], jr[3];
                     mat3t_vec(R, jphi, jf);                   // d/d psi_1 = R^T jphi
                     mat3t_vec(R, a, jt);                      // d/d dT_1  = R^T a
-                    cross3(s, a, sc);                         // tau_2 = psi x s  ->  a . (psi x s) = psi . (s x a)
+                    cross3(s, a, sc);                         // a . (psi x s) = psi . (s x a)
                     jr[0] = jphi[0] + sc[0]; jr[1] = jphi[1] + sc[1]; jr[2] = jphi[2] + sc[2];
-                    double* row = rows[4 * tid + 2 + r];
 #pragma unroll
                     for (int k = 0; k < 3; ++k) row[k] = jf[0] * Jl1[k] + jf[1] * Jl1[3 + k] + jf[2] * Jl1[6 + k];
 #pragma unroll
@@ -166,97 +173,109 @@ __global__ void __launch_bounds__(kStThreads) stereo_frame_kernel(StereoProblem 
                     for (int k = 0; k < 3; ++k) row[9 + k] = a[k];
 #pragma unroll
                     for (int k = 0; k < 10; ++k) { row[12 + k] = 0.0; row[22 + k] = Jin[10 * r + k]; }
-                    row[32] = err[r];
                 }
+                row[32] = err[r];
             }
+        } else {
+#pragma unroll
+            for (int k = 0; k < kStW; ++k) { row0[k] = 0.0; row1[k] = 0.0; }     // rows past the last corner add zeros
         }
-        __syncthreads();
+        __syncwarp();
+        const int ksteps = nc;                   // 4 rows per corner = one k-step per corner
+        for (int ks = 0; ks < ksteps; ++ks) {
+            const double* r = rows + (4 * ks + t) * kStLd + g;
+            double fr[5];
+            fr[0] = r[0]; fr[1] = r[8]; fr[2] = r[16]; fr[3] = r[24]; fr[4] = g == 0 ? r[32] : 0.0;
+            int q = 0;
 #pragma unroll
-        for (int k = 0; k < 3; ++k)
-            if (tid + k * kStThreads < kStTri)
-                for (int r = 0; r < 4 * nc; ++r) acc[k] = fma(rows[r][gi[k]], rows[r][gj[k]], acc[k]);
-        __syncthreads();
+            for (int a = 0; a < 5; ++a)
+#pragma unroll
+                for (int c = a; c < 5; ++c) { dmma(acc[q][0], acc[q][1], fr[a], fr[c]); ++q; }
+        }
     }
+    __syncwarp();
+    double (*M)[kStW] = reinterpret_cast<double (*)[kStW]>(rows);   // the Gram matrix takes the place of the staged rows
+    {
+        int q = 0;
 #pragma unroll
-    for (int k = 0; k < 3; ++k)
-        if (tid + k * kStThreads < kStTri) { M[gi[k]][gj[k]] = acc[k]; M[gj[k]][gi[k]] = acc[k]; }
+        for (int a = 0; a < 5; ++a)
+#pragma unroll
+            for (int c = a; c < 5; ++c) {
+#pragma unroll
+                for (int h2 = 0; h2 < 2; ++h2) {
+                    const int r = 8 * a + g, cc = 8 * c + 2 * t + h2;
+                    if (r < kStW && cc < kStW && r <= cc) { M[r][cc] = acc[q][h2]; M[cc][r] = acc[q][h2]; }
+                }
+                ++q;
+            }
+    }
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        double v = mom[k];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if ((tid & 31) == 0) smom[k][tid >> 5] = v;
+        for (int o = 16; o > 0; o >>= 1) mom[k] += __shfl_xor_sync(0xffffffffu, mom[k], o);
     }
-    __syncthreads();
+    __syncwarp();
     if (P.dump)
-        for (int t = tid; t < kStW * kStW; t += blockDim.x) P.dump[(int64_t)f * kStW * kStW + t] = M[t / kStW][t % kStW];
+        for (int k = lane; k < kStW * kStW; k += 32) P.dump[(int64_t)f * kStW * kStW + k] = M[k / kStW][k % kStW];
     int bad = 0;
-    if (tid == 0) {
-        double U[21], zg[6], zu[6];
+    if (lane == 0) {
+        double U[21];
 #pragma unroll
         for (int i = 0; i < 6; ++i)
 #pragma unroll
             for (int j = i; j < 6; ++j) U[tri6(i, j)] = M[i][j];
         if (!chol6_packed(U)) bad = 1;
 #pragma unroll
-        for (int i = 0; i < 6; ++i) { zg[i] = M[i][32]; zu[i] = 1.0; }
-        chol6_forward(U, zg, 1);
-        chol6_forward(U, zu, 1);
-#pragma unroll
         for (int i = 0; i < 21; ++i) sU[i] = U[i];
-#pragma unroll
-        for (int i = 0; i < 6; ++i) { szg[i] = zg[i]; szu[i] = zu[i]; }
     }
-    __syncthreads();
-    if (tid < kStNS) {
+    __syncwarp();
+    if (lane < kStNS + 2) {                      // Y columns (26), z_g, z_u
         double U[21], col[6];
 #pragma unroll
         for (int i = 0; i < 21; ++i) U[i] = sU[i];
 #pragma unroll
-        for (int i = 0; i < 6; ++i) col[i] = M[i][6 + tid];
+        for (int i = 0; i < 6; ++i) col[i] = lane < kStNS ? M[i][6 + lane] : (lane == kStNS ? M[i][32] : 1.0);
         chol6_forward(U, col, 1);
 #pragma unroll
-        for (int i = 0; i < 6; ++i) sY[i][tid] = col[i];
+        for (int i = 0; i < 6; ++i) {
+            if (lane < kStNS) sY[i][lane] = col[i];
+            else if (lane == kStNS) szg[i] = col[i];
+            else szu[i] = col[i];
+        }
     }
-    __syncthreads();
+    __syncwarp();
     const int64_t nf = n;
-    for (int t = tid; t < kStRec; t += blockDim.x) {
+    for (int tt = lane; tt < kStRec; tt += 32) {
         double v = 0.0;
-        if (t < kStSTri) {                       // S: upper triangle of H_SS - Y^T Y
-            int a = 0, rem = t;
+        if (tt < kStSTri) {                      // S: upper triangle of H_SS - Y^T Y
+            int a = 0, rem = tt;
             while (rem >= kStNS - a) { rem -= kStNS - a; ++a; }
             const int c = a + rem;
             v = M[6 + a][6 + c];
 #pragma unroll
             for (int k = 0; k < 6; ++k) v -= sY[k][a] * sY[k][c];
-        } else if (t < kStSTri + kStNS) {        // r_g
-            const int a = t - kStSTri;
+        } else if (tt < kStSTri + kStNS) {       // r_g
+            const int a = tt - kStSTri;
             v = M[6 + a][32];
 #pragma unroll
             for (int k = 0; k < 6; ++k) v -= sY[k][a] * szg[k];
-        } else if (t < kStSTri + 2 * kStNS) {    // r_u
-            const int a = t - kStSTri - kStNS;
+        } else if (tt < kStSTri + 2 * kStNS) {   // r_u
+            const int a = tt - kStSTri - kStNS;
 #pragma unroll
             for (int k = 0; k < 6; ++k) v -= sY[k][a] * szu[k];
         } else {
-            const int q = t - kStSTri - 2 * kStNS;
+            const int q = tt - kStSTri - 2 * kStNS;
             if (q == 0) { for (int k = 0; k < 6; ++k) v += szu[k] * szu[k]; }
             else if (q == 1) { for (int k = 0; k < 6; ++k) v += szu[k] * szg[k]; }
             else if (q == 2) v = M[32][32];
-            else { for (int w = 0; w < kStThreads / 32; ++w) v += smom[q - 3][w]; }
+            else v = mom[q - 3];
         }
-        P.rec[(int64_t)t * nf + f] = v;
+        P.rec[(int64_t)tt * nf + f] = v;
     }
-    for (int t = tid; t < kStSave; t += blockDim.x) {
-        double v;
-        if (t < 21) v = sU[t];
-        else if (t < 27) v = szg[t - 21];
-        else if (t < 33) v = szu[t - 27];
-        else v = sY[(t - 33) / kStNS][(t - 33) % kStNS];
-        P.save[(int64_t)t * nf + f] = v;
-    }
-    if (tid == 0 && bad) P.st->status = 4;
+    for (int k = lane; k < kStSave; k += 32) P.save[(int64_t)k * nf + f] = sU[k];     // U | z_g | z_u | Y are contiguous
+    if (lane == 0 && bad) P.st->status = 4;
 }
+constexpr int kStFrameSmem = (kStWarps * kStRows * kStLd + kStWarps * 192) * 8;
 
 __global__ void __launch_bounds__(256) stereo_reduce_kernel(StereoProblem P, int forced)
 {
