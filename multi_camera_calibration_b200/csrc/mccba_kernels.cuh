@@ -960,6 +960,27 @@ __device__ __forceinline__ void reduce_store36(const double* v, double* dst, int
     dst[lane] = a[0];
     if ((lane & 7) == 0) dst[32 + (lane >> 3)] = b[0];
 }
+// warp sum of the LOWER triangle of a symmetric 6 x 6 block held per lane (v[i * 6 + j], i >= j) -> dst[i * 6 + j], i >= j;
+// the upper entries of dst are not written (reduce_records mirrors the diagonal blocks): 21 values travel instead of 36
+__device__ __forceinline__ void reduce_store21(const double* v, double* dst, int lane)
+{
+    double a[16], b[4], c;
+#pragma unroll
+    for (int i = 0, t = 0; i < 6; ++i)
+#pragma unroll
+        for (int j = 0; j <= i; ++j, ++t) {
+            if (t < 16) a[t] = v[i * 6 + j];
+            else if (t < 20) b[t - 16] = v[i * 6 + j];
+            else c = v[i * 6 + j];
+        }
+    warp_tr_reduce<16>(a, lane);
+    warp_tr_reduce<4>(b, lane);
+    c = warp_sum(c);
+    auto at = [](int t) { const int i = (t >= 1) + (t >= 3) + (t >= 6) + (t >= 10) + (t >= 15); return i * 6 + (t - i * (i + 1) / 2); };
+    if ((lane & 1) == 0) dst[at(lane >> 1)] = a[0];
+    if ((lane & 7) == 0) dst[at(16 + (lane >> 3))] = b[0];
+    if (lane == 0) dst[35] = c;
+}
 // warp sum of 6 values -> dst[0..6)
 __device__ __forceinline__ void reduce_store6(const double* v, double* dst, int lane)
 {
@@ -977,21 +998,26 @@ template <int kMinBlocks>
 __global__ void __launch_bounds__(kK2Threads, kMinBlocks) frame_schur_kernel(Problem P, int sel_arg, double lambda_arg)
 {
     const DevState* st = P.st;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
+    if (warp >= P.n_warps) return;
+    // first-level loads that do not depend on the loop state are requested together with it (the head of this kernel was
+    // a chain of five dependent round trips: 18 % of the stall samples, profiles/r2_ncu_iteration_kernels.txt)
+    const int4 m0 = P.wmeta[2 * warp], m1 = P.wmeta[2 * warp + 1];
+    const int slot = warp * 32 + lane;
+    const int frame = P.slot_frame[slot];
     int sel;
     double lambda;
     if (sel_arg >= 0) { sel = sel_arg; lambda = lambda_arg; }
     else {
-        if (st->done) return;
-        if (st->phase == kPhaseDecide) { sel = 1 - st->cur; lambda = st->lambda_spec; }
-        else { sel = st->cur; lambda = st->lambda; }
+        const int done = st->done, phase = st->phase, cur = st->cur;
+        const double lam_spec = st->lambda_spec, lam = st->lambda;
+        if (done) return;
+        if (phase == kPhaseDecide) { sel = 1 - cur; lambda = lam_spec; }
+        else { sel = cur; lambda = lam; }
     }
     extern __shared__ __align__(128) unsigned char k2_smem[];
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
-    if (warp >= P.n_warps) return;
-    const int4 m0 = P.wmeta[2 * warp], m1 = P.wmeta[2 * warp + 1];
     const int V = m0.x;
     const int* gc = P.group_cams + m0.y;
-    const int slot = warp * 32 + lane;
     const int ls = m1.x + lane;
     const int ebase = m0.z, stride = m0.w;
     const double* __restrict__ blk = P.blocks[sel];
@@ -1007,7 +1033,7 @@ __global__ void __launch_bounds__(kK2Threads, kMinBlocks) frame_schur_kernel(Pro
         if (V > 1) tma_load_1d(stage + 36 * 32, blk + (int64_t)((ebase + stride + ls) >> 5) * kBlk * 32, kBlk * 256u, bar);
     }
     __syncwarp();
-    const int frame = P.slot_frame[slot];
+    const int c0 = gc[0], c1 = V > 1 ? gc[1] : 0;      // camera ids of the two staged views, in one round
     const bool active = frame >= 0;
     const double* __restrict__ x = P.x[sel];
     const double* __restrict__ vR = P.vR[sel];
@@ -1028,7 +1054,7 @@ __global__ void __launch_bounds__(kK2Threads, kMinBlocks) frame_schur_kernel(Pro
     mbar_wait(bar, 0);
     // pass 1: pattern-pose block
     for (int v = 0; v < V; ++v) {
-        const int c = gc[v];
+        const int c = v == 0 ? c0 : (v == 1 ? c1 : gc[v]);
         if (c != 0) ++Va;
         if (!active) continue;
         const int64_t e = ebase + (int64_t)v * stride + ls;
@@ -1069,7 +1095,7 @@ __global__ void __launch_bounds__(kK2Threads, kMinBlocks) frame_schur_kernel(Pro
     // pass 2: camera blocks of each non-gauge view
     int ai = 0;
     for (int v = 0; v < V; ++v) {
-        const int c = gc[v];
+        const int c = v == 0 ? c0 : (v == 1 ? c1 : gc[v]);
         if (c == 0) continue;
         const int64_t e = ebase + (int64_t)v * stride + ls;
         double D[36], gd[6];
@@ -1107,7 +1133,7 @@ __global__ void __launch_bounds__(kK2Threads, kMinBlocks) frame_schur_kernel(Pro
 #pragma unroll
             for (int i = 0; i < 6; ++i) {
 #pragma unroll
-                for (int j = 0; j < 6; ++j) {
+                for (int j = 0; j <= i; ++j) {      // the camera block is symmetric: lower triangle only
                     double acc = 0;
 #pragma unroll
                     for (int k = 0; k < 6; ++k) acc += Y[k * 6 + i] * Y[k * 6 + j];
@@ -1119,7 +1145,7 @@ __global__ void __launch_bounds__(kK2Threads, kMinBlocks) frame_schur_kernel(Pro
                 gd[i] = gcv[i] - acc;
             }
         }
-        reduce_store36(D, rec + 2 + 36 * ai, lane);
+        reduce_store21(D, rec + 2 + 36 * ai, lane);
         reduce_store6(gd, rec + 2 + 36 * Va + 6 * ai, lane);
         ++ai;
     }
@@ -1171,11 +1197,13 @@ __global__ void __launch_bounds__(kK2Threads, kMinBlocks) frame_schur_kernel(Pro
 constexpr int kK3Threads = 256;
 __global__ void __launch_bounds__(kK3Threads) reduce_records_kernel(Problem P, int forced)
 {
-    if (!forced && P.st->done) return;
     __shared__ double s_part[kK3Threads / 32][40];
     const int dest = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // the static tables are requested together with the loop state (this kernel is a chain of dependent round trips)
     const int kind = P.dest_info[4 * dest], A = P.dest_info[4 * dest + 1], B = P.dest_info[4 * dest + 2];
     const int s0 = P.dest_src0[dest], s1 = P.dest_src0[dest + 1];
+    const int done = P.st->done;
+    if (!forced && done) return;
     const int ns = P.ns;
     double* S = P.ar_part;
     double* gs = P.ar_part + P.ar_goff;
@@ -1247,15 +1275,20 @@ __global__ void __launch_bounds__(kK3Threads) reduce_records_kernel(Problem P, i
             if (A != B || i >= j) S[(int64_t)row * NW + (col - row + w)] = half ? a1 : a0;
         }
     } else if (kind == 0) {
+        // diagonal blocks (A == B) arrive as their lower triangle only (reduce_store21) and are mirrored here
         {
             const int i = lane / 6, j = lane % 6;
-            S[(int64_t)(6 * A + i) * ns + 6 * B + j] = a0;
-            if (A != B) S[(int64_t)(6 * B + j) * ns + 6 * A + i] = a0;
+            if (A != B || i >= j) {
+                S[(int64_t)(6 * A + i) * ns + 6 * B + j] = a0;
+                S[(int64_t)(6 * B + j) * ns + 6 * A + i] = a0;
+            }
         }
         if (lane < 4) {
             const int k = 32 + lane, i = k / 6, j = k % 6;
-            S[(int64_t)(6 * A + i) * ns + 6 * B + j] = a1;
-            if (A != B) S[(int64_t)(6 * B + j) * ns + 6 * A + i] = a1;
+            if (A != B || i >= j) {
+                S[(int64_t)(6 * A + i) * ns + 6 * B + j] = a1;
+                S[(int64_t)(6 * B + j) * ns + 6 * A + i] = a1;
+            }
         }
     } else if (lane < 6) {
         gs[6 * A + lane] = a0;
@@ -1554,6 +1587,7 @@ __global__ void __launch_bounds__(kK5Threads) camera_update_kernel(Problem P)
 #ifndef MCCBA_K4_MINBLOCKS
 #define MCCBA_K4_MINBLOCKS 3
 #endif
+
 constexpr int kK4MinBlocks = MCCBA_K4_MINBLOCKS;
 constexpr int kK4WarpBytes = 2 * 32 * (int)sizeof(EdgeRec);
 constexpr int kK4SmemBytes = (kK4Threads / 32) * kK4WarpBytes;
@@ -1561,23 +1595,34 @@ __global__ void __launch_bounds__(kK4Threads, kK4MinBlocks) frame_update_kernel(
 {
     extern __shared__ __align__(128) unsigned char k4_smem[];
     const DevState* st = P.st;
-    if (st->done || !st->solved) return;
-    const int cur = st->cur, tr = 1 - cur;
-    const double alpha = st->alpha;
     const int slot = blockIdx.x * blockDim.x + threadIdx.x;
     const int wic = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool in = slot < P.n_slots;         // n_slots is a multiple of 32: whole warps
+    // The kernel is a chain of dependent loads (profiles/r2_ncu_iteration_kernels.txt: 69 % of the stall samples are
+    // long-scoreboard): everything that does not depend on the loop state is requested together with it ...
+    int frame = -1;
+    int4 m0 = make_int4(0, 0, 0, 0), m1 = m0;
+    if (in) {
+        frame = P.slot_frame[slot];
+        m0 = P.wmeta[2 * (slot >> 5)];
+        m1 = P.wmeta[2 * (slot >> 5) + 1];
+    }
+    const int done = st->done, solved = st->solved, cur = st->cur, tr = 1 - cur;
+    const double alpha = st->alpha;
+    if (done || !solved) return;
     EdgeRec* stage = reinterpret_cast<EdgeRec*>(k4_smem + wic * kK4WarpBytes);
     double step2 = 0, par2 = 0;
-    if (slot < P.n_slots) {   // n_slots is a multiple of 32: whole warps
-        const int frame = P.slot_frame[slot];
+    if (in) {
         const int warp = slot >> 5;
-        const int4 m0 = P.wmeta[2 * warp], m1 = P.wmeta[2 * warp + 1];
         const int V = m0.x;
         const int* gc = P.group_cams + m0.y;
         const int ls = m1.x + lane;
         const int64_t ebase = m0.z, stride = m0.w;
         const double* __restrict__ fl = P.frameL + (int64_t)warp * 27 * 32 + lane;
         const double* __restrict__ dc = P.dc;
+        // ... and the camera ids of the first two views come in one round.  (Pulling the second view's Y tile into L2 with
+        // prefetch.global.L2 while the first is consumed was measured slower: 30.5 vs 29.0 us.)
+        const int c0 = gc[0], c1 = V > 1 ? gc[1] : 0;
         if (frame >= 0) {
             const int64_t pv = P.n_cam + frame;
             double U[21], r[6], pold[6];
@@ -1588,7 +1633,7 @@ __global__ void __launch_bounds__(kK4Threads, kK4MinBlocks) frame_update_kernel(
 #pragma unroll
             for (int k = 0; k < 6; ++k) pold[k] = P.x[cur][6 * (pv - 1) + k];
             for (int v = 0; v < V; ++v) {
-                const int c = gc[v];
+                const int c = v == 0 ? c0 : (v == 1 ? c1 : gc[v]);
                 if (c == 0) continue;
                 const double* __restrict__ y = P.edgeY + ((ebase + v * stride + ls) >> 5) * 36 * 32 + lane;   // ls & 31 == lane
                 double d[6];
@@ -1620,7 +1665,7 @@ __global__ void __launch_bounds__(kK4Threads, kK4MinBlocks) frame_update_kernel(
             // composed poses the residual kernel evaluates next: the first two views go out through shared memory as
             // one 3 KB bulk store per view (32 consecutive edge records), the rest straight from registers
             for (int v = 0; v < V; ++v) {
-                const int c = gc[v];
+                const int c = v == 0 ? c0 : (v == 1 ? c1 : gc[v]);
                 double Rc[9], tc[3];
 #pragma unroll
                 for (int k = 0; k < 9; ++k) Rc[k] = c != 0 ? P.vR[tr][9 * c + k] : ((k == 0 || k == 4 || k == 8) ? 1.0 : 0.0);
