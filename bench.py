@@ -152,6 +152,32 @@ def _cpu_threads(orc):
     return orc.num_threads()
 
 
+def _bind_to_gpu_numa(local):
+    """Multi-GPU runs: pin this rank to the CPUs of its GPU's NUMA node before the pinned host buffers are allocated and
+    first touched, so that the per-step uploads of the N ranks do not cross the socket interconnect (what `numactl
+    --cpunodebind --membind` does for a launcher that knows the topology).  Returns what was done, or None."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = int(vis.split(",")[local]) if vis and all(t.strip().isdigit() for t in vis.split(",")) else local
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(idx)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        dev = "/sys/bus/pci/devices/" + bus.lower()[-12:]
+        node = int(open(dev + "/numa_node").read())
+        cpus = set()
+        for part in open(dev + "/local_cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if node < 0 or not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return {"node": node, "cpus": len(cpus)}
+    except Exception:
+        return None
+
+
 def run_reference(args):
     """CPU arm: the restated reference algorithm (oracle port -- the reference itself needs OpenCV C++ and Eigen and
     cannot be built in this image) with all host threads, on a bounded sample of the same workload: rank 0's shard of
@@ -446,6 +472,7 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    numa = _bind_to_gpu_numa(local) if world > 1 else None
     rig = _rig(args, rank)
     M = rig["n_points"]
     # pinned host copies for the end-to-end leg
@@ -586,6 +613,8 @@ def run_ours(args):
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                         "ms_per_step": e2e_ms, "steps": e2e_steps},
                 "gpu_launches": int(launches), "clocks": clocks}
+        if numa:
+            line["host_numa_binding"] = numa     # rank 0's; every rank binds to its own GPU's node
         line.update(extra)
         if cpu:
             line["cpu_baseline"] = cpu

@@ -261,16 +261,28 @@ __device__ inline void bcr_stage(const double* __restrict__ A, int n, int packed
         return A[(size_t)r * n + c];
     };
     const int total = Nb * B * B;
-    for (int idx = tid; idx < total; idx += nthr) {
-        const int I = idx / (B * B), pq = idx - I * B * B, p = pq / B, q = pq - p * B;
-        const int r = I * B + p, c = I * B + q;
-        double v;
-        if (r >= n || c >= n) v = (p == q) ? 1.0 : 0.0;
-        else v = r >= c ? at(r, c) : at(c, r);
-        Dg[idx] = v;
-        double l = 0.0;
-        if (I > 0 && r < n) l = at(r, (I - 1) * B + q);
-        Lo[idx] = l;
+    // kU elements per thread and trip, all their loads issued before the first store: the staging is a handful of L2 round
+    // trips, and one element per trip serialised them (7 300 cycles for 2 268 elements on 992 threads)
+    constexpr int kU = 4;
+    for (int base = tid; base < total; base += nthr * kU) {
+        double v[kU], l[kU];
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+            const int idx = base + u * nthr;
+            v[u] = 0.0; l[u] = 0.0;
+            if (idx < total) {
+                const int I = idx / (B * B), pq = idx - I * B * B, p = pq / B, q = pq - p * B;
+                const int r = I * B + p, c = I * B + q;
+                if (r >= n || c >= n) v[u] = (p == q) ? 1.0 : 0.0;
+                else v[u] = r >= c ? at(r, c) : at(c, r);
+                if (I > 0 && r < n) l[u] = at(r, (I - 1) * B + q);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+            const int idx = base + u * nthr;
+            if (idx < total) { Dg[idx] = v[u]; Lo[idx] = l[u]; }
+        }
     }
     const size_t goff = packed ? (size_t)n * NW : (size_t)n * n;
     for (int idx = tid; idx < Nb * B; idx += nthr) rhs[idx] = idx < n ? A[goff + idx] : 0.0;
