@@ -33,7 +33,9 @@ MC_HD f2 operator+(f2 a, f2 b) { f2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.v
 MC_HD f2 operator-(f2 a, f2 b) { f2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
 MC_HD f2 operator*(f2 a, f2 b) { f2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
 MC_HD f2 f2_fma(f2 a, f2 b, f2 c) { f2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v)); return r; }
-MC_HD f2 f2_neg(f2 a) { f2 r; r.v = a.v ^ 0x8000000080000000ull; return r; }
+// negation as "unpack, negate both halves, repack": ptxas folds exactly this form into the operand modifier of the consuming
+// FFMA2 / FMUL2 (-R.F32x2.HI_LO); the 64-bit XOR of the sign bits it does not (two LOP3 per negation, 16 per step)
+MC_HD f2 f2_neg(f2 a) { return f2_make(-f2_lo(a), -f2_hi(a)); }
 MC_HD f2 f2_rcp(f2 a)   // positive, normal arguments (depths, distortion denominators); ~1 ulp
 {
     float lo = f2_lo(a), hi = f2_hi(a), ylo, yhi;
@@ -69,28 +71,31 @@ MC_HD f2 f2_rsqrt(f2 a) { return f2_make(1.0f / sqrtf(a.x), 1.0f / sqrtf(a.y)); 
 #endif
 MC_HD f2 f2_dup(float a) { return f2_make(a, a); }
 
-// Intrinsics of one camera as duplicated float pairs, with the constant factors the Jacobian needs folded in once.
+// Intrinsics of one camera in single precision, with the constant factors the Jacobian needs folded in once.  Plain floats:
+// a value duplicated into both halves at its use (f2_dup: mov.b64 {x, x}) is folded by ptxas into the scalar-broadcast
+// operand form of the packed instruction (FFMA2 R, R.F32x2.HI_LO, R.F32, ...), so a constant costs one register and 4 bytes
+// of shared memory instead of a register pair and 8 bytes.
 struct alignas(16) CamF2 {
-    f2 fx, fy, skew, xi;
-    f2 cx, cy;
-    f2 k1, k2, k3, k4, k5, k6, p1, p2;
-    f2 k1_2, k2_4, k3_6;      // 2 k1, 4 k2, 6 k3 (d rad / d r2, doubled)
-    f2 k4_1, k5_2, k6_3;      // k4, 2 k5, 3 k6
-    f2 p1_2, p2_2, p1_6, p2_6;
+    float fx, fy, skew, xi;
+    float cx, cy;
+    float k1, k2, k3, k4, k5, k6, p1, p2;
+    float k1_2, k2_4, k3_6;      // 2 k1, 4 k2, 6 k3 (d rad / d r2, doubled)
+    float k4_1, k5_2, k6_3;      // k4, 2 k5, 3 k6
+    float p1_2, p2_2, p1_6, p2_6;
     int model, rational;
 };
 MC_HD CamF2 make_cam_f2(const CamParams& c)
 {
     CamF2 r;
-    r.fx = f2_dup((float)c.fx); r.fy = f2_dup((float)c.fy); r.skew = f2_dup((float)c.skew); r.xi = f2_dup((float)c.xi);
-    r.cx = f2_dup((float)c.cx); r.cy = f2_dup((float)c.cy);
-    r.k1 = f2_dup((float)c.k1); r.k2 = f2_dup((float)c.k2); r.k3 = f2_dup((float)c.k3);
-    r.k4 = f2_dup((float)c.k4); r.k5 = f2_dup((float)c.k5); r.k6 = f2_dup((float)c.k6);
-    r.p1 = f2_dup((float)c.p1); r.p2 = f2_dup((float)c.p2);
-    r.k1_2 = f2_dup((float)(2.0 * c.k1)); r.k2_4 = f2_dup((float)(4.0 * c.k2)); r.k3_6 = f2_dup((float)(6.0 * c.k3));
-    r.k4_1 = f2_dup((float)c.k4); r.k5_2 = f2_dup((float)(2.0 * c.k5)); r.k6_3 = f2_dup((float)(3.0 * c.k6));
-    r.p1_2 = f2_dup((float)(2.0 * c.p1)); r.p2_2 = f2_dup((float)(2.0 * c.p2));
-    r.p1_6 = f2_dup((float)(6.0 * c.p1)); r.p2_6 = f2_dup((float)(6.0 * c.p2));
+    r.fx = (float)c.fx; r.fy = (float)c.fy; r.skew = (float)c.skew; r.xi = (float)c.xi;
+    r.cx = (float)c.cx; r.cy = (float)c.cy;
+    r.k1 = (float)c.k1; r.k2 = (float)c.k2; r.k3 = (float)c.k3;
+    r.k4 = (float)c.k4; r.k5 = (float)c.k5; r.k6 = (float)c.k6;
+    r.p1 = (float)c.p1; r.p2 = (float)c.p2;
+    r.k1_2 = (float)(2.0 * c.k1); r.k2_4 = (float)(4.0 * c.k2); r.k3_6 = (float)(6.0 * c.k3);
+    r.k4_1 = (float)c.k4; r.k5_2 = (float)(2.0 * c.k5); r.k6_3 = (float)(3.0 * c.k6);
+    r.p1_2 = (float)(2.0 * c.p1); r.p2_2 = (float)(2.0 * c.p2);
+    r.p1_6 = (float)(6.0 * c.p1); r.p2_6 = (float)(6.0 * c.p2);
     r.model = c.model; r.rational = c.rational;
     return r;
 }
@@ -106,27 +111,27 @@ MC_HD void pinhole_pair(const CamF2& c, const f2* Xc, f2 iu, f2 iv, f2* e, f2* A
     const f2 x = Xc[0] * iz, y = Xc[1] * iz;
     const f2 xx = x * x, xy = x * y, yy = y * y;
     const f2 r2 = xx + yy;
-    f2 rad = f2_fma(r2, f2_fma(r2, f2_fma(r2, c.k3, c.k2), c.k1), one);
-    f2 dd2 = f2_fma(r2, f2_fma(r2, c.k3_6, c.k2_4), c.k1_2);          // 2 d rad / d r2
+    f2 rad = f2_fma(r2, f2_fma(r2, f2_fma(r2, f2_dup(c.k3), f2_dup(c.k2)), f2_dup(c.k1)), one);
+    f2 dd2 = f2_fma(r2, f2_fma(r2, f2_dup(c.k3_6), f2_dup(c.k2_4)), f2_dup(c.k1_2));          // 2 d rad / d r2
     if (kRational) {
-        const f2 den = f2_fma(r2, f2_fma(r2, f2_fma(r2, c.k6, c.k5), c.k4), one);
-        const f2 dden2 = f2_fma(r2, f2_fma(r2, c.k6_3, c.k5_2), c.k4_1);
+        const f2 den = f2_fma(r2, f2_fma(r2, f2_fma(r2, f2_dup(c.k6), f2_dup(c.k5)), f2_dup(c.k4)), one);
+        const f2 dden2 = f2_fma(r2, f2_fma(r2, f2_dup(c.k6_3), f2_dup(c.k5_2)), f2_dup(c.k4_1));
         const f2 iden = f2_rcp(den);
         rad = rad * iden;
         dd2 = (dd2 - (rad + rad) * dden2) * iden;                      // 2 (drad - rad dden) / den
     }
     if (kNeedE) {
         const f2 xy2 = xy + xy;
-        const f2 xd = f2_fma(x, rad, f2_fma(c.p1, xy2, c.p2 * f2_fma(xx, f2_dup(2.0f), r2)));
-        const f2 yd = f2_fma(y, rad, f2_fma(c.p2, xy2, c.p1 * f2_fma(yy, f2_dup(2.0f), r2)));
-        e[0] = f2_fma(f2_neg(c.fx), xd, iu - c.cx);
-        e[1] = f2_fma(f2_neg(c.fy), yd, iv - c.cy);
+        const f2 xd = f2_fma(x, rad, f2_fma(f2_dup(c.p1), xy2, f2_dup(c.p2) * f2_fma(xx, f2_dup(2.0f), r2)));
+        const f2 yd = f2_fma(y, rad, f2_fma(f2_dup(c.p2), xy2, f2_dup(c.p1) * f2_fma(yy, f2_dup(2.0f), r2)));
+        e[0] = f2_fma(f2_neg(f2_dup(c.fx)), xd, iu - f2_dup(c.cx));
+        e[1] = f2_fma(f2_neg(f2_dup(c.fy)), yd, iv - f2_dup(c.cy));
     }
-    const f2 t = f2_fma(c.p1_2, x, c.p2_2 * y);
-    const f2 dxdx = f2_fma(dd2, xx, rad) + f2_fma(c.p1_2, y, c.p2_6 * x);
+    const f2 t = f2_fma(f2_dup(c.p1_2), x, f2_dup(c.p2_2) * y);
+    const f2 dxdx = f2_fma(dd2, xx, rad) + f2_fma(f2_dup(c.p1_2), y, f2_dup(c.p2_6) * x);
     const f2 dxdy = f2_fma(dd2, xy, t);
-    const f2 dydy = f2_fma(dd2, yy, rad) + f2_fma(c.p1_6, y, c.p2_2 * x);
-    const f2 fxz = c.fx * iz, fyz = c.fy * iz;
+    const f2 dydy = f2_fma(dd2, yy, rad) + f2_fma(f2_dup(c.p1_6), y, f2_dup(c.p2_2) * x);
+    const f2 fxz = f2_dup(c.fx) * iz, fyz = f2_dup(c.fy) * iz;
     const f2 nx = f2_neg(x), ny = f2_neg(y);
     A[0] = fxz * dxdx; A[1] = fxz * dxdy; A[2] = f2_fma(A[0], nx, A[1] * ny);
     A[3] = fyz * dxdy; A[4] = fyz * dydy; A[5] = f2_fma(A[3], nx, A[4] * ny);
@@ -139,25 +144,25 @@ MC_HD void omnidir_pair(const CamF2& c, const f2* Xc, f2 iu, f2 iv, f2* e, f2* A
     const f2 n2 = f2_fma(Xc[0], Xc[0], f2_fma(Xc[1], Xc[1], Xc[2] * Xc[2]));
     const f2 rn = f2_rsqrt(n2);
     const f2 s0 = Xc[0] * rn, s1 = Xc[1] * rn, s2 = Xc[2] * rn;
-    const f2 id = f2_rcp(s2 + c.xi);
+    const f2 id = f2_rcp(s2 + f2_dup(c.xi));
     const f2 x = s0 * id, y = s1 * id;
     const f2 xx = x * x, xy = x * y, yy = y * y;
     const f2 r2 = xx + yy;
-    const f2 rad = f2_fma(r2, f2_fma(r2, c.k2, c.k1), one);
-    const f2 dd2 = f2_fma(r2, c.k2_4, c.k1_2);
+    const f2 rad = f2_fma(r2, f2_fma(r2, f2_dup(c.k2), f2_dup(c.k1)), one);
+    const f2 dd2 = f2_fma(r2, f2_dup(c.k2_4), f2_dup(c.k1_2));
     if (kNeedE) {
         const f2 xy2 = xy + xy;
-        const f2 xd = f2_fma(x, rad, f2_fma(c.p1, xy2, c.p2 * f2_fma(xx, f2_dup(2.0f), r2)));
-        const f2 yd = f2_fma(y, rad, f2_fma(c.p2, xy2, c.p1 * f2_fma(yy, f2_dup(2.0f), r2)));
-        e[0] = f2_fma(f2_neg(c.fx), xd, f2_fma(f2_neg(c.skew), yd, iu - c.cx));
-        e[1] = f2_fma(f2_neg(c.fy), yd, iv - c.cy);
+        const f2 xd = f2_fma(x, rad, f2_fma(f2_dup(c.p1), xy2, f2_dup(c.p2) * f2_fma(xx, f2_dup(2.0f), r2)));
+        const f2 yd = f2_fma(y, rad, f2_fma(f2_dup(c.p2), xy2, f2_dup(c.p1) * f2_fma(yy, f2_dup(2.0f), r2)));
+        e[0] = f2_fma(f2_neg(f2_dup(c.fx)), xd, f2_fma(f2_neg(f2_dup(c.skew)), yd, iu - f2_dup(c.cx)));
+        e[1] = f2_fma(f2_neg(f2_dup(c.fy)), yd, iv - f2_dup(c.cy));
     }
-    const f2 t = f2_fma(c.p1_2, x, c.p2_2 * y);
-    const f2 dxdx = f2_fma(dd2, xx, rad) + f2_fma(c.p1_2, y, c.p2_6 * x);
+    const f2 t = f2_fma(f2_dup(c.p1_2), x, f2_dup(c.p2_2) * y);
+    const f2 dxdx = f2_fma(dd2, xx, rad) + f2_fma(f2_dup(c.p1_2), y, f2_dup(c.p2_6) * x);
     const f2 dxdy = f2_fma(dd2, xy, t);
-    const f2 dydy = f2_fma(dd2, yy, rad) + f2_fma(c.p1_6, y, c.p2_2 * x);
-    const f2 m00 = f2_fma(c.fx, dxdx, c.skew * dxdy), m01 = f2_fma(c.fx, dxdy, c.skew * dydy);
-    const f2 m10 = c.fy * dxdy, m11 = c.fy * dydy;
+    const f2 dydy = f2_fma(dd2, yy, rad) + f2_fma(f2_dup(c.p1_6), y, f2_dup(c.p2_2) * x);
+    const f2 m00 = f2_fma(f2_dup(c.fx), dxdx, f2_dup(c.skew) * dxdy), m01 = f2_fma(f2_dup(c.fx), dxdy, f2_dup(c.skew) * dydy);
+    const f2 m10 = f2_dup(c.fy) * dxdy, m11 = f2_dup(c.fy) * dydy;
     const f2 k = rn * id;
     const f2 nx = f2_neg(x), ny = f2_neg(y);
     {
@@ -197,14 +202,14 @@ MC_HD void corner_residual(const CamParams& c, const double* R3, const double* T
 // upper triangle of sum J^T J (21) | sum J^T e (6) | sum |e|^2.  w = 1 for a live corner, 0 for layout padding.
 // kExactE: the residual pair (ex0, ex1) was evaluated in double by the caller (corner_residual) and replaces the float one.
 template <int kModel, bool kRational, bool kExactE>
-MC_HD void corner_pair_accumulate(const CamF2& c, const f2* R3, const f2* T3, f2 ox, f2 oy, f2 oz, f2 iu, f2 iv, f2 w, bool masked,
+MC_HD void corner_pair_accumulate(const CamF2& c, const float* R3, const float* T3, f2 ox, f2 oy, f2 oz, f2 iu, f2 iv, f2 w, bool masked,
                                   f2* acc, f2 ex0, f2 ex1)
 {
     f2 Q[3], Xc[3], e[2], A[6];
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
-        Q[i] = f2_fma(R3[3 * i], ox, f2_fma(R3[3 * i + 1], oy, R3[3 * i + 2] * oz));
-        Xc[i] = Q[i] + T3[i];
+        Q[i] = f2_fma(f2_dup(R3[3 * i]), ox, f2_fma(f2_dup(R3[3 * i + 1]), oy, f2_dup(R3[3 * i + 2]) * oz));
+        Xc[i] = Q[i] + f2_dup(T3[i]);
     }
     if (kModel == kPinhole) pinhole_pair<kRational, !kExactE>(c, Xc, iu, iv, e, A);
     else omnidir_pair<!kExactE>(c, Xc, iu, iv, e, A);

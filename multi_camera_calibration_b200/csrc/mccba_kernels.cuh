@@ -514,19 +514,22 @@ __device__ __forceinline__ float2 ldg_f2(const float2* p)
 
 // The stream of observation steps a warp consumes, across tile boundaries.  A step is one contiguous 1280-byte block
 // (5 planes x 32 lanes x 2 floats), so ONE lane programs the TMA engine (cp.async.bulk + mbarrier) to drop it into the
-// warp's private ring in shared memory kObsStages steps ahead of its use; when the current tile runs out the next tile
+// warp's private ring in shared memory kObsStages chunks ahead of its use; when the current tile runs out the next tile
 // of this CTA (tile + gridDim.x) takes over without a bubble -- its offset and step count were fetched one tile earlier.
 // (First version: register double buffer filled by LDG.  The compiler rotated the buffer at the END of a step, the
 // prefetch distance collapsed to < 1 step and a third of all stall samples sat on that move waiting for DRAM --
 // profiles/r2_k1_f32_v1.txt.)
+// One copy moves a CHUNK of up to kObsChunk consecutive steps (they are contiguous in the packed layout) into one ring stage:
+// the producer code (address arithmetic, expect-tx, the bulk copy: ~45 instructions that the whole warp sits through
+// while lane 0 executes them) and the mbarrier wait run once per chunk instead of once per step (profiles/r2_experiments_late.md).
 #ifndef MCCBA_OBS_STAGES
-#define MCCBA_OBS_STAGES 8
+#define MCCBA_OBS_STAGES 2
+#endif
+#ifndef MCCBA_OBS_CHUNK
+#define MCCBA_OBS_CHUNK 4
 #endif
 #ifndef MCCBA_F32_MINBLOCKS
 #define MCCBA_F32_MINBLOCKS 3
-#endif
-#ifndef MCCBA_F32_PAIRSTEPS
-#define MCCBA_F32_PAIRSTEPS 0
 #endif
 #ifndef MCCBA_F32_RELOAD
 #define MCCBA_F32_RELOAD 1
@@ -535,13 +538,15 @@ __device__ __forceinline__ float2 ldg_f2(const float2* p)
 #define MCCBA_F32_POSE_REGS 0
 #endif
 constexpr int kObsStages = MCCBA_OBS_STAGES;   // power of two: stage and phase are a mask and a shift
+constexpr int kObsChunk = MCCBA_OBS_CHUNK;     // steps per copy
 constexpr int kObsStepBytes = 5 * 32 * 8;
+constexpr int kObsStageF2 = kObsChunk * 5 * 32;   // float2 elements of one ring stage
 struct ObsStream {
     const float2* base;     // current tile: first float2 of this warp's block
     int k, kp, tile;        // next step to load, steps of the current tile, current tile
     int kp_next;            // prefetched for tile + stride
     int64_t off_next;
-    int issued;             // steps issued so far (stage = issued % kObsStages)
+    int issued;             // chunks issued so far (stage = issued % kObsStages)
 };
 __device__ __forceinline__ void obs_stream_open(ObsStream& S, const Problem& P, int tile, int stride, int n_tiles, int wq)
 {
@@ -552,16 +557,20 @@ __device__ __forceinline__ void obs_stream_open(ObsStream& S, const Problem& P, 
     S.kp_next = nt < n_tiles ? P.tile_kp[nt] : 0;
     S.off_next = nt < n_tiles ? P.tile_off[nt] : 0;
 }
-// called by ONE lane of the warp: issue the copy of the next step of the stream into its ring stage
+// called by ONE lane of the warp: issue the copy of the next chunk of the stream (chunks do not span tiles: the consumer
+// cuts a tile into the same min(kObsChunk, kp - k) pieces) into its ring stage
 __device__ __forceinline__ void obs_stream_issue(ObsStream& S, const Problem& P, int stride, int n_tiles, int wq, float2* ring,
                                                  unsigned long long* bars)
 {
     if (S.tile >= n_tiles) return;
     const int stg = S.issued & (kObsStages - 1);
-    mbar_expect_tx(&bars[stg], kObsStepBytes);
-    tma_load_1d(ring + (size_t)stg * 5 * 32, S.base + (size_t)S.k * 5 * 32, kObsStepBytes, &bars[stg]);
+    const int nst = min(kObsChunk, S.kp - S.k);
+    const unsigned bytes = (unsigned)nst * kObsStepBytes;
+    mbar_expect_tx(&bars[stg], bytes);
+    tma_load_1d(ring + (size_t)stg * kObsStageF2, S.base + (size_t)S.k * 5 * 32, bytes, &bars[stg]);
     ++S.issued;
-    if (++S.k == S.kp) {    // on to the next tile of this CTA; fetch the layout of the one after it
+    S.k += nst;
+    if (S.k == S.kp) {    // on to the next tile of this CTA; fetch the layout of the one after it
         S.tile += stride; S.k = 0; S.kp = S.kp_next;
         S.base = P.obs2 + S.off_next + (size_t)wq * S.kp * 5 * 32;
         const int nt = S.tile + stride;
@@ -571,27 +580,27 @@ __device__ __forceinline__ void obs_stream_issue(ObsStream& S, const Problem& P,
 }
 
 // Per-edge pose of the packed pass in shared memory, one record per edge of the warp's quarter tile: the double pose
-// (for the MIXED policy's residual) and the float pose as duplicated pairs (for the f32x2 Jacobian).  26-word stride
-// for the double part: the 8 edges of a warp land in distinct banks.
+// (for the MIXED policy's residual) and the float pose (for the f32x2 Jacobian; broadcast operands, see CamF2).  36-word
+// stride: the 8 edges of a warp land in distinct banks.
 struct alignas(16) PackedPose {
     double Rd[9], Td[3];
-    f2 Rf[9], Tf[3];
-    double pad[2];
+    float Rf[9], Tf[3];
 };
 __host__ __device__ inline size_t f32_smem_bytes(int n_cam)
 {
-    return (size_t)4 * kObsStages * kObsStepBytes + 4 * kObsStages * 8 + 32 * sizeof(PackedPose) + (sizeof(CamF2) + sizeof(CamParams)) * (size_t)n_cam;
+    return (size_t)4 * kObsStages * kObsChunk * kObsStepBytes + 4 * kObsStages * 8 + 32 * sizeof(PackedPose) + (sizeof(CamF2) + sizeof(CamParams)) * (size_t)n_cam;
 }
 
 // One step of one lane: two corners.  kMixed: the residual pair comes from a double projection (corner_residual) and the
 // cost is summed in double (g[6]); Jacobian, J^T J and J^T e in f32x2 (acc[0..26]).  Else everything in f32x2 (acc[0..27]).
-template <int kModel, bool kRational, bool kMixed>
-__device__ __forceinline__ void packed_step(const float2 (&cur)[5], int k, int n, int q, int k_full, const CamF2& cam,
+template <int kModel, bool kRational, bool kMixed, bool kMasked>
+__device__ __forceinline__ void packed_step(const float2 (&cur)[5], int k, int n, int q, const CamF2& cam,
                                             const CamParams& camd, const PackedPose& pose, f2* acc, double* g)
 {
-    const bool masked = k >= k_full;              // warp-uniform: some lane runs out of corners in this step
+    // kMasked: some lane of the warp runs out of corners in this step (k >= k_full, warp-uniform: the last step of an edge);
+    // the full steps carry no weights and no selects at all
     const int c0 = 8 * k + 2 * q;
-    const f2 w = f2_make(c0 < n ? 1.0f : 0.0f, c0 + 1 < n ? 1.0f : 0.0f);
+    const f2 w = kMasked ? f2_make(c0 < n ? 1.0f : 0.0f, c0 + 1 < n ? 1.0f : 0.0f) : f2_dup(1.0f);
     f2 e0 = f2_dup(0.0f), e1 = f2_dup(0.0f);
     if (kMixed) {
         double ea[2], eb[2];
@@ -601,12 +610,12 @@ __device__ __forceinline__ void packed_step(const float2 (&cur)[5], int k, int n
         e1 = f2_make((float)ea[1], (float)eb[1]);
         // the cost the accept / reject test compares is summed in double from the exact residuals
         const double ca = fma(ea[0], ea[0], ea[1] * ea[1]), cb = fma(eb[0], eb[0], eb[1] * eb[1]);
-        if (masked) g[6] += (c0 < n ? ca : 0.0) + (c0 + 1 < n ? cb : 0.0);
+        if (kMasked) g[6] += (c0 < n ? ca : 0.0) + (c0 + 1 < n ? cb : 0.0);
         else g[6] += ca + cb;
     }
     corner_pair_accumulate<kModel, kRational, kMixed>(cam, pose.Rf, pose.Tf, f2_make(cur[0].x, cur[0].y), f2_make(cur[1].x, cur[1].y),
                                                       f2_make(cur[2].x, cur[2].y), f2_make(cur[3].x, cur[3].y),
-                                                      f2_make(cur[4].x, cur[4].y), w, masked, acc, e0, e1);
+                                                      f2_make(cur[4].x, cur[4].y), w, kMasked, acc, e0, e1);
 }
 
 template <int kModel, bool kRational, bool kExactE>
@@ -614,44 +623,26 @@ __device__ __forceinline__ void packed_edge_loop(ObsStream& S, int& consumed, fl
                                                  int stride, int n_tiles, int wq, int lane, int kp, int n, int q, int k_full,
                                                  const CamF2& cam, const CamParams& camd, const PackedPose& pose, f2* acc, double* cost)
 {
-    int k = 0;
-#if MCCBA_F32_PAIRSTEPS
-    // Two steps per trip, evaluated in ONE basic block: their projection chains are independent, so the scheduler can
-    // interleave them -- with 3 warps per scheduler and dependent f32x2 / f64 chains a single step left the issue slots
-    // half empty (profiles/r2_k1_f32_v3.txt: 53 % issue slots busy, "wait" the top stall).
-    for (; k + 1 < kp; k += 2) {
-        const int s0 = consumed & (kObsStages - 1), s1 = (consumed + 1) & (kObsStages - 1);
-        mbar_wait(&bars[s0], (unsigned)((consumed / kObsStages) & 1));
-        mbar_wait(&bars[s1], (unsigned)(((consumed + 1) / kObsStages) & 1));
-        float2 c0[5], c1[5];
-#pragma unroll
-        for (int pl = 0; pl < 5; ++pl) { c0[pl] = ring[((size_t)s0 * 5 + pl) * 32 + lane]; c1[pl] = ring[((size_t)s1 * 5 + pl) * 32 + lane]; }
-        consumed += 2;
-        __syncwarp();                                   // every lane has taken its pairs out of the two stages ...
-        if (lane == 0) {                                // ... which are refilled kObsStages steps ahead
-            obs_stream_issue(S, P, stride, n_tiles, wq, ring, bars);
-            obs_stream_issue(S, P, stride, n_tiles, wq, ring, bars);
-        }
-#if MCCBA_F32_RELOAD
-        asm volatile("" ::: "memory");     // pose and intrinsics are re-read from shared memory per trip, not kept in ~90 registers
-#endif
-        packed_step<kModel, kRational, kExactE>(c0, k, n, q, k_full, cam, camd, pose, acc, cost);
-        packed_step<kModel, kRational, kExactE>(c1, k + 1, n, q, k_full, cam, camd, pose, acc, cost);
-    }
-#endif
-    for (; k < kp; ++k) {
+    for (int k = 0; k < kp;) {
+        const int nst = min(kObsChunk, kp - k);
         const int stg = consumed & (kObsStages - 1);
         mbar_wait(&bars[stg], (unsigned)((consumed / kObsStages) & 1));
-        float2 cur[5];
+        const float2* src = ring + (size_t)stg * kObsStageF2 + lane;
+        for (int j = 0; j < nst; ++j, ++k) {
+            float2 cur[5];
 #pragma unroll
-        for (int pl = 0; pl < 5; ++pl) cur[pl] = ring[((size_t)stg * 5 + pl) * 32 + lane];
-        ++consumed;
-        __syncwarp();
-        if (lane == 0) obs_stream_issue(S, P, stride, n_tiles, wq, ring, bars);
+            for (int pl = 0; pl < 5; ++pl) cur[pl] = src[(j * 5 + pl) * 32];
+            if (j == nst - 1) {                     // every lane has taken the last pairs out of the stage: refill it
+                ++consumed;
+                __syncwarp();
+                if (lane == 0) obs_stream_issue(S, P, stride, n_tiles, wq, ring, bars);
+            }
 #if MCCBA_F32_RELOAD
-        asm volatile("" ::: "memory");     // pose and intrinsics are re-read from shared memory per step, not kept in ~90 registers
+            asm volatile("" ::: "memory");     // pose and intrinsics are re-read from shared memory per step, not kept in ~90 registers
 #endif
-        packed_step<kModel, kRational, kExactE>(cur, k, n, q, k_full, cam, camd, pose, acc, cost);
+            if (k < k_full) packed_step<kModel, kRational, kExactE, false>(cur, k, n, q, cam, camd, pose, acc, cost);
+            else packed_step<kModel, kRational, kExactE, true>(cur, k, n, q, cam, camd, pose, acc, cost);
+        }
     }
 }
 
@@ -660,8 +651,8 @@ template <bool kExactE>
 __global__ void __launch_bounds__(kF32Threads, MCCBA_F32_MINBLOCKS) resid_jac_accum_f32_kernel(Problem P, int forced)
 {
     extern __shared__ __align__(128) unsigned char f32_smem[];
-    float2* s_ring = reinterpret_cast<float2*>(f32_smem);                                   // [4 warps][kObsStages][5][32]
-    unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(s_ring + 4 * kObsStages * 5 * 32);   // [4][kObsStages]
+    float2* s_ring = reinterpret_cast<float2*>(f32_smem);                                   // [4 warps][kObsStages][kObsChunk][5][32]
+    unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(s_ring + 4 * kObsStages * kObsStageF2);   // [4][kObsStages]
     PackedPose* s_pose = reinterpret_cast<PackedPose*>(s_bar + 4 * kObsStages);            // [32]
     CamF2* s_cam = reinterpret_cast<CamF2*>(s_pose + 32);
     CamParams* s_camd = reinterpret_cast<CamParams*>(s_cam + P.n_cam);
@@ -679,7 +670,7 @@ __global__ void __launch_bounds__(kF32Threads, MCCBA_F32_MINBLOCKS) resid_jac_ac
         s_cam[c] = make_cam_f2(cp);
     }
     const int lane = threadIdx.x & 31, q = lane & 3, el = lane >> 2, wq = threadIdx.x >> 5;
-    float2* ring = s_ring + (size_t)wq * kObsStages * 5 * 32;
+    float2* ring = s_ring + (size_t)wq * kObsStages * kObsStageF2;
     unsigned long long* bars = s_bar + wq * kObsStages;
     if (lane == 0) {
 #pragma unroll
@@ -715,8 +706,8 @@ __global__ void __launch_bounds__(kF32Threads, MCCBA_F32_MINBLOCKS) resid_jac_ac
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
             const int j = q + 4 * i;
-            if (j < 9) { pose.Rd[j] = rq[i]; pose.Rf[j] = f2_dup((float)rq[i]); }
-            else { pose.Td[j - 9] = rq[i]; pose.Tf[j - 9] = f2_dup((float)rq[i]); }
+            if (j < 9) { pose.Rd[j] = rq[i]; pose.Rf[j] = (float)rq[i]; }
+            else { pose.Td[j - 9] = rq[i]; pose.Tf[j - 9] = (float)rq[i]; }
         }
         __syncwarp();
         {   // the next tile's records travel while this one is evaluated
@@ -735,7 +726,7 @@ __global__ void __launch_bounds__(kF32Threads, MCCBA_F32_MINBLOCKS) resid_jac_ac
         for (int k = 0; k < kBlk; ++k) acc[k] = f2_dup(0.0f);
         double cost[7] = {0, 0, 0, 0, 0, 0, 0};      // MIXED: [6] = sum |e|^2 in double
 #if MCCBA_F32_POSE_REGS
-        PackedPose pose_r;      // the edge's pose in registers for the whole edge (48 registers, no reloads)
+        PackedPose pose_r;      // the edge's pose in registers for the whole edge (36 registers, no reloads)
 #pragma unroll
         for (int i = 0; i < 9; ++i) { pose_r.Rd[i] = pose.Rd[i]; pose_r.Rf[i] = pose.Rf[i]; }
 #pragma unroll

@@ -47,9 +47,9 @@ static void edge_block_f32(const CamParams& cam, const double* Rc, const double*
 {
     double R3d[9], T3d[3];
     compose_pose(Rc, tc, Rp, tp, R3d, T3d);
-    f2 R3[9], T3[3];
-    for (int i = 0; i < 9; ++i) R3[i] = f2_dup((float)R3d[i]);
-    for (int i = 0; i < 3; ++i) T3[i] = f2_dup((float)T3d[i]);
+    float R3[9], T3[3];
+    for (int i = 0; i < 9; ++i) R3[i] = (float)R3d[i];
+    for (int i = 0; i < 3; ++i) T3[i] = (float)T3d[i];
     const CamF2 c2 = make_cam_f2(cam);
     const int n = (int)(e - b), kp = (n + 7) / 8;
     float v[4][kBlk];
