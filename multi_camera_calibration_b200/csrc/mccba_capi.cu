@@ -1029,6 +1029,9 @@ int mccba_set_observations(mccba_handle h, int n_frame, int n_edge, const int* e
         float2* obs2 = nullptr;
         if ((rc = dev_alloc(h, &obs2, (size_t)std::max<int64_t>(tot, 1)))) return rc;
         P.obs2 = obs2;
+        int* nonplanar = nullptr;
+        if ((rc = dev_alloc(h, &nonplanar, 1, true))) return rc;      // zeroed on the stream the gather kernel runs on
+        P.obs_nonplanar = nonplanar;
         h->f32_smem = (int)f32_smem_bytes(nC);
         int per_sm_f = 1;
         if (P.prec == MCCBA_PRECISION_MIXED) {
@@ -1043,7 +1046,7 @@ int mccba_set_observations(mccba_handle h, int n_frame, int n_edge, const int* e
         h->f32_grid = std::max(1, std::min(n_tiles, h->num_sms * std::max(per_sm_f, 1)));
         CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_copy, 0));
         gather_obs_packed_kernel<<<std::min(n_tiles, h->num_sms * 16), 256, 0, h->stream>>>(n_tiles, P.tile_off, P.tile_kp, P.e_off, d_esrc,
-                                                                                            d_obj, d_img, obs2);
+                                                                                            d_obj, d_img, obs2, nonplanar);
         if (autop) edge_extent_kernel<<<h->num_sms * 8, 256, 0, h->stream>>>(P.n_edge_int, P.e_off, d_esrc, d_obj, const_cast<float*>(P.edge_extent));
     }
     if (!P.prec || autop) {

@@ -126,6 +126,7 @@ struct Problem {
     // a warp reads five contiguous 256-byte lines per step
     int prec;                // 0: fp64 per-corner arithmetic (SoA planes); 1: packed f32x2 Jacobian + fp64 residual; 2: all f32x2
     const float2* obs2;
+    const int* obs_nonplanar; // 1 if any object point of the packed layout has z != 0 (set by gather_obs_packed_kernel); flat boards skip the z terms
     const int64_t* tile_off; // per tile: first float2 of its block
     const int* tile_kp;      // per tile: steps per quarter = ceil(max corners per edge / 8)
     EdgeRec* erec;       // n_edge_int composed poses of the point the residual kernel evaluates next
@@ -588,14 +589,14 @@ struct alignas(16) PackedPose {
 };
 __host__ __device__ inline size_t f32_smem_bytes(int n_cam)
 {
-    return (size_t)4 * kObsStages * kObsChunk * kObsStepBytes + 4 * kObsStages * 8 + 32 * sizeof(PackedPose) + (sizeof(CamF2) + sizeof(CamParams)) * (size_t)n_cam;
+    return (size_t)4 * kObsStages * kObsChunk * kObsStepBytes + 4 * kObsStages * 8 + 32 * sizeof(PackedPose) + (sizeof(CamF2) + sizeof(CamResid)) * (size_t)n_cam;
 }
 
 // One step of one lane: two corners.  kMixed: the residual pair comes from a double projection (corner_residual) and the
 // cost is summed in double (g[6]); Jacobian, J^T J and J^T e in f32x2 (acc[0..26]).  Else everything in f32x2 (acc[0..27]).
-template <int kModel, bool kRational, bool kMixed, bool kMasked>
+template <int kModel, bool kRational, bool kMixed, bool kMasked, bool kPlanar>
 __device__ __forceinline__ void packed_step(const float2 (&cur)[5], int k, int n, int q, const CamF2& cam,
-                                            const CamParams& camd, const PackedPose& pose, f2* acc, double* g)
+                                            const CamResid& camd, const PackedPose& pose, f2* acc, double* g)
 {
     // kMasked: some lane of the warp runs out of corners in this step (k >= k_full, warp-uniform: the last step of an edge);
     // the full steps carry no weights and no selects at all
@@ -604,8 +605,8 @@ __device__ __forceinline__ void packed_step(const float2 (&cur)[5], int k, int n
     f2 e0 = f2_dup(0.0f), e1 = f2_dup(0.0f);
     if (kMixed) {
         double ea[2], eb[2];
-        corner_residual<kModel, kRational>(camd, pose.Rd, pose.Td, cur[0].x, cur[1].x, cur[2].x, cur[3].x, cur[4].x, ea);
-        corner_residual<kModel, kRational>(camd, pose.Rd, pose.Td, cur[0].y, cur[1].y, cur[2].y, cur[3].y, cur[4].y, eb);
+        corner_residual<kModel, kRational, kPlanar>(camd, pose.Rd, pose.Td, cur[0].x, cur[1].x, cur[2].x, cur[3].x, cur[4].x, ea);
+        corner_residual<kModel, kRational, kPlanar>(camd, pose.Rd, pose.Td, cur[0].y, cur[1].y, cur[2].y, cur[3].y, cur[4].y, eb);
         e0 = f2_make((float)ea[0], (float)eb[0]);
         e1 = f2_make((float)ea[1], (float)eb[1]);
         // the cost the accept / reject test compares is summed in double from the exact residuals
@@ -613,15 +614,15 @@ __device__ __forceinline__ void packed_step(const float2 (&cur)[5], int k, int n
         if (kMasked) g[6] += (c0 < n ? ca : 0.0) + (c0 + 1 < n ? cb : 0.0);
         else g[6] += ca + cb;
     }
-    corner_pair_accumulate<kModel, kRational, kMixed>(cam, pose.Rf, pose.Tf, f2_make(cur[0].x, cur[0].y), f2_make(cur[1].x, cur[1].y),
+    corner_pair_accumulate<kModel, kRational, kMixed, kPlanar>(cam, pose.Rf, pose.Tf, f2_make(cur[0].x, cur[0].y), f2_make(cur[1].x, cur[1].y),
                                                       f2_make(cur[2].x, cur[2].y), f2_make(cur[3].x, cur[3].y),
                                                       f2_make(cur[4].x, cur[4].y), w, kMasked, acc, e0, e1);
 }
 
-template <int kModel, bool kRational, bool kExactE>
+template <int kModel, bool kRational, bool kExactE, bool kPlanar>
 __device__ __forceinline__ void packed_edge_loop(ObsStream& S, int& consumed, float2* ring, unsigned long long* bars, const Problem& P,
                                                  int stride, int n_tiles, int wq, int lane, int kp, int n, int q, int k_full,
-                                                 const CamF2& cam, const CamParams& camd, const PackedPose& pose, f2* acc, double* cost)
+                                                 const CamF2& cam, const CamResid& camd, const PackedPose& pose, f2* acc, double* cost)
 {
     for (int k = 0; k < kp;) {
         const int nst = min(kObsChunk, kp - k);
@@ -640,8 +641,8 @@ __device__ __forceinline__ void packed_edge_loop(ObsStream& S, int& consumed, fl
 #if MCCBA_F32_RELOAD
             asm volatile("" ::: "memory");     // pose and intrinsics are re-read from shared memory per step, not kept in ~90 registers
 #endif
-            if (k < k_full) packed_step<kModel, kRational, kExactE, false>(cur, k, n, q, cam, camd, pose, acc, cost);
-            else packed_step<kModel, kRational, kExactE, true>(cur, k, n, q, cam, camd, pose, acc, cost);
+            if (k < k_full) packed_step<kModel, kRational, kExactE, false, kPlanar>(cur, k, n, q, cam, camd, pose, acc, cost);
+            else packed_step<kModel, kRational, kExactE, true, kPlanar>(cur, k, n, q, cam, camd, pose, acc, cost);
         }
     }
 }
@@ -655,7 +656,7 @@ __global__ void __launch_bounds__(kF32Threads, MCCBA_F32_MINBLOCKS) resid_jac_ac
     unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(s_ring + 4 * kObsStages * kObsStageF2);   // [4][kObsStages]
     PackedPose* s_pose = reinterpret_cast<PackedPose*>(s_bar + 4 * kObsStages);            // [32]
     CamF2* s_cam = reinterpret_cast<CamF2*>(s_pose + 32);
-    CamParams* s_camd = reinterpret_cast<CamParams*>(s_cam + P.n_cam);
+    CamResid* s_camd = reinterpret_cast<CamResid*>(s_cam + P.n_cam);
     const DevState* st = P.st;
     int which;
     if (forced) which = st->cur;
@@ -664,9 +665,10 @@ __global__ void __launch_bounds__(kF32Threads, MCCBA_F32_MINBLOCKS) resid_jac_ac
         which = 1 - st->cur;
     }
     double* __restrict__ out = P.blocks[which];
+    const bool planar = *P.obs_nonplanar == 0;
     for (int c = threadIdx.x; c < P.n_cam; c += blockDim.x) {
         const CamParams cp = P.cams[c];
-        s_camd[c] = cp;
+        s_camd[c] = make_cam_resid(cp);
         s_cam[c] = make_cam_f2(cp);
     }
     const int lane = threadIdx.x & 31, q = lane & 3, el = lane >> 2, wq = threadIdx.x >> 5;
@@ -736,13 +738,22 @@ __global__ void __launch_bounds__(kF32Threads, MCCBA_F32_MINBLOCKS) resid_jac_ac
 #define MCCBA_POSE pose
 #endif
         const CamF2& cam = s_cam[cam_idx];      // the 32 edges of a tile are one (group, view) run: one camera per warp
-        const CamParams& camd = s_camd[cam_idx];
-        if (cam.model == kPinhole) {
-            if (cam.rational) packed_edge_loop<kPinhole, true, kExactE>(S, consumed, ring, bars, P, stride, n_tiles, wq, lane, kp, n, q, k_full, cam, camd, MCCBA_POSE, acc, cost);
-            else packed_edge_loop<kPinhole, false, kExactE>(S, consumed, ring, bars, P, stride, n_tiles, wq, lane, kp, n, q, k_full, cam, camd, MCCBA_POSE, acc, cost);
+        const CamResid& camd = s_camd[cam_idx];
+#define MCCBA_EDGE_LOOP(MODEL, RATIONAL, PLANAR)                                                                                   \
+    packed_edge_loop<MODEL, RATIONAL, kExactE, PLANAR>(S, consumed, ring, bars, P, stride, n_tiles, wq, lane, kp, n, q, k_full, cam, \
+                                                       camd, MCCBA_POSE, acc, cost)
+        if (planar) {       // flat boards (every object z is 0): the z column of the pose drops out, bit-identically
+            if (cam.model == kPinhole) {
+                if (cam.rational) MCCBA_EDGE_LOOP(kPinhole, true, true);
+                else MCCBA_EDGE_LOOP(kPinhole, false, true);
+            } else MCCBA_EDGE_LOOP(kOmnidir, false, true);
         } else {
-            packed_edge_loop<kOmnidir, false, kExactE>(S, consumed, ring, bars, P, stride, n_tiles, wq, lane, kp, n, q, k_full, cam, camd, MCCBA_POSE, acc, cost);
+            if (cam.model == kPinhole) {
+                if (cam.rational) MCCBA_EDGE_LOOP(kPinhole, true, false);
+                else MCCBA_EDGE_LOOP(kPinhole, false, false);
+            } else MCCBA_EDGE_LOOP(kOmnidir, false, false);
         }
+#undef MCCBA_EDGE_LOOP
         // halves, then the 4 lanes of the edge: 28 -> 14 -> 7 values per lane (transposed butterfly)
         float v[kBlk];
 #pragma unroll
@@ -838,7 +849,8 @@ __global__ void __launch_bounds__(kF32Threads) reproj_error_packed_kernel(Proble
 // observations: AoS host layout -> packed pair layout of the single-precision pass.  One thread per (step, lane) slot.
 __global__ void gather_obs_packed_kernel(int n_tiles, const int64_t* __restrict__ tile_off, const int* __restrict__ tile_kp,
                                          const int* __restrict__ e_off, const int64_t* __restrict__ e_src,
-                                         const float* __restrict__ obj, const float* __restrict__ img, float2* __restrict__ obs2)
+                                         const float* __restrict__ obj, const float* __restrict__ img, float2* __restrict__ obs2,
+                                         int* __restrict__ nonplanar)
 {
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int kp = tile_kp[tile];
@@ -860,6 +872,7 @@ __global__ void gather_obs_packed_kernel(int n_tiles, const int64_t* __restrict_
             }
 #pragma unroll
             for (int pl = 0; pl < 5; ++pl) dst[((size_t)wk * 5 + pl) * 32 + lane] = make_float2(a[pl], b[pl]);
+            if (a[2] != 0.0f || b[2] != 0.0f) *nonplanar = 1;   // benign race: every writer stores the same value
         }
     }
 }

@@ -68,10 +68,11 @@ static void edge_block_f32(const CamParams& cam, const double* Rc, const double*
             if (kExactE)
                 for (int h = 0; h < 2; ++h) {
                     double ed[2];
+                    const CamResid camr = make_cam_resid(cam);
                     if (cam.model == kPinhole) {
-                        if (cam.rational) corner_residual<kPinhole, true>(cam, R3d, T3d, o[0][h], o[1][h], o[2][h], o[3][h], o[4][h], ed);
-                        else corner_residual<kPinhole, false>(cam, R3d, T3d, o[0][h], o[1][h], o[2][h], o[3][h], o[4][h], ed);
-                    } else corner_residual<kOmnidir, false>(cam, R3d, T3d, o[0][h], o[1][h], o[2][h], o[3][h], o[4][h], ed);
+                        if (cam.rational) corner_residual<kPinhole, true, false>(camr, R3d, T3d, o[0][h], o[1][h], o[2][h], o[3][h], o[4][h], ed);
+                        else corner_residual<kPinhole, false, false>(camr, R3d, T3d, o[0][h], o[1][h], o[2][h], o[3][h], o[4][h], ed);
+                    } else corner_residual<kOmnidir, false, false>(camr, R3d, T3d, o[0][h], o[1][h], o[2][h], o[3][h], o[4][h], ed);
                     ex[0][h] = (float)ed[0]; ex[1][h] = (float)ed[1];
                 }
             const f2 w = f2_make(c0 < n ? 1.0f : 0.0f, c0 + 1 < n ? 1.0f : 0.0f);

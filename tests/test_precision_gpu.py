@@ -140,3 +140,49 @@ def test_auto_policy_follows_the_board_geometry(oracle_lib):
             sm.solve(**kw)
             assert _param_rel(sm.get_parameters(), ref["params"]) > 1e-6      # what AUTO avoided
             sm.close()
+
+
+@pytest.mark.parametrize("name", ["mixed4_v3_ragged", "rational2"])
+def test_non_planar_object_points(solvers, oracle_lib, name):
+    """The packed pass drops the z column of the composed pose when every object point of the problem has z = 0 (a flat
+    board, decided on the device while the packed layout is built).  Every other rig of the suite is flat; here the object
+    points get a z coordinate (a 3-D target, or a back pattern moved into the front pattern's frame), so the general
+    path runs: per-edge blocks against the fp64 pass and Gauss-Newton iterates against the oracle; and the general path
+    on a numerically flat problem (z = 1e-30) must reproduce the blocks of the flat path."""
+    import multi_camera_calibration_b200 as m
+    rig = dict(rigs.make_rig(**RIGS[name]))
+    rng = np.random.default_rng(11)
+    obj = np.array(rig["obj"], dtype=np.float32, copy=True)
+    assert not obj[:, 2].any()
+    flat_blocks = {}
+    for p in (m.capi.PRECISION_MIXED, m.capi.PRECISION_FAST32):
+        s = solvers[p]
+        s.set_rig(rig); s.set_parameters(rig["params_init"])
+        flat_blocks[p] = s.eval()
+    # (a) z = a tiny value: the general path, numerically the flat problem -> same blocks to float32 rounding
+    tiny = dict(rig); tiny["obj"] = obj.copy(); tiny["obj"][:, 2] = np.float32(1e-30)
+    for p in (m.capi.PRECISION_MIXED, m.capi.PRECISION_FAST32):
+        s = solvers[p]
+        s.set_rig(tiny); s.set_parameters(rig["params_init"])
+        o = s.eval()
+        for key in ("H6", "g6", "edge_cost"):
+            assert np.abs(o[key] - flat_blocks[p][key]).max() <= 2e-7 * np.abs(flat_blocks[p][key]).max(), (p, key)   # float32 ulps
+    # (b) a genuinely three-dimensional target
+    bumpy = dict(rig); bumpy["obj"] = obj.copy()
+    bumpy["obj"][:, 2] = (0.05 * np.abs(obj[:, :2]).max() * rng.standard_normal(obj.shape[0])).astype(np.float32)
+    outs = {}
+    for p, s in solvers.items():
+        s.set_rig(bumpy); s.set_parameters(rig["params_init"])
+        outs[p] = s.eval()
+    a = outs[m.capi.PRECISION_FP64]
+    for p in (m.capi.PRECISION_MIXED, m.capi.PRECISION_FAST32):
+        for key in ("H6", "g6", "edge_cost"):
+            assert np.abs(outs[p][key] - a[key]).max() <= 5e-6 * np.abs(a[key]).max(), (p, key)
+    O = rigs.to_oracle_rig(bumpy)
+    ref = O.solve(rig["params_init"], mode=0, crit_type=1, max_count=6)
+    for p, tol in ((m.capi.PRECISION_FP64, 1e-8), (m.capi.PRECISION_MIXED, 1e-6)):
+        s = solvers[p]
+        s.set_rig(bumpy); s.set_parameters(rig["params_init"])
+        rep = s.solve(mode=0, crit_type=1, max_count=6)
+        assert rep["iterations"] == ref["iters"]
+        assert _param_rel(s.get_parameters(), ref["params"]) < tol, (p, _param_rel(s.get_parameters(), ref["params"]))
