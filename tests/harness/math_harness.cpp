@@ -40,8 +40,8 @@ static void edge_block(const CamParams& cam, const double* Rc, const double* tc,
 // The packed single-precision pass re-enacted in the device kernel's own order: 4 lanes per edge, lane q takes corners
 // 8k + 2q, 8k + 2q + 1 in step k as one f32x2 pair; halves, then lanes (q, q^2), then (q, q^1) are added in float; the
 // 28 sums are promoted to double (resid_jac_accum_f32_kernel).  exact_e: MIXED policy (residual from the double
-// projection); otherwise the all-float32 variant.
-template <bool kExactE>
+// projection); otherwise the all-float32 variant.  kPlanar: the flat-board variant of both projections (object z = 0).
+template <bool kExactE, bool kPlanar>
 static void edge_block_f32(const CamParams& cam, const double* Rc, const double* tc, const double* Rp, const double* tp,
                            int64_t b, int64_t e, const float* obj, const float* img, double* acc)
 {
@@ -70,9 +70,9 @@ static void edge_block_f32(const CamParams& cam, const double* Rc, const double*
                     double ed[2];
                     const CamResid camr = make_cam_resid(cam);
                     if (cam.model == kPinhole) {
-                        if (cam.rational) corner_residual<kPinhole, true, false>(camr, R3d, T3d, o[0][h], o[1][h], o[2][h], o[3][h], o[4][h], ed);
-                        else corner_residual<kPinhole, false, false>(camr, R3d, T3d, o[0][h], o[1][h], o[2][h], o[3][h], o[4][h], ed);
-                    } else corner_residual<kOmnidir, false, false>(camr, R3d, T3d, o[0][h], o[1][h], o[2][h], o[3][h], o[4][h], ed);
+                        if (cam.rational) corner_residual<kPinhole, true, kPlanar>(camr, R3d, T3d, o[0][h], o[1][h], o[2][h], o[3][h], o[4][h], ed);
+                        else corner_residual<kPinhole, false, kPlanar>(camr, R3d, T3d, o[0][h], o[1][h], o[2][h], o[3][h], o[4][h], ed);
+                    } else corner_residual<kOmnidir, false, kPlanar>(camr, R3d, T3d, o[0][h], o[1][h], o[2][h], o[3][h], o[4][h], ed);
                     ex[0][h] = (float)ed[0]; ex[1][h] = (float)ed[1];
                 }
             const f2 w = f2_make(c0 < n ? 1.0f : 0.0f, c0 + 1 < n ? 1.0f : 0.0f);
@@ -81,9 +81,9 @@ static void edge_block_f32(const CamParams& cam, const double* Rc, const double*
             const f2 U = f2_make(o[3][0], o[3][1]), V = f2_make(o[4][0], o[4][1]);
             const f2 e0 = f2_make(ex[0][0], ex[0][1]), e1 = f2_make(ex[1][0], ex[1][1]);
             if (cam.model == kPinhole) {
-                if (cam.rational) corner_pair_accumulate<kPinhole, true, kExactE>(c2, R3, T3, X0, X1, X2, U, V, w, masked, a, e0, e1);
-                else corner_pair_accumulate<kPinhole, false, kExactE>(c2, R3, T3, X0, X1, X2, U, V, w, masked, a, e0, e1);
-            } else corner_pair_accumulate<kOmnidir, false, kExactE>(c2, R3, T3, X0, X1, X2, U, V, w, masked, a, e0, e1);
+                if (cam.rational) corner_pair_accumulate<kPinhole, true, kExactE, kPlanar>(c2, R3, T3, X0, X1, X2, U, V, w, masked, a, e0, e1);
+                else corner_pair_accumulate<kPinhole, false, kExactE, kPlanar>(c2, R3, T3, X0, X1, X2, U, V, w, masked, a, e0, e1);
+            } else corner_pair_accumulate<kOmnidir, false, kExactE, kPlanar>(c2, R3, T3, X0, X1, X2, U, V, w, masked, a, e0, e1);
         }
         for (int k = 0; k < kBlk; ++k) v[q][k] = f2_lo(a[k]) + f2_hi(a[k]);
     }
@@ -114,8 +114,10 @@ int hm_rig_step(int n_cam, int n_frame, int n_edge, const int* edge_cam, const i
         const CamParams& cm = cams[edge_cam[e]];
         const double *Rc = &vR[9 * edge_cam[e]], *tc = &vt[3 * edge_cam[e]], *Rp = &vR[9 * edge_pv[e]], *tp = &vt[3 * edge_pv[e]];
         double* blk = blocks + (size_t)kBlk * e;
-        if (policy == 1) edge_block_f32<true>(cm, Rc, tc, Rp, tp, edge_off[e], edge_off[e + 1], obj, img, blk);        // MIXED
-        else if (policy == 2) edge_block_f32<false>(cm, Rc, tc, Rp, tp, edge_off[e], edge_off[e + 1], obj, img, blk);  // all float32
+        if (policy == 1) edge_block_f32<true, false>(cm, Rc, tc, Rp, tp, edge_off[e], edge_off[e + 1], obj, img, blk);        // MIXED
+        else if (policy == 2) edge_block_f32<false, false>(cm, Rc, tc, Rp, tp, edge_off[e], edge_off[e + 1], obj, img, blk);  // all float32
+        else if (policy == 3) edge_block_f32<true, true>(cm, Rc, tc, Rp, tp, edge_off[e], edge_off[e + 1], obj, img, blk);    // MIXED, flat-board path
+        else if (policy == 4) edge_block_f32<false, true>(cm, Rc, tc, Rp, tp, edge_off[e], edge_off[e + 1], obj, img, blk);   // all float32, flat-board path
         else edge_block(cm, Rc, tc, Rp, tp, edge_off[e], edge_off[e + 1], obj, img, blk);
     }
     for (int i = 0; i < ns * ns; ++i) S[i] = 0;
