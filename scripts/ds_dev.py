@@ -1,5 +1,7 @@
+"""Deviation of the first Gauss-Newton iterates of the double-sided problem (tests/test_double_side.py) from the oracle,
+per precision policy (development aid; MCCBA_LIB selects a kernel variant):  python scripts/ds_dev.py"""
 import sys, os
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import multi_camera_calibration_b200 as m
 from tests import test_double_side as t
