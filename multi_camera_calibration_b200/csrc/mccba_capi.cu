@@ -1018,7 +1018,7 @@ int mccba_set_observations(mccba_handle h, int n_frame, int n_edge, const int* e
         for (int t = 0; t < n_tiles; ++t) {
             int mx = 0;
             for (int e = 32 * t; e < 32 * t + 32; ++e) mx = std::max(mx, e_off[(size_t)e + 1] - e_off[(size_t)e]);
-            const int kp = (mx + 7) / 8;
+            const int kp = std::max(1, (mx + 7) / 8);    // a tile of empty edges still gets one (all-padding) step: the stream never issues an empty copy
             tile_kp[(size_t)t] = kp;
             tile_off[(size_t)t] = tot;
             tot += (int64_t)4 * kp * 5 * 32;
